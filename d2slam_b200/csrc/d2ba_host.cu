@@ -1,0 +1,946 @@
+// d2ba_host.cu -- host side of libd2ba.so: C-ABI entry points (include/d2ba.h), problem assembly
+// (pair-major sorting, 32-observation tiles, landmark CSR), device arena, launch sequencing / CUDA
+// graph, NCCL consensus exchange.  No numerics of the solve run on the host; there is no CPU
+// fallback (d2ba_create fails without a CUDA device).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/d2ba.h"
+#include "d2ba_types.cuh"
+
+namespace d2ba {
+// launchers implemented in d2ba_kernels.cu
+void launch_state_prep(const Dev &d, int n6_total, int buf, cudaStream_t s);
+void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s);
+void launch_prior_prep(const Dev &d, cudaStream_t s);
+void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s);
+int configure_kernels(int max_rows, int max_nc, int max_prior_m);
+void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int job_count, cudaStream_t s);
+void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s);
+void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s);
+void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s);
+void launch_chol(const Dev &d, int max_rows, cudaStream_t s);
+void launch_step(const Dev &d, int max_nc, cudaStream_t s);
+void launch_control(const Dev &d, int init, cudaStream_t s);
+void launch_tr_reset(const Dev &d, int first, cudaStream_t s);
+void launch_cons_init(const Dev &d, int n6_total, cudaStream_t s);
+void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
+void launch_cons_apply(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
+void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_win, const int *lm_win, cudaStream_t s);
+struct SchurTileH { int win, kind, tm, tn; };
+}  // namespace d2ba
+
+using namespace d2ba;
+
+namespace {
+
+struct HObs { int type, pi, pj, ea, eb, lm; double f[kObsFields]; int64_t seq; };
+struct HImu { int pi, si, pj, sj; double c[kImuStride]; };
+struct HPriorBlk { int kind, index, off, eff; double x0[9]; };
+
+struct HostWin {
+  bool used = false;
+  std::vector<int64_t> pose_id, ext_id, sb_id, lm_id;
+  std::unordered_map<int64_t, int> pose_map, ext_map, sb_map, lm_map;
+  std::vector<double> pose, ext, sb, lm;
+  std::vector<uint8_t> pose_c, ext_c, sb_c;
+  double td = 0; bool has_td = false; uint8_t td_c = 1;
+  std::vector<HObs> obs;
+  std::vector<HImu> imu;
+  int prior_m = 0; std::vector<double> prior_J, prior_e0; std::vector<HPriorBlk> prior_blk; bool prior_is_info = false;
+  std::vector<int> pose_slot, ext_slot; bool admm = false; int n_slots = 0;
+  // derived at finalize
+  std::vector<int> pose_col, ext_col, sb_col; int td_col = -1, n_lc = 0, n_c = 0;
+  std::vector<HObs> sorted;          // sorted observation list
+  std::vector<int> sorted_pos;       // position (tile slot) of sorted[k] inside the window
+  void clear() { *this = HostWin(); }
+};
+
+// ---- minimal NCCL surface resolved with dlopen (torch ships libnccl.so.2; no link-time dependency)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct Nccl {
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err) {
+    if (lib) return true;
+    const char *env = getenv("D2BA_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { if (!n) continue; lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (int (*)(ncclUniqueId_t *))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId_t, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+Nccl g_nccl;
+
+template <typename T>
+struct DBuf {
+  T *p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct d2ba_handle {
+  d2ba_config cfg;
+  std::string err;
+  std::vector<HostWin> win;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool finalized = false, state_dirty = false;
+  // device arena
+  DBuf<WinDesc> d_win; DBuf<Ctl> d_ctl;
+  DBuf<double> d_x6[2], d_R6[2], d_xsb[2], d_xlm[2], d_xtd[2];
+  DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_lm_obs, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
+  DBuf<Group> d_grp; DBuf<Job> d_job; DBuf<ImuDesc> d_imu; DBuf<PriorBlk> d_prior_blk;
+  DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
+      d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_dbg;
+  DBuf<SchurTileH> d_schur;
+  Dev dev;
+  std::vector<WinDesc> h_win;
+  std::vector<Ctl> h_ctl;
+  std::vector<Group> h_grp;
+  std::vector<int> h_tile_win;
+  int n_used = 0, n6_total = 0, nsb_total = 0, nl_total = 0, n_tiles = 0, n_imu_total = 0, n_schur = 0;
+  int job_begin[4] = {0, 0, 0, 0}, job_count[4] = {0, 0, 0, 0};
+  int max_rows = 1, max_nc = 1, max_prior_m = 0, max_ldw = 8, n_slots = 0;
+  int64_t totH = 0, totW = 0, totc = 0;
+  bool any_admm = false;
+  // host mirrors of the solved state
+  std::vector<double> h_x6[2], h_xsb[2], h_xlm[2], h_xtd[2];
+  // graph cache
+  cudaGraphExec_t iter_graph = nullptr; int graph_key = -1;
+  // comm
+  ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 100 + (int)e_; } } while (0)
+
+int fail(d2ba_handle *h, int rc, const std::string &m) { h->err = m; return rc; }
+
+HostWin *get_win(d2ba_handle *h, int w) {
+  if (!h || w < 0 || w >= (int)h->win.size()) return nullptr;
+  return &h->win[w];
+}
+
+void tangent_base(const double *pts_j, double *tb) {
+  // ProjectionTwoFrameOneCamFactor ctor (projectionTwoFrameOneCamFactor.cpp:34-45)
+  double n = sqrt(pts_j[0] * pts_j[0] + pts_j[1] * pts_j[1] + pts_j[2] * pts_j[2]);
+  double a[3] = {pts_j[0] / n, pts_j[1] / n, pts_j[2] / n}, t[3] = {0, 0, 1};
+  if (a[0] == t[0] && a[1] == t[1] && a[2] == t[2]) { t[0] = 1; t[2] = 0; }
+  double dt = a[0] * t[0] + a[1] * t[1] + a[2] * t[2];
+  double b1[3] = {t[0] - a[0] * dt, t[1] - a[1] * dt, t[2] - a[2] * dt};
+  double n1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+  for (int k = 0; k < 3; k++) b1[k] /= n1;
+  tb[0] = b1[0]; tb[1] = b1[1]; tb[2] = b1[2];
+  tb[3] = a[1] * b1[2] - a[2] * b1[1]; tb[4] = a[2] * b1[0] - a[0] * b1[2]; tb[5] = a[0] * b1[1] - a[1] * b1[0];
+}
+
+int find_in(const std::unordered_map<int64_t, int> &m, int64_t id) { auto it = m.find(id); return it == m.end() ? -1 : it->second; }
+
+int kind_size(int k) { return (k == D2BA_POSE || k == D2BA_EXTRINSIC) ? 7 : (k == D2BA_SPEED_BIAS ? 9 : 1); }
+int kind_eff(int k) { return (k == D2BA_POSE || k == D2BA_EXTRINSIC) ? 6 : (k == D2BA_SPEED_BIAS ? 9 : 1); }
+
+int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+void release_graph(d2ba_handle *h) {
+  if (h->iter_graph) { cudaGraphExecDestroy(h->iter_graph); h->iter_graph = nullptr; }
+  h->graph_key = -1;
+}
+
+template <typename T>
+int upload(d2ba_handle *h, DBuf<T> &b, const std::vector<T> &v) {
+  CK(b.alloc(v.size()));
+  if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+template <typename T>
+int alloc_zero(d2ba_handle *h, DBuf<T> &b, size_t n) {
+  CK(b.alloc(n));
+  CK(cudaMemsetAsync(b.p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int d2ba_default_config(d2ba_config *c) {
+  if (!c) return 1;
+  memset(c, 0, sizeof(*c));
+  c->version = D2BA_VERSION; c->device = 0; c->max_windows = 1; c->max_num_iterations = 8; c->consensus_max_steps = 0;
+  c->use_cuda_graph = 1; c->focal_length = 460.0; c->depth_sqrt_inf = 20.0; c->gravity_norm = 9.805; c->huber_delta = 1.0;
+  c->rho_frame_T = 100.0; c->rho_frame_theta = 100.0; c->rho_landmark = 1.0; c->relaxation_alpha = 0.0;
+  return 0;
+}
+
+int d2ba_create(const d2ba_config *cfg, d2ba_handle **out) {
+  if (!cfg || !out) return 1;
+  if (cfg->version != D2BA_VERSION) return 2;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { fprintf(stderr, "d2ba_create: no CUDA device (there is no CPU fallback)\n"); return 3; }
+  if (cfg->device < 0 || cfg->device >= ndev) return 4;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return 5;
+  d2ba_handle *h = new d2ba_handle();
+  h->cfg = *cfg;
+  if (h->cfg.max_windows < 1) h->cfg.max_windows = 1;
+  if (h->cfg.initial_trust_region_radius <= 0) h->cfg.initial_trust_region_radius = 1e4;
+  if (h->cfg.max_trust_region_radius <= 0) h->cfg.max_trust_region_radius = 1e16;
+  if (h->cfg.min_relative_decrease <= 0) h->cfg.min_relative_decrease = 1e-3;
+  if (h->cfg.function_tolerance <= 0) h->cfg.function_tolerance = 1e-6;
+  if (h->cfg.gradient_tolerance <= 0) h->cfg.gradient_tolerance = 1e-10;
+  if (h->cfg.parameter_tolerance <= 0) h->cfg.parameter_tolerance = 1e-8;
+  h->win.resize(h->cfg.max_windows);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  memset(&h->dev, 0, sizeof(h->dev));
+  *out = h;
+  return 0;
+}
+
+int d2ba_destroy(d2ba_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  release_graph(h);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  // DBuf members: release explicitly
+  h->d_win.release(); h->d_ctl.release();
+  for (int b = 0; b < 2; b++) { h->d_x6[b].release(); h->d_R6[b].release(); h->d_xsb[b].release(); h->d_xlm[b].release(); h->d_xtd[b].release(); h->d_rec[b].release(); h->d_H[b].release(); h->d_gc[b].release(); }
+  h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_lm_obs.release();
+  h->d_slot6.release(); h->d_lm_win.release(); h->d_blk_win.release(); h->d_sb_win.release(); h->d_tile_win.release();
+  h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release();
+  h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
+  h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
+  h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_dbg.release(); h->d_schur.release();
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int d2ba_reset(d2ba_handle *h) {
+  if (!h) return 1;
+  for (auto &w : h->win) w.clear();
+  h->finalized = false;
+  return 0;
+}
+
+const char *d2ba_last_error(const d2ba_handle *h) { return h ? h->err.c_str() : "null handle"; }
+int d2ba_num_windows(const d2ba_handle *h) { return h ? h->n_used : 0; }
+
+int d2ba_set_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, const int64_t *ids, const double *values,
+                    const uint8_t *is_const) {
+  HostWin *w = get_win(h, window);
+  if (!w) return 1;
+  w->used = true;
+  bool structural = false;
+  for (int i = 0; i < n; i++) {
+    uint8_t c = is_const ? is_const[i] : 0;
+    switch (kind) {
+      case D2BA_POSE: {
+        int k = find_in(w->pose_map, ids[i]);
+        if (k < 0) { k = (int)w->pose_id.size(); w->pose_id.push_back(ids[i]); w->pose_map[ids[i]] = k; w->pose.resize(7 * (k + 1)); w->pose_c.push_back(c); w->pose_slot.push_back(-1); structural = true; }
+        else if (w->pose_c[k] != c) structural = true;
+        memcpy(&w->pose[7 * k], values + 7 * i, 56); w->pose_c[k] = c; break;
+      }
+      case D2BA_EXTRINSIC: {
+        int k = find_in(w->ext_map, ids[i]);
+        if (k < 0) { k = (int)w->ext_id.size(); w->ext_id.push_back(ids[i]); w->ext_map[ids[i]] = k; w->ext.resize(7 * (k + 1)); w->ext_c.push_back(c); w->ext_slot.push_back(-1); structural = true; }
+        else if (w->ext_c[k] != c) structural = true;
+        memcpy(&w->ext[7 * k], values + 7 * i, 56); w->ext_c[k] = c; break;
+      }
+      case D2BA_SPEED_BIAS: {
+        int k = find_in(w->sb_map, ids[i]);
+        if (k < 0) { k = (int)w->sb_id.size(); w->sb_id.push_back(ids[i]); w->sb_map[ids[i]] = k; w->sb.resize(9 * (k + 1)); w->sb_c.push_back(c); structural = true; }
+        else if (w->sb_c[k] != c) structural = true;
+        memcpy(&w->sb[9 * k], values + 9 * i, 72); w->sb_c[k] = c; break;
+      }
+      case D2BA_TD:
+        if (!w->has_td || w->td_c != c) structural = true;
+        w->td = values[i]; w->td_c = c; w->has_td = true; break;
+      case D2BA_LANDMARK: {
+        int k = find_in(w->lm_map, ids[i]);
+        if (k < 0) { k = (int)w->lm_id.size(); w->lm_id.push_back(ids[i]); w->lm_map[ids[i]] = k; w->lm.push_back(0); structural = true; }
+        w->lm[k] = values[i]; break;
+      }
+      default: return fail(h, 2, "unknown block kind");
+    }
+  }
+  if (structural) h->finalized = false; else h->state_dirty = true;
+  return 0;
+}
+
+int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs *in) {
+  HostWin *w = get_win(h, window);
+  if (!w) return 1;
+  w->used = true; h->finalized = false;
+  for (int i = 0; i < n; i++) {
+    const d2ba_proj_obs &p = in[i];
+    HObs o; memset(&o, 0, sizeof o);
+    o.type = p.type; o.pi = o.pj = o.ea = o.eb = -1;
+    o.lm = find_in(w->lm_map, p.landmark_id);
+    if (o.lm < 0) return fail(h, 3, "add_proj: unknown landmark id");
+    if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
+      // block lists: ParamResidualInfo.hpp:34-43 (2F1C), :72-82 (2F2C), :107-115 (1F2C)
+      o.ea = find_in(w->ext_map, p.cam_a);
+      if (o.ea < 0) return fail(h, 4, "add_proj: unknown camera id");
+      if (p.type == D2BA_PROJ_2F2C || p.type == D2BA_PROJ_1F2C) { o.eb = find_in(w->ext_map, p.cam_b); if (o.eb < 0) return fail(h, 4, "add_proj: unknown camera id (b)"); }
+      if (p.type != D2BA_PROJ_1F2C) {
+        o.pi = find_in(w->pose_map, p.frame_a); o.pj = find_in(w->pose_map, p.frame_b);
+        if (o.pi < 0 || o.pj < 0) return fail(h, 5, "add_proj: unknown frame id");
+      }
+      memcpy(o.f + 0, p.pts_i, 24); memcpy(o.f + 3, p.pts_j, 24); memcpy(o.f + 6, p.vel_i, 24); memcpy(o.f + 9, p.vel_j, 24);
+      o.f[12] = p.td_i; o.f[13] = p.td_j;
+      tangent_base(p.pts_j, o.f + 14);
+      o.f[20] = (p.type == D2BA_PROJ_2F1C_DEPTH) ? 1.0 / p.depth : 0.0;
+    } else {
+      o.f[20] = 1.0 / p.depth;
+    }
+    o.seq = (int64_t)w->obs.size();
+    w->obs.push_back(o);
+  }
+  return 0;
+}
+
+int d2ba_add_landmark_tracks(d2ba_handle *h, int32_t window, int32_t n_landmarks, const int64_t *landmark_ids,
+                             const int32_t *track_ptr, const d2ba_track_obs *tobs, int32_t fuse_dep, double min_d,
+                             double max_d, int32_t n_ignore, const int64_t *ignore) {
+  // Anchor / factor-type dispatch of D2Estimator::setupLandmarkFactors (d2estimator.cpp:796-874).
+  auto ignored = [&](int64_t f) { for (int k = 0; k < n_ignore; k++) if (ignore[k] == f) return true; return false; };
+  auto depth_ok = [&](const d2ba_track_obs &t) { return t.depth_mea && fuse_dep && t.depth < max_d && t.depth > min_d; };
+  std::vector<d2ba_proj_obs> out;
+  for (int l = 0; l < n_landmarks; l++) {
+    const int b = track_ptr[l], e = track_ptr[l + 1];
+    if (e <= b) continue;
+    const d2ba_track_obs &anchor = tobs[b];
+    if (ignored(anchor.frame_id)) continue;
+    if (depth_ok(anchor)) {
+      d2ba_proj_obs p; memset(&p, 0, sizeof p);
+      p.type = D2BA_PROJ_DEPTH_PRIOR; p.frame_a = anchor.frame_id; p.cam_a = anchor.camera_id; p.landmark_id = landmark_ids[l]; p.depth = anchor.depth;
+      out.push_back(p);
+    }
+    for (int k = b + 1; k < e; k++) {
+      const d2ba_track_obs &t = tobs[k];
+      if (ignored(t.frame_id)) continue;
+      const bool same_cam = t.camera_id == anchor.camera_id, same_frame = t.frame_id == anchor.frame_id;
+      if (same_cam && same_frame) continue;
+      d2ba_proj_obs p; memset(&p, 0, sizeof p);
+      p.frame_a = anchor.frame_id; p.frame_b = t.frame_id; p.cam_a = anchor.camera_id; p.cam_b = t.camera_id; p.landmark_id = landmark_ids[l];
+      memcpy(p.pts_i, anchor.pt3d_norm, 24); memcpy(p.pts_j, t.pt3d_norm, 24); memcpy(p.vel_i, anchor.velocity, 24); memcpy(p.vel_j, t.velocity, 24);
+      p.td_i = anchor.cur_td; p.td_j = t.cur_td;
+      if (same_cam) { if (depth_ok(t)) { p.type = D2BA_PROJ_2F1C_DEPTH; p.depth = t.depth; } else p.type = D2BA_PROJ_2F1C; }
+      else p.type = same_frame ? D2BA_PROJ_1F2C : D2BA_PROJ_2F2C;
+      out.push_back(p);
+    }
+  }
+  return d2ba_add_proj(h, window, (int)out.size(), out.data());
+}
+
+int d2ba_add_imu(d2ba_handle *h, int32_t window, int32_t n, const d2ba_imu *in) {
+  HostWin *w = get_win(h, window);
+  if (!w) return 1;
+  w->used = true; h->finalized = false;
+  for (int i = 0; i < n; i++) {
+    HImu m;
+    m.pi = find_in(w->pose_map, in[i].frame_a); m.pj = find_in(w->pose_map, in[i].frame_b);
+    m.si = find_in(w->sb_map, in[i].frame_a); m.sj = find_in(w->sb_map, in[i].frame_b);
+    if (m.pi < 0 || m.pj < 0 || m.si < 0 || m.sj < 0) return fail(h, 6, "add_imu: unknown frame id");
+    double *c = m.c;
+    c[0] = in[i].sum_dt; memcpy(c + 1, in[i].delta_p, 24); memcpy(c + 4, in[i].delta_q, 32); memcpy(c + 8, in[i].delta_v, 24);
+    memcpy(c + 11, in[i].linearized_ba, 24); memcpy(c + 14, in[i].linearized_bg, 24);
+    memcpy(c + 17, in[i].jacobian, 225 * 8); memcpy(c + 17 + 225, in[i].covariance, 225 * 8);
+    w->imu.push_back(m);
+  }
+  return 0;
+}
+
+static int set_prior_common(d2ba_handle *h, int32_t window, int32_t m, const double *J, const double *e0, int32_t nblk,
+                            const d2ba_blockref *refs, const double *x0, bool is_info) {
+  HostWin *w = get_win(h, window);
+  if (!w) return 1;
+  w->used = true; h->finalized = false;
+  w->prior_m = m; w->prior_J.assign(J, J + (size_t)m * m); w->prior_e0.assign(e0, e0 + m); w->prior_is_info = is_info;
+  w->prior_blk.clear();
+  int off = 0, xo = 0;
+  for (int i = 0; i < nblk; i++) {
+    HPriorBlk b; memset(&b, 0, sizeof b);
+    b.kind = refs[i].kind;
+    switch (b.kind) {
+      case D2BA_POSE: b.index = find_in(w->pose_map, refs[i].id); break;
+      case D2BA_EXTRINSIC: b.index = find_in(w->ext_map, refs[i].id); break;
+      case D2BA_SPEED_BIAS: b.index = find_in(w->sb_map, refs[i].id); break;
+      case D2BA_TD: b.index = w->has_td ? 0 : -1; break;
+      case D2BA_LANDMARK: b.index = find_in(w->lm_map, refs[i].id); break;
+      default: b.index = -1;
+    }
+    if (b.index < 0) return fail(h, 7, "set_prior: unknown block");
+    b.off = off; b.eff = kind_eff(b.kind); off += b.eff;
+    memcpy(b.x0, x0 + xo, 8 * kind_size(b.kind)); xo += kind_size(b.kind);
+    w->prior_blk.push_back(b);
+  }
+  if (off != m) return fail(h, 8, "set_prior: dimension mismatch");
+  return 0;
+}
+
+int d2ba_set_prior(d2ba_handle *h, int32_t window, int32_t m, const double *J, const double *e0, int32_t nblk,
+                   const d2ba_blockref *refs, const double *x0) {
+  return set_prior_common(h, window, m, J, e0, nblk, refs, x0, false);
+}
+
+int d2ba_set_consensus(d2ba_handle *h, int32_t window, int32_t n, const d2ba_blockref *refs, const int32_t *slot,
+                       int32_t n_slots_global) {
+  HostWin *w = get_win(h, window);
+  if (!w) return 1;
+  w->used = true; h->finalized = false; w->admm = true; w->n_slots = n_slots_global;
+  for (int i = 0; i < n; i++) {
+    if (refs[i].kind == D2BA_POSE) { int k = find_in(w->pose_map, refs[i].id); if (k < 0) return fail(h, 9, "set_consensus: unknown frame"); w->pose_slot[k] = slot[i]; }
+    else if (refs[i].kind == D2BA_EXTRINSIC) { int k = find_in(w->ext_map, refs[i].id); if (k < 0) return fail(h, 9, "set_consensus: unknown camera"); w->ext_slot[k] = slot[i]; }
+    else return fail(h, 10, "set_consensus: only POSE / EXTRINSIC blocks take part");
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+int d2ba_finalize(d2ba_handle *h) {
+  if (!h) return 1;
+  cudaSetDevice(h->cfg.device);
+  release_graph(h);
+  std::vector<WinDesc> wd;
+  std::vector<double> x6, xsb, xlm, xtd, obs_f, imu_c, prior_J, prior_e0, lmzero;
+  std::vector<int> col6, colsb, tile_grp, obs_lm, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, tile_win;
+  std::vector<Group> grp;
+  std::vector<Job> jobs[4];
+  std::vector<ImuDesc> imu;
+  std::vector<PriorBlk> pblk;
+  std::vector<SchurTileH> schur;
+  h->n_used = 0; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
+  int64_t offH = 0, offW = 0, offc = 0, off_rec = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0;
+  int total_tiles_est = 0;
+  for (auto &w : h->win) if (w.used) total_tiles_est += (int)(w.obs.size() / kTile) + 1;
+  int tpj = std::max(1, std::min(8, total_tiles_est / (148 * 8)));
+  int wi = 0;
+  for (auto &w : h->win) {
+    if (!w.used) { continue; }
+    if (wi != (int)(&w - &h->win[0])) return fail(h, 20, "windows must be used contiguously from index 0");
+    WinDesc d; memset(&d, 0, sizeof d);
+    const int np = (int)w.pose_id.size(), ne = (int)w.ext_id.size(), nsb = (int)w.sb_id.size(), nl = (int)w.lm_id.size();
+    d.np = np; d.ne = ne; d.n6 = np + ne; d.nsb = nsb; d.nl = nl; d.has_td = w.has_td ? 1 : 0;
+    // reduced-system columns: free poses, free extrinsics, td, then speed-bias
+    int c = 0;
+    w.pose_col.assign(np, -1); w.ext_col.assign(ne, -1); w.sb_col.assign(nsb, -1);
+    for (int i = 0; i < np; i++) if (!w.pose_c[i]) { w.pose_col[i] = c; c += 6; }
+    for (int i = 0; i < ne; i++) if (!w.ext_c[i]) { w.ext_col[i] = c; c += 6; }
+    w.td_col = (w.has_td && !w.td_c) ? c : -1;
+    if (w.td_col >= 0) c += 1;
+    w.n_lc = c;
+    for (int i = 0; i < nsb; i++) if (!w.sb_c[i]) { w.sb_col[i] = c; c += 9; }
+    w.n_c = c;
+    d.td_col = w.td_col; d.n_lc = w.n_lc; d.n_c = w.n_c; d.ldh = std::max(4, roundup(w.n_c, 4));
+    d.ldw = roundup(w.n_lc + 1, 8); d.nl_pad = roundup(nl, 32);
+    d.off6 = (int)(x6.size() / 8); d.offsb = (int)(xsb.size() / 9); d.offlm = (int)xlm.size();
+    for (int i = 0; i < np; i++) { for (int q = 0; q < 7; q++) x6.push_back(w.pose[7 * i + q]); x6.push_back(0); col6.push_back(w.pose_col[i]); slot6.push_back(w.admm ? w.pose_slot[i] : -1); blk_win.push_back(wi); }
+    for (int i = 0; i < ne; i++) { for (int q = 0; q < 7; q++) x6.push_back(w.ext[7 * i + q]); x6.push_back(0); col6.push_back(w.ext_col[i]); slot6.push_back(w.admm ? w.ext_slot[i] : -1); blk_win.push_back(wi); }
+    for (int i = 0; i < nsb; i++) { for (int q = 0; q < 9; q++) xsb.push_back(w.sb[9 * i + q]); colsb.push_back(w.sb_col[i]); sb_win.push_back(wi); }
+    for (int i = 0; i < nl; i++) { xlm.push_back(w.lm[i]); lm_win.push_back(wi); }
+    xtd.push_back(w.td);
+    d.admm_on = w.admm ? 1 : 0;
+    if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
+    // ---- pair-major sort of the observations
+    w.sorted = w.obs;
+    std::stable_sort(w.sorted.begin(), w.sorted.end(), [](const HObs &a, const HObs &b) {
+      if (a.type != b.type) return a.type < b.type;
+      if (a.pi != b.pi) return a.pi < b.pi;
+      if (a.pj != b.pj) return a.pj < b.pj;
+      if (a.ea != b.ea) return a.ea < b.ea;
+      if (a.eb != b.eb) return a.eb < b.eb;
+      return a.seq < b.seq;
+    });
+    w.sorted_pos.assign(w.sorted.size(), -1);
+    d.off_tile = (int)tile_grp.size(); d.off_grp = (int)grp.size();
+    d.off_rec = (int64_t)d.off_tile * kTile;   // records are addressed by global tile slot
+    bool any_wide = false;
+    std::vector<std::vector<int>> lm_lists(nl);
+    size_t k = 0;
+    while (k < w.sorted.size()) {
+      size_t e = k;
+      const HObs &o0 = w.sorted[k];
+      while (e < w.sorted.size() && w.sorted[e].type == o0.type && w.sorted[e].pi == o0.pi && w.sorted[e].pj == o0.pj &&
+             w.sorted[e].ea == o0.ea && w.sorted[e].eb == o0.eb) e++;
+      Group g; memset(&g, 0, sizeof g);
+      g.type = o0.type;
+      g.blk[0] = o0.pi; g.blk[1] = o0.pj; g.blk[2] = o0.ea >= 0 ? np + o0.ea : -1; g.blk[3] = o0.eb >= 0 ? np + o0.eb : -1;
+      int cols[4] = {o0.pi >= 0 ? w.pose_col[o0.pi] : -1, o0.pj >= 0 ? w.pose_col[o0.pj] : -1, o0.ea >= 0 ? w.ext_col[o0.ea] : -1,
+                     o0.eb >= 0 ? w.ext_col[o0.eb] : -1};
+      if (o0.type == D2BA_PROJ_DEPTH_PRIOR) { cols[0] = cols[1] = cols[2] = cols[3] = -1; }
+      int ns = 0;
+      for (int s = 0; s < 4; s++) { g.slot_src[s] = -1; g.slot_col[s] = -1; }
+      for (int s = 0; s < 4; s++) if (cols[s] >= 0) { g.slot_src[ns] = s; g.slot_col[ns] = cols[s]; ns++; }
+      g.td_col = (o0.type == D2BA_PROJ_DEPTH_PRIOR) ? -1 : w.td_col;
+      g.need_td = g.td_col >= 0; g.need_ext = 0;
+      for (int s = 0; s < ns; s++) if (g.slot_src[s] >= 2) g.need_ext = 1;
+      g.nct = (ns <= 2 && !g.need_td) ? 2 : 4;
+      g.rows = o0.type == D2BA_PROJ_2F1C_DEPTH ? 3 : (o0.type == D2BA_PROJ_DEPTH_PRIOR ? 1 : 2);
+      if (g.nct == 4) any_wide = true;
+      const int variant = (g.nct == 4 ? 1 : 0) + (g.rows == 3 ? 2 : 0);
+      const int gi = (int)grp.size();
+      grp.push_back(g);
+      const int cnt = (int)(e - k), ntile = (cnt + kTile - 1) / kTile;
+      const int tile0 = (int)tile_grp.size();
+      for (int t = 0; t < ntile; t++) {
+        tile_grp.push_back(gi); tile_win.push_back(wi);
+        size_t base = obs_f.size();
+        obs_f.resize(base + (size_t)kObsFields * kTile, 0.0);
+        for (int lane = 0; lane < kTile; lane++) {
+          int idx = t * kTile + lane;
+          if (idx < cnt) {
+            const HObs &o = w.sorted[k + idx];
+            for (int f = 0; f < kObsFields; f++) obs_f[base + (size_t)f * kTile + lane] = o.f[f];
+            obs_lm.push_back(o.lm);
+            int pos = (tile0 + t - d.off_tile) * kTile + lane;
+            w.sorted_pos[k + idx] = pos;
+            lm_lists[o.lm].push_back(pos);
+          } else {
+            obs_f[base + (size_t)0 * kTile + lane] = 0; obs_f[base + (size_t)2 * kTile + lane] = 1.0; obs_f[base + (size_t)5 * kTile + lane] = 1.0;
+            obs_f[base + (size_t)14 * kTile + lane] = 1.0; obs_f[base + (size_t)18 * kTile + lane] = 1.0; obs_f[base + (size_t)20 * kTile + lane] = 1.0;
+            obs_lm.push_back(-1);
+          }
+        }
+      }
+      for (int t = 0; t < ntile; t += tpj) { Job j; j.win = wi; j.grp = gi; j.tile_begin = tile0 + t; j.ntiles = std::min(tpj, ntile - t); jobs[variant].push_back(j); }
+      k = e;
+    }
+    d.n_tile = (int)tile_grp.size() - d.off_tile; d.n_grp = (int)grp.size() - d.off_grp;
+    d.rec_stride = any_wide ? 32 : 16;
+    // landmark CSR (positions ascending = deterministic reduction order)
+    d.off_lmptr = (int)lm_ptr.size(); d.off_lmobs = off_lmobs;
+    int run = 0;
+    for (int l = 0; l < nl; l++) { lm_ptr.push_back(run); std::sort(lm_lists[l].begin(), lm_lists[l].end()); for (int p : lm_lists[l]) lm_obs.push_back(p); run += (int)lm_lists[l].size(); }
+    lm_ptr.push_back(run);
+    off_lmobs += run;
+    // imu
+    d.off_imu = (int)imu.size(); d.n_imu = (int)w.imu.size();
+    for (auto &m : w.imu) { ImuDesc di{m.pi, m.si, m.pj, m.sj}; imu.push_back(di); imu_c.insert(imu_c.end(), m.c, m.c + kImuStride); }
+    // prior
+    d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size(); d.off_prior_blk = (int)pblk.size(); d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
+    if (w.prior_m > 0) {
+      if (w.prior_is_info) return fail(h, 21, "internal: prior still in information form");
+      prior_J.insert(prior_J.end(), w.prior_J.begin(), w.prior_J.end()); prior_e0.insert(prior_e0.end(), w.prior_e0.begin(), w.prior_e0.end());
+      for (auto &b : w.prior_blk) {
+        PriorBlk pb; memset(&pb, 0, sizeof pb);
+        pb.kind = b.kind; pb.off = b.off; pb.eff = b.eff; memcpy(pb.x0, b.x0, sizeof pb.x0);
+        pb.index = (b.kind == D2BA_EXTRINSIC) ? np + b.index : b.index;
+        pblk.push_back(pb);
+      }
+      off_pJ += (int64_t)w.prior_m * w.prior_m; off_pv += w.prior_m;
+      h->max_prior_m = std::max(h->max_prior_m, w.prior_m);
+    }
+    // dense storage
+    d.offH = offH; offH += (int64_t)(d.n_c + 1) * d.ldh;
+    d.offW = offW; offW += (int64_t)std::max(d.nl_pad, 32) * d.ldw;
+    d.offc = offc; offc += roundup(d.n_c + 1, 4);
+    h->max_rows = std::max(h->max_rows, d.n_c + 1); h->max_nc = std::max(h->max_nc, d.n_c); h->max_ldw = std::max(h->max_ldw, d.ldw);
+    // Schur tiles: W-space SYRK tiles (lower) + copy tiles for the speed-bias rows and the rhs row
+    {
+      int ntw = (d.n_lc + 1 + 31) / 32;
+      if (d.n_lc > 0) for (int tm = 0; tm < ntw; tm++) for (int tn = 0; tn <= tm; tn++) schur.push_back({wi, 0, tm, tn});
+      int t_lo = d.n_lc / 32, t_hi = d.n_c / 32;
+      for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) schur.push_back({wi, 1, tm, tn});
+    }
+    wd.push_back(d);
+    wi++;
+  }
+  if (wi == 0) return fail(h, 22, "finalize: no window in use");
+  h->n_used = wi; h->h_win = wd; h->h_grp = grp; h->h_tile_win = tile_win;
+  h->n6_total = (int)col6.size(); h->nsb_total = (int)colsb.size(); h->nl_total = (int)xlm.size(); h->n_tiles = (int)tile_grp.size();
+  h->n_imu_total = (int)imu.size(); h->n_schur = (int)schur.size(); h->totH = offH; h->totW = offW; h->totc = offc;
+  std::vector<Job> all_jobs;
+  for (int v = 0; v < 4; v++) { h->job_begin[v] = (int)all_jobs.size(); h->job_count[v] = (int)jobs[v].size(); all_jobs.insert(all_jobs.end(), jobs[v].begin(), jobs[v].end()); }
+  // ---- uploads
+  int rc;
+  if ((rc = upload(h, h->d_win, wd))) return rc;
+  CK(h->d_ctl.alloc(wi)); CK(cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Ctl) * wi, h->stream));
+  for (int b = 0; b < 2; b++) {
+    if ((rc = upload(h, h->d_x6[b], x6))) return rc;
+    if ((rc = alloc_zero(h, h->d_R6[b], (size_t)h->n6_total * 12))) return rc;
+    if ((rc = upload(h, h->d_xsb[b], xsb))) return rc;
+    if ((rc = upload(h, h->d_xlm[b], xlm))) return rc;
+    if ((rc = upload(h, h->d_xtd[b], xtd))) return rc;
+    if ((rc = alloc_zero(h, h->d_rec[b], (size_t)h->n_tiles * kTile * 32))) return rc;
+    if ((rc = alloc_zero(h, h->d_H[b], (size_t)offH))) return rc;
+    if ((rc = alloc_zero(h, h->d_gc[b], (size_t)offc))) return rc;
+  }
+  if ((rc = upload(h, h->d_col6, col6))) return rc;
+  if ((rc = upload(h, h->d_colsb, colsb))) return rc;
+  if ((rc = upload(h, h->d_tile_grp, tile_grp))) return rc;
+  if ((rc = upload(h, h->d_tile_win, tile_win))) return rc;
+  if ((rc = upload(h, h->d_obs_lm, obs_lm))) return rc;
+  if ((rc = upload(h, h->d_obs, obs_f))) return rc;
+  if ((rc = upload(h, h->d_lm_ptr, lm_ptr))) return rc;
+  if ((rc = upload(h, h->d_lm_obs, lm_obs))) return rc;
+  if ((rc = upload(h, h->d_slot6, slot6))) return rc;
+  if ((rc = upload(h, h->d_lm_win, lm_win))) return rc;
+  if ((rc = upload(h, h->d_blk_win, blk_win))) return rc;
+  if ((rc = upload(h, h->d_sb_win, sb_win))) return rc;
+  if ((rc = upload(h, h->d_grp, grp))) return rc;
+  if ((rc = upload(h, h->d_job, all_jobs))) return rc;
+  if ((rc = upload(h, h->d_imu, imu))) return rc;
+  if ((rc = upload(h, h->d_imu_c, imu_c))) return rc;
+  if ((rc = alloc_zero(h, h->d_imu_U, (size_t)h->n_imu_total * 225))) return rc;
+  if ((rc = upload(h, h->d_prior_blk, pblk))) return rc;
+  if ((rc = upload(h, h->d_prior_J, prior_J))) return rc;
+  if ((rc = upload(h, h->d_prior_e0, prior_e0))) return rc;
+  if ((rc = alloc_zero(h, h->d_prior_A, prior_J.size()))) return rc;
+  if ((rc = alloc_zero(h, h->d_z6, (size_t)h->n6_total * 8))) return rc;
+  if ((rc = alloc_zero(h, h->d_tilde6, (size_t)h->n6_total * 6))) return rc;
+  if ((rc = alloc_zero(h, h->d_lm_ref, h->nl_total))) return rc;
+  if ((rc = alloc_zero(h, h->d_sb_ref, (size_t)h->nsb_total * 9))) return rc;
+  if ((rc = alloc_zero(h, h->d_td_ref, wi))) return rc;
+  if ((rc = alloc_zero(h, h->d_cons, (size_t)std::max(h->n_slots, 1) * 14))) return rc;
+  if ((rc = alloc_zero(h, h->d_Wt, (size_t)offW))) return rc;
+  if ((rc = alloc_zero(h, h->d_dinv, h->nl_total))) return rc;
+  if ((rc = alloc_zero(h, h->d_hl, h->nl_total))) return rc;
+  if ((rc = alloc_zero(h, h->d_gl, h->nl_total))) return rc;
+  if ((rc = alloc_zero(h, h->d_S, (size_t)offH))) return rc;
+  if ((rc = alloc_zero(h, h->d_gred, (size_t)offc))) return rc;
+  if ((rc = alloc_zero(h, h->d_D2c, (size_t)offc))) return rc;
+  if ((rc = alloc_zero(h, h->d_gn_c, (size_t)offc))) return rc;
+  if ((rc = alloc_zero(h, h->d_gn_l, h->nl_total))) return rc;
+  if ((rc = alloc_zero(h, h->d_step_c, (size_t)offc))) return rc;
+  if ((rc = alloc_zero(h, h->d_step_l, h->nl_total))) return rc;
+  if ((rc = alloc_zero(h, h->d_wu, h->nl_total))) return rc;
+  if ((rc = upload(h, h->d_schur, schur))) return rc;
+  // ---- device view
+  Dev &D = h->dev;
+  memset(&D, 0, sizeof D);
+  D.win = h->d_win.p; D.ctl = h->d_ctl.p; D.n_win = wi;
+  for (int b = 0; b < 2; b++) { D.x6[b] = h->d_x6[b].p; D.R6[b] = h->d_R6[b].p; D.xsb[b] = h->d_xsb[b].p; D.xlm[b] = h->d_xlm[b].p; D.xtd[b] = h->d_xtd[b].p; D.rec[b] = h->d_rec[b].p; D.Hcc[b] = h->d_H[b].p; D.gc[b] = h->d_gc[b].p; }
+  D.col6 = h->d_col6.p; D.colsb = h->d_colsb.p; D.grp = h->d_grp.p; D.job = h->d_job.p; D.n_job = (int)all_jobs.size();
+  D.tile_grp = h->d_tile_grp.p; D.obs = h->d_obs.p; D.obs_lm = h->d_obs_lm.p; D.lm_ptr = h->d_lm_ptr.p; D.lm_obs = h->d_lm_obs.p;
+  D.imu = h->d_imu.p; D.imu_c = h->d_imu_c.p; D.imu_U = h->d_imu_U.p; D.prior_blk = h->d_prior_blk.p; D.prior_J = h->d_prior_J.p;
+  D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
+  D.lm_ref = h->d_lm_ref.p; D.sb_ref = h->d_sb_ref.p; D.td_ref = h->d_td_ref.p; D.cons_buf = h->d_cons.p; D.n_slots = h->n_slots;
+  D.Wt = h->d_Wt.p; D.dinv = h->d_dinv.p; D.hl = h->d_hl.p; D.gl = h->d_gl.p; D.S = h->d_S.p; D.gred = h->d_gred.p; D.D2c = h->d_D2c.p;
+  D.gn_c = h->d_gn_c.p; D.gn_l = h->d_gn_l.p; D.step_c = h->d_step_c.p; D.step_l = h->d_step_l.p; D.wu = h->d_wu.p;
+  SolverParams &P = D.prm;
+  P.sqrt_info_px = h->cfg.focal_length / 1.5; P.depth_sqrt_inf = h->cfg.depth_sqrt_inf; P.gravity = h->cfg.gravity_norm; P.huber = h->cfg.huber_delta;
+  P.rho_T = h->cfg.rho_frame_T; P.rho_theta = h->cfg.rho_frame_theta; P.rho_landmark = h->cfg.rho_landmark; P.relaxation_alpha = h->cfg.relaxation_alpha;
+  P.initial_radius = h->cfg.initial_trust_region_radius; P.max_radius = h->cfg.max_trust_region_radius; P.min_rel_decrease = h->cfg.min_relative_decrease;
+  P.ftol = h->cfg.function_tolerance; P.gtol = h->cfg.gradient_tolerance; P.ptol = h->cfg.parameter_tolerance;
+  P.max_iter = h->cfg.max_num_iterations; P.fixed_mode = 0;
+  if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
+  launch_state_prep(D, h->n6_total, 0, h->stream);
+  launch_imu_prep(D, h->n_imu_total, h->stream);
+  launch_prior_prep(D, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->h_ctl.assign(wi, Ctl());
+  for (int b = 0; b < 2; b++) { h->h_x6[b] = x6; h->h_xsb[b] = xsb; h->h_xlm[b] = xlm; h->h_xtd[b] = xtd; }
+  h->finalized = true; h->state_dirty = false;
+  return 0;
+}
+
+// Prior given in information form: toJacRes (prior_factor.cpp:132-177).  The eigen-decomposition of the
+// m x m information matrix is a one-off setup step (m <= ~130); it runs in double precision on the
+// device through a Jacobi sweep kernel in d2ba_margin.cu.
+int d2ba_prior_info_to_jac(d2ba_handle *h, int m, const double *A, const double *b, double *J, double *e0);
+
+int d2ba_set_prior_info(d2ba_handle *h, int32_t window, int32_t m, const double *A, const double *b, int32_t nblk,
+                        const d2ba_blockref *refs, const double *x0) {
+  if (!h) return 1;
+  std::vector<double> J((size_t)m * m), e0(m);
+  int rc = d2ba_prior_info_to_jac(h, m, A, b, J.data(), e0.data());
+  if (rc) return rc;
+  return set_prior_common(h, window, m, J.data(), e0.data(), nblk, refs, x0, false);
+}
+
+// ------------------------------------------------------------------------------------------------ solve
+static int upload_state(d2ba_handle *h) {
+  std::vector<double> x6, xsb, xlm, xtd;
+  for (auto &w : h->win) {
+    if (!w.used) continue;
+    for (size_t i = 0; i < w.pose_id.size(); i++) { for (int q = 0; q < 7; q++) x6.push_back(w.pose[7 * i + q]); x6.push_back(0); }
+    for (size_t i = 0; i < w.ext_id.size(); i++) { for (int q = 0; q < 7; q++) x6.push_back(w.ext[7 * i + q]); x6.push_back(0); }
+    xsb.insert(xsb.end(), w.sb.begin(), w.sb.end()); xlm.insert(xlm.end(), w.lm.begin(), w.lm.end()); xtd.push_back(w.td);
+  }
+  CK(cudaMemcpyAsync(h->d_x6[0].p, x6.data(), x6.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  if (!xsb.empty()) CK(cudaMemcpyAsync(h->d_xsb[0].p, xsb.data(), xsb.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  if (!xlm.empty()) CK(cudaMemcpyAsync(h->d_xlm[0].p, xlm.data(), xlm.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_xtd[0].p, xtd.data(), xtd.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  launch_state_prep(h->dev, h->n6_total, 0, h->stream);
+  CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+  h->state_dirty = false;
+  return 0;
+}
+
+static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
+  launch_misc_lin(h->dev, eval_cur, h->max_prior_m, h->stream);
+  for (int v = 0; v < 4; v++) launch_proj_lin(h->dev, v, eval_cur, h->job_begin[v], h->job_count[v], h->stream);
+}
+
+static void enqueue_iteration(d2ba_handle *h) {
+  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+  launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+  launch_chol(h->dev, h->max_rows, h->stream);
+  launch_step(h->dev, h->max_nc, h->stream);
+  enqueue_linearize(h, 0);
+  launch_control(h->dev, 0, h->stream);
+}
+
+static int consensus_exchange(d2ba_handle *h) {
+  CK(cudaMemsetAsync(h->d_cons.p, 0, (size_t)std::max(h->n_slots, 1) * 14 * 8, h->stream));
+  launch_cons_pack(h->dev, h->n6_total, h->d_blk_win.p, h->stream);
+  if (h->comm) {
+    int r = g_nccl.AllReduce(h->d_cons.p, h->d_cons.p, (size_t)h->n_slots * 14, /*ncclFloat64*/ 8, /*ncclSum*/ 0, h->comm, h->stream);
+    if (r) return fail(h, 40, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  }
+  launch_cons_apply(h->dev, h->n6_total, h->d_blk_win.p, h->stream);
+  launch_cons_refs(h->dev, h->nsb_total, h->nl_total, h->d_sb_win.p, h->d_lm_win.p, h->stream);
+  return 0;
+}
+
+static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
+  if (!h) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!h->finalized) { int rc = d2ba_finalize(h); if (rc) return rc; }
+  if (h->state_dirty) { int rc = upload_state(h); if (rc) return rc; }
+  const bool fixed = fixed_iters > 0;
+  const int steps = (h->any_admm && h->cfg.consensus_max_steps > 0) ? h->cfg.consensus_max_steps : 1;
+  int iters = fixed ? fixed_iters : h->cfg.max_num_iterations;
+  if (steps > 1 || h->any_admm) iters = std::max(1, iters / steps);   // d2vins_params.cpp:156-158
+  h->dev.prm.fixed_mode = fixed ? 1 : 0; h->dev.prm.max_iter = iters;
+  const int key = (fixed ? 1 : 0) * 100000 + iters;
+  if (h->graph_key != key) release_graph(h);
+  CK(cudaEventRecord(h->ev0, h->stream));
+  launch_tr_reset(h->dev, 1, h->stream);
+  if (h->any_admm) launch_cons_init(h->dev, h->n6_total, h->stream);
+  for (int st = 0; st < steps; st++) {
+    if (st > 0) launch_tr_reset(h->dev, 0, h->stream);
+    if (h->any_admm) { int rc = consensus_exchange(h); if (rc) return rc; }
+    enqueue_linearize(h, 1);
+    launch_control(h->dev, st == 0 ? 1 : 2, h->stream);
+    if (h->cfg.use_cuda_graph) {
+      if (!h->iter_graph) {
+        cudaGraph_t g;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_iteration(h);
+        CK(cudaStreamEndCapture(h->stream, &g));
+        CK(cudaGraphInstantiate(&h->iter_graph, g, 0));
+        cudaGraphDestroy(g);
+        h->graph_key = key;
+      }
+      for (int it = 0; it < iters; it++) CK(cudaGraphLaunch(h->iter_graph, h->stream));
+    } else {
+      for (int it = 0; it < iters; it++) enqueue_iteration(h);
+    }
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  // read back control blocks and both state buffers (the accepted buffer differs per window)
+  CK(cudaMemcpyAsync(h->h_ctl.data(), h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
+  for (int b = 0; b < 2; b++) {
+    CK(cudaMemcpyAsync(h->h_x6[b].data(), h->d_x6[b].p, h->h_x6[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->h_xsb[b].empty()) CK(cudaMemcpyAsync(h->h_xsb[b].data(), h->d_xsb[b].p, h->h_xsb[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->h_xlm[b].empty()) CK(cudaMemcpyAsync(h->h_xlm[b].data(), h->d_xlm[b].p, h->h_xlm[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_xtd[b].data(), h->d_xtd[b].p, h->h_xtd[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  // write the solved state back into the host windows (so a following solve starts from it)
+  int wi = 0;
+  for (auto &w : h->win) {
+    if (!w.used) continue;
+    const WinDesc &d = h->h_win[wi]; const int cur = h->h_ctl[wi].cur;
+    for (int i = 0; i < d.np; i++) memcpy(&w.pose[7 * i], &h->h_x6[cur][(size_t)(d.off6 + i) * 8], 56);
+    for (int i = 0; i < d.ne; i++) memcpy(&w.ext[7 * i], &h->h_x6[cur][(size_t)(d.off6 + d.np + i) * 8], 56);
+    if (d.nsb) memcpy(w.sb.data(), &h->h_xsb[cur][(size_t)d.offsb * 9], (size_t)d.nsb * 72);
+    if (d.nl) memcpy(w.lm.data(), &h->h_xlm[cur][d.offlm], (size_t)d.nl * 8);
+    w.td = h->h_xtd[cur][wi];
+    if (reports) {
+      const Ctl &c = h->h_ctl[wi]; d2ba_report &r = reports[wi];
+      r.total_iterations = c.lin_count; r.successful_steps = c.succ; r.termination = c.term; r.succ = c.term != 4;
+      r.total_time = ms * 1e-3; r.initial_cost = c.initial_cost; r.final_cost = c.cost; r.state_changes = 0;
+      r.final_gradient_max_norm = c.gmax_c; r.final_radius = c.radius;
+    }
+    wi++;
+  }
+  h->state_dirty = true;   // device buffer 0 no longer holds the accepted state of every window
+  return 0;
+}
+
+int d2ba_solve(d2ba_handle *h, d2ba_report *reports) { return run_solve(h, 0, reports); }
+int d2ba_solve_fixed(d2ba_handle *h, int32_t iters, d2ba_report *reports) { return run_solve(h, iters < 1 ? 1 : iters, reports); }
+
+int d2ba_get_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, const int64_t *ids, double *out) {
+  HostWin *w = get_win(h, window);
+  if (!w || !w->used) return 1;
+  for (int i = 0; i < n; i++) {
+    int k;
+    switch (kind) {
+      case D2BA_POSE: k = find_in(w->pose_map, ids[i]); if (k < 0) return fail(h, 2, "get_blocks: unknown id"); memcpy(out + 7 * i, &w->pose[7 * k], 56); break;
+      case D2BA_EXTRINSIC: k = find_in(w->ext_map, ids[i]); if (k < 0) return fail(h, 2, "get_blocks: unknown id"); memcpy(out + 7 * i, &w->ext[7 * k], 56); break;
+      case D2BA_SPEED_BIAS: k = find_in(w->sb_map, ids[i]); if (k < 0) return fail(h, 2, "get_blocks: unknown id"); memcpy(out + 9 * i, &w->sb[9 * k], 72); break;
+      case D2BA_TD: out[i] = w->td; break;
+      case D2BA_LANDMARK: k = find_in(w->lm_map, ids[i]); if (k < 0) return fail(h, 2, "get_blocks: unknown id"); out[i] = w->lm[k]; break;
+      default: return 3;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ comm
+int d2ba_comm_unique_id(uint8_t out[128]) {
+  std::string err;
+  if (!g_nccl.load(err)) { fprintf(stderr, "d2ba: %s\n", err.c_str()); return 1; }
+  ncclUniqueId_t id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r) return 2;
+  memcpy(out, id.internal, 128);
+  return 0;
+}
+int d2ba_comm_init(d2ba_handle *h, const uint8_t unique_id[128], int32_t rank, int32_t nranks) {
+  if (!h) return 1;
+  if (!g_nccl.load(h->err)) return 2;
+  cudaSetDevice(h->cfg.device);
+  ncclUniqueId_t id; memcpy(id.internal, unique_id, 128);
+  int r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (r) return fail(h, 3, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  h->rank = rank; h->nranks = nranks;
+  return 0;
+}
+int d2ba_consensus_buffer(d2ba_handle *h, void **dev_ptr, int64_t *n_doubles) {
+  if (!h || !h->finalized) return 1;
+  *dev_ptr = h->d_cons.p; *n_doubles = (int64_t)h->n_slots * 14;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ debug
+int d2ba_debug_linearize(d2ba_handle *h) {
+  if (!h) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!h->finalized) { int rc = d2ba_finalize(h); if (rc) return rc; }
+  if (h->state_dirty) { int rc = upload_state(h); if (rc) return rc; }
+  h->dev.prm.fixed_mode = 1; h->dev.prm.max_iter = 1;
+  launch_tr_reset(h->dev, 1, h->stream);
+  enqueue_linearize(h, 1);
+  launch_control(h->dev, 1, h->stream);
+  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+  launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+  // keep an un-factored copy of S in the debug buffer
+  CK(h->d_dbg.alloc((size_t)h->totH));
+  CK(cudaMemcpyAsync(h->d_dbg.p, h->d_S.p, (size_t)h->totH * 8, cudaMemcpyDeviceToDevice, h->stream));
+  launch_chol(h->dev, h->max_rows, h->stream);
+  launch_step(h->dev, h->max_nc, h->stream);
+  CK(cudaMemcpyAsync(h->h_ctl.data(), h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  release_graph(h);
+  return 0;
+}
+
+int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int64_t out_bytes, int64_t *needed) {
+  HostWin *w = get_win(h, window);
+  if (!w || !w->used || !h->finalized) return 1;
+  cudaSetDevice(h->cfg.device);
+  const WinDesc &d = h->h_win[window];
+  const int n = d.n_c, nlc = d.n_lc, nl = d.nl, ld = d.ldh;
+  std::vector<uint8_t> buf;
+  auto put_d = [&](const std::vector<double> &v) { buf.resize(v.size() * 8); memcpy(buf.data(), v.data(), buf.size()); };
+  auto fetch = [&](const double *src, size_t cnt) { std::vector<double> v(cnt); if (cnt) cudaMemcpy(v.data(), src, cnt * 8, cudaMemcpyDeviceToHost); return v; };
+  const int cur = h->h_ctl[window].cur;
+  switch (item) {
+    case D2BA_DBG_N_CAM: { int64_t v = n; buf.resize(8); memcpy(buf.data(), &v, 8); break; }
+    case D2BA_DBG_N_LC: { int64_t v = nlc; buf.resize(8); memcpy(buf.data(), &v, 8); break; }
+    case D2BA_DBG_HCC: {
+      auto H = fetch(h->d_H[cur].p + d.offH, (size_t)n * ld);
+      std::vector<double> o((size_t)n * n);
+      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) o[(size_t)i * n + j] = H[(size_t)i * ld + j];
+      put_d(o); break;
+    }
+    case D2BA_DBG_GC: put_d(fetch(h->d_gc[cur].p + d.offc, n)); break;
+    case D2BA_DBG_HLL: put_d(fetch(h->d_hl.p + d.offlm, nl)); break;
+    case D2BA_DBG_GL: put_d(fetch(h->d_gl.p + d.offlm, nl)); break;
+    case D2BA_DBG_W: {
+      auto Wt = fetch(h->d_Wt.p + d.offW, (size_t)nl * d.ldw);
+      auto di = fetch(h->d_dinv.p + d.offlm, nl);
+      std::vector<double> o((size_t)nl * nlc);
+      for (int l = 0; l < nl; l++) for (int c = 0; c < nlc; c++) o[(size_t)l * nlc + c] = Wt[(size_t)l * d.ldw + c] / di[l];
+      put_d(o); break;
+    }
+    case D2BA_DBG_COST: { std::vector<double> v(1, h->h_ctl[window].cost); put_d(v); break; }
+    case D2BA_DBG_S: {
+      if (h->d_dbg.n < (size_t)h->totH) return fail(h, 4, "debug_get(S): call d2ba_debug_linearize first");
+      auto S = fetch(h->d_dbg.p + d.offH, (size_t)n * ld);
+      std::vector<double> o((size_t)n * n);
+      for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { o[(size_t)i * n + j] = S[(size_t)i * ld + j]; o[(size_t)j * n + i] = S[(size_t)i * ld + j]; }
+      put_d(o); break;
+    }
+    case D2BA_DBG_GN_STEP: case D2BA_DBG_STEP: {
+      auto a = fetch((item == D2BA_DBG_GN_STEP ? h->d_gn_c.p : h->d_step_c.p) + d.offc, n);
+      auto b = fetch((item == D2BA_DBG_GN_STEP ? h->d_gn_l.p : h->d_step_l.p) + d.offlm, nl);
+      a.insert(a.end(), b.begin(), b.end()); put_d(a); break;
+    }
+    case D2BA_DBG_OBS_INDEX: {
+      std::vector<int32_t> v;
+      for (auto &o : w->sorted) { v.push_back(o.type); v.push_back(o.pi); v.push_back(o.pj); v.push_back(o.ea < 0 ? -1 : d.np + o.ea); v.push_back(o.eb < 0 ? -1 : d.np + o.eb); v.push_back(o.lm); }
+      buf.resize(v.size() * 4); memcpy(buf.data(), v.data(), buf.size()); break;
+    }
+    case D2BA_DBG_COL_OF_BLOCK: {
+      std::vector<int32_t> v;
+      for (int c : w->pose_col) v.push_back(c);
+      for (int c : w->ext_col) v.push_back(c);
+      for (int c : w->sb_col) v.push_back(c);
+      v.push_back(w->td_col);
+      buf.resize(v.size() * 4); memcpy(buf.data(), v.data(), buf.size()); break;
+    }
+    case D2BA_DBG_PROJ_RESJAC: {
+      DBuf<double> tmp;
+      if (tmp.alloc((size_t)h->n_tiles * kTile * 81) != cudaSuccess) return fail(h, 5, "debug alloc");
+      launch_proj_debug(h->dev, tmp.p, h->n_tiles, h->d_tile_win.p, h->stream);
+      cudaStreamSynchronize(h->stream);
+      std::vector<double> all((size_t)d.n_tile * kTile * 81);
+      if (!all.empty()) cudaMemcpy(all.data(), tmp.p + (size_t)d.off_tile * kTile * 81, all.size() * 8, cudaMemcpyDeviceToHost);
+      tmp.release();
+      std::vector<double> o(w->obs.size() * 81, 0.0);
+      for (size_t k = 0; k < w->sorted.size(); k++) memcpy(&o[(size_t)w->sorted[k].seq * 81], &all[(size_t)w->sorted_pos[k] * 81], 81 * 8);
+      put_d(o); break;
+    }
+    default: return fail(h, 6, "debug_get: unknown item");
+  }
+  if (needed) *needed = (int64_t)buf.size();
+  if (out) { if (out_bytes < (int64_t)buf.size()) return 2; memcpy(out, buf.data(), buf.size()); }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1258 @@
+// d2ba_kernels.cu -- sm_100a kernels of the sliding-window BA solver.
+//
+//   k_state_prep      rotation matrices of every six-dof block
+//   k_imu_prep        IMU sqrt-information U = chol(cov^-1)^T            (imu_factor.h:29)
+//   k_prior_prep      A' = J_lin^T J_lin of the marginalisation prior
+//   k_misc_lin        IMU + prior + ADMM terms -> Hcc, gc, cost          (one CTA / window)
+//   k_proj_lin<..>    fused reprojection residual + Jacobian + Huber + DMMA J^T J accumulation
+//   k_lm_gather       per-landmark reduction -> scaled coupling rows Wt, h, g
+//   k_schur           S = Hcc + mu D^2 - Wt^T Wt  (fp64 tensor-core SYRK) + bordered rhs row
+//   k_chol            blocked bordered Cholesky + back substitution        (one CTA / window)
+//   k_step            landmark back-substitution, Cauchy point, dogleg, retraction
+//   k_control         accept / reject, radius, convergence
+//   k_cons_*          ADMM consensus pack / apply
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "d2ba_math.cuh"
+#include "d2ba_proj.cuh"
+#include "d2ba_types.cuh"
+
+namespace d2ba {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_state_prep(Dev d, int n6_total, int buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n6_total) return;
+  const double *x = d.x6[buf] + (size_t)i * 8;
+  q2R(qload(x + 3), d.R6[buf] + (size_t)i * 12);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sqrt_info = LLT(cov^-1).matrixL().transpose(): one thread per IMU factor (setup, once per finalize)
+__global__ void k_imu_prep(Dev d, int n_imu) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_imu) return;
+  const double *cov = d.imu_c + (size_t)f * kImuStride + 17 + 225;
+  double *U = d.imu_U + (size_t)f * 225;
+  double L[225], inv[225];
+  for (int i = 0; i < 225; i++) L[i] = cov[i];
+  // cholesky (lower) of cov
+  for (int j = 0; j < 15; j++) {
+    double dd = L[j * 15 + j];
+    for (int k = 0; k < j; k++) dd -= L[j * 15 + k] * L[j * 15 + k];
+    dd = sqrt(dd);
+    L[j * 15 + j] = dd;
+    for (int i = j + 1; i < 15; i++) {
+      double s = L[i * 15 + j];
+      for (int k = 0; k < j; k++) s -= L[i * 15 + k] * L[j * 15 + k];
+      L[i * 15 + j] = s / dd;
+    }
+  }
+  // inverse via two triangular solves per unit vector
+  for (int c = 0; c < 15; c++) {
+    double y[15], x[15];
+    for (int i = 0; i < 15; i++) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; k++) s -= L[i * 15 + k] * y[k];
+      y[i] = s / L[i * 15 + i];
+    }
+    for (int i = 14; i >= 0; i--) {
+      double s = y[i];
+      for (int k = i + 1; k < 15; k++) s -= L[k * 15 + i] * x[k];
+      x[i] = s / L[i * 15 + i];
+    }
+    for (int i = 0; i < 15; i++) inv[i * 15 + c] = x[i];
+  }
+  for (int i = 0; i < 15; i++)
+    for (int j = i + 1; j < 15; j++) { double m = 0.5 * (inv[i * 15 + j] + inv[j * 15 + i]); inv[i * 15 + j] = m; inv[j * 15 + i] = m; }
+  for (int j = 0; j < 15; j++) {
+    double dd = inv[j * 15 + j];
+    for (int k = 0; k < j; k++) dd -= inv[j * 15 + k] * inv[j * 15 + k];
+    dd = sqrt(dd);
+    inv[j * 15 + j] = dd;
+    for (int i = j + 1; i < 15; i++) {
+      double s = inv[i * 15 + j];
+      for (int k = 0; k < j; k++) s -= inv[i * 15 + k] * inv[j * 15 + k];
+      inv[i * 15 + j] = s / dd;
+    }
+  }
+  for (int i = 0; i < 15; i++)
+    for (int j = 0; j < 15; j++) U[i * 15 + j] = (j >= i) ? inv[j * 15 + i] : 0.0;
+}
+
+// A' = J^T J of each window's prior (constant across iterations: the prior is linear in dx)
+__global__ void k_prior_prep(Dev d) {
+  const WinDesc &w = d.win[blockIdx.x];
+  int m = w.prior_m;
+  if (m <= 0) return;
+  const double *J = d.prior_J + w.off_prior_J;
+  double *A = d.prior_A + w.off_prior_J;
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    int i = e / m, j = e % m;
+    double s = 0;
+    for (int k = 0; k < m; k++) s += J[(size_t)k * m + i] * J[(size_t)k * m + j];
+    A[e] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMU raw residual (15) and raw Jacobian (15 x 30: pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9) before the
+// sqrt-information is applied.  Same terms as IMUFactor::Evaluate (d2vins/src/factors/imu_factor.h:41-213)
+// and IntegrationBase::evaluate (d2common/include/d2common/integration_base.h:201-227).
+__device__ void imu_raw(const double *c, const double *pi, const double *si, const double *pj, const double *sj,
+                        double g, double *res, double *J /*15x30 zeroed*/) {
+  const double dt = c[0];
+  const double *dp = c + 1, *dq = c + 4, *dv = c + 8, *ba0 = c + 11, *bg0 = c + 14, *Jp = c + 17;
+  Q4 Qi = qload(pi + 3), Qj = qload(pj + 3), Dq = qload(dq);
+  double Ri[9];
+  q2R(Qi, Ri);
+  auto jb = [&](int r, int col, double *o) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) o[a * 3 + b] = Jp[(r + a) * 15 + col + b];
+  };
+  double dp_dba[9], dp_dbg[9], dq_dbg[9], dv_dba[9], dv_dbg[9];
+  jb(0, 9, dp_dba); jb(0, 12, dp_dbg); jb(3, 12, dq_dbg); jb(6, 9, dv_dba); jb(6, 12, dv_dbg);
+  double dba[3] = {si[3] - ba0[0], si[4] - ba0[1], si[5] - ba0[2]};
+  double dbg[3] = {si[6] - bg0[0], si[7] - bg0[1], si[8] - bg0[2]};
+  double th[3], t1[3], t2[3];
+  mv3(dq_dbg, dbg, th);
+  Q4 cq = qmul(Dq, Q4{0.5 * th[0], 0.5 * th[1], 0.5 * th[2], 1.0});
+  double cv[3], cp[3];
+  mv3(dv_dba, dba, t1); mv3(dv_dbg, dbg, t2);
+  for (int k = 0; k < 3; k++) cv[k] = dv[k] + t1[k] + t2[k];
+  mv3(dp_dba, dba, t1); mv3(dp_dbg, dbg, t2);
+  for (int k = 0; k < 3; k++) cp[k] = dp[k] + t1[k] + t2[k];
+  double G[3] = {0, 0, g};
+  double a1[3], a2[3], ra1[3], ra2[3];
+  for (int k = 0; k < 3; k++) { a1[k] = 0.5 * G[k] * dt * dt + pj[k] - pi[k] - si[k] * dt; a2[k] = G[k] * dt + sj[k] - si[k]; }
+  mtv3(Ri, a1, ra1); mtv3(Ri, a2, ra2);
+  Q4 qij = qmul(qinv(Qi), Qj);
+  Q4 er = qmul(qinv(cq), qij);
+  for (int k = 0; k < 3; k++) { res[k] = ra1[k] - cp[k]; res[6 + k] = ra2[k] - cv[k]; res[9 + k] = sj[3 + k] - si[3 + k]; res[12 + k] = sj[6 + k] - si[6 + k]; }
+  res[3] = 2 * er.x; res[4] = 2 * er.y; res[5] = 2 * er.z;
+  if (!J) return;
+  auto put = [&](int r, int col, const double *m, double s) {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) J[(r + a) * 30 + col + b] = s * m[a * 3 + b];
+  };
+  auto skewm = [&](const double *v, double *o) { o[0] = 0; o[1] = -v[2]; o[2] = v[1]; o[3] = v[2]; o[4] = 0; o[5] = -v[0]; o[6] = -v[1]; o[7] = v[0]; o[8] = 0; };
+  // bottom-right 3x3 of Qleft(a) (and of Qleft(a) Qright(b)), both after positify (utils.hpp:85-104)
+  auto qleft3 = [&](Q4 a, double *o) {
+    a = qpos(a);
+    o[0] = a.w; o[1] = -a.z; o[2] = a.y; o[3] = a.z; o[4] = a.w; o[5] = -a.x; o[6] = -a.y; o[7] = a.x; o[8] = a.w;
+  };
+  double RiT[9] = {Ri[0], Ri[3], Ri[6], Ri[1], Ri[4], Ri[7], Ri[2], Ri[5], Ri[8]};
+  double S[9], M[9], I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  // pose_i (cols 0..5)
+  put(0, 0, RiT, -1.0);
+  skewm(ra1, S); put(0, 3, S, 1.0);
+  {
+    Q4 a = qpos(qmul(qinv(Qj), Qi)), b = qpos(cq);
+    double L3[9], R3[9];
+    qleft3(a, L3);
+    R3[0] = b.w; R3[1] = b.z; R3[2] = -b.y; R3[3] = -b.z; R3[4] = b.w; R3[5] = b.x; R3[6] = b.y; R3[7] = -b.x; R3[8] = b.w;
+    mm3(L3, R3, M);
+    double av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z};
+    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) M[r * 3 + cc] -= av[r] * bv[cc];
+    put(3, 3, M, -1.0);
+  }
+  skewm(ra2, S); put(6, 3, S, 1.0);
+  // sb_i (cols 6..14): V 6, BA 9, BG 12
+  put(0, 6, RiT, -dt); put(0, 9, dp_dba, -1.0); put(0, 12, dp_dbg, -1.0);
+  {
+    double L3[9];
+    qleft3(qmul(qmul(qinv(Qj), Qi), Dq), L3);  // uncorrected delta_q (imu_factor.h:159)
+    mm3(L3, dq_dbg, M);
+    put(3, 12, M, -1.0);
+  }
+  put(6, 6, RiT, -1.0); put(6, 9, dv_dba, -1.0); put(6, 12, dv_dbg, -1.0);
+  put(9, 9, I3, -1.0); put(12, 12, I3, -1.0);
+  // pose_j (cols 15..20)
+  put(0, 15, RiT, 1.0);
+  {
+    double L3[9];
+    qleft3(qmul(qmul(qinv(cq), qinv(Qi)), Qj), L3);
+    put(3, 18, L3, 1.0);
+  }
+  // sb_j (cols 21..29)
+  put(6, 21, RiT, 1.0); put(9, 24, I3, 1.0); put(12, 27, I3, 1.0);
+}
+
+D2BA_DEV void prior_dx_pose(const double *x, const double *x0, double *dx) {  // prior_factor.cpp:57-68
+  dx[0] = x[0] - x0[0]; dx[1] = x[1] - x0[1]; dx[2] = x[2] - x0[2];
+  Q4 e = qmul(qinv(qload(x0 + 3)), qload(x + 3));
+  Q4 p = qpos(e);
+  double s = (e.w >= 0) ? 2.0 : -2.0;  // the `!(w >= 0)` branch negates the positified vector again
+  if (!(e.w >= 0)) { dx[3] = -2.0 * p.x; dx[4] = -2.0 * p.y; dx[5] = -2.0 * p.z; (void)s; }
+  else { dx[3] = 2.0 * p.x; dx[4] = 2.0 * p.y; dx[5] = 2.0 * p.z; }
+}
+
+// One CTA per window: zero Hcc/gc of the evaluated buffer, then add IMU, prior and ADMM terms.
+// Runs before k_proj_lin (which adds the reprojection blocks with atomics).
+constexpr int kMiscThreads = 256;
+__global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || (!eval_cur && !ctl->step_valid)) return;
+  const int buf = eval_cur ? ctl->cur : 1 - ctl->cur;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  extern __shared__ double sm[];
+  double *red = sm;             // 40
+  double *Jr = sm + 40;         // chunk of IMU factors: raw J (15x30) + r(15) + J (15x30) + r(15)
+  const int n = w.n_c, ld = w.ldh;
+  double *H = d.Hcc[buf] + w.offH;
+  double *g = d.gc[buf] + w.offc;
+  const double *x6 = d.x6[buf] + (size_t)w.off6 * 8;
+  const double *xsb = d.xsb[buf] + (size_t)w.offsb * 9;
+  const double *xlm = d.xlm[buf] + w.offlm;
+  const int *col6 = d.col6 + w.off6;
+  const int *colsb = d.colsb + w.offsb;
+  // ---- zero
+  {
+    double2 *H2 = reinterpret_cast<double2 *>(H);
+    size_t tot2 = ((size_t)(n + 1) * ld) / 2;  // ld is a multiple of 4
+    for (size_t e = tid; e < tot2; e += nt) H2[e] = make_double2(0.0, 0.0);
+    for (int e = tid; e < n; e += nt) g[e] = 0.0;
+  }
+  __syncthreads();
+  double cost = 0.0;
+  // ---- IMU factors, processed in chunks of kImuChunk to bound shared memory
+  constexpr int kImuChunk = 4;
+  constexpr int kF = 15 * 30 + 15;  // doubles per factor for (J, r)
+  for (int f0 = 0; f0 < w.n_imu; f0 += kImuChunk) {
+    int nf = min(kImuChunk, w.n_imu - f0);
+    double *raw = Jr, *fin = Jr + kImuChunk * kF;
+    for (int e = tid; e < nf * kF; e += nt) raw[e] = 0.0;
+    __syncthreads();
+    if (tid < nf) {
+      const ImuDesc &im = d.imu[w.off_imu + f0 + tid];
+      imu_raw(d.imu_c + (size_t)(w.off_imu + f0 + tid) * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8,
+              xsb + im.sj * 9, d.prm.gravity, raw + tid * kF + 450, raw + tid * kF);
+    }
+    __syncthreads();
+    // J = U Jraw, r = U rraw
+    for (int e = tid; e < nf * kF; e += nt) {
+      int f = e / kF, k = e % kF;
+      const double *U = d.imu_U + (size_t)(w.off_imu + f0 + f) * 225;
+      const double *src = raw + f * kF;
+      double s = 0;
+      if (k < 450) {
+        int i = k / 30, j = k % 30;
+        for (int q = i; q < 15; q++) s += U[i * 15 + q] * src[q * 30 + j];  // U is upper triangular
+      } else {
+        int i = k - 450;
+        for (int q = i; q < 15; q++) s += U[i * 15 + q] * src[450 + q];
+      }
+      fin[e] = s;
+    }
+    __syncthreads();
+    // accumulate: 30x30 + gradient per factor
+    for (int e = tid; e < nf * 930; e += nt) {
+      int f = e / 930, k = e % 930;
+      const ImuDesc &im = d.imu[w.off_imu + f0 + f];
+      const double *Jf = fin + f * kF, *rf = Jf + 450;
+      int cols[4] = {col6[im.pi], colsb[im.si], col6[im.pj], colsb[im.sj]};
+      auto gcol = [&](int a) -> int {  // local 0..29 -> reduced column
+        int b = a < 6 ? 0 : (a < 15 ? 1 : (a < 21 ? 2 : 3));
+        int o = a < 6 ? a : (a < 15 ? a - 6 : (a < 21 ? a - 15 : a - 21));
+        return cols[b] < 0 ? -1 : cols[b] + o;
+      };
+      if (k < 900) {
+        int a = k / 30, b = k % 30;
+        int ga = gcol(a), gb = gcol(b);
+        if (ga < 0 || gb < 0) continue;
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < 15; q++) s += Jf[q * 30 + a] * Jf[q * 30 + b];
+        if (s != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], s);
+      } else {
+        int a = k - 900;
+        int ga = gcol(a);
+        if (ga < 0) continue;
+        double s = 0;
+#pragma unroll
+        for (int q = 0; q < 15; q++) s += Jf[q * 30 + a] * rf[q];
+        atomicAdd(&g[ga], s);
+      }
+    }
+    if (tid < nf) {
+      const double *rf = fin + tid * kF + 450;
+      double s = 0;
+      for (int q = 0; q < 15; q++) s += rf[q] * rf[q];
+      cost += 0.5 * s;
+    }
+    __syncthreads();
+  }
+  // ---- prior: r = e0 + J dx ; H += J^T J ; g += J^T r
+  if (w.prior_m > 0) {
+    const int m = w.prior_m;
+    double *dx = Jr, *r = Jr + m;
+    int *cmap = reinterpret_cast<int *>(Jr + 2 * m);
+    const PriorBlk *pb = d.prior_blk + w.off_prior_blk;
+    if (tid < w.prior_nblk) {
+      const PriorBlk &b = pb[tid];
+      int col;
+      if (b.kind == 0 || b.kind == 1) { prior_dx_pose(x6 + b.index * 8, b.x0, dx + b.off); col = col6[b.index]; }
+      else if (b.kind == 2) { for (int q = 0; q < 9; q++) dx[b.off + q] = xsb[b.index * 9 + q] - b.x0[q]; col = colsb[b.index]; }
+      else if (b.kind == 3) { dx[b.off] = d.xtd[buf][wi] - b.x0[0]; col = w.td_col; }
+      else { dx[b.off] = xlm[b.index] - b.x0[0]; col = -1; }
+      for (int q = 0; q < b.eff; q++) cmap[b.off + q] = col < 0 ? -1 : col + q;
+    }
+    __syncthreads();
+    const double *J = d.prior_J + w.off_prior_J, *e0 = d.prior_e0 + w.off_prior_v, *A = d.prior_A + w.off_prior_J;
+    {
+      int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+      for (int i = warp; i < m; i += nw) {
+        double s = 0;
+        for (int j = lane; j < m; j += 32) s += J[(size_t)i * m + j] * dx[j];
+        s = warp_sum(s);
+        if (lane == 0) r[i] = e0[i] + s;
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += nt) {
+      cost += 0.5 * r[j] * r[j];
+      int gj = cmap[j];
+      if (gj < 0) continue;
+      double s = 0;
+      for (int i = 0; i < m; i++) s += J[(size_t)i * m + j] * r[i];
+      atomicAdd(&g[gj], s);
+    }
+    for (int e = tid; e < m * m; e += nt) {
+      int i = e / m, j = e % m;
+      int gi = cmap[i], gj = cmap[j];
+      if (gi < 0 || gj < 0) continue;
+      double v = A[e];
+      if (v != 0.0) atomicAdd(&H[(size_t)gi * ld + gj], v);
+    }
+    __syncthreads();
+  }
+  // ---- ADMM terms (ConsensusSolver::updateTilde, ConsensusSolver.cpp:108-164)
+  if (w.admm_on) {
+    const int *slot = d.slot6 + w.off6;
+    for (int b = tid; b < w.n6; b += nt) {
+      if (slot[b] < 0) continue;
+      // ConsenusPoseFactor::Evaluate (consenus_factor.cpp:19-51); NB q weight = rho_T, T weight = rho_theta
+      const double *z = d.z6 + (size_t)(w.off6 + b) * 8, *tl = d.tilde6 + (size_t)(w.off6 + b) * 6;
+      const double *x = x6 + b * 8;
+      double Rz[9], dd[3] = {x[0] - z[0], x[1] - z[1], x[2] - z[2]}, t[3];
+      Q4 qz = qload(z + 3);
+      q2R(qz, Rz);
+      mtv3(Rz, dd, t);
+      Q4 qe = qmul(qinv(qz), qload(x + 3));
+      const double wq = d.prm.rho_T, wT = d.prm.rho_theta;
+      double r[6] = {wT * (t[0] + tl[0]), wT * (t[1] + tl[1]), wT * (t[2] + tl[2]),
+                     wq * (2 * qe.x + tl[3]), wq * (2 * qe.y + tl[4]), wq * (2 * qe.z + tl[5])};
+      for (int q = 0; q < 6; q++) cost += 0.5 * r[q] * r[q];
+      int c = col6[b];
+      if (c < 0) continue;
+      Q4 p = qpos(qe);
+      double L3[9] = {p.w, -p.z, p.y, p.z, p.w, -p.x, -p.y, p.x, p.w};
+      // J_T = wT Rz^T (3x3), J_q = wq L3
+      for (int i = 0; i < 3; i++) {
+        double gi = 0, gq = 0;
+        for (int k = 0; k < 3; k++) { gi += wT * Rz[i * 3 + k] * r[k]; gq += wq * L3[k * 3 + i] * r[3 + k]; }
+        atomicAdd(&g[c + i], gi); atomicAdd(&g[c + 3 + i], gq);
+        for (int j = 0; j < 3; j++) {
+          double hT = 0, hq = 0;
+          for (int k = 0; k < 3; k++) { hT += Rz[i * 3 + k] * Rz[j * 3 + k]; hq += L3[k * 3 + i] * L3[k * 3 + j]; }
+          atomicAdd(&H[(size_t)(c + i) * ld + c + j], wT * wT * hT);
+          atomicAdd(&H[(size_t)(c + 3 + i) * ld + c + 3 + j], wq * wq * hq);
+        }
+      }
+    }
+    // ceres::NormalPrior(A, x_ref): A = I for SPEED_BIAS / TD, rho_landmark for LANDMARK (:113-125)
+    for (int e = tid; e < w.nsb * 9; e += nt) {
+      int b = e / 9, q = e % 9;
+      double rr = xsb[e] - d.sb_ref[(size_t)w.offsb * 9 + e];
+      cost += 0.5 * rr * rr;
+      int c = colsb[b];
+      if (c >= 0) { atomicAdd(&H[(size_t)(c + q) * ld + c + q], 1.0); atomicAdd(&g[c + q], rr); }
+    }
+    if (tid == 0 && w.has_td) {
+      double rr = d.xtd[buf][wi] - d.td_ref[wi];
+      cost += 0.5 * rr * rr;
+      if (w.td_col >= 0) { atomicAdd(&H[(size_t)w.td_col * ld + w.td_col], 1.0); atomicAdd(&g[w.td_col], rr); }
+    }
+    const double rl = d.prm.rho_landmark;
+    for (int l = tid; l < w.nl; l += nt) {
+      double rr = rl * (xlm[l] - d.lm_ref[w.offlm + l]);
+      cost += 0.5 * rr * rr;
+    }
+  }
+  cost = block_sum(cost, red);
+  if (tid == 0) { ctl->cand_cost_misc = cost; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused reprojection linearisation.  One warp = one job (a run of 32-observation tiles of one group).
+//   per observation : residual, Jacobians, Huber  ->  landmark-side record {h, g, w_td, w_slot[..]}
+//   per group       : [J_slots | (J_td) | r]^T [J_slots | (J_td) | r] accumulated with fp64 tensor-core
+//                     MMAs (m8n8k4) from a shared-memory staging tile, flushed with atomics.
+// NCT = 8-column tiles of the staged matrix (2: two six-dof slots + r, 4: four slots + td + r)
+// KR  = staged rows per observation (2, or 4 for the 3-row depth factor)
+template <int NCT, int KR>
+__global__ void __launch_bounds__(128) k_proj_lin(Dev d, int eval_cur, int job_begin, int job_count) {
+  constexpr int NS = (NCT == 2) ? 2 : 4;
+  constexpr int NCOL = NCT * 8;
+  constexpr int LDJ = kTile * KR + 4;
+  constexpr int ROWS = (KR == 2) ? 2 : 3;
+  constexpr int TDCOL = (NCT == 2) ? -1 : 24;
+  constexpr int RCOL = (NCT == 2) ? 12 : 25;
+  constexpr int NPAIR = NCT * (NCT + 1) / 2;
+  constexpr int kWarpDoubles = GC_SIZE + NCOL * LDJ;
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ji = blockIdx.x * 4 + warp;
+  if (ji >= job_count) return;
+  const Job jb = d.job[job_begin + ji];
+  const WinDesc &w = d.win[jb.win];
+  Ctl *ctl = d.ctl + jb.win;
+  if (ctl->done || (!eval_cur && !ctl->step_valid)) return;
+  const int buf = eval_cur ? ctl->cur : 1 - ctl->cur;
+  const Group &g = d.grp[jb.grp];
+  double *gc = sm + warp * kWarpDoubles;
+  double *Js = gc + GC_SIZE;
+  const double *x6 = d.x6[buf] + (size_t)w.off6 * 8;
+  const double *R6 = d.R6[buf] + (size_t)w.off6 * 12;
+  const int type = g.type;
+  if (type != PDEPTH) {
+    const int bi = g.blk[0], bj = g.blk[1], ba = g.blk[2], bb = g.blk[3];
+    build_group_consts(type, bi >= 0 ? R6 + bi * 12 : nullptr, bi >= 0 ? x6 + bi * 8 : nullptr,
+                       bj >= 0 ? R6 + bj * 12 : nullptr, bj >= 0 ? x6 + bj * 8 : nullptr, R6 + ba * 12, x6 + ba * 8,
+                       bb >= 0 ? R6 + bb * 12 : nullptr, bb >= 0 ? x6 + bb * 8 : nullptr, gc);
+  }
+  const double td = d.xtd[buf][jb.win];
+  const double *xlm = d.xlm[buf] + w.offlm;
+  const bool need_ext = g.need_ext, need_td = g.need_td;
+  const bool has_cols = (g.slot_src[0] >= 0) || (NS > 2 && g.td_col >= 0);
+  double acc[NPAIR][2];
+#pragma unroll
+  for (int p = 0; p < NPAIR; p++) { acc[p][0] = 0.0; acc[p][1] = 0.0; }
+  double cost = 0.0;
+  // zero the padding columns of the staging tile once
+  for (int c = RCOL + 1; c < NCOL; c++)
+    for (int q = 0; q < KR; q++) Js[c * LDJ + lane * KR + q] = 0.0;
+  for (int t = 0; t < jb.ntiles; t++) {
+    const int tile = jb.tile_begin + t;
+    const double *ob = d.obs + (size_t)tile * kObsFields * kTile;
+    const int lm = d.obs_lm[(size_t)tile * kTile + lane];
+    double f[kObsFields];
+#pragma unroll
+    for (int k = 0; k < kObsFields; k++) f[k] = ob[k * kTile + lane];
+    ProjOut<ROWS> o;
+    double lam = lm >= 0 ? xlm[lm] : 1.0;
+    if (type == PDEPTH) {
+      // OneFrameDepth (depth_factor.h:9-29): r = (lambda - 1/depth) * depth_sqrt_inf, f[20] = 1/depth
+#pragma unroll
+      for (int q = 0; q < ROWS; q++) { o.r[q] = 0; o.jl[q] = 0; o.jt[q] = 0; }
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int q = 0; q < ROWS; q++)
+#pragma unroll
+          for (int k = 0; k < 6; k++) o.J[s][q][k] = 0;
+      double r0 = (lam - f[20]) * d.prm.depth_sqrt_inf, s2 = r0 * r0, sc = 1.0, hub = d.prm.huber;
+      if (hub > 0 && s2 > hub * hub) { double rs = sqrt(s2); o.cost = 0.5 * (2 * hub * rs - hub * hub); sc = sqrt(hub / rs); }
+      else o.cost = 0.5 * s2;
+      o.r[0] = r0 * sc; o.jl[0] = d.prm.depth_sqrt_inf * sc;
+    } else if (need_ext) {
+      if (need_td) proj_eval<ROWS, true, true>(type, gc, f, lam, td, d.prm.sqrt_info_px, d.prm.depth_sqrt_inf, d.prm.huber, o);
+      else proj_eval<ROWS, true, false>(type, gc, f, lam, td, d.prm.sqrt_info_px, d.prm.depth_sqrt_inf, d.prm.huber, o);
+    } else {
+      if (need_td) proj_eval<ROWS, false, true>(type, gc, f, lam, td, d.prm.sqrt_info_px, d.prm.depth_sqrt_inf, d.prm.huber, o);
+      else proj_eval<ROWS, false, false>(type, gc, f, lam, td, d.prm.sqrt_info_px, d.prm.depth_sqrt_inf, d.prm.huber, o);
+    }
+    const bool valid = lm >= 0;
+    // ---- landmark-side record
+    double hl = 0, gl = 0, wtd = 0;
+#pragma unroll
+    for (int q = 0; q < ROWS; q++) { hl += o.jl[q] * o.jl[q]; gl += o.jl[q] * o.r[q]; if (NS > 2 && need_td) wtd += o.jt[q] * o.jl[q]; }
+    double *rec = d.rec[buf] + ((size_t)w.off_rec + (size_t)(tile - w.off_tile) * kTile + lane) * w.rec_stride;
+    if (valid) {
+      cost += o.cost;
+      reinterpret_cast<double2 *>(rec)[0] = make_double2(hl, gl);
+      reinterpret_cast<double2 *>(rec)[1] = make_double2(wtd, 0.0);
+    }
+    // ---- slots -> staging tile + coupling vector
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      const int src = g.slot_src[s];
+      double wv[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        double jq[ROWS];
+#pragma unroll
+        for (int q = 0; q < ROWS; q++) {
+          double v = 0.0;
+          if (src == 0) v = o.J[0][q][k];
+          else if (src == 1) v = o.J[1][q][k];
+          else if (src == 2) v = o.J[2][q][k];
+          else if (src == 3) v = o.J[3][q][k];
+          jq[q] = valid ? v : 0.0;
+        }
+        double ws = 0;
+#pragma unroll
+        for (int q = 0; q < ROWS; q++) ws += jq[q] * o.jl[q];
+        wv[k] = ws;
+        double *dst = Js + (s * 6 + k) * LDJ + lane * KR;
+        if (KR == 2) *reinterpret_cast<double2 *>(dst) = make_double2(jq[0], jq[1]);
+        else { reinterpret_cast<double2 *>(dst)[0] = make_double2(jq[0], jq[1]); reinterpret_cast<double2 *>(dst)[1] = make_double2(jq[ROWS - 1], 0.0); }
+      }
+      if (valid && src >= 0) {
+        double2 *r2 = reinterpret_cast<double2 *>(rec + 4 + s * 6);
+        r2[0] = make_double2(wv[0], wv[1]); r2[1] = make_double2(wv[2], wv[3]); r2[2] = make_double2(wv[4], wv[5]);
+      }
+    }
+    if (NS > 2) {
+      double *dst = Js + TDCOL * LDJ + lane * KR;
+      double t0 = (valid && need_td) ? o.jt[0] : 0.0, t1 = (valid && need_td) ? o.jt[1] : 0.0;
+      if (KR == 2) *reinterpret_cast<double2 *>(dst) = make_double2(t0, t1);
+      else { reinterpret_cast<double2 *>(dst)[0] = make_double2(t0, t1); reinterpret_cast<double2 *>(dst)[1] = make_double2((valid && need_td) ? o.jt[ROWS - 1] : 0.0, 0.0); }
+    }
+    {
+      double *dst = Js + RCOL * LDJ + lane * KR;
+      double r0 = valid ? o.r[0] : 0.0, r1 = valid ? o.r[1] : 0.0;
+      if (KR == 2) *reinterpret_cast<double2 *>(dst) = make_double2(r0, r1);
+      else { reinterpret_cast<double2 *>(dst)[0] = make_double2(r0, r1); reinterpret_cast<double2 *>(dst)[1] = make_double2(valid ? o.r[ROWS - 1] : 0.0, 0.0); }
+    }
+    __syncwarp();
+    if (has_cols) {
+      // ---- tensor-core accumulation: K = 32*KR staged rows, 4 per MMA
+      const int kq = lane & 3, cr = lane >> 2;
+#pragma unroll 4
+      for (int st = 0; st < kTile * KR / 4; st++) {
+        double v[NCT];
+#pragma unroll
+        for (int c = 0; c < NCT; c++) v[c] = Js[(c * 8 + cr) * LDJ + st * 4 + kq];
+        int p = 0;
+#pragma unroll
+        for (int cm = 0; cm < NCT; cm++)
+#pragma unroll
+          for (int cn = cm; cn < NCT; cn++) { dmma(acc[p][0], acc[p][1], v[cm], v[cn]); p++; }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- flush
+  cost = warp_sum(cost);
+  if (lane == 0) atomicAdd(&ctl->cand_cost_proj, cost);
+  if (!has_cols) return;
+  double *H = d.Hcc[buf] + w.offH;
+  double *gv = d.gc[buf] + w.offc;
+  const int ld = w.ldh;
+  auto l2g = [&](int m) -> int {
+    if (m < NS * 6) { int sc = g.slot_col[m / 6]; return sc < 0 ? -1 : sc + m % 6; }
+    if (m == TDCOL) return g.td_col;
+    return -1;
+  };
+  const int row = lane >> 2, c0 = (lane & 3) * 2;
+  int p = 0;
+#pragma unroll
+  for (int cm = 0; cm < NCT; cm++)
+#pragma unroll
+    for (int cn = cm; cn < NCT; cn++) {
+      const int m = cm * 8 + row, gm = l2g(m);
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int n = cn * 8 + c0 + e;
+        const double v = acc[p][e];
+        if (gm >= 0) {
+          if (n == RCOL) atomicAdd(&gv[gm], v);
+          else {
+            const int gn = l2g(n);
+            if (gn >= 0) {
+              atomicAdd(&H[(size_t)gm * ld + gn], v);
+              if (cm != cn) atomicAdd(&H[(size_t)gn * ld + gm], v);
+            }
+          }
+        }
+      }
+      p++;
+    }
+}
+
+// explicit instantiations used by the host launcher
+template __global__ void k_proj_lin<2, 2>(Dev, int, int, int);
+template __global__ void k_proj_lin<4, 2>(Dev, int, int, int);
+template __global__ void k_proj_lin<2, 4>(Dev, int, int, int);
+template __global__ void k_proj_lin<4, 4>(Dev, int, int, int);
+
+// debug: raw (un-robustified) residual + full 3x26 Jacobian per observation tile slot
+__global__ void k_proj_debug(Dev d, double *out /*[tiles*32][81]*/, int n_tiles_total, const int *tile_win) {
+  const int tile = blockIdx.x;
+  if (tile >= n_tiles_total) return;
+  const int lane = threadIdx.x & 31;
+  __shared__ double gc[GC_SIZE];
+  const int wi = tile_win[tile];
+  const WinDesc &w = d.win[wi];
+  const int buf = d.ctl[wi].cur;
+  const Group &g = d.grp[d.tile_grp[tile]];
+  const double *x6 = d.x6[buf] + (size_t)w.off6 * 8;
+  const double *R6 = d.R6[buf] + (size_t)w.off6 * 12;
+  const double *ob = d.obs + (size_t)tile * kObsFields * kTile;
+  const int lm = d.obs_lm[(size_t)tile * kTile + lane];
+  double f[kObsFields];
+  for (int k = 0; k < kObsFields; k++) f[k] = ob[k * kTile + lane];
+  double *rec = out + ((size_t)tile * kTile + lane) * 81;
+  for (int k = 0; k < 81; k++) rec[k] = 0.0;
+  double lam = lm >= 0 ? d.xlm[buf][w.offlm + lm] : 1.0;
+  if (g.type == PDEPTH) {
+    if (lm >= 0) { rec[0] = (lam - f[20]) * d.prm.depth_sqrt_inf; rec[3 + 24] = d.prm.depth_sqrt_inf; }
+    return;
+  }
+  const int bi = g.blk[0], bj = g.blk[1], ba = g.blk[2], bb = g.blk[3];
+  build_group_consts(g.type, bi >= 0 ? R6 + bi * 12 : nullptr, bi >= 0 ? x6 + bi * 8 : nullptr, bj >= 0 ? R6 + bj * 12 : nullptr,
+                     bj >= 0 ? x6 + bj * 8 : nullptr, R6 + ba * 12, x6 + ba * 8, bb >= 0 ? R6 + bb * 12 : nullptr,
+                     bb >= 0 ? x6 + bb * 8 : nullptr, gc);
+  if (lm < 0) return;
+  ProjOut<3> o;
+  o.r[2] = 0; o.jl[2] = 0; o.jt[2] = 0;
+  const double td = d.xtd[buf][wi];
+  if (g.type == P2F1CD) proj_eval<3, true, true>(g.type, gc, f, lam, td, d.prm.sqrt_info_px, d.prm.depth_sqrt_inf, -1.0, o);
+  else {
+    ProjOut<2> o2;
+    proj_eval<2, true, true>(g.type, gc, f, lam, td, d.prm.sqrt_info_px, d.prm.depth_sqrt_inf, -1.0, o2);
+    for (int q = 0; q < 2; q++) { o.r[q] = o2.r[q]; o.jl[q] = o2.jl[q]; o.jt[q] = o2.jt[q]; for (int s = 0; s < 4; s++) for (int k = 0; k < 6; k++) o.J[s][q][k] = o2.J[s][q][k]; }
+    for (int s = 0; s < 4; s++) for (int k = 0; k < 6; k++) o.J[s][2][k] = 0;
+  }
+  const int rows = g.type == P2F1CD ? 3 : 2;
+  for (int q = 0; q < rows; q++) {
+    rec[q] = o.r[q];
+    double *Jr = rec + 3 + q * 26;
+    for (int s = 0; s < 4; s++) {
+      bool present = (s < 2) ? (g.type != P1F2C) : (s == 2 ? true : (g.type == P2F2C || g.type == P1F2C));
+      for (int k = 0; k < 6; k++) Jr[s * 6 + k] = present ? o.J[s][q][k] : 0.0;
+    }
+    Jr[24] = o.jl[q]; Jr[25] = o.jt[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-landmark reduction (warp per landmark).  Observations of a landmark are visited serially, the
+// 16/32 record entries in parallel across lanes, so there are no write conflicts and the result is
+// deterministic.  Output: Wt[l][0..n_lc) = w_l / sqrt(h'), Wt[l][n_lc] = g_l / sqrt(h'),
+// h' = h_l + mu D_l^2.
+constexpr int kGatherWarps = 8;
+__global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const int *lm_win, int n_lm_total, int max_ldw) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gl_idx = blockIdx.x * kGatherWarps + warp;
+  if (gl_idx >= n_lm_total) return;
+  const int wi = lm_win[gl_idx];
+  const WinDesc &w = d.win[wi];
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse) return;
+  const int buf = ctl->cur;
+  const int l = gl_idx - w.offlm;
+  double *row = sm + warp * max_ldw;
+  const int nlc = w.n_lc;
+  for (int c = lane; c <= nlc; c += 32) row[c] = 0.0;
+  __syncwarp();
+  const int *ptr = d.lm_ptr + w.off_lmptr;
+  const int *lo = d.lm_obs + w.off_lmobs;
+  const int stride = w.rec_stride;
+  const double *recs = d.rec[buf] + (size_t)w.off_rec * stride;
+  double h = 0, g = 0;
+  for (int k = ptr[l]; k < ptr[l + 1]; k++) {
+    const int pos = lo[k];  // window-local sorted observation position
+    const Group &gr = d.grp[d.tile_grp[w.off_tile + pos / kTile]];
+    const double *rec = recs + (size_t)pos * stride;
+    double v = lane < stride ? rec[lane] : 0.0;
+    if (lane == 0) h += v;
+    if (lane == 1) g += v;
+    int col = -1;
+    if (lane == 2) col = gr.td_col;
+    else if (lane >= 4 && lane < 28) { int s = (lane - 4) / 6; if (lane < 4 + (stride == 16 ? 12 : 24)) { int sc = gr.slot_col[s]; if (gr.slot_src[s] >= 0 && sc >= 0) col = sc + (lane - 4) % 6; } }
+    if (col >= 0) row[col] += v;
+    __syncwarp();
+  }
+  h = __shfl_sync(0xffffffffu, h, 0);
+  g = __shfl_sync(0xffffffffu, g, 1);
+  if (w.admm_on) {
+    double rl = d.prm.rho_landmark;
+    h += rl * rl;
+    g += rl * rl * (d.xlm[buf][w.offlm + l] - d.lm_ref[w.offlm + l]);
+  }
+  const double hp = h + ctl->mu * d2_of(h);
+  const double di = 1.0 / sqrt(hp);
+  double *Wt = d.Wt + w.offW + (size_t)l * w.ldw;
+  for (int c = lane; c < w.ldw; c += 32) Wt[c] = (c < nlc) ? row[c] * di : (c == nlc ? g * di : 0.0);
+  if (lane == 0) {
+    d.hl[w.offlm + l] = h; d.gl[w.offlm + l] = g; d.dinv[w.offlm + l] = di;
+    if (!(hp > 0.0)) ctl->chol_fail = 1;
+    atomicMax(&ctl->gmax_l_bits, (unsigned long long)__double_as_longlong(fabs(g)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reduced camera system.  Tile list entries: kind 0 = SYRK tile in W-space (32x32), kind 1 = copy tile
+// (rows/cols of the speed-bias part, which have no landmark coupling).
+struct SchurTile { int win, kind, tm, tn; };
+constexpr int kSyrkK = 32;
+constexpr int kSyrkLd = 36;  // == 4 (mod 16): conflict-free fragment loads
+__global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
+  const SchurTile t = tiles[blockIdx.x];
+  const WinDesc &w = d.win[t.win];
+  Ctl *ctl = d.ctl + t.win;
+  if (ctl->done || ctl->reuse) return;
+  const int buf = ctl->cur;
+  const int n = w.n_c, nlc = w.n_lc, ld = w.ldh;
+  const double mu = ctl->mu;
+  const double *H = d.Hcc[buf] + w.offH;
+  const double *gcv = d.gc[buf] + w.offc;
+  double *S = d.S + w.offH;
+  const int tid = threadIdx.x;
+  if (t.kind == 1) {
+    // plain copy region: S[i][j] = H[i][j] + mu D^2 (i == j) for i in [nlc, n), j <= i; rhs row j in [nlc, n)
+    const int i0 = t.tm * 32, j0 = t.tn * 32;
+    for (int e = tid; e < 1024; e += 128) {
+      int i = i0 + e / 32, j = j0 + e % 32;
+      if (i < n && j <= i && i >= nlc) {
+        double v = H[(size_t)i * ld + j];
+        if (i == j) v += mu * d2_of(v);
+        S[(size_t)i * ld + j] = v;
+      }
+      if (i == n && j < n && j >= nlc) S[(size_t)n * ld + j] = gcv[j];
+    }
+    return;
+  }
+  __shared__ double As[kSyrkK * kSyrkLd], Bs[kSyrkK * kSyrkLd];
+  const int warp = tid >> 5, lane = tid & 31;
+  const int m0 = t.tm * 32, n0 = t.tn * 32;   // W-space offsets (0..nlc inclusive is valid)
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+  double acc[2][2][2] = {};
+  const double *Wt = d.Wt + w.offW;
+  const int ldw = w.ldw;
+  const int kq = lane & 3, cr = lane >> 2;
+  for (int k0 = 0; k0 < w.nl_pad; k0 += kSyrkK) {
+    for (int e = tid; e < kSyrkK * 32; e += 128) {
+      int k = e / 32, c = e % 32;
+      const double *rowp = Wt + (size_t)(k0 + k) * ldw;
+      As[k * kSyrkLd + c] = (m0 + c < ldw) ? rowp[m0 + c] : 0.0;
+      Bs[k * kSyrkLd + c] = (n0 + c < ldw) ? rowp[n0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < kSyrkK; ks += 4) {
+      double a0 = As[(ks + kq) * kSyrkLd + wm + cr], a1 = As[(ks + kq) * kSyrkLd + wm + 8 + cr];
+      double b0 = Bs[(ks + kq) * kSyrkLd + wn + cr], b1 = Bs[(ks + kq) * kSyrkLd + wn + 8 + cr];
+      dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+    __syncthreads();
+  }
+  // epilogue: W-space (m, c) -> S-space; index nlc of W-space is the rhs row n of S
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int m = m0 + wm + a * 8 + cr, c = n0 + wn + b * 8 + kq * 2 + e;
+        double v = acc[a][b][e];
+        if (m < nlc && c <= m) {
+          double hv = H[(size_t)m * ld + c];
+          if (m == c) hv += mu * d2_of(hv);
+          S[(size_t)m * ld + c] = hv - v;
+        } else if (m == nlc && c < nlc) {
+          S[(size_t)n * ld + c] = gcv[c] - v;
+        }
+      }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked bordered Cholesky of the reduced system, one CTA per window.
+// S is (n+1) x ld row-major, lower part valid; row n carries the right-hand side, so after the
+// factorisation it holds y = L^-1 g ("forward substitution for free").  Back substitution then gives
+// the Gauss-Newton camera step dc = -L^-T y.
+constexpr int kCholThreads = 512;
+constexpr int kNB = 32;
+__global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse) return;
+  if (ctl->chol_fail) return;
+  extern __shared__ double sm[];
+  const int ldp = max_rows + 4;     // panel stored transposed: Pt[c][r]
+  double *Pt = sm;                  // kNB * ldp
+  double *xs = sm + kNB * ldp;      // solution / scratch (max_rows)
+  double *redb = xs + max_rows + 8; // 16 x 32 partial sums
+  double *Lb = redb + 16 * 32;      // kNB x (kNB+1) diagonal block
+  __shared__ int fail;
+  const int n = w.n_c, n1 = n + 1, ld = w.ldh;
+  double *S = d.S + w.offH;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) fail = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += kNB) {
+    const int nb = min(kNB, n - k0), nr = n1 - k0;
+    // load panel (rows k0..n, cols k0..k0+nb)
+    for (int e = tid; e < nr * kNB; e += nt) {
+      int r = e / kNB, c = e % kNB;
+      Pt[c * ldp + r] = (c < nb && (k0 + r) < n1) ? S[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < nb; c++) {
+      double dd = Pt[c * ldp + c];
+      if (!(dd > 0.0) || !isfinite(dd)) { if (tid == 0) fail = 1; dd = 1.0; }
+      const double sd = sqrt(dd), isd = 1.0 / sd;
+      __syncthreads();
+      for (int r = c + tid; r < nr; r += nt) Pt[c * ldp + r] = (r == c) ? sd : Pt[c * ldp + r] * isd;
+      __syncthreads();
+      // rank-1 update of the remaining panel columns
+      const int ncol = nb - c - 1;
+      for (int e = tid; e < ncol * nr; e += nt) {
+        int c2 = c + 1 + e / nr, r = e % nr;
+        if (r >= c2) Pt[c2 * ldp + r] -= Pt[c * ldp + r] * Pt[c * ldp + c2];
+      }
+      __syncthreads();
+    }
+    // write the factored panel back
+    for (int e = tid; e < nr * kNB; e += nt) {
+      int r = e / kNB, c = e % kNB;
+      if (c < nb && r >= c) S[(size_t)(k0 + r) * ld + k0 + c] = Pt[c * ldp + r];
+    }
+    // trailing update S[i][j] -= sum_c P[i][c] P[j][c], i >= j >= k0+nb, 4x4 register tiles
+    const int t0 = nb;                  // panel-local first trailing row
+    const int ntr = nr - t0;            // trailing rows (incl. rhs row)
+    const int nt4 = (ntr + 3) / 4;
+    for (int tile = tid; tile < nt4 * nt4; tile += nt) {
+      int ti = tile / nt4, tj = tile % nt4;
+      if (tj > ti) continue;
+      int ri = t0 + ti * 4, rj = t0 + tj * 4;
+      double a[4][4] = {};
+      for (int c = 0; c < nb; c++) {
+        const double *pc = Pt + c * ldp;
+        double vi[4], vj[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { vi[q] = (ri + q < nr) ? pc[ri + q] : 0.0; vj[q] = (rj + q < nr) ? pc[rj + q] : 0.0; }
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) a[p][q] += vi[p] * vj[q];
+      }
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int gi = k0 + ri + p, gj = k0 + rj + q;
+          if (gi < n1 && gj < n && gj <= gi) S[(size_t)gi * ld + gj] -= a[p][q];
+        }
+    }
+    __syncthreads();
+  }
+  if (fail) { if (tid == 0) ctl->chol_fail = 1; return; }
+  // ---- back substitution  L^T x = y, blocked from the last block
+  const int nblk = (n + kNB - 1) / kNB;
+  const double *y = S + (size_t)n * ld;
+  for (int b = nblk - 1; b >= 0; b--) {
+    const int k0 = b * kNB, nb = min(kNB, n - k0);
+    // partial sums over already solved x_k, k >= k0+nb: 16 slices x 32 columns
+    const int col = tid & 31, slice = tid >> 5;  // 16 slices
+    double s = 0;
+    if (col < nb)
+      for (int k = k0 + nb + slice; k < n; k += 16) s += S[(size_t)k * ld + k0 + col] * xs[k];
+    redb[slice * 32 + col] = s;
+    __syncthreads();
+    // diagonal block of L into shared memory (avoids a global round trip per substitution step)
+    for (int e = tid; e < kNB * kNB; e += nt) {
+      int i = e / kNB, j = e % kNB;
+      Lb[i * (kNB + 1) + j] = (i < nb && j <= i) ? S[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      double acc = 0;
+      for (int q = 0; q < 16; q++) acc += redb[q * 32 + tid];
+      double rhs = (tid < nb) ? y[k0 + tid] - acc : 0.0;
+      // triangular solve inside the block with warp shuffles: x_i = (rhs_i - sum_{j>i} L[j][i] x_j) / L[i][i]
+      double xi = 0;
+      for (int i = nb - 1; i >= 0; i--) {
+        double v = __shfl_sync(0xffffffffu, rhs, i) / Lb[i * (kNB + 1) + i];
+        if (tid == i) xi = v;
+        if (tid < i) rhs -= Lb[i * (kNB + 1) + tid] * v;   // rhs_j -= L[i][j] * x_i for j < i
+      }
+      if (tid < nb) xs[k0 + tid] = xi;
+    }
+    __syncthreads();
+  }
+  double *gn = d.gn_c + w.offc;
+  for (int i = tid; i < n; i += nt) gn[i] = -xs[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Step kernel: one CTA per window.
+constexpr int kStepThreads = 256;
+__global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done) return;
+  extern __shared__ double sm[];
+  double *red = sm;               // 40
+  double *uc = sm + 40;           // n_c : g / D^2
+  double *dcs = uc + max_nc;      // n_c : GN camera step
+  double *D2 = dcs + max_nc;      // n_c
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int cur = ctl->cur, cand = 1 - cur;
+  const int n = w.n_c, nlc = w.n_lc, ld = w.ldh, nl = w.nl;
+  const double *H = d.Hcc[cur] + w.offH;
+  const double *gcv = d.gc[cur] + w.offc;
+  const double *hl = d.hl + w.offlm, *glv = d.gl + w.offlm, *dinv = d.dinv + w.offlm;
+  double *gn_c = d.gn_c + w.offc, *gn_l = d.gn_l + w.offlm;
+  const SolverParams &P = d.prm;
+  for (int i = tid; i < n; i += nt) { double dd = d2_of(H[(size_t)i * ld + i]); D2[i] = dd; uc[i] = gcv[i] / dd; dcs[i] = gn_c[i]; }
+  __syncthreads();
+  if (!ctl->reuse) {
+    // gradient tolerance (checked at the top of a trust-region iteration, on a fresh linearisation)
+    double gm = 0;
+    for (int i = tid; i < n; i += nt) gm = fmax(gm, fabs(gcv[i]));
+    gm = block_max(gm, red);
+    double gml = __longlong_as_double((long long)ctl->gmax_l_bits);
+    gm = fmax(gm, gml);
+    if (tid == 0) { ctl->gmax_c = gm; }
+    if (!P.fixed_mode && gm <= P.gtol) { if (tid == 0) { ctl->done = 1; ctl->term = 2; } return; }
+    if (ctl->chol_fail) { if (tid == 0) ctl->step_valid = 0; return; }
+    // landmark back-substitution and Cauchy dot products
+    const double *Wt = d.Wt + w.offW;
+    double s_gg = 0, s_uHu = 0, s_nn = 0, s_gdn = 0;
+    for (int l = warp; l < nl; l += nw) {
+      const double *row = Wt + (size_t)l * w.ldw;
+      double a = 0, b = 0;
+      for (int c = lane; c < nlc; c += 32) { double wv = row[c]; a += wv * dcs[c]; b += wv * uc[c]; }
+      a = warp_sum(a); b = warp_sum(b);
+      if (lane == 0) {
+        double di = dinv[l], gt = row[nlc];
+        double gnl = -di * (gt + a);
+        gn_l[l] = gnl;
+        double h = hl[l], g = glv[l], dl2 = d2_of(h), ul = g / dl2, wu = b / di;
+        s_gg += g * ul;
+        s_uHu += 2.0 * ul * wu + h * ul * ul;
+        s_nn += gnl * gnl * dl2;
+        s_gdn += g * gnl;
+      }
+    }
+    // camera part: u^T Hcc u via column-parallel mat-vec (H symmetric)
+    for (int j = tid; j < n; j += nt) {
+      double s = 0;
+      for (int i = 0; i < n; i++) s += H[(size_t)i * ld + j] * uc[i];
+      s_uHu += uc[j] * s;
+      s_gg += gcv[j] * uc[j];
+      s_nn += dcs[j] * dcs[j] * D2[j];
+      s_gdn += gcv[j] * dcs[j];
+    }
+    s_gg = block_sum(s_gg, red); s_uHu = block_sum(s_uHu, red); s_nn = block_sum(s_nn, red); s_gdn = block_sum(s_gdn, red);
+    if (tid == 0) {
+      ctl->gg = s_gg; ctl->nn = s_nn; ctl->gdn = s_gdn; ctl->alpha = s_gg / s_uHu;
+      // successful linear solve: mu relaxes (dogleg_strategy.cc ComputeGaussNewtonStep)
+    }
+    __syncthreads();
+  }
+  // ---- traditional dogleg
+  const double gg = ctl->gg, nn = ctl->nn, gdn = ctl->gdn, alpha = ctl->alpha, radius = ctl->radius, mu = ctl->mu;
+  const double gn_norm = sqrt(nn), g_norm = sqrt(gg);
+  double c1, c2, step_norm;
+  if (gn_norm <= radius) { c1 = 0; c2 = 1; step_norm = gn_norm; }
+  else if (g_norm * alpha >= radius) { c1 = radius / g_norm; c2 = 0; step_norm = radius; }
+  else {
+    double b_dot_a = -alpha * gdn, a_sq = alpha * alpha * gg, bma = nn - 2 * b_dot_a + a_sq;
+    double c = b_dot_a - a_sq, dd = sqrt(c * c + bma * (radius * radius - a_sq));
+    double beta = (c <= 0) ? (dd - c) / bma : (radius * radius - a_sq) / (dd + c);
+    c1 = alpha * (1 - beta); c2 = beta; step_norm = radius;
+  }
+  // model cost change from scalars: H gn = -g - mu D^2 gn (to solver precision)
+  const double uHu = gg / alpha;
+  const double sg = -c1 * gg + c2 * gdn;
+  const double uHgn = -gg - mu * gdn, gnHgn = -gdn - mu * nn;
+  const double sHs = c1 * c1 * uHu - 2.0 * c1 * c2 * uHgn + c2 * c2 * gnHgn;
+  const double model_change = -(sg + 0.5 * sHs);
+  if (!(model_change > 0.0) || !isfinite(model_change)) {
+    if (tid == 0) { ctl->step_valid = 0; ctl->model_change = model_change; }
+    return;
+  }
+  // ---- candidate state
+  double *step_c = d.step_c + w.offc, *step_l = d.step_l + w.offlm;
+  for (int i = tid; i < n; i += nt) { double s = -c1 * uc[i] + c2 * dcs[i]; step_c[i] = s; uc[i] = s; }
+  __syncthreads();
+  double xn = 0, dxn = 0;
+  const double *x6 = d.x6[cur] + (size_t)w.off6 * 8;
+  double *y6 = d.x6[cand] + (size_t)w.off6 * 8;
+  double *R6 = d.R6[cand] + (size_t)w.off6 * 12;
+  const int *col6 = d.col6 + w.off6;
+  for (int b = tid; b < w.n6; b += nt) {
+    const double *x = x6 + b * 8;
+    double o[7];
+    int c = col6[b];
+    if (c >= 0) {
+      pose_plus(x, uc + c, o);
+      for (int q = 0; q < 7; q++) { double df = x[q] - o[q]; xn += x[q] * x[q]; dxn += df * df; }
+    } else for (int q = 0; q < 7; q++) o[q] = x[q];
+    for (int q = 0; q < 7; q++) y6[b * 8 + q] = o[q];
+    q2R(qload(o + 3), R6 + b * 12);
+  }
+  const double *xsb = d.xsb[cur] + (size_t)w.offsb * 9;
+  double *ysb = d.xsb[cand] + (size_t)w.offsb * 9;
+  const int *colsb = d.colsb + w.offsb;
+  for (int e = tid; e < w.nsb * 9; e += nt) {
+    int c = colsb[e / 9];
+    double x = xsb[e], s = c >= 0 ? uc[c + e % 9] : 0.0;
+    ysb[e] = x + s;
+    if (c >= 0) { xn += x * x; dxn += s * s; }
+  }
+  if (tid == 0 && w.has_td) {
+    double x = d.xtd[cur][wi], s = w.td_col >= 0 ? uc[w.td_col] : 0.0;
+    d.xtd[cand][wi] = x + s;
+    if (w.td_col >= 0) { xn += x * x; dxn += s * s; }
+  }
+  const double *xlm = d.xlm[cur] + w.offlm;
+  double *ylm = d.xlm[cand] + w.offlm;
+  for (int l = tid; l < nl; l += nt) {
+    double g = glv[l], h = hl[l];
+    double s = -c1 * g / d2_of(h) + c2 * gn_l[l];
+    step_l[l] = s;
+    double x = xlm[l];
+    ylm[l] = x + s;
+    xn += x * x; dxn += s * s;
+  }
+  xn = block_sum(xn, red); dxn = block_sum(dxn, red);
+  if (tid == 0) {
+    ctl->x_norm2 = xn; ctl->dx_norm2 = dxn; ctl->model_change = model_change; ctl->step_norm = step_norm;
+    ctl->step_valid = 1; ctl->cand_cost_proj = 0.0; ctl->cand_cost_misc = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Trust-region bookkeeping, one thread per window (TrustRegionMinimizer / DoglegStrategy)
+__global__ void k_control(Dev d, int init) {
+  const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= d.n_win) return;
+  Ctl *c = d.ctl + wi;
+  const SolverParams &P = d.prm;
+  if (init) {
+    // the evaluated buffer is the accepted point
+    c->cost = c->cand_cost_misc + c->cand_cost_proj;
+    if (init == 1) c->initial_cost = c->cost;
+    c->reuse = 0; c->chol_fail = 0; c->step_valid = 1; c->gmax_l_bits = 0ull;
+    c->cand_cost_misc = 0; c->cand_cost_proj = 0;
+    return;
+  }
+  if (c->done) return;
+  if (!c->step_valid) {
+    // linear solver failure or non-positive model decrease: StepIsInvalid -> mu *= 10
+    if (!c->chol_fail && !c->reuse) c->mu = fmax(1e-8, 2.0 * c->mu / 10.0);  // the factorisation itself succeeded
+    c->mu *= 10.0; c->reuse = 0; c->chol_fail = 0; c->iter++; c->lin_count++; c->invalid_run++;
+    c->step_valid = 1; c->gmax_l_bits = 0ull;
+    if (c->invalid_run >= 5 || c->mu > 10.0) { c->done = 1; c->term = 4; }
+    else if (c->iter >= P.max_iter) { c->done = 1; c->term = 0; }
+    return;
+  }
+  c->invalid_run = 0;
+  if (!c->reuse) c->mu = fmax(1e-8, 2.0 * c->mu / 10.0);  // relax after a successful factorisation
+  const double cand = c->cand_cost_misc + c->cand_cost_proj;
+  c->iter++; c->lin_count++;
+  if (!P.fixed_mode) {
+    const double xn = sqrt(c->x_norm2), dxn = sqrt(c->dx_norm2);
+    if (dxn <= P.ptol * (xn + P.ptol)) { c->done = 1; c->term = 3; c->iter--; c->lin_count--; return; }
+    if (fabs(c->cost - cand) <= P.ftol * c->cost) { c->done = 1; c->term = 1; c->iter--; c->lin_count--; return; }
+  }
+  const double rel = (c->cost - cand) / c->model_change;
+  if (rel > P.min_rel_decrease) {
+    c->cur = 1 - c->cur; c->cost = cand; c->succ++;
+    if (rel < 0.25) c->radius *= 0.5;
+    if (rel > 0.75) c->radius = fmax(c->radius, 3.0 * c->step_norm);
+    c->radius = fmin(P.max_radius, c->radius);
+    c->reuse = 0; c->gmax_l_bits = 0ull;
+  } else {
+    c->radius *= 0.5; c->reuse = 1;
+    if (c->radius < 1e-32) { c->done = 1; c->term = 4; }
+  }
+  if (!c->done && c->iter >= P.max_iter) { c->done = 1; c->term = 0; }
+}
+
+// reset the per-sub-step trust-region state (a fresh ceres::Solve)
+__global__ void k_tr_reset(Dev d, int first) {
+  const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= d.n_win) return;
+  Ctl *c = d.ctl + wi;
+  c->radius = d.prm.initial_radius; c->mu = 1e-8; c->reuse = 0; c->done = 0; c->term = 0; c->step_valid = 1;
+  c->invalid_run = 0; c->iter = 0; c->chol_fail = 0; c->gmax_l_bits = 0ull;
+  c->cand_cost_misc = 0; c->cand_cost_proj = 0;
+  if (first) { c->cur = 0; c->succ = 0; c->lin_count = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ADMM consensus exchange (replaces broadcastData / waitForSync / updateGlobal,
+// VINSConsenusSolver.cpp:11-120, ConsensusSolver.cpp:166-228): per slot sum of [p(3), vech(q q^T)(10), 1].
+__global__ void k_cons_pack(Dev d, int n6_total, const int *blk_win) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n6_total) return;
+  int s = d.slot6[b];
+  if (s < 0) return;
+  const int wi = blk_win[b];
+  const double *x = d.x6[d.ctl[wi].cur] + (size_t)b * 8;
+  double *o = d.cons_buf + (size_t)s * 14;
+  atomicAdd(o + 0, x[0]); atomicAdd(o + 1, x[1]); atomicAdd(o + 2, x[2]);
+  int k = 3;
+  for (int i = 0; i < 4; i++)
+    for (int j = i; j < 4; j++) atomicAdd(o + (k++), x[3 + i] * x[3 + j]);
+  atomicAdd(o + 13, 1.0);
+}
+
+// principal eigenvector of a symmetric 4x4 (cyclic Jacobi), Utility::averageQuaterions (utils.hpp:213-228)
+D2BA_DEV void eig4_principal(const double *Min, double *q) {
+  double A[16], V[16];
+  for (int i = 0; i < 16; i++) { A[i] = Min[i]; V[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 30; sweep++) {
+    double off = 0;
+    for (int i = 0; i < 4; i++) for (int j = i + 1; j < 4; j++) off += A[i * 4 + j] * A[i * 4 + j];
+    if (off < 1e-40) break;
+    for (int p = 0; p < 4; p++)
+      for (int r = p + 1; r < 4; r++) {
+        double apq = A[p * 4 + r];
+        if (apq == 0.0) continue;
+        double tau = (A[r * 4 + r] - A[p * 4 + p]) / (2.0 * apq);
+        double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+        for (int k = 0; k < 4; k++) { double a = A[k * 4 + p], b = A[k * 4 + r]; A[k * 4 + p] = c * a - s * b; A[k * 4 + r] = s * a + c * b; }
+        for (int k = 0; k < 4; k++) { double a = A[p * 4 + k], b = A[r * 4 + k]; A[p * 4 + k] = c * a - s * b; A[r * 4 + k] = s * a + c * b; }
+        for (int k = 0; k < 4; k++) { double a = V[k * 4 + p], b = V[k * 4 + r]; V[k * 4 + p] = c * a - s * b; V[k * 4 + r] = s * a + c * b; }
+      }
+  }
+  int m = 0;
+  for (int i = 1; i < 4; i++) if (A[i * 4 + i] > A[m * 4 + m]) m = i;
+  for (int k = 0; k < 4; k++) q[k] = V[k * 4 + m];
+}
+
+__global__ void k_cons_apply(Dev d, int n6_total, const int *blk_win) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n6_total) return;
+  int s = d.slot6[b];
+  if (s < 0) return;
+  const int wi = blk_win[b];
+  const double *x = d.x6[d.ctl[wi].cur] + (size_t)b * 8;
+  const double *o = d.cons_buf + (size_t)s * 14;
+  double cnt = o[13];
+  if (!(cnt > 0.5)) return;
+  double *z = d.z6 + (size_t)b * 8;
+  z[0] = o[0] / cnt; z[1] = o[1] / cnt; z[2] = o[2] / cnt;
+  double M[16], q[4];
+  int k = 3;
+  for (int i = 0; i < 4; i++) for (int j = i; j < 4; j++) { M[i * 4 + j] = o[k]; M[j * 4 + i] = o[k]; k++; }
+  if (cnt < 1.5) { q[0] = x[3]; q[1] = x[4]; q[2] = x[5]; q[3] = x[6]; }   // single holder: quats[0] returned as is
+  else eig4_principal(M, q);
+  // hemisphere of the local estimate (eigenvector sign is arbitrary)
+  double dot = q[0] * x[3] + q[1] * x[4] + q[2] * x[5] + q[3] * x[6];
+  double sg = dot < 0 ? -1.0 : 1.0;
+  z[3] = sg * q[0]; z[4] = sg * q[1]; z[5] = sg * q[2]; z[6] = sg * q[3];
+  // tilde += (1 + alpha) * Log(z^-1 x)   (ConsensusSolver.cpp:127-133; DeltaPose/tangentSpace of swarm_msgs)
+  Q4 qz = qload(z + 3);
+  double dd[3] = {x[0] - z[0], x[1] - z[1], x[2] - z[2]}, t[3], Rz[9];
+  q2R(qz, Rz); mtv3(Rz, dd, t);
+  // rotate with the inverse quaternion exactly like the oracle (q^-1 * v)
+  Q4 qe = qmul(qinv(qz), qload(x + 3));
+  double nv = sqrt(qe.x * qe.x + qe.y * qe.y + qe.z * qe.z), th[3] = {0, 0, 0};
+  if (nv > 0) { double ang = 2.0 * atan2(nv, fabs(qe.w)), sgn = qe.w < 0 ? -1.0 : 1.0; th[0] = ang * sgn * qe.x / nv; th[1] = ang * sgn * qe.y / nv; th[2] = ang * sgn * qe.z / nv; }
+  double *tl = d.tilde6 + (size_t)b * 6;
+  const double f = 1.0 + d.prm.relaxation_alpha;
+  for (int i = 0; i < 3; i++) { tl[i] += f * t[i]; tl[3 + i] += f * th[i]; }
+}
+
+// snapshot of the local-only parameters for the NormalPrior terms of this ADMM sub-step
+__global__ void k_cons_refs(Dev d, int nsb9_total, int nl_total, const int *sb_win, const int *lm_win) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nsb9_total) { int wi = sb_win[i / 9]; d.sb_ref[i] = d.xsb[d.ctl[wi].cur][i]; }
+  if (i < nl_total) { int wi = lm_win[i]; d.lm_ref[i] = d.xlm[d.ctl[wi].cur][i]; }
+  if (i < d.n_win) d.td_ref[i] = d.xtd[d.ctl[i].cur][i];
+}
+
+// z := x, tilde := 0 at the start of a solve (ConsenusParamState::create, ConsensusSolver.hpp:31-44)
+__global__ void k_cons_init(Dev d, int n6_total) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n6_total) return;
+  for (int q = 0; q < 8; q++) d.z6[(size_t)b * 8 + q] = d.x6[0][(size_t)b * 8 + q];
+  for (int q = 0; q < 6; q++) d.tilde6[(size_t)b * 6 + q] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-callable launchers (keeps <<<>>> syntax inside this translation unit)
+void launch_state_prep(const Dev &d, int n6_total, int buf, cudaStream_t s) {
+  if (n6_total > 0) k_state_prep<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total, buf);
+}
+void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s) {
+  if (n_imu > 0) k_imu_prep<<<(n_imu + 31) / 32, 32, 0, s>>>(d, n_imu);
+}
+void launch_prior_prep(const Dev &d, cudaStream_t s) { k_prior_prep<<<d.n_win, 256, 0, s>>>(d); }
+
+size_t misc_smem_bytes(int max_prior_m) {
+  size_t imu = (size_t)(40 + 2 * 4 * (15 * 30 + 15)) * 8;
+  size_t pri = (size_t)(40 + 3 * max_prior_m + 8) * 8;
+  return imu > pri ? imu : pri;
+}
+void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s) {
+  k_misc_lin<<<d.n_win, kMiscThreads, misc_smem_bytes(max_prior_m), s>>>(d, eval_cur);
+}
+
+template <int NCT, int KR>
+static size_t proj_smem() { return (size_t)4 * (GC_SIZE + NCT * 8 * (kTile * KR + 4)) * 8; }
+
+int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_proj_lin<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 2>()); if (e) return e;
+  e = cudaFuncSetAttribute(k_proj_lin<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 2>()); if (e) return e;
+  e = cudaFuncSetAttribute(k_proj_lin<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 4>()); if (e) return e;
+  e = cudaFuncSetAttribute(k_proj_lin<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 4>()); if (e) return e;
+  size_t chol = (size_t)(kNB * (max_rows + 4) + max_rows + 8 + 16 * 32 + kNB * (kNB + 1)) * 8;
+  e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol); if (e) return e;
+  size_t st = (size_t)(40 + 3 * max_nc) * 8;
+  e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st); if (e) return e;
+  e = cudaFuncSetAttribute(k_misc_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)misc_smem_bytes(max_prior_m)); if (e) return e;
+  return 0;
+}
+
+void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int job_count, cudaStream_t s) {
+  if (job_count <= 0) return;
+  int grid = (job_count + 3) / 4;
+  switch (variant) {
+    case 0: k_proj_lin<2, 2><<<grid, 128, proj_smem<2, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 1: k_proj_lin<4, 2><<<grid, 128, proj_smem<4, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 2: k_proj_lin<2, 4><<<grid, 128, proj_smem<2, 4>(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 3: k_proj_lin<4, 4><<<grid, 128, proj_smem<4, 4>(), s>>>(d, eval_cur, job_begin, job_count); break;
+  }
+}
+void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s) {
+  if (n_tiles > 0) k_proj_debug<<<n_tiles, 32, 0, s>>>(d, out, n_tiles, tile_win);
+}
+void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s) {
+  if (n_lm_total <= 0) return;
+  k_lm_gather<<<(n_lm_total + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, (size_t)kGatherWarps * max_ldw * 8, s>>>(d, lm_win, n_lm_total, max_ldw);
+}
+void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) {
+  if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));
+}
+void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
+  size_t sm = (size_t)(kNB * (max_rows + 4) + max_rows + 8 + 16 * 32 + kNB * (kNB + 1)) * 8;
+  k_chol<<<d.n_win, kCholThreads, sm, s>>>(d, max_rows);
+}
+void launch_step(const Dev &d, int max_nc, cudaStream_t s) {
+  k_step<<<d.n_win, kStepThreads, (size_t)(40 + 3 * max_nc) * 8, s>>>(d, max_nc);
+}
+void launch_control(const Dev &d, int init, cudaStream_t s) { k_control<<<(d.n_win + 127) / 128, 128, 0, s>>>(d, init); }
+void launch_tr_reset(const Dev &d, int first, cudaStream_t s) { k_tr_reset<<<(d.n_win + 127) / 128, 128, 0, s>>>(d, first); }
+void launch_cons_init(const Dev &d, int n6_total, cudaStream_t s) { if (n6_total > 0) k_cons_init<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total); }
+void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s) { if (n6_total > 0) k_cons_pack<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total, blk_win); }
+void launch_cons_apply(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s) { if (n6_total > 0) k_cons_apply<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total, blk_win); }
+void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_win, const int *lm_win, cudaStream_t s) {
+  int n = nsb_total * 9; if (nl_total > n) n = nl_total; if (d.n_win > n) n = d.n_win;
+  if (n > 0) k_cons_refs<<<(n + 127) / 128, 128, 0, s>>>(d, nsb_total * 9, nl_total, sb_win, lm_win);
+}
+
+}  // namespace d2ba

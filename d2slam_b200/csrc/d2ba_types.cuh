@@ -1,0 +1,153 @@
+// d2ba_types.cuh -- device-visible data layout of libd2ba (sm_100a).
+//
+// HBM layout.  One handle holds B windows; every array below is a single
+// allocation shared by all windows, indexed through the per-window WinDesc offsets so that one
+// launch covers the whole batch (grid.y / flattened job lists).
+#pragma once
+#include <stdint.h>
+
+namespace d2ba {
+
+constexpr int kTile = 32;        // observations per tile == warp width
+constexpr int kObsFields = 21;   // pts_i(3) pts_j(3) vel_i(3) vel_j(3) td_i td_j tangent_base(6) inv_depth_j
+constexpr int kMaxImuPerWin = 64;
+
+enum ProjType { P2F1C = 0, P2F2C = 1, P1F2C = 2, P2F1CD = 3, PDEPTH = 4 };
+
+// A "group" = all reprojection residuals of one window that share (type, pose_i, pose_j, ext_a, ext_b):
+// they share every camera-side parameter block, so their J^T J contributions reduce into the same
+// blocks (pair-major ordering).
+struct Group {
+  int type;
+  int blk[4];       // window-local six-dof block index of pose_i, pose_j, ext_a, ext_b (-1 = absent)
+  int slot_src[4];  // which factor block (0..3) feeds J-slot s, -1 = slot unused
+  int slot_col[4];  // reduced-system column of slot s
+  int td_col;       // reduced column of td or -1
+  int nct;          // column tiles of the staged J (2: [s0 s1 r], 4: [s0 s1 s2 s3 td r])
+  int rows;         // residual rows (1, 2 or 3)
+  int need_ext;     // any extrinsic Jacobian needed
+  int need_td;
+};
+
+struct Job {       // one warp's work: a run of tiles of one group
+  int win, grp, tile_begin, ntiles;
+};
+
+struct ImuDesc {
+  int pi, si, pj, sj;  // window-local indices (six-dof table / speed-bias table)
+};
+
+struct WinDesc {
+  int n6, np, ne, nsb, nl, has_td, td_col;
+  int n_lc, n_c, ldh;          // reduced dims, leading dim of Hcc/S (multiple of 4)
+  int ldw;                     // leading dim of Wt rows (>= n_lc+1, multiple of 8)
+  int nl_pad;                  // landmarks padded to a multiple of 32
+  int off6, offsb, offlm;      // offsets into block tables
+  int off_tile, n_tile;
+  int off_grp, n_grp;
+  int off_imu, n_imu;
+  int rec_stride;              // doubles per landmark-side record (16 or 32)
+  int64_t off_rec;             // first record (in records) = off_tile*32
+  int64_t offH;                // Hcc / S offset (doubles)
+  int64_t offW;                // Wt offset (doubles)
+  int64_t offc;                // offset into n_c sized vectors
+  int off_lmptr;               // landmark CSR pointer offset (nl+1 entries)
+  int64_t off_lmobs;           // landmark CSR entries
+  // prior
+  int prior_m, prior_nblk, off_prior_blk;
+  int64_t off_prior_J, off_prior_v;
+  // consensus
+  int admm_on;
+};
+
+struct PriorBlk {
+  int kind, index, off, eff;   // index: window-local (six-dof index for POSE/EXTRINSIC)
+  double x0[9];
+};
+
+// Trust-region state of one window (device resident; the whole solve runs without host round trips).
+struct Ctl {
+  int cur;            // which linearisation / state buffer holds the accepted point
+  int reuse;          // previous step rejected: reuse GN / Cauchy data (dogleg_strategy reuse_)
+  int done;
+  int term;
+  int step_valid;     // 0: this iteration produced no candidate (solver failure / model change <= 0)
+  int invalid_run;
+  int iter, succ;
+  int chol_fail;
+  int lin_count;
+  double radius, mu;
+  double cost, cand_cost_misc, cand_cost_proj, model_change;
+  double gg, nn, gdn, alpha, step_norm;
+  double x_norm2, dx_norm2;
+  double gmax_c, gmax_l;
+  double initial_cost;
+  unsigned long long gmax_l_bits;
+};
+
+struct SolverParams {
+  double sqrt_info_px, depth_sqrt_inf, gravity, huber;
+  double rho_T, rho_theta, rho_landmark, relaxation_alpha;
+  double initial_radius, max_radius, min_rel_decrease, ftol, gtol, ptol;
+  int max_iter, fixed_mode;
+};
+
+// All device pointers of a handle (passed to kernels by value).
+struct Dev {
+  const WinDesc *win;
+  Ctl *ctl;
+  int n_win;
+  // block tables
+  double *x6[2];        // [N6][8]  (x y z qx qy qz qw pad)
+  double *R6[2];        // [N6][12] rotation matrix row-major (9) + pad
+  double *xsb[2];       // [NSB][9]
+  double *xlm[2];       // [NL]
+  double *xtd[2];       // [B]
+  const int *col6;      // [N6] reduced column or -1
+  const int *colsb;     // [NSB]
+  // reprojection
+  const Group *grp;
+  const Job *job;
+  int n_job;
+  const int *tile_grp;  // [T]
+  const double *obs;    // [T][kObsFields][32]
+  const int *obs_lm;    // [T][32] window-local landmark index, -1 = padding
+  double *rec[2];       // landmark-side per-observation records
+  // landmark CSR
+  const int *lm_ptr;
+  const int *lm_obs;
+  // imu
+  const ImuDesc *imu;
+  const double *imu_c;  // [NIMU][kImuStride]
+  double *imu_U;        // [NIMU][225] sqrt_info
+  // prior
+  const PriorBlk *prior_blk;
+  const double *prior_J;  // m x m
+  const double *prior_e0; // packed in prior_v: e0[m]
+  double *prior_A;        // J^T J (m x m) computed on device
+  // consensus
+  const int *slot6;       // [N6] global slot or -1
+  double *z6;             // [N6][8]
+  double *tilde6;         // [N6][6]
+  double *lm_ref, *sb_ref, *td_ref;
+  double *cons_buf;       // [n_slots][14] all-reduce payload
+  int n_slots;
+  // linearisation (double buffered)
+  double *Hcc[2];
+  double *gc[2];
+  // Schur / solve
+  double *Wt;           // [nl_pad][ldw] scaled coupling rows (+ g~ column)
+  double *dinv;         // [NL] 1/sqrt(h + mu d^2)
+  double *hl, *gl;      // [NL]
+  double *S;            // reduced system (lower) per window
+  double *gred;         // n_c
+  double *D2c;          // n_c
+  double *gn_c, *gn_l;  // Gauss-Newton step
+  double *step_c, *step_l;
+  double *wu;           // [NL] w_l . u_c
+  SolverParams prm;
+};
+
+constexpr int kImuStride = 1 + 3 + 4 + 3 + 3 + 3 + 225 + 225;  // sum_dt dp dq dv ba bg jac cov = 467
+
+}  // namespace d2ba
