@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- BA solver iterations/s on synthetic sliding windows (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--batch B] [--iters I] [--impl reference]
+
+A "step" = one solve of `iters` trust-region iterations (fixed schedule, convergence exits off so the
+work per step is constant) on every window of the batch.  An iteration = one trust-region step attempt:
+linearise all residuals (Jacobians + Huber), build and Schur-reduce the normal equations, solve the
+reduced camera system, dogleg step, retract, evaluate the candidate, accept/reject -- the counting of
+report.total_iterations (d2common/src/solver/SolverWrapper.cpp:41-42).
+
+Workload at N=1 (BASELINE.json configs[1]): B independent single-drone 11-frame / 300-landmark windows
+(W1; 3000 reprojection + 10 IMU + 1 prior residual blocks each), distinct seeds.
+N>1: the 4-/8-drone swarm configs shard one agent per GPU (ADMM, NCCL consensus exchange per sub-step);
+here every rank solves its own batch of agent windows.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from d2slam_b200 import abi, synth  # noqa: E402
+
+OBS_BYTES = 176                      # 20 f64 constants + 4 i32 ids
+JAC_BYTES_2F1C = 8 * 2 * (20 + 1)    # 336
+IMU_BYTES = 3736 + 3720
+
+
+def bytes_iter_w1(pr):
+    """Algorithmic bytes of one iteration of one window (SURVEY.md 8d BYTES_ITER)."""
+    types = pr["obs"]["type"]
+    p_of = {abi.PROJ_2F1C: (20, 2), abi.PROJ_2F2C: (26, 2), abi.PROJ_1F2C: (14, 2), abi.PROJ_2F1C_DEPTH: (20, 3), abi.PROJ_DEPTH_PRIOR: (1, 1)}
+    b = 0
+    for t, cnt in zip(*np.unique(types, return_counts=True)):
+        p, d = p_of[int(t)]
+        b += cnt * (OBS_BYTES + 8 * d * (p + 1))
+    proj = b
+    F = int(pr["n_own"]); npose = len(pr["frame_ids"]); C = len(pr["cam_ids"]); L = len(pr["lm_ids"])
+    b += len(pr["imu"]) * IMU_BYTES
+    if pr.get("prior") is not None:
+        m = len(pr["prior"][1]); b += 8 * m * (m + 1)
+    n_c = 6 * npose + 9 * F
+    b += 8 * (7 * (npose + C) + 9 * F + L + 1) + 8 * n_c * n_c
+    return b, proj
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index; self.p = None; self.lines = []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(B, seed0, n_frames=11, n_landmarks=300):
+    return [synth.make_window(seed=seed0 + i, n_frames=n_frames, n_landmarks=n_landmarks) for i in range(B)]
+
+
+def load_all(solver, probs):
+    for i, p in enumerate(probs):
+        p.load(solver, i)
+
+
+def reset_state(solver, probs):
+    for i, p in enumerate(probs):
+        solver.set_blocks(i, abi.POSE, p["frame_ids"], p["poses"], p["pose_const"])
+        solver.set_blocks(i, abi.SPEED_BIAS, p["sb_ids"], p["sb"], None)
+        solver.set_blocks(i, abi.LANDMARK, p["lm_ids"], p["inv_dep"], None)
+
+
+def h2d_bytes(probs):
+    b = 0
+    for p in probs:
+        b += p["obs"].nbytes + p["imu"].nbytes + p["poses"].nbytes + p["sb"].nbytes + p["inv_dep"].nbytes + p["ext"].nbytes
+        if p.get("prior") is not None:
+            b += p["prior"][0].nbytes + p["prior"][1].nbytes
+    return int(b)
+
+
+def d2h_bytes(probs):
+    return int(sum(p["poses"].nbytes + p["sb"].nbytes + p["inv_dep"].nbytes for p in probs))
+
+
+def cpu_sample(probs, iters, nthreads, max_windows):
+    """Oracle (restated Ceres-equivalent CPU path) on a bounded sample of the same workload."""
+    from oracle import orc
+    sample = probs[:max_windows]
+    oras = []
+    for p in sample:
+        o = orc.Oracle(max_num_iterations=iters); p.load(o); oras.append(o)
+    t = time.perf_counter()
+    reps = orc.solve_many(oras, nthreads, fixed_iters=iters)
+    dt = time.perf_counter() - t
+    its = sum(r.total_iterations for r in reps)
+    return its / dt, len(sample), dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_win = max(cores, min(args.batch, 4 * cores))
+    probs = make_batch(n_win, 1000)
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, n, dt = cpu_sample(probs, args.iters, cores, n_win)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals])); ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    line = {
+        "impl": "reference", "metric": "BA solver iterations/sec", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"W1 single-drone 11-frame/300-landmark windows, {args.iters} trust-region iterations per solve",
+                   "windows_per_step": n_win, "iters_per_solve": args.iters},
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_win} windows x {args.iters} iterations per step, one solver thread per window on {cores} host threads "
+                                   "(restated Ceres-equivalent DENSE_SCHUR+DOGLEG path; the reference itself cannot be built here)"},
+        "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from d2slam_b200.solver import Solver
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, iters = args.batch, args.iters
+    probs = make_batch(B, 1000 + rank * 100000)
+    solver = Solver(max_windows=B, device=local_rank, max_num_iterations=iters)
+    load_all(solver, probs)
+    solver.finalize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: problem already in HBM, only the (small) state is restored per step
+    for _ in range(args.warmup):
+        reset_state(solver, probs); solver.solve_fixed(iters)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        reset_state(solver, probs)
+        reps = solver.solve_fixed(iters)
+        dev_ms += reps[0].total_time * 1e3
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = dev_ms * 1e-3
+    tt = torch.tensor([wall, t_dev], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall_max, dev_max = tt.tolist()
+    total_iters = B * iters * args.steps * world
+    value = total_iters / dev_max
+    # ---- end to end through the C ABI with host buffers: reset, add every block / residual, finalize (H2D),
+    #      solve, read back the solved state (D2H)
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(1):
+        solver.reset(); load_all(solver, probs); solver.finalize(); solver.solve_fixed(iters)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.reset(); load_all(solver, probs); solver.finalize(); solver.solve_fixed(iters)
+        for i, p in enumerate(probs):
+            solver.get_blocks(i, abi.POSE, p["frame_ids"]); solver.get_blocks(i, abi.SPEED_BIAS, p["sb_ids"]); solver.get_blocks(i, abi.LANDMARK, p["lm_ids"])
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = B * iters * e2e_steps * world / te.item()
+    # ---- per-kernel device times and roofline of the dominant kernel (CUDA events on the solver stream)
+    reset_state(solver, probs)
+    kt = solver.kernel_times(iters)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    bi, proj_bytes = bytes_iter_w1(probs[0])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    dom = max(kt, key=kt.get)
+    proj_gbs = B * proj_bytes / (kt["proj_lin"] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("proj_lin_bytes_per_launch")
+    except Exception:
+        pass
+    # CPU baseline on rank 0, bounded sample, one thread (ceres_options.num_threads = 1)
+    cpu_v, cpu_n, cpu_dt = cpu_sample(probs, iters, 1, min(B, args.cpu_windows))
+    n_variants = 1
+    launches = args.steps * (3 + n_variants + iters * (6 + n_variants))
+    line = {
+        "metric": "BA solver iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"W1 single-drone 11-frame/300-landmark windows (configs[1]); batch of {B} independent windows per GPU, "
+                               f"{iters} trust-region iterations per solve, fixed schedule",
+                   "windows_per_gpu": B, "iters_per_solve": iters, "frames": 11, "landmarks": 300, "residual_blocks": len(probs[0]["obs"]) + 11,
+                   "l2_policy": "inputs larger than L2 (batch working set >> 126 MB)" if B >= 128 else "batch smaller than L2",
+                   "wall_ms_per_step": wall_max * 1e3 / args.steps, "bytes_iter_per_window": int(bi)},
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": h2d_bytes(probs), "d2h_bytes_per_step": d2h_bytes(probs),
+                "steps": e2e_steps, "note": "reset + set_blocks/add_proj/add_imu/set_prior + finalize (sort, tile, H2D) + solve + get_blocks (D2H)"},
+        "roofline": {"bound": "hbm", "kernel": "k_proj_lin<2,2>", "achieved": proj_gbs, "peak": peak, "unit": "GB/s", "frac": proj_gbs / peak,
+                     "traffic": traffic, "peak_source": peak_src, "dominant_kernel_by_time": dom,
+                     "algorithmic_bytes_per_launch": int(B * proj_bytes), "kernel_ms_per_iteration": kt,
+                     "whole_iteration_frac": B * bi / (sum(kt.values()) * 1e-3) / 1e9 / peak},
+        "cpu_baseline": {"value": cpu_v, "unit": "iter/s", "cores": 1, "kind": "port",
+                         "sample": f"{cpu_n} of the {B} windows x {iters} iterations, single thread ({cpu_dt:.1f} s)"},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=8)
+    ap.add_argument("--cpu-windows", type=int, default=96)
+    ap.add_argument("--impl", default="ours")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -943,4 +943,40 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
   return 0;
 }
 
+// Per-kernel device time of the iteration sequence (CUDA events on the solver stream, no graph):
+// ms_out[0..6] = lm_gather, schur, chol, step, misc_lin, proj_lin, control, summed over `iters` iterations;
+// ms_out[7] = number of iterations timed.  Used by bench.py for the roofline of the dominant kernel.
+int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
+  if (!h) return 1;
+  cudaSetDevice(h->cfg.device);
+  if (!h->finalized) { int rc = d2ba_finalize(h); if (rc) return rc; }
+  if (h->state_dirty) { int rc = upload_state(h); if (rc) return rc; }
+  h->dev.prm.fixed_mode = 1; h->dev.prm.max_iter = iters;
+  release_graph(h);
+  launch_tr_reset(h->dev, 1, h->stream);
+  if (h->any_admm) { launch_cons_init(h->dev, h->n6_total, h->stream); int rc = consensus_exchange(h); if (rc) return rc; }
+  enqueue_linearize(h, 1);
+  launch_control(h->dev, 1, h->stream);
+  cudaEvent_t ev[8];
+  for (int i = 0; i < 8; i++) cudaEventCreate(&ev[i]);
+  for (int i = 0; i < 8; i++) ms_out[i] = 0;
+  for (int it = 0; it < iters; it++) {
+    cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+    cudaEventRecord(ev[1], h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+    cudaEventRecord(ev[2], h->stream); launch_chol(h->dev, h->max_rows, h->stream);
+    cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);
+    cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream);
+    cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 4; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);
+    cudaEventRecord(ev[6], h->stream); launch_control(h->dev, 0, h->stream);
+    cudaEventRecord(ev[7], h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); ms_out[i] += ms; }
+  }
+  ms_out[7] = iters;
+  for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
+  CK(cudaGetLastError());
+  h->state_dirty = true;
+  return 0;
+}
+
 }  // extern "C"

@@ -48,7 +48,7 @@ EXPORTED = [
     "d2ba_add_proj", "d2ba_add_landmark_tracks", "d2ba_add_imu", "d2ba_set_prior", "d2ba_set_prior_info",
     "d2ba_set_consensus", "d2ba_comm_unique_id", "d2ba_comm_init", "d2ba_consensus_buffer", "d2ba_finalize",
     "d2ba_solve", "d2ba_solve_fixed", "d2ba_get_blocks", "d2ba_num_windows", "d2ba_marginalize",
-    "d2ba_debug_linearize", "d2ba_debug_get",
+    "d2ba_debug_linearize", "d2ba_debug_get", "d2ba_debug_kernel_times",
 ]
 
 
@@ -158,6 +158,11 @@ class Solver:
                   "get_blocks")
         return out
 
+    def kernel_times(self, iters):
+        out = np.zeros(8)
+        self._chk(lib().d2ba_debug_kernel_times(self.h, C.c_int32(iters), abi.ptr(out)), "kernel_times")
+        return {k: out[i] / max(out[7], 1) for i, k in enumerate(KERNEL_NAMES)}
+
     def debug_linearize(self):
         self._chk(lib().d2ba_debug_linearize(self.h), "debug_linearize")
 
@@ -168,6 +173,9 @@ class Solver:
         self._chk(lib().d2ba_debug_get(self.h, C.c_int32(window), C.c_int32(item), abi.ptr(out), C.c_int64(out.nbytes), C.byref(need)),
                   "debug_get")
         return out[: need.value // np.dtype(dtype).itemsize]
+
+
+KERNEL_NAMES = ["lm_gather", "schur", "chol", "step", "misc_lin", "proj_lin", "control"]
 
 
 def comm_unique_id():

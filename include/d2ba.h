@@ -276,6 +276,9 @@ enum d2ba_debug_item {
 int d2ba_debug_linearize(d2ba_handle *h);
 int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int64_t out_bytes,
                    int64_t *needed_bytes);
+/* Device time (ms, CUDA events on the solver stream) of each kernel of the iteration sequence, summed over
+ * `iters` iterations: [lm_gather, schur, chol, step, misc_lin, proj_lin, control, iters]. */
+int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out /* [8] */);
 
 #ifdef __cplusplus
 }

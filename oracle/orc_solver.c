@@ -764,16 +764,25 @@ done:
 }
 
 static void ensure_cand(orc_handle *o) { (void)o; }
+int orc_admm_solve(orc_handle **ag, int32_t n, int32_t fixed_mode, d2ba_report *reports);
 
 int orc_solve(orc_handle *o, d2ba_report *rep) {
   d2ba_report r; memset(&r, 0, sizeof r);
   ensure_cand(o);
+  if (o->admm_on) { orc_handle *one[1] = {o}; return orc_admm_solve(one, 1, 0, rep); }  /* a swarm of one */
   tr_solve(o, o->cfg.max_num_iterations, 0, &r);
   if (rep) *rep = r;
   return 0;
 }
 int orc_solve_fixed(orc_handle *o, int32_t iters, d2ba_report *rep) {
   d2ba_report r; memset(&r, 0, sizeof r);
+  if (o->admm_on) {
+    int keep = o->cfg.max_num_iterations; o->cfg.max_num_iterations = iters;
+    orc_handle *one[1] = {o};
+    int rc = orc_admm_solve(one, 1, 1, rep);
+    o->cfg.max_num_iterations = keep;
+    return rc;
+  }
   tr_solve(o, iters, 1, &r);
   if (rep) *rep = r;
   return 0;
