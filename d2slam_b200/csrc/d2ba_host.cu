@@ -10,7 +10,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -38,6 +41,8 @@ void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream
 void launch_cons_apply(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
 void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_win, const int *lm_win, cudaStream_t s);
 struct SchurTileH { int win, kind, tm, tn; };
+void launch_prior_from_info(int n_win, int max_m, const int *m_of, const long long *offJ, const long long *offv, const int *is_info,
+                            double *A, double *V, double *b, cudaStream_t s);
 }  // namespace d2ba
 
 using namespace d2ba;
@@ -61,8 +66,8 @@ struct HostWin {
   std::vector<int> pose_slot, ext_slot; bool admm = false; int n_slots = 0;
   // derived at finalize
   std::vector<int> pose_col, ext_col, sb_col; int td_col = -1, n_lc = 0, n_c = 0;
-  std::vector<HObs> sorted;          // sorted observation list
-  std::vector<int> sorted_pos;       // position (tile slot) of sorted[k] inside the window
+  std::vector<int> order;            // pair-major order: sorted index -> observation index
+  std::vector<int> sorted_pos;       // tile slot (window-local) of the k-th sorted observation
   void clear() { *this = HostWin(); }
 };
 
@@ -124,6 +129,8 @@ struct d2ba_handle {
   DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_dbg;
   DBuf<SchurTileH> d_schur;
+  DBuf<int> d_pr_m, d_pr_info; DBuf<long long> d_pr_oJ, d_pr_ov;
+  int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1;
   Dev dev;
   std::vector<WinDesc> h_win;
   std::vector<Ctl> h_ctl;
@@ -194,6 +201,8 @@ int alloc_zero(d2ba_handle *h, DBuf<T> &b, size_t n) {
 
 }  // namespace
 
+void d2ba_release_staging(d2ba_handle *h);
+
 extern "C" {
 
 int d2ba_default_config(d2ba_config *c) {
@@ -244,6 +253,8 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
   h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_dbg.release(); h->d_schur.release();
+  h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release();
+  d2ba_release_staging(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -306,19 +317,26 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   HostWin *w = get_win(h, window);
   if (!w) return 1;
   w->used = true; h->finalized = false;
+  w->obs.reserve(w->obs.size() + n);
+  // one-entry lookup caches: consecutive residuals of a track share landmark, anchor frame and cameras
+  struct Cache { int64_t id = INT64_MIN; int idx = -1; } c_lm, c_fa, c_fb, c_ca, c_cb;
+  auto cached = [](Cache &c, const std::unordered_map<int64_t, int> &m, int64_t id) {
+    if (c.id != id) { c.id = id; c.idx = find_in(m, id); }
+    return c.idx;
+  };
   for (int i = 0; i < n; i++) {
     const d2ba_proj_obs &p = in[i];
     HObs o; memset(&o, 0, sizeof o);
     o.type = p.type; o.pi = o.pj = o.ea = o.eb = -1;
-    o.lm = find_in(w->lm_map, p.landmark_id);
+    o.lm = cached(c_lm, w->lm_map, p.landmark_id);
     if (o.lm < 0) return fail(h, 3, "add_proj: unknown landmark id");
     if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
       // block lists: ParamResidualInfo.hpp:34-43 (2F1C), :72-82 (2F2C), :107-115 (1F2C)
-      o.ea = find_in(w->ext_map, p.cam_a);
+      o.ea = cached(c_ca, w->ext_map, p.cam_a);
       if (o.ea < 0) return fail(h, 4, "add_proj: unknown camera id");
-      if (p.type == D2BA_PROJ_2F2C || p.type == D2BA_PROJ_1F2C) { o.eb = find_in(w->ext_map, p.cam_b); if (o.eb < 0) return fail(h, 4, "add_proj: unknown camera id (b)"); }
+      if (p.type == D2BA_PROJ_2F2C || p.type == D2BA_PROJ_1F2C) { o.eb = cached(c_cb, w->ext_map, p.cam_b); if (o.eb < 0) return fail(h, 4, "add_proj: unknown camera id (b)"); }
       if (p.type != D2BA_PROJ_1F2C) {
-        o.pi = find_in(w->pose_map, p.frame_a); o.pj = find_in(w->pose_map, p.frame_b);
+        o.pi = cached(c_fa, w->pose_map, p.frame_a); o.pj = cached(c_fb, w->pose_map, p.frame_b);
         if (o.pi < 0 || o.pj < 0) return fail(h, 5, "add_proj: unknown frame id");
       }
       memcpy(o.f + 0, p.pts_i, 24); memcpy(o.f + 3, p.pts_j, 24); memcpy(o.f + 6, p.vel_i, 24); memcpy(o.f + 9, p.vel_j, 24);
@@ -433,31 +451,115 @@ int d2ba_set_consensus(d2ba_handle *h, int32_t window, int32_t n, const d2ba_blo
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+struct HBuf {   // pinned host staging buffer (grows, never shrinks)
+  T *p = nullptr; size_t cap = 0, n = 0;
+  bool resize(size_t count) {
+    n = count;
+    if (count <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = count + count / 4 + 16;
+    if (cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
+};
+
+struct WinPlan {
+  WinDesc d;
+  std::vector<Group> groups;
+  std::vector<int> grp_begin, grp_cnt, grp_tile0;   // sorted-obs range and first (window-local) tile of each group
+  std::vector<Job> jobs[4];                         // tile_begin window-local, grp window-local
+  std::vector<SchurTileH> schur;
+  int n_tiles = 0, n_lmobs = 0;
+  int job_off[4] = {0, 0, 0, 0};
+  int schur_off = 0;
+};
+
+template <typename F>
+void parallel_for(int n, F f) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 16) nt = 16;
+  if (nt > n) nt = n;
+  if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back([&]() { for (;;) { int i = next.fetch_add(1); if (i >= n) break; f(i); } });
+  for (auto &t : th) t.join();
+}
+
+struct Staging {
+  HBuf<WinDesc> win; HBuf<double> x6, xsb, xlm, xtd, obs, imu_c, prior_J, prior_e0;
+  HBuf<int> col6, colsb, tile_grp, tile_win, obs_lm, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
+  HBuf<long long> pr_offJ, pr_offv;
+  HBuf<Group> grp; HBuf<Job> job; HBuf<ImuDesc> imu; HBuf<PriorBlk> pblk; HBuf<SchurTileH> schur;
+};
+std::map<d2ba_handle *, Staging *> g_staging;   // owned per handle, freed in d2ba_destroy
+std::mutex g_staging_mu;
+
+Staging *staging_of(d2ba_handle *h) {
+  std::lock_guard<std::mutex> lk(g_staging_mu);
+  auto it = g_staging.find(h);
+  if (it != g_staging.end()) return it->second;
+  Staging *s = new Staging();
+  g_staging[h] = s;
+  return s;
+}
+
+template <typename T>
+int up(d2ba_handle *h, DBuf<T> &b, const HBuf<T> &v) {
+  CK(b.alloc(v.n));
+  if (v.n) CK(cudaMemcpyAsync(b.p, v.p, v.n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+}  // namespace
+
+void d2ba_release_staging(d2ba_handle *h) {
+  std::lock_guard<std::mutex> lk(g_staging_mu);
+  auto it = g_staging.find(h);
+  if (it == g_staging.end()) return;
+  Staging *s = it->second;
+  s->win.release(); s->x6.release(); s->xsb.release(); s->xlm.release(); s->xtd.release(); s->obs.release(); s->imu_c.release();
+  s->prior_J.release(); s->prior_e0.release(); s->col6.release(); s->colsb.release(); s->tile_grp.release(); s->tile_win.release();
+  s->obs_lm.release(); s->lm_ptr.release(); s->lm_obs.release(); s->slot6.release(); s->lm_win.release(); s->blk_win.release();
+  s->sb_win.release(); s->pr_m.release(); s->pr_info.release(); s->pr_offJ.release(); s->pr_offv.release(); s->grp.release();
+  s->job.release(); s->imu.release(); s->pblk.release(); s->schur.release();
+  delete s;
+  g_staging.erase(it);
+}
+
+extern "C" {
+
 int d2ba_finalize(d2ba_handle *h) {
   if (!h) return 1;
   cudaSetDevice(h->cfg.device);
   release_graph(h);
-  std::vector<WinDesc> wd;
-  std::vector<double> x6, xsb, xlm, xtd, obs_f, imu_c, prior_J, prior_e0, lmzero;
-  std::vector<int> col6, colsb, tile_grp, obs_lm, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, tile_win;
-  std::vector<Group> grp;
-  std::vector<Job> jobs[4];
-  std::vector<ImuDesc> imu;
-  std::vector<PriorBlk> pblk;
-  std::vector<SchurTileH> schur;
-  h->n_used = 0; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
-  int64_t offH = 0, offW = 0, offc = 0, off_rec = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0;
-  int total_tiles_est = 0;
-  for (auto &w : h->win) if (w.used) total_tiles_est += (int)(w.obs.size() / kTile) + 1;
-  int tpj = std::max(1, std::min(8, total_tiles_est / (148 * 8)));
-  int wi = 0;
-  for (auto &w : h->win) {
-    if (!w.used) { continue; }
-    if (wi != (int)(&w - &h->win[0])) return fail(h, 20, "windows must be used contiguously from index 0");
-    WinDesc d; memset(&d, 0, sizeof d);
+  int nw = 0;
+  for (size_t i = 0; i < h->win.size(); i++) {
+    if (h->win[i].used) { if ((int)i != nw) return fail(h, 20, "windows must be used contiguously from index 0"); nw++; }
+  }
+  if (nw == 0) return fail(h, 22, "finalize: no window in use");
+  Staging &st = *staging_of(h);
+  std::vector<WinPlan> plan(nw);
+  size_t total_obs = 0;
+  for (int i = 0; i < nw; i++) total_obs += h->win[i].obs.size();
+  const int tiles_est = (int)(total_obs / kTile) + nw;
+  const int tpj_target = std::max(1, std::min(8, tiles_est / (148 * 8)));
+  // ---- pass A (parallel): columns, pair-major order, groups, tiles, jobs, Schur tiles
+  parallel_for(nw, [&](int wi) {
+    HostWin &w = h->win[wi];
+    WinPlan &pl = plan[wi];
+    WinDesc &d = pl.d; memset(&d, 0, sizeof d);
     const int np = (int)w.pose_id.size(), ne = (int)w.ext_id.size(), nsb = (int)w.sb_id.size(), nl = (int)w.lm_id.size();
     d.np = np; d.ne = ne; d.n6 = np + ne; d.nsb = nsb; d.nl = nl; d.has_td = w.has_td ? 1 : 0;
-    // reduced-system columns: free poses, free extrinsics, td, then speed-bias
     int c = 0;
     w.pose_col.assign(np, -1); w.ext_col.assign(ne, -1); w.sb_col.assign(nsb, -1);
     for (int i = 0; i < np; i++) if (!w.pose_c[i]) { w.pose_col[i] = c; c += 6; }
@@ -469,35 +571,26 @@ int d2ba_finalize(d2ba_handle *h) {
     w.n_c = c;
     d.td_col = w.td_col; d.n_lc = w.n_lc; d.n_c = w.n_c; d.ldh = std::max(4, roundup(w.n_c, 4));
     d.ldw = roundup(w.n_lc + 1, 8); d.nl_pad = roundup(nl, 32);
-    d.off6 = (int)(x6.size() / 8); d.offsb = (int)(xsb.size() / 9); d.offlm = (int)xlm.size();
-    for (int i = 0; i < np; i++) { for (int q = 0; q < 7; q++) x6.push_back(w.pose[7 * i + q]); x6.push_back(0); col6.push_back(w.pose_col[i]); slot6.push_back(w.admm ? w.pose_slot[i] : -1); blk_win.push_back(wi); }
-    for (int i = 0; i < ne; i++) { for (int q = 0; q < 7; q++) x6.push_back(w.ext[7 * i + q]); x6.push_back(0); col6.push_back(w.ext_col[i]); slot6.push_back(w.admm ? w.ext_slot[i] : -1); blk_win.push_back(wi); }
-    for (int i = 0; i < nsb; i++) { for (int q = 0; q < 9; q++) xsb.push_back(w.sb[9 * i + q]); colsb.push_back(w.sb_col[i]); sb_win.push_back(wi); }
-    for (int i = 0; i < nl; i++) { xlm.push_back(w.lm[i]); lm_win.push_back(wi); }
-    xtd.push_back(w.td);
-    d.admm_on = w.admm ? 1 : 0;
-    if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
-    // ---- pair-major sort of the observations
-    w.sorted = w.obs;
-    std::stable_sort(w.sorted.begin(), w.sorted.end(), [](const HObs &a, const HObs &b) {
-      if (a.type != b.type) return a.type < b.type;
-      if (a.pi != b.pi) return a.pi < b.pi;
-      if (a.pj != b.pj) return a.pj < b.pj;
-      if (a.ea != b.ea) return a.ea < b.ea;
-      if (a.eb != b.eb) return a.eb < b.eb;
-      return a.seq < b.seq;
-    });
-    w.sorted_pos.assign(w.sorted.size(), -1);
-    d.off_tile = (int)tile_grp.size(); d.off_grp = (int)grp.size();
-    d.off_rec = (int64_t)d.off_tile * kTile;   // records are addressed by global tile slot
+    d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
+    d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size();
+    // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order
+    const size_t M = w.obs.size();
+    std::vector<std::pair<uint64_t, uint32_t>> keys(M);
+    for (size_t k = 0; k < M; k++) {
+      const HObs &o = w.obs[k];
+      uint64_t key = ((uint64_t)(o.type & 0xF) << 60) | ((uint64_t)((o.pi + 1) & 0x7FFF) << 45) | ((uint64_t)((o.pj + 1) & 0x7FFF) << 30) |
+                     ((uint64_t)((o.ea + 1) & 0x7FFF) << 15) | (uint64_t)((o.eb + 1) & 0x7FFF);
+      keys[k] = {key, (uint32_t)k};
+    }
+    std::sort(keys.begin(), keys.end());
+    w.order.resize(M); w.sorted_pos.assign(M, -1);
+    for (size_t k = 0; k < M; k++) w.order[k] = (int)keys[k].second;
     bool any_wide = false;
-    std::vector<std::vector<int>> lm_lists(nl);
-    size_t k = 0;
-    while (k < w.sorted.size()) {
+    size_t k = 0; int tile_run = 0;
+    while (k < M) {
       size_t e = k;
-      const HObs &o0 = w.sorted[k];
-      while (e < w.sorted.size() && w.sorted[e].type == o0.type && w.sorted[e].pi == o0.pi && w.sorted[e].pj == o0.pj &&
-             w.sorted[e].ea == o0.ea && w.sorted[e].eb == o0.eb) e++;
+      while (e < M && keys[e].first == keys[k].first) e++;
+      const HObs &o0 = w.obs[w.order[k]];
       Group g; memset(&g, 0, sizeof g);
       g.type = o0.type;
       g.blk[0] = o0.pi; g.blk[1] = o0.pj; g.blk[2] = o0.ea >= 0 ? np + o0.ea : -1; g.blk[3] = o0.eb >= 0 ? np + o0.eb : -1;
@@ -514,139 +607,174 @@ int d2ba_finalize(d2ba_handle *h) {
       g.rows = o0.type == D2BA_PROJ_2F1C_DEPTH ? 3 : (o0.type == D2BA_PROJ_DEPTH_PRIOR ? 1 : 2);
       if (g.nct == 4) any_wide = true;
       const int variant = (g.nct == 4 ? 1 : 0) + (g.rows == 3 ? 2 : 0);
-      const int gi = (int)grp.size();
-      grp.push_back(g);
       const int cnt = (int)(e - k), ntile = (cnt + kTile - 1) / kTile;
-      const int tile0 = (int)tile_grp.size();
-      for (int t = 0; t < ntile; t++) {
-        tile_grp.push_back(gi); tile_win.push_back(wi);
-        size_t base = obs_f.size();
-        obs_f.resize(base + (size_t)kObsFields * kTile, 0.0);
-        for (int lane = 0; lane < kTile; lane++) {
-          int idx = t * kTile + lane;
-          if (idx < cnt) {
-            const HObs &o = w.sorted[k + idx];
-            for (int f = 0; f < kObsFields; f++) obs_f[base + (size_t)f * kTile + lane] = o.f[f];
-            obs_lm.push_back(o.lm);
-            int pos = (tile0 + t - d.off_tile) * kTile + lane;
-            w.sorted_pos[k + idx] = pos;
-            lm_lists[o.lm].push_back(pos);
-          } else {
-            obs_f[base + (size_t)0 * kTile + lane] = 0; obs_f[base + (size_t)2 * kTile + lane] = 1.0; obs_f[base + (size_t)5 * kTile + lane] = 1.0;
-            obs_f[base + (size_t)14 * kTile + lane] = 1.0; obs_f[base + (size_t)18 * kTile + lane] = 1.0; obs_f[base + (size_t)20 * kTile + lane] = 1.0;
-            obs_lm.push_back(-1);
-          }
-        }
+      const int gi = (int)pl.groups.size();
+      pl.groups.push_back(g); pl.grp_begin.push_back((int)k); pl.grp_cnt.push_back(cnt); pl.grp_tile0.push_back(tile_run);
+      // balanced split of the group's tiles into jobs
+      const int njob = (ntile + tpj_target - 1) / tpj_target;
+      for (int j = 0; j < njob; j++) {
+        int b = (int)((int64_t)ntile * j / njob), en = (int)((int64_t)ntile * (j + 1) / njob);
+        Job jb; jb.win = wi; jb.grp = gi; jb.tile_begin = tile_run + b; jb.ntiles = en - b;
+        pl.jobs[variant].push_back(jb);
       }
-      for (int t = 0; t < ntile; t += tpj) { Job j; j.win = wi; j.grp = gi; j.tile_begin = tile0 + t; j.ntiles = std::min(tpj, ntile - t); jobs[variant].push_back(j); }
+      tile_run += ntile;
       k = e;
     }
-    d.n_tile = (int)tile_grp.size() - d.off_tile; d.n_grp = (int)grp.size() - d.off_grp;
+    pl.n_tiles = tile_run; d.n_tile = tile_run; d.n_grp = (int)pl.groups.size();
     d.rec_stride = any_wide ? 32 : 16;
-    // landmark CSR (positions ascending = deterministic reduction order)
-    d.off_lmptr = (int)lm_ptr.size(); d.off_lmobs = off_lmobs;
-    int run = 0;
-    for (int l = 0; l < nl; l++) { lm_ptr.push_back(run); std::sort(lm_lists[l].begin(), lm_lists[l].end()); for (int p : lm_lists[l]) lm_obs.push_back(p); run += (int)lm_lists[l].size(); }
-    lm_ptr.push_back(run);
-    off_lmobs += run;
-    // imu
-    d.off_imu = (int)imu.size(); d.n_imu = (int)w.imu.size();
-    for (auto &m : w.imu) { ImuDesc di{m.pi, m.si, m.pj, m.sj}; imu.push_back(di); imu_c.insert(imu_c.end(), m.c, m.c + kImuStride); }
-    // prior
-    d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size(); d.off_prior_blk = (int)pblk.size(); d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
-    if (w.prior_m > 0) {
-      if (w.prior_is_info) return fail(h, 21, "internal: prior still in information form");
-      prior_J.insert(prior_J.end(), w.prior_J.begin(), w.prior_J.end()); prior_e0.insert(prior_e0.end(), w.prior_e0.begin(), w.prior_e0.end());
-      for (auto &b : w.prior_blk) {
-        PriorBlk pb; memset(&pb, 0, sizeof pb);
-        pb.kind = b.kind; pb.off = b.off; pb.eff = b.eff; memcpy(pb.x0, b.x0, sizeof pb.x0);
-        pb.index = (b.kind == D2BA_EXTRINSIC) ? np + b.index : b.index;
-        pblk.push_back(pb);
-      }
-      off_pJ += (int64_t)w.prior_m * w.prior_m; off_pv += w.prior_m;
-      h->max_prior_m = std::max(h->max_prior_m, w.prior_m);
-    }
-    // dense storage
+    pl.n_lmobs = (int)M;
+    int ntw = (d.n_lc + 1 + 31) / 32;
+    if (d.n_lc > 0) for (int tm = 0; tm < ntw; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 0, tm, tn});
+    int t_lo = d.n_lc / 32, t_hi = d.n_c / 32;
+    for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 1, tm, tn});
+  });
+  // ---- serial prefix sums
+  h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
+  int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0;
+  int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0;
+  int njobs[4] = {0, 0, 0, 0};
+  bool any_info = false;
+  for (int wi = 0; wi < nw; wi++) {
+    HostWin &w = h->win[wi]; WinPlan &pl = plan[wi]; WinDesc &d = pl.d;
+    d.off6 = off6; off6 += d.n6; d.offsb = offsb; offsb += d.nsb; d.offlm = offlm; offlm += d.nl;
+    d.off_tile = off_tile; off_tile += d.n_tile; d.off_rec = off_rec; off_rec += (int64_t)d.n_tile * kTile * d.rec_stride;
+    d.off_grp = off_grp; off_grp += d.n_grp; d.off_imu = off_imu; off_imu += d.n_imu;
+    d.off_lmptr = off_lmptr; off_lmptr += d.nl + 1; d.off_lmobs = off_lmobs; off_lmobs += pl.n_lmobs;
+    d.off_prior_blk = off_pblk; off_pblk += d.prior_nblk; d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
+    off_pJ += (int64_t)d.prior_m * d.prior_m; off_pv += d.prior_m;
     d.offH = offH; offH += (int64_t)(d.n_c + 1) * d.ldh;
     d.offW = offW; offW += (int64_t)std::max(d.nl_pad, 32) * d.ldw;
     d.offc = offc; offc += roundup(d.n_c + 1, 4);
+    for (int v = 0; v < 4; v++) { pl.job_off[v] = njobs[v]; njobs[v] += (int)pl.jobs[v].size(); }
+    pl.schur_off = n_schur; n_schur += (int)pl.schur.size();
     h->max_rows = std::max(h->max_rows, d.n_c + 1); h->max_nc = std::max(h->max_nc, d.n_c); h->max_ldw = std::max(h->max_ldw, d.ldw);
-    // Schur tiles: W-space SYRK tiles (lower) + copy tiles for the speed-bias rows and the rhs row
-    {
-      int ntw = (d.n_lc + 1 + 31) / 32;
-      if (d.n_lc > 0) for (int tm = 0; tm < ntw; tm++) for (int tn = 0; tn <= tm; tn++) schur.push_back({wi, 0, tm, tn});
-      int t_lo = d.n_lc / 32, t_hi = d.n_c / 32;
-      for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) schur.push_back({wi, 1, tm, tn});
+    h->max_prior_m = std::max(h->max_prior_m, d.prior_m);
+    if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
+    if (w.prior_m > 0 && w.prior_is_info) any_info = true;
+  }
+  int jbase[4]; { int r = 0; for (int v = 0; v < 4; v++) { jbase[v] = r; h->job_begin[v] = r; h->job_count[v] = njobs[v]; r += njobs[v]; } }
+  const int n_jobs = jbase[3] + njobs[3];
+  h->n6_total = off6; h->nsb_total = offsb; h->nl_total = offlm; h->n_tiles = off_tile; h->n_imu_total = off_imu; h->n_schur = n_schur;
+  h->totH = offH; h->totW = offW; h->totc = offc;
+  // ---- staging sizes
+  bool ok = st.win.resize(nw) && st.x6.resize((size_t)off6 * 8) && st.xsb.resize((size_t)offsb * 9) && st.xlm.resize(offlm) && st.xtd.resize(nw) &&
+            st.col6.resize(off6) && st.colsb.resize(offsb) && st.slot6.resize(off6) && st.blk_win.resize(off6) && st.sb_win.resize(offsb) &&
+            st.lm_win.resize(offlm) && st.tile_grp.resize(off_tile) && st.tile_win.resize(off_tile) && st.obs_lm.resize((size_t)off_tile * kTile) &&
+            st.obs.resize((size_t)off_tile * kTile * kObsFields) && st.lm_ptr.resize(off_lmptr) && st.lm_obs.resize((size_t)off_lmobs) &&
+            st.grp.resize(off_grp) && st.job.resize(n_jobs) && st.imu.resize(off_imu) && st.imu_c.resize((size_t)off_imu * kImuStride) &&
+            st.pblk.resize(off_pblk) && st.prior_J.resize((size_t)off_pJ) && st.prior_e0.resize((size_t)off_pv) && st.schur.resize(n_schur) &&
+            st.pr_m.resize(nw) && st.pr_info.resize(nw) && st.pr_offJ.resize(nw) && st.pr_offv.resize(nw);
+  if (!ok) return fail(h, 24, "pinned staging allocation failed");
+  // ---- pass B (parallel): fill the staging buffers
+  parallel_for(nw, [&](int wi) {
+    HostWin &w = h->win[wi]; WinPlan &pl = plan[wi]; const WinDesc &d = pl.d;
+    st.win.p[wi] = d;
+    const int np = d.np, ne = d.ne;
+    for (int i = 0; i < np; i++) {
+      double *x = st.x6.p + (size_t)(d.off6 + i) * 8; memcpy(x, &w.pose[7 * i], 56); x[7] = 0;
+      st.col6.p[d.off6 + i] = w.pose_col[i]; st.slot6.p[d.off6 + i] = w.admm ? w.pose_slot[i] : -1; st.blk_win.p[d.off6 + i] = wi;
     }
-    wd.push_back(d);
-    wi++;
-  }
-  if (wi == 0) return fail(h, 22, "finalize: no window in use");
-  h->n_used = wi; h->h_win = wd; h->h_grp = grp; h->h_tile_win = tile_win;
-  h->n6_total = (int)col6.size(); h->nsb_total = (int)colsb.size(); h->nl_total = (int)xlm.size(); h->n_tiles = (int)tile_grp.size();
-  h->n_imu_total = (int)imu.size(); h->n_schur = (int)schur.size(); h->totH = offH; h->totW = offW; h->totc = offc;
-  std::vector<Job> all_jobs;
-  for (int v = 0; v < 4; v++) { h->job_begin[v] = (int)all_jobs.size(); h->job_count[v] = (int)jobs[v].size(); all_jobs.insert(all_jobs.end(), jobs[v].begin(), jobs[v].end()); }
-  // ---- uploads
+    for (int i = 0; i < ne; i++) {
+      double *x = st.x6.p + (size_t)(d.off6 + np + i) * 8; memcpy(x, &w.ext[7 * i], 56); x[7] = 0;
+      st.col6.p[d.off6 + np + i] = w.ext_col[i]; st.slot6.p[d.off6 + np + i] = w.admm ? w.ext_slot[i] : -1; st.blk_win.p[d.off6 + np + i] = wi;
+    }
+    if (d.nsb) memcpy(st.xsb.p + (size_t)d.offsb * 9, w.sb.data(), (size_t)d.nsb * 72);
+    for (int i = 0; i < d.nsb; i++) { st.colsb.p[d.offsb + i] = w.sb_col[i]; st.sb_win.p[d.offsb + i] = wi; }
+    if (d.nl) memcpy(st.xlm.p + d.offlm, w.lm.data(), (size_t)d.nl * 8);
+    for (int i = 0; i < d.nl; i++) st.lm_win.p[d.offlm + i] = wi;
+    st.xtd.p[wi] = w.td;
+    // observation tiles (AoSoA [field][lane]) + landmark CSR by counting sort
+    int *lmp = st.lm_ptr.p + d.off_lmptr;
+    for (int l = 0; l <= d.nl; l++) lmp[l] = 0;
+    for (const HObs &o : w.obs) lmp[o.lm + 1]++;
+    for (int l = 0; l < d.nl; l++) lmp[l + 1] += lmp[l];
+    std::vector<int> cursor(lmp, lmp + d.nl);
+    int *lmo = st.lm_obs.p + d.off_lmobs;
+    for (int gi = 0; gi < (int)pl.groups.size(); gi++) {
+      st.grp.p[d.off_grp + gi] = pl.groups[gi];
+      const int cnt = pl.grp_cnt[gi], ntile = (cnt + kTile - 1) / kTile, k0 = pl.grp_begin[gi], t0 = pl.grp_tile0[gi];
+      for (int t = 0; t < ntile; t++) {
+        const int gt = d.off_tile + t0 + t;
+        st.tile_grp.p[gt] = d.off_grp + gi; st.tile_win.p[gt] = wi;
+        double *ob = st.obs.p + (size_t)gt * kObsFields * kTile;
+        int *ol = st.obs_lm.p + (size_t)gt * kTile;
+        for (int lane = 0; lane < kTile; lane++) {
+          const int idx = t * kTile + lane;
+          if (idx < cnt) {
+            const HObs &o = w.obs[w.order[k0 + idx]];
+            for (int f = 0; f < kObsFields; f++) ob[f * kTile + lane] = o.f[f];
+            ol[lane] = o.lm;
+            const int pos = (t0 + t) * kTile + lane;
+            w.sorted_pos[k0 + idx] = pos;
+          } else {
+            for (int f = 0; f < kObsFields; f++) ob[f * kTile + lane] = 0.0;
+            ob[2 * kTile + lane] = 1.0; ob[5 * kTile + lane] = 1.0; ob[14 * kTile + lane] = 1.0; ob[18 * kTile + lane] = 1.0; ob[20 * kTile + lane] = 1.0;
+            ol[lane] = -1;
+          }
+        }
+      }
+    }
+    // CSR entries in ascending position order (deterministic reduction order): positions increase with sorted index
+    for (size_t k = 0; k < w.order.size(); k++) { const HObs &o = w.obs[w.order[k]]; lmo[cursor[o.lm]++] = w.sorted_pos[k]; }
+    for (int v = 0; v < 4; v++)
+      for (size_t j = 0; j < pl.jobs[v].size(); j++) {
+        Job jb = pl.jobs[v][j]; jb.grp += d.off_grp; jb.tile_begin += d.off_tile;
+        st.job.p[jbase[v] + pl.job_off[v] + j] = jb;
+      }
+    for (size_t t = 0; t < pl.schur.size(); t++) st.schur.p[pl.schur_off + t] = pl.schur[t];
+    for (int i = 0; i < d.n_imu; i++) {
+      const HImu &m = w.imu[i];
+      st.imu.p[d.off_imu + i] = ImuDesc{m.pi, m.si, m.pj, m.sj};
+      memcpy(st.imu_c.p + (size_t)(d.off_imu + i) * kImuStride, m.c, sizeof(double) * kImuStride);
+    }
+    st.pr_m.p[wi] = d.prior_m; st.pr_info.p[wi] = (d.prior_m > 0 && w.prior_is_info) ? 1 : 0; st.pr_offJ.p[wi] = d.off_prior_J; st.pr_offv.p[wi] = d.off_prior_v;
+    if (d.prior_m > 0) {
+      memcpy(st.prior_J.p + d.off_prior_J, w.prior_J.data(), (size_t)d.prior_m * d.prior_m * 8);
+      memcpy(st.prior_e0.p + d.off_prior_v, w.prior_e0.data(), (size_t)d.prior_m * 8);
+      for (int i = 0; i < d.prior_nblk; i++) {
+        const HPriorBlk &b = w.prior_blk[i];
+        PriorBlk pb; memset(&pb, 0, sizeof pb);
+        pb.kind = b.kind; pb.off = b.off; pb.eff = b.eff; memcpy(pb.x0, b.x0, sizeof pb.x0);
+        pb.index = (b.kind == D2BA_EXTRINSIC) ? np + b.index : b.index;
+        st.pblk.p[d.off_prior_blk + i] = pb;
+      }
+    }
+  });
+  h->h_win.assign(st.win.p, st.win.p + nw);
+  h->h_grp.assign(st.grp.p, st.grp.p + off_grp);
+  // ---- uploads (pinned -> device, async on the solver stream)
   int rc;
-  if ((rc = upload(h, h->d_win, wd))) return rc;
-  CK(h->d_ctl.alloc(wi)); CK(cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Ctl) * wi, h->stream));
+  if ((rc = up(h, h->d_win, st.win))) return rc;
+  CK(h->d_ctl.alloc(nw)); CK(cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Ctl) * nw, h->stream));
+  if ((rc = up(h, h->d_x6[0], st.x6)) || (rc = up(h, h->d_xsb[0], st.xsb)) || (rc = up(h, h->d_xlm[0], st.xlm)) || (rc = up(h, h->d_xtd[0], st.xtd))) return rc;
+  CK(h->d_x6[1].alloc(st.x6.n)); CK(h->d_xsb[1].alloc(st.xsb.n)); CK(h->d_xlm[1].alloc(st.xlm.n)); CK(h->d_xtd[1].alloc(st.xtd.n));
+  const size_t rec_doubles = (size_t)off_rec;
   for (int b = 0; b < 2; b++) {
-    if ((rc = upload(h, h->d_x6[b], x6))) return rc;
-    if ((rc = alloc_zero(h, h->d_R6[b], (size_t)h->n6_total * 12))) return rc;
-    if ((rc = upload(h, h->d_xsb[b], xsb))) return rc;
-    if ((rc = upload(h, h->d_xlm[b], xlm))) return rc;
-    if ((rc = upload(h, h->d_xtd[b], xtd))) return rc;
-    if ((rc = alloc_zero(h, h->d_rec[b], (size_t)h->n_tiles * kTile * 32))) return rc;
-    if ((rc = alloc_zero(h, h->d_H[b], (size_t)offH))) return rc;
-    if ((rc = alloc_zero(h, h->d_gc[b], (size_t)offc))) return rc;
+    CK(h->d_R6[b].alloc((size_t)off6 * 12)); CK(h->d_rec[b].alloc(rec_doubles));
+    CK(h->d_H[b].alloc((size_t)offH)); CK(h->d_gc[b].alloc((size_t)offc));
   }
-  if ((rc = upload(h, h->d_col6, col6))) return rc;
-  if ((rc = upload(h, h->d_colsb, colsb))) return rc;
-  if ((rc = upload(h, h->d_tile_grp, tile_grp))) return rc;
-  if ((rc = upload(h, h->d_tile_win, tile_win))) return rc;
-  if ((rc = upload(h, h->d_obs_lm, obs_lm))) return rc;
-  if ((rc = upload(h, h->d_obs, obs_f))) return rc;
-  if ((rc = upload(h, h->d_lm_ptr, lm_ptr))) return rc;
-  if ((rc = upload(h, h->d_lm_obs, lm_obs))) return rc;
-  if ((rc = upload(h, h->d_slot6, slot6))) return rc;
-  if ((rc = upload(h, h->d_lm_win, lm_win))) return rc;
-  if ((rc = upload(h, h->d_blk_win, blk_win))) return rc;
-  if ((rc = upload(h, h->d_sb_win, sb_win))) return rc;
-  if ((rc = upload(h, h->d_grp, grp))) return rc;
-  if ((rc = upload(h, h->d_job, all_jobs))) return rc;
-  if ((rc = upload(h, h->d_imu, imu))) return rc;
-  if ((rc = upload(h, h->d_imu_c, imu_c))) return rc;
-  if ((rc = alloc_zero(h, h->d_imu_U, (size_t)h->n_imu_total * 225))) return rc;
-  if ((rc = upload(h, h->d_prior_blk, pblk))) return rc;
-  if ((rc = upload(h, h->d_prior_J, prior_J))) return rc;
-  if ((rc = upload(h, h->d_prior_e0, prior_e0))) return rc;
-  if ((rc = alloc_zero(h, h->d_prior_A, prior_J.size()))) return rc;
-  if ((rc = alloc_zero(h, h->d_z6, (size_t)h->n6_total * 8))) return rc;
-  if ((rc = alloc_zero(h, h->d_tilde6, (size_t)h->n6_total * 6))) return rc;
-  if ((rc = alloc_zero(h, h->d_lm_ref, h->nl_total))) return rc;
-  if ((rc = alloc_zero(h, h->d_sb_ref, (size_t)h->nsb_total * 9))) return rc;
-  if ((rc = alloc_zero(h, h->d_td_ref, wi))) return rc;
+  if ((rc = up(h, h->d_col6, st.col6)) || (rc = up(h, h->d_colsb, st.colsb)) || (rc = up(h, h->d_tile_grp, st.tile_grp)) ||
+      (rc = up(h, h->d_tile_win, st.tile_win)) || (rc = up(h, h->d_obs_lm, st.obs_lm)) || (rc = up(h, h->d_obs, st.obs)) ||
+      (rc = up(h, h->d_lm_ptr, st.lm_ptr)) || (rc = up(h, h->d_lm_obs, st.lm_obs)) || (rc = up(h, h->d_slot6, st.slot6)) ||
+      (rc = up(h, h->d_lm_win, st.lm_win)) || (rc = up(h, h->d_blk_win, st.blk_win)) || (rc = up(h, h->d_sb_win, st.sb_win)) ||
+      (rc = up(h, h->d_grp, st.grp)) || (rc = up(h, h->d_job, st.job)) || (rc = up(h, h->d_imu, st.imu)) || (rc = up(h, h->d_imu_c, st.imu_c)) ||
+      (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
+      (rc = up(h, h->d_schur, st.schur)))
+    return rc;
+  CK(h->d_imu_U.alloc((size_t)off_imu * 225)); CK(h->d_prior_A.alloc((size_t)off_pJ));
+  CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
+  CK(h->d_td_ref.alloc(nw));
   if ((rc = alloc_zero(h, h->d_cons, (size_t)std::max(h->n_slots, 1) * 14))) return rc;
-  if ((rc = alloc_zero(h, h->d_Wt, (size_t)offW))) return rc;
-  if ((rc = alloc_zero(h, h->d_dinv, h->nl_total))) return rc;
-  if ((rc = alloc_zero(h, h->d_hl, h->nl_total))) return rc;
-  if ((rc = alloc_zero(h, h->d_gl, h->nl_total))) return rc;
-  if ((rc = alloc_zero(h, h->d_S, (size_t)offH))) return rc;
-  if ((rc = alloc_zero(h, h->d_gred, (size_t)offc))) return rc;
-  if ((rc = alloc_zero(h, h->d_D2c, (size_t)offc))) return rc;
-  if ((rc = alloc_zero(h, h->d_gn_c, (size_t)offc))) return rc;
-  if ((rc = alloc_zero(h, h->d_gn_l, h->nl_total))) return rc;
-  if ((rc = alloc_zero(h, h->d_step_c, (size_t)offc))) return rc;
-  if ((rc = alloc_zero(h, h->d_step_l, h->nl_total))) return rc;
-  if ((rc = alloc_zero(h, h->d_wu, h->nl_total))) return rc;
-  if ((rc = upload(h, h->d_schur, schur))) return rc;
+  if ((rc = alloc_zero(h, h->d_Wt, (size_t)offW))) return rc;   // padding rows / columns must be zero
+  CK(h->d_dinv.alloc(offlm)); CK(h->d_hl.alloc(offlm)); CK(h->d_gl.alloc(offlm)); CK(h->d_S.alloc((size_t)offH));
+  CK(h->d_gred.alloc((size_t)offc)); CK(h->d_D2c.alloc((size_t)offc)); CK(h->d_gn_c.alloc((size_t)offc)); CK(h->d_gn_l.alloc(offlm));
+  CK(h->d_step_c.alloc((size_t)offc)); CK(h->d_step_l.alloc(offlm)); CK(h->d_wu.alloc(offlm));
   // ---- device view
   Dev &D = h->dev;
   memset(&D, 0, sizeof D);
-  D.win = h->d_win.p; D.ctl = h->d_ctl.p; D.n_win = wi;
+  D.win = h->d_win.p; D.ctl = h->d_ctl.p; D.n_win = nw;
   for (int b = 0; b < 2; b++) { D.x6[b] = h->d_x6[b].p; D.R6[b] = h->d_R6[b].p; D.xsb[b] = h->d_xsb[b].p; D.xlm[b] = h->d_xlm[b].p; D.xtd[b] = h->d_xtd[b].p; D.rec[b] = h->d_rec[b].p; D.Hcc[b] = h->d_H[b].p; D.gc[b] = h->d_gc[b].p; }
-  D.col6 = h->d_col6.p; D.colsb = h->d_colsb.p; D.grp = h->d_grp.p; D.job = h->d_job.p; D.n_job = (int)all_jobs.size();
+  D.col6 = h->d_col6.p; D.colsb = h->d_colsb.p; D.grp = h->d_grp.p; D.job = h->d_job.p; D.n_job = n_jobs;
   D.tile_grp = h->d_tile_grp.p; D.obs = h->d_obs.p; D.obs_lm = h->d_obs_lm.p; D.lm_ptr = h->d_lm_ptr.p; D.lm_obs = h->d_lm_obs.p;
   D.imu = h->d_imu.p; D.imu_c = h->d_imu_c.p; D.imu_U = h->d_imu_U.p; D.prior_blk = h->d_prior_blk.p; D.prior_J = h->d_prior_J.p;
   D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
@@ -659,30 +787,34 @@ int d2ba_finalize(d2ba_handle *h) {
   P.initial_radius = h->cfg.initial_trust_region_radius; P.max_radius = h->cfg.max_trust_region_radius; P.min_rel_decrease = h->cfg.min_relative_decrease;
   P.ftol = h->cfg.function_tolerance; P.gtol = h->cfg.gradient_tolerance; P.ptol = h->cfg.parameter_tolerance;
   P.max_iter = h->cfg.max_num_iterations; P.fixed_mode = 0;
-  if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
+  if (h->cfg_max_rows != h->max_rows || h->cfg_max_nc != h->max_nc || h->cfg_max_prior != h->max_prior_m) {
+    if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
+    h->cfg_max_rows = h->max_rows; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
+  }
   launch_state_prep(D, h->n6_total, 0, h->stream);
   launch_imu_prep(D, h->n_imu_total, h->stream);
+  if (any_info) {
+    if ((rc = up(h, h->d_pr_m, st.pr_m)) || (rc = up(h, h->d_pr_info, st.pr_info)) || (rc = up(h, h->d_pr_oJ, st.pr_offJ)) || (rc = up(h, h->d_pr_ov, st.pr_offv))) return rc;
+    launch_prior_from_info(nw, h->max_prior_m, h->d_pr_m.p, h->d_pr_oJ.p, h->d_pr_ov.p, h->d_pr_info.p, h->d_prior_J.p, h->d_prior_A.p, h->d_prior_e0.p, h->stream);
+  }
   launch_prior_prep(D, h->stream);
-  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // staging buffers are reused by the next finalize
   CK(cudaGetLastError());
-  h->h_ctl.assign(wi, Ctl());
-  for (int b = 0; b < 2; b++) { h->h_x6[b] = x6; h->h_xsb[b] = xsb; h->h_xlm[b] = xlm; h->h_xtd[b] = xtd; }
+  h->h_ctl.assign(nw, Ctl());
+  for (int b = 0; b < 2; b++) {
+    h->h_x6[b].assign(st.x6.p, st.x6.p + st.x6.n); h->h_xsb[b].assign(st.xsb.p, st.xsb.p + st.xsb.n);
+    h->h_xlm[b].assign(st.xlm.p, st.xlm.p + st.xlm.n); h->h_xtd[b].assign(st.xtd.p, st.xtd.p + st.xtd.n);
+  }
   h->finalized = true; h->state_dirty = false;
   return 0;
 }
 
-// Prior given in information form: toJacRes (prior_factor.cpp:132-177).  The eigen-decomposition of the
-// m x m information matrix is a one-off setup step (m <= ~130); it runs in double precision on the
-// device through a Jacobi sweep kernel in d2ba_margin.cu.
-int d2ba_prior_info_to_jac(d2ba_handle *h, int m, const double *A, const double *b, double *J, double *e0);
-
+// Prior given in information form (A, b): the reference's toJacRes (prior_factor.cpp:132-177) runs on the
+// device, batched over windows, as part of d2ba_finalize (k_prior_from_info in d2ba_margin.cu).
 int d2ba_set_prior_info(d2ba_handle *h, int32_t window, int32_t m, const double *A, const double *b, int32_t nblk,
                         const d2ba_blockref *refs, const double *x0) {
   if (!h) return 1;
-  std::vector<double> J((size_t)m * m), e0(m);
-  int rc = d2ba_prior_info_to_jac(h, m, A, b, J.data(), e0.data());
-  if (rc) return rc;
-  return set_prior_common(h, window, m, J.data(), e0.data(), nblk, refs, x0, false);
+  return set_prior_common(h, window, m, A, b, nblk, refs, x0, true);
 }
 
 // ------------------------------------------------------------------------------------------------ solve
@@ -913,7 +1045,7 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
     }
     case D2BA_DBG_OBS_INDEX: {
       std::vector<int32_t> v;
-      for (auto &o : w->sorted) { v.push_back(o.type); v.push_back(o.pi); v.push_back(o.pj); v.push_back(o.ea < 0 ? -1 : d.np + o.ea); v.push_back(o.eb < 0 ? -1 : d.np + o.eb); v.push_back(o.lm); }
+      for (int oi : w->order) { const HObs &o = w->obs[oi]; v.push_back(o.type); v.push_back(o.pi); v.push_back(o.pj); v.push_back(o.ea < 0 ? -1 : d.np + o.ea); v.push_back(o.eb < 0 ? -1 : d.np + o.eb); v.push_back(o.lm); }
       buf.resize(v.size() * 4); memcpy(buf.data(), v.data(), buf.size()); break;
     }
     case D2BA_DBG_COL_OF_BLOCK: {
@@ -933,7 +1065,7 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
       if (!all.empty()) cudaMemcpy(all.data(), tmp.p + (size_t)d.off_tile * kTile * 81, all.size() * 8, cudaMemcpyDeviceToHost);
       tmp.release();
       std::vector<double> o(w->obs.size() * 81, 0.0);
-      for (size_t k = 0; k < w->sorted.size(); k++) memcpy(&o[(size_t)w->sorted[k].seq * 81], &all[(size_t)w->sorted_pos[k] * 81], 81 * 8);
+      for (size_t k = 0; k < w->order.size(); k++) memcpy(&o[(size_t)w->order[k] * 81], &all[(size_t)w->sorted_pos[k] * 81], 81 * 8);
       put_d(o); break;
     }
     default: return fail(h, 6, "debug_get: unknown item");

@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(128) k_proj_lin(Dev d, int eval_cur, int job_b
     double hl = 0, gl = 0, wtd = 0;
 #pragma unroll
     for (int q = 0; q < ROWS; q++) { hl += o.jl[q] * o.jl[q]; gl += o.jl[q] * o.r[q]; if (NS > 2 && need_td) wtd += o.jt[q] * o.jl[q]; }
-    double *rec = d.rec[buf] + ((size_t)w.off_rec + (size_t)(tile - w.off_tile) * kTile + lane) * w.rec_stride;
+    double *rec = d.rec[buf] + (size_t)w.off_rec + ((size_t)(tile - w.off_tile) * kTile + lane) * w.rec_stride;
     if (valid) {
       cost += o.cost;
       reinterpret_cast<double2 *>(rec)[0] = make_double2(hl, gl);
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   const int *ptr = d.lm_ptr + w.off_lmptr;
   const int *lo = d.lm_obs + w.off_lmobs;
   const int stride = w.rec_stride;
-  const double *recs = d.rec[buf] + (size_t)w.off_rec * stride;
+  const double *recs = d.rec[buf] + (size_t)w.off_rec;
   double h = 0, g = 0;
   for (int k = ptr[l]; k < ptr[l + 1]; k++) {
     const int pos = lo[k];  // window-local sorted observation position
@@ -774,6 +774,9 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
 // S is (n+1) x ld row-major, lower part valid; row n carries the right-hand side, so after the
 // factorisation it holds y = L^-1 g ("forward substitution for free").  Back substitution then gives
 // the Gauss-Newton camera step dc = -L^-T y.
+// Per 32-column panel: (a) warp 0 factors the 32x32 diagonal block in shared memory (one row per lane),
+// (b) every remaining row is solved against it by its own thread (TRSM, registers), (c) the trailing
+// matrix is updated with 4x4 register tiles.  Only two block barriers per panel phase.
 constexpr int kCholThreads = 512;
 constexpr int kNB = 32;
 __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
@@ -787,42 +790,71 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
   double *Pt = sm;                  // kNB * ldp
   double *xs = sm + kNB * ldp;      // solution / scratch (max_rows)
   double *redb = xs + max_rows + 8; // 16 x 32 partial sums
-  double *Lb = redb + 16 * 32;      // kNB x (kNB+1) diagonal block
+  double *Dg = redb + 16 * 32;      // kNB x (kNB+1) diagonal block (row-major, lower)
+  double *invd = Dg + kNB * (kNB + 1);  // reciprocal diagonal of L, all n columns
   __shared__ int fail;
   const int n = w.n_c, n1 = n + 1, ld = w.ldh;
   double *S = d.S + w.offH;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) fail = 0;
   __syncthreads();
   for (int k0 = 0; k0 < n; k0 += kNB) {
     const int nb = min(kNB, n - k0), nr = n1 - k0;
-    // load panel (rows k0..n, cols k0..k0+nb)
+    // load panel (rows k0..n, cols k0..k0+nb); diagonal block also into Dg (identity padded)
     for (int e = tid; e < nr * kNB; e += nt) {
       int r = e / kNB, c = e % kNB;
-      Pt[c * ldp + r] = (c < nb && (k0 + r) < n1) ? S[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+      double v = (c < nb) ? S[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+      Pt[c * ldp + r] = v;
+      if (r < kNB) Dg[r * (kNB + 1) + c] = (c < nb) ? v : (r == c ? 1.0 : 0.0);   // rows nb..31 (if any) ride along
+    }
+    for (int e = tid + nr * kNB; e < kNB * kNB; e += nt) {  // rows of Dg beyond nr (tiny last panel)
+      int r = e / kNB, c = e % kNB;
+      if (r >= nr) Dg[r * (kNB + 1) + c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
-    for (int c = 0; c < nb; c++) {
-      double dd = Pt[c * ldp + c];
-      if (!(dd > 0.0) || !isfinite(dd)) { if (tid == 0) fail = 1; dd = 1.0; }
-      const double sd = sqrt(dd), isd = 1.0 / sd;
-      __syncthreads();
-      for (int r = c + tid; r < nr; r += nt) Pt[c * ldp + r] = (r == c) ? sd : Pt[c * ldp + r] * isd;
-      __syncthreads();
-      // rank-1 update of the remaining panel columns
-      const int ncol = nb - c - 1;
-      for (int e = tid; e < ncol * nr; e += nt) {
-        int c2 = c + 1 + e / nr, r = e % nr;
-        if (r >= c2) Pt[c2 * ldp + r] -= Pt[c * ldp + r] * Pt[c * ldp + c2];
+    // (a) diagonal block: lane = row
+    if (warp == 0) {
+      for (int c = 0; c < nb; c++) {
+        const double dcc = Dg[c * (kNB + 1) + c];
+        if (!(dcc > 0.0) || !isfinite(dcc)) fail = 1;
+        const double inv = 1.0 / sqrt(dcc > 0.0 ? dcc : 1.0);
+        double lrc = 0.0;
+        if (lane > c) { lrc = Dg[lane * (kNB + 1) + c] * inv; Dg[lane * (kNB + 1) + c] = lrc; }
+        if (lane == c) { Dg[c * (kNB + 1) + c] = dcc * inv; invd[k0 + c] = inv; }
+        __syncwarp();
+        const int c2max = min(lane, nb - 1);
+        for (int c2 = c + 1; c2 <= c2max; c2++) Dg[lane * (kNB + 1) + c2] -= lrc * Dg[c2 * (kNB + 1) + c];
+        __syncwarp();
       }
-      __syncthreads();
     }
+    __syncthreads();
+    // (b) rows below the diagonal block: x L_d^T = a, one row per thread
+    for (int r = kNB + tid; r < nr; r += nt) {
+      double a[kNB];
+#pragma unroll
+      for (int c = 0; c < kNB; c++) a[c] = Pt[c * ldp + r];
+#pragma unroll
+      for (int c = 0; c < kNB; c++) {
+        double s_ = a[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) s_ -= a[k] * Dg[c * (kNB + 1) + k];
+        a[c] = (c < nb) ? s_ * invd[k0 + c] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < kNB; c++) Pt[c * ldp + r] = a[c];
+    }
+    // factored diagonal block back into the panel (rows < kNB)
+    for (int e = tid; e < kNB * kNB; e += nt) {
+      int r = e / kNB, c = e % kNB;
+      if (r < nr && c <= r && c < nb) Pt[c * ldp + r] = Dg[r * (kNB + 1) + c];
+    }
+    __syncthreads();
     // write the factored panel back
     for (int e = tid; e < nr * kNB; e += nt) {
       int r = e / kNB, c = e % kNB;
       if (c < nb && r >= c) S[(size_t)(k0 + r) * ld + k0 + c] = Pt[c * ldp + r];
     }
-    // trailing update S[i][j] -= sum_c P[i][c] P[j][c], i >= j >= k0+nb, 4x4 register tiles
+    // (c) trailing update S[i][j] -= sum_c P[i][c] P[j][c], i >= j >= k0+nb, 4x4 register tiles
     const int t0 = nb;                  // panel-local first trailing row
     const int ntr = nr - t0;            // trailing rows (incl. rhs row)
     const int nt4 = (ntr + 3) / 4;
@@ -863,23 +895,23 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
     if (col < nb)
       for (int k = k0 + nb + slice; k < n; k += 16) s += S[(size_t)k * ld + k0 + col] * xs[k];
     redb[slice * 32 + col] = s;
-    __syncthreads();
-    // diagonal block of L into shared memory (avoids a global round trip per substitution step)
     for (int e = tid; e < kNB * kNB; e += nt) {
       int i = e / kNB, j = e % kNB;
-      Lb[i * (kNB + 1) + j] = (i < nb && j <= i) ? S[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+      Dg[i * (kNB + 1) + j] = (i < nb && j <= i) ? S[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
     }
     __syncthreads();
     if (tid < 32) {
       double acc = 0;
+#pragma unroll
       for (int q = 0; q < 16; q++) acc += redb[q * 32 + tid];
       double rhs = (tid < nb) ? y[k0 + tid] - acc : 0.0;
-      // triangular solve inside the block with warp shuffles: x_i = (rhs_i - sum_{j>i} L[j][i] x_j) / L[i][i]
+      const double myinv = (tid < nb) ? invd[k0 + tid] : 1.0;
+      // x_i = (rhs_i - sum_{j>i} L[j][i] x_j) / L[i][i], lanes hold the running right-hand sides
       double xi = 0;
       for (int i = nb - 1; i >= 0; i--) {
-        double v = __shfl_sync(0xffffffffu, rhs, i) / Lb[i * (kNB + 1) + i];
+        double v = __shfl_sync(0xffffffffu, rhs * myinv, i);
         if (tid == i) xi = v;
-        if (tid < i) rhs -= Lb[i * (kNB + 1) + tid] * v;   // rhs_j -= L[i][j] * x_i for j < i
+        if (tid < i) rhs -= Dg[i * (kNB + 1) + tid] * v;
       }
       if (tid < nb) xs[k0 + tid] = xi;
     }
@@ -1210,7 +1242,7 @@ int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   e = cudaFuncSetAttribute(k_proj_lin<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 2>()); if (e) return e;
   e = cudaFuncSetAttribute(k_proj_lin<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 4>()); if (e) return e;
   e = cudaFuncSetAttribute(k_proj_lin<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 4>()); if (e) return e;
-  size_t chol = (size_t)(kNB * (max_rows + 4) + max_rows + 8 + 16 * 32 + kNB * (kNB + 1)) * 8;
+  size_t chol = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol); if (e) return e;
   size_t st = (size_t)(40 + 3 * max_nc) * 8;
   e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st); if (e) return e;
@@ -1239,7 +1271,7 @@ void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) 
   if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));
 }
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
-  size_t sm = (size_t)(kNB * (max_rows + 4) + max_rows + 8 + 16 * 32 + kNB * (kNB + 1)) * 8;
+  size_t sm = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   k_chol<<<d.n_win, kCholThreads, sm, s>>>(d, max_rows);
 }
 void launch_step(const Dev &d, int max_nc, cudaStream_t s) {

@@ -47,7 +47,7 @@ struct WinDesc {
   int off_grp, n_grp;
   int off_imu, n_imu;
   int rec_stride;              // doubles per landmark-side record (16 or 32)
-  int64_t off_rec;             // first record (in records) = off_tile*32
+  int64_t off_rec;             // offset of the window's records (doubles)
   int64_t offH;                // Hcc / S offset (doubles)
   int64_t offW;                // Wt offset (doubles)
   int64_t offc;                // offset into n_c sized vectors
