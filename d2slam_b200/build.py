@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libd2ba.so")
 SOURCES = ["d2ba_kernels.cu", "d2ba_host.cu", "d2ba_margin.cu"]
+EXTRA_DEPS = ["d2ba_harness.cpp"]
 HEADERS = ["d2ba_types.cuh", "d2ba_math.cuh", "d2ba_proj.cuh", os.path.join("..", "..", "include", "d2ba.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -16,7 +17,7 @@ def _stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + EXTRA_DEPS] + [os.path.abspath(__file__)]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -41,6 +42,10 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {s}")
     link = [nvcc, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(link)
+    # host-side harness (C++ stand-in for the D2Estimator call sequence), links against libd2ba.so
+    harness = os.path.join(HERE, "libd2ba_harness.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", os.path.join(CSRC, "d2ba_harness.cpp"), "-o", harness,
+                           "-L" + HERE, "-ld2ba", "-Wl,-rpath,$ORIGIN"])
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -50,14 +50,17 @@ if __name__ == "__main__":
     check(synth.make_window(seed=2, cams="stereo", estimate_extrinsic=True, estimate_td=True, td_offset=0.002), "stereo + free ext/td")
     check(synth.make_window(seed=3, with_prior=False), "mono, first pose fixed")
     sw = synth.make_swarm(seed=4, n_agents=4)
-    check(sw[1], "W4 agent 1 (local problem, consensus terms at z=x)", consensus_max_steps=0)
-    # batch throughput smoke
-    B = 64
-    prs = [synth.make_window(seed=100 + i) for i in range(B)]
-    s = Solver(max_windows=B)
-    for i, p in enumerate(prs): p.load(s, i)
-    s.finalize()
-    for _ in range(2):
-        t = time.time(); reps = s.solve_fixed(8); dt = time.time() - t
-        for i, p in enumerate(prs): p.load(s, i)   # reset state (structural no-op)
-        print(f"batch {B}: wall {dt*1e3:.2f} ms, device {reps[0].total_time*1e3:.3f} ms -> {B*8/reps[0].total_time:.0f} iter/s; final costs {reps[0].final_cost:.3f} {reps[-1].final_cost:.3f}")
+    check(sw[1], "W4 agent 1 (swarm of one: consensus terms at z=x)")
+    # batch throughput + per-kernel times
+    for B in (1, 64, 512):
+        prs = [synth.make_window(seed=100 + i) for i in range(B)]
+        s = Solver(max_windows=B)
+        for i, p in enumerate(prs): p.load(s, i)
+        s.finalize()
+        for _ in range(2):
+            reps = s.solve_fixed(8)
+            for i, p in enumerate(prs):
+                s.set_blocks(i, abi.POSE, p["frame_ids"], p["poses"], p["pose_const"]); s.set_blocks(i, abi.SPEED_BIAS, p["sb_ids"], p["sb"], None); s.set_blocks(i, abi.LANDMARK, p["lm_ids"], p["inv_dep"], None)
+        print(f"batch {B}: device {reps[0].total_time*1e3:.3f} ms -> {B*8/reps[0].total_time:.0f} iter/s; cost {reps[0].final_cost:.3f}")
+        kt = s.kernel_times(8)
+        print("   kernel us/iter:", {k: round(v * 1e3, 1) for k, v in kt.items()})
