@@ -127,7 +127,7 @@ struct d2ba_handle {
   DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_lm_obs, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
   DBuf<Group> d_grp; DBuf<Job> d_job; DBuf<ImuDesc> d_imu; DBuf<PriorBlk> d_prior_blk;
   DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
-      d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_dbg;
+      d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
   DBuf<SchurTileH> d_schur;
   DBuf<int> d_pr_m, d_pr_info; DBuf<long long> d_pr_oJ, d_pr_ov;
   int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1;
@@ -252,7 +252,7 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release();
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
-  h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_dbg.release(); h->d_schur.release();
+  h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release();
   h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release();
   d2ba_release_staging(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -768,7 +768,7 @@ int d2ba_finalize(d2ba_handle *h) {
   if ((rc = alloc_zero(h, h->d_Wt, (size_t)offW))) return rc;   // padding rows / columns must be zero
   CK(h->d_dinv.alloc(offlm)); CK(h->d_hl.alloc(offlm)); CK(h->d_gl.alloc(offlm)); CK(h->d_S.alloc((size_t)offH));
   CK(h->d_gred.alloc((size_t)offc)); CK(h->d_D2c.alloc((size_t)offc)); CK(h->d_gn_c.alloc((size_t)offc)); CK(h->d_gn_l.alloc(offlm));
-  CK(h->d_step_c.alloc((size_t)offc)); CK(h->d_step_l.alloc(offlm)); CK(h->d_wu.alloc(offlm));
+  CK(h->d_step_c.alloc((size_t)offc)); CK(h->d_step_l.alloc(offlm)); CK(h->d_wu.alloc(offlm)); CK(h->d_uc.alloc((size_t)offc)); CK(h->d_D2l.alloc(offlm));
   // ---- device view
   Dev &D = h->dev;
   memset(&D, 0, sizeof D);
@@ -780,7 +780,7 @@ int d2ba_finalize(d2ba_handle *h) {
   D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
   D.lm_ref = h->d_lm_ref.p; D.sb_ref = h->d_sb_ref.p; D.td_ref = h->d_td_ref.p; D.cons_buf = h->d_cons.p; D.n_slots = h->n_slots;
   D.Wt = h->d_Wt.p; D.dinv = h->d_dinv.p; D.hl = h->d_hl.p; D.gl = h->d_gl.p; D.S = h->d_S.p; D.gred = h->d_gred.p; D.D2c = h->d_D2c.p;
-  D.gn_c = h->d_gn_c.p; D.gn_l = h->d_gn_l.p; D.step_c = h->d_step_c.p; D.step_l = h->d_step_l.p; D.wu = h->d_wu.p;
+  D.gn_c = h->d_gn_c.p; D.gn_l = h->d_gn_l.p; D.step_c = h->d_step_c.p; D.step_l = h->d_step_l.p; D.wu = h->d_wu.p; D.uc = h->d_uc.p; D.D2l = h->d_D2l.p;
   SolverParams &P = D.prm;
   P.sqrt_info_px = h->cfg.focal_length / 1.5; P.depth_sqrt_inf = h->cfg.depth_sqrt_inf; P.gravity = h->cfg.gravity_norm; P.huber = h->cfg.huber_delta;
   P.rho_T = h->cfg.rho_frame_T; P.rho_theta = h->cfg.rho_frame_theta; P.rho_landmark = h->cfg.rho_landmark; P.relaxation_alpha = h->cfg.relaxation_alpha;

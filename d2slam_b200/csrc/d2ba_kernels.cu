@@ -195,6 +195,7 @@ D2BA_DEV void prior_dx_pose(const double *x, const double *x0, double *dx) {  //
 // One CTA per window: zero Hcc/gc of the evaluated buffer, then add IMU, prior and ADMM terms.
 // Runs before k_proj_lin (which adds the reprojection blocks with atomics).
 constexpr int kMiscThreads = 256;
+constexpr int kMiscImuChunk = 12;
 __global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) 
   __syncthreads();
   double cost = 0.0;
   // ---- IMU factors, processed in chunks of kImuChunk to bound shared memory
-  constexpr int kImuChunk = 4;
+  constexpr int kImuChunk = kMiscImuChunk;
   constexpr int kF = 15 * 30 + 15;  // doubles per factor for (J, r)
   for (int f0 = 0; f0 < w.n_imu; f0 += kImuChunk) {
     int nf = min(kImuChunk, w.n_imu - f0);
@@ -680,12 +681,20 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
     h += rl * rl;
     g += rl * rl * (d.xlm[buf][w.offlm + l] - d.lm_ref[w.offlm + l]);
   }
-  const double hp = h + ctl->mu * d2_of(h);
+  const double dl2 = d2_of(h);
+  const double hp = h + ctl->mu * dl2;
   const double di = 1.0 / sqrt(hp);
   double *Wt = d.Wt + w.offW + (size_t)l * w.ldw;
-  for (int c = lane; c < w.ldw; c += 32) Wt[c] = (c < nlc) ? row[c] * di : (c == nlc ? g * di : 0.0);
+  const double *uc = d.uc + w.offc;
+  double wu = 0;
+  for (int c = lane; c < w.ldw; c += 32) {
+    double rv = (c < nlc) ? row[c] : 0.0;
+    Wt[c] = (c < nlc) ? rv * di : (c == nlc ? g * di : 0.0);
+    if (c < nlc) wu += rv * uc[c];
+  }
+  wu = warp_sum(wu);
   if (lane == 0) {
-    d.hl[w.offlm + l] = h; d.gl[w.offlm + l] = g; d.dinv[w.offlm + l] = di;
+    d.hl[w.offlm + l] = h; d.gl[w.offlm + l] = g; d.dinv[w.offlm + l] = di; d.wu[w.offlm + l] = wu; d.D2l[w.offlm + l] = dl2;
     if (!(hp > 0.0)) ctl->chol_fail = 1;
     atomicMax(&ctl->gmax_l_bits, (unsigned long long)__double_as_longlong(fabs(g)));
   }
@@ -709,6 +718,11 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
   const double *gcv = d.gc[buf] + w.offc;
   double *S = d.S + w.offH;
   const int tid = threadIdx.x;
+  const double *ucv = d.uc + w.offc;
+  const double *D2v = d.D2c + w.offc;
+  __shared__ double As[kSyrkK * kSyrkLd], Bs[kSyrkK * kSyrkLd];
+  __shared__ double redq[40];
+  double uhu = 0.0;   // this tile's share of u^T Hcc u (lower elements, off-diagonal counted twice)
   if (t.kind == 1) {
     // plain copy region: S[i][j] = H[i][j] + mu D^2 (i == j) for i in [nlc, n), j <= i; rhs row j in [nlc, n)
     const int i0 = t.tm * 32, j0 = t.tn * 32;
@@ -716,14 +730,16 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
       int i = i0 + e / 32, j = j0 + e % 32;
       if (i < n && j <= i && i >= nlc) {
         double v = H[(size_t)i * ld + j];
-        if (i == j) v += mu * d2_of(v);
+        uhu += (i == j ? 1.0 : 2.0) * v * ucv[i] * ucv[j];
+        if (i == j) v += mu * D2v[i];
         S[(size_t)i * ld + j] = v;
       }
       if (i == n && j < n && j >= nlc) S[(size_t)n * ld + j] = gcv[j];
     }
+    uhu = block_sum(uhu, redq);
+    if (tid == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
     return;
   }
-  __shared__ double As[kSyrkK * kSyrkLd], Bs[kSyrkK * kSyrkLd];
   const int warp = tid >> 5, lane = tid & 31;
   const int m0 = t.tm * 32, n0 = t.tn * 32;   // W-space offsets (0..nlc inclusive is valid)
   const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
@@ -761,12 +777,15 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
         double v = acc[a][b][e];
         if (m < nlc && c <= m) {
           double hv = H[(size_t)m * ld + c];
-          if (m == c) hv += mu * d2_of(hv);
+          uhu += (m == c ? 1.0 : 2.0) * hv * ucv[m] * ucv[c];
+          if (m == c) hv += mu * D2v[m];
           S[(size_t)m * ld + c] = hv - v;
         } else if (m == nlc && c < nlc) {
           S[(size_t)n * ld + c] = gcv[c] - v;
         }
       }
+  uhu = block_sum(uhu, redq);
+  if (tid == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -777,7 +796,7 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
 // Per 32-column panel: (a) warp 0 factors the 32x32 diagonal block in shared memory (one row per lane),
 // (b) every remaining row is solved against it by its own thread (TRSM, registers), (c) the trailing
 // matrix is updated with 4x4 register tiles.  Only two block barriers per panel phase.
-constexpr int kCholThreads = 512;
+constexpr int kCholThreads = 256;
 constexpr int kNB = 32;
 __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
   const int wi = blockIdx.x;
@@ -812,20 +831,30 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
       if (r >= nr) Dg[r * (kNB + 1) + c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
-    // (a) diagonal block: lane = row
+    // (a) diagonal block: lane = row, the row lives in registers; column c is broadcast with shuffles
     if (warp == 0) {
-      for (int c = 0; c < nb; c++) {
-        const double dcc = Dg[c * (kNB + 1) + c];
-        if (!(dcc > 0.0) || !isfinite(dcc)) fail = 1;
-        const double inv = 1.0 / sqrt(dcc > 0.0 ? dcc : 1.0);
-        double lrc = 0.0;
-        if (lane > c) { lrc = Dg[lane * (kNB + 1) + c] * inv; Dg[lane * (kNB + 1) + c] = lrc; }
-        if (lane == c) { Dg[c * (kNB + 1) + c] = dcc * inv; invd[k0 + c] = inv; }
-        __syncwarp();
-        const int c2max = min(lane, nb - 1);
-        for (int c2 = c + 1; c2 <= c2max; c2++) Dg[lane * (kNB + 1) + c2] -= lrc * Dg[c2 * (kNB + 1) + c];
-        __syncwarp();
+      double row[kNB];
+#pragma unroll
+      for (int c = 0; c < kNB; c++) row[c] = Dg[lane * (kNB + 1) + c];
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < kNB; c++) {
+        const double dcc = __shfl_sync(0xffffffffu, row[c], c);
+        const bool live = c < nb;
+        if (live && (!(dcc > 0.0) || !isfinite(dcc))) bad = true;
+        const double inv = (live && dcc > 0.0) ? rsqrt(dcc) : 1.0;
+        const double lrc = (lane > c) ? row[c] * inv : 0.0;
+        if (lane > c) row[c] = lrc;
+        if (lane == c) { row[c] = live ? dcc * inv : row[c]; if (live) invd[k0 + c] = inv; }
+#pragma unroll
+        for (int c2 = c + 1; c2 < kNB; c2++) {
+          const double l2 = __shfl_sync(0xffffffffu, lrc, c2);   // L[c2][c]
+          if (live && c2 <= lane && c2 < nb) row[c2] -= lrc * l2;
+        }
       }
+      if (bad) fail = 1;
+#pragma unroll
+      for (int c = 0; c < kNB; c++) Dg[lane * (kNB + 1) + c] = row[c];
     }
     __syncthreads();
     // (b) rows below the diagonal block: x L_d^T = a, one row per thread
@@ -858,9 +887,13 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
     const int t0 = nb;                  // panel-local first trailing row
     const int ntr = nr - t0;            // trailing rows (incl. rhs row)
     const int nt4 = (ntr + 3) / 4;
-    for (int tile = tid; tile < nt4 * nt4; tile += nt) {
-      int ti = tile / nt4, tj = tile % nt4;
-      if (tj > ti) continue;
+    const int ntri = nt4 * (nt4 + 1) / 2;
+    for (int tile = tid; tile < ntri; tile += nt) {
+      // triangular index -> (ti, tj), tj <= ti
+      int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+      while (ti * (ti + 1) / 2 > tile) ti--;
+      int tj = tile - ti * (ti + 1) / 2;
       int ri = t0 + ti * 4, rj = t0 + tj * 4;
       double a[4][4] = {};
       for (int c = 0; c < nb; c++) {
@@ -890,10 +923,10 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
   for (int b = nblk - 1; b >= 0; b--) {
     const int k0 = b * kNB, nb = min(kNB, n - k0);
     // partial sums over already solved x_k, k >= k0+nb: 16 slices x 32 columns
-    const int col = tid & 31, slice = tid >> 5;  // 16 slices
+    const int col = tid & 31, slice = tid >> 5, nslice = nt >> 5;
     double s = 0;
     if (col < nb)
-      for (int k = k0 + nb + slice; k < n; k += 16) s += S[(size_t)k * ld + k0 + col] * xs[k];
+      for (int k = k0 + nb + slice; k < n; k += nslice) s += S[(size_t)k * ld + k0 + col] * xs[k];
     redb[slice * 32 + col] = s;
     for (int e = tid; e < kNB * kNB; e += nt) {
       int i = e / kNB, j = e % kNB;
@@ -902,8 +935,7 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
     __syncthreads();
     if (tid < 32) {
       double acc = 0;
-#pragma unroll
-      for (int q = 0; q < 16; q++) acc += redb[q * 32 + tid];
+      for (int q = 0; q < (nt >> 5); q++) acc += redb[q * 32 + tid];
       double rhs = (tid < nb) ? y[k0 + tid] - acc : 0.0;
       const double myinv = (tid < nb) ? invd[k0 + tid] : 1.0;
       // x_i = (rhs_i - sum_{j>i} L[j][i] x_j) / L[i][i], lanes hold the running right-hand sides
@@ -942,50 +974,38 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
   const double *hl = d.hl + w.offlm, *glv = d.gl + w.offlm, *dinv = d.dinv + w.offlm;
   double *gn_c = d.gn_c + w.offc, *gn_l = d.gn_l + w.offlm;
   const SolverParams &P = d.prm;
-  for (int i = tid; i < n; i += nt) { double dd = d2_of(H[(size_t)i * ld + i]); D2[i] = dd; uc[i] = gcv[i] / dd; dcs[i] = gn_c[i]; }
+  const double *D2g = d.D2c + w.offc, *ucg = d.uc + w.offc, *D2l = d.D2l + w.offlm, *wuv = d.wu + w.offlm;
+  for (int i = tid; i < n; i += nt) { D2[i] = D2g[i]; uc[i] = ucg[i]; dcs[i] = gn_c[i]; }
   __syncthreads();
   if (!ctl->reuse) {
     // gradient tolerance (checked at the top of a trust-region iteration, on a fresh linearisation)
-    double gm = 0;
-    for (int i = tid; i < n; i += nt) gm = fmax(gm, fabs(gcv[i]));
-    gm = block_max(gm, red);
-    double gml = __longlong_as_double((long long)ctl->gmax_l_bits);
-    gm = fmax(gm, gml);
-    if (tid == 0) { ctl->gmax_c = gm; }
+    double gm = fmax(ctl->gmax_c, __longlong_as_double((long long)ctl->gmax_l_bits));
     if (!P.fixed_mode && gm <= P.gtol) { if (tid == 0) { ctl->done = 1; ctl->term = 2; } return; }
     if (ctl->chol_fail) { if (tid == 0) ctl->step_valid = 0; return; }
-    // landmark back-substitution and Cauchy dot products
+    // landmark back-substitution and the landmark part of the Cauchy / dogleg dot products
     const double *Wt = d.Wt + w.offW;
     double s_gg = 0, s_uHu = 0, s_nn = 0, s_gdn = 0;
     for (int l = warp; l < nl; l += nw) {
       const double *row = Wt + (size_t)l * w.ldw;
-      double a = 0, b = 0;
-      for (int c = lane; c < nlc; c += 32) { double wv = row[c]; a += wv * dcs[c]; b += wv * uc[c]; }
-      a = warp_sum(a); b = warp_sum(b);
+      double a = 0;
+      for (int c = lane; c < nlc; c += 32) a += row[c] * dcs[c];
+      a = warp_sum(a);
       if (lane == 0) {
         double di = dinv[l], gt = row[nlc];
         double gnl = -di * (gt + a);
         gn_l[l] = gnl;
-        double h = hl[l], g = glv[l], dl2 = d2_of(h), ul = g / dl2, wu = b / di;
+        double h = hl[l], g = glv[l], dl2 = D2l[l], ul = g / dl2;
         s_gg += g * ul;
-        s_uHu += 2.0 * ul * wu + h * ul * ul;
+        s_uHu += 2.0 * ul * wuv[l] + h * ul * ul;
         s_nn += gnl * gnl * dl2;
         s_gdn += g * gnl;
       }
     }
-    // camera part: u^T Hcc u via column-parallel mat-vec (H symmetric)
-    for (int j = tid; j < n; j += nt) {
-      double s = 0;
-      for (int i = 0; i < n; i++) s += H[(size_t)i * ld + j] * uc[i];
-      s_uHu += uc[j] * s;
-      s_gg += gcv[j] * uc[j];
-      s_nn += dcs[j] * dcs[j] * D2[j];
-      s_gdn += gcv[j] * dcs[j];
-    }
+    for (int j = tid; j < n; j += nt) { s_nn += dcs[j] * dcs[j] * D2[j]; s_gdn += gcv[j] * dcs[j]; }
     s_gg = block_sum(s_gg, red); s_uHu = block_sum(s_uHu, red); s_nn = block_sum(s_nn, red); s_gdn = block_sum(s_gdn, red);
     if (tid == 0) {
+      s_gg += ctl->gg_cam; s_uHu += ctl->uHu_cam;
       ctl->gg = s_gg; ctl->nn = s_nn; ctl->gdn = s_gdn; ctl->alpha = s_gg / s_uHu;
-      // successful linear solve: mu relaxes (dogleg_strategy.cc ComputeGaussNewtonStep)
     }
     __syncthreads();
   }
@@ -1048,8 +1068,8 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
   const double *xlm = d.xlm[cur] + w.offlm;
   double *ylm = d.xlm[cand] + w.offlm;
   for (int l = tid; l < nl; l += nt) {
-    double g = glv[l], h = hl[l];
-    double s = -c1 * g / d2_of(h) + c2 * gn_l[l];
+    double g = glv[l];
+    double s = -c1 * g / D2l[l] + c2 * gn_l[l];
     step_l[l] = s;
     double x = xlm[l];
     ylm[l] = x + s;
@@ -1063,14 +1083,13 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Trust-region bookkeeping, one thread per window (TrustRegionMinimizer / DoglegStrategy)
-__global__ void k_control(Dev d, int init) {
-  const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wi >= d.n_win) return;
-  Ctl *c = d.ctl + wi;
-  const SolverParams &P = d.prm;
+// Trust-region bookkeeping (TrustRegionMinimizer / DoglegStrategy): one small CTA per
+// window.  Thread 0 takes the accept / reject decision; when the window then holds a fresh accepted
+// linearisation all threads derive the vectors every later kernel of the next iteration needs:
+// D_c^2 = clamp(diag Hcc), u_c = g_c / D_c^2, and the camera part of |g~|^2 and of the gradient max-norm.
+constexpr int kCtlThreads = 128;
+__device__ void control_decide(Ctl *c, const SolverParams &P, int init) {
   if (init) {
-    // the evaluated buffer is the accepted point
     c->cost = c->cand_cost_misc + c->cand_cost_proj;
     if (init == 1) c->initial_cost = c->cost;
     c->reuse = 0; c->chol_fail = 0; c->step_valid = 1; c->gmax_l_bits = 0ull;
@@ -1108,6 +1127,28 @@ __global__ void k_control(Dev d, int init) {
     if (c->radius < 1e-32) { c->done = 1; c->term = 4; }
   }
   if (!c->done && c->iter >= P.max_iter) { c->done = 1; c->term = 0; }
+}
+
+__global__ void __launch_bounds__(kCtlThreads) k_control(Dev d, int init) {
+  const int wi = blockIdx.x;
+  Ctl *c = d.ctl + wi;
+  __shared__ double red[40];
+  if (threadIdx.x == 0) control_decide(c, d.prm, init);
+  __syncthreads();
+  if (c->done || c->reuse) return;
+  // fresh accepted linearisation in buffer `cur`
+  const WinDesc &w = d.win[wi];
+  const int n = w.n_c, ld = w.ldh, cur = c->cur;
+  const double *H = d.Hcc[cur] + w.offH, *g = d.gc[cur] + w.offc;
+  double *D2 = d.D2c + w.offc, *uc = d.uc + w.offc;
+  double gg = 0, gm = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double dd = d2_of(H[(size_t)i * ld + i]), gi = g[i], u = gi / dd;
+    D2[i] = dd; uc[i] = u; gg += gi * u; gm = fmax(gm, fabs(gi));
+  }
+  gg = block_sum(gg, red);
+  gm = block_max(gm, red);
+  if (threadIdx.x == 0) { c->gg_cam = gg; c->gmax_c = gm; c->uHu_cam = 0.0; }
 }
 
 // reset the per-sub-step trust-region state (a fresh ceres::Solve)
@@ -1225,7 +1266,7 @@ void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s) {
 void launch_prior_prep(const Dev &d, cudaStream_t s) { k_prior_prep<<<d.n_win, 256, 0, s>>>(d); }
 
 size_t misc_smem_bytes(int max_prior_m) {
-  size_t imu = (size_t)(40 + 2 * 4 * (15 * 30 + 15)) * 8;
+  size_t imu = (size_t)(40 + 2 * kMiscImuChunk * (15 * 30 + 15)) * 8;
   size_t pri = (size_t)(40 + 3 * max_prior_m + 8) * 8;
   return imu > pri ? imu : pri;
 }
@@ -1277,7 +1318,7 @@ void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
 void launch_step(const Dev &d, int max_nc, cudaStream_t s) {
   k_step<<<d.n_win, kStepThreads, (size_t)(40 + 3 * max_nc) * 8, s>>>(d, max_nc);
 }
-void launch_control(const Dev &d, int init, cudaStream_t s) { k_control<<<(d.n_win + 127) / 128, 128, 0, s>>>(d, init); }
+void launch_control(const Dev &d, int init, cudaStream_t s) { k_control<<<d.n_win, kCtlThreads, 0, s>>>(d, init); }
 void launch_tr_reset(const Dev &d, int first, cudaStream_t s) { k_tr_reset<<<(d.n_win + 127) / 128, 128, 0, s>>>(d, first); }
 void launch_cons_init(const Dev &d, int n6_total, cudaStream_t s) { if (n6_total > 0) k_cons_init<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total); }
 void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s) { if (n6_total > 0) k_cons_pack<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total, blk_win); }

@@ -81,6 +81,7 @@ struct Ctl {
   double gg, nn, gdn, alpha, step_norm;
   double x_norm2, dx_norm2;
   double gmax_c, gmax_l;
+  double uHu_cam, gg_cam;   // camera-part partial sums of the Cauchy quadratic form
   double initial_cost;
   unsigned long long gmax_l_bits;
 };
@@ -145,6 +146,8 @@ struct Dev {
   double *gn_c, *gn_l;  // Gauss-Newton step
   double *step_c, *step_l;
   double *wu;           // [NL] w_l . u_c
+  double *uc;           // n_c : g_c / D_c^2 of the accepted linearisation
+  double *D2l;          // [NL] landmark trust-region metric
   SolverParams prm;
 };
 
