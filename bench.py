@@ -218,6 +218,7 @@ def run_ours(args, rank, world, local_rank):
     rp.run(solver, 2, iters, host_threads)
     barrier()
     e2e_wall, _ = rp.run(solver, e2e_steps, iters, host_threads)
+    e2e_breakdown = {k: round(v / e2e_steps * 1e3, 3) for k, v in rp.breakdown.items()}
     barrier()
     te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -261,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
                    "wall_ms_per_step": wall_max * 1e3 / args.steps, "bytes_iter_per_window": int(bi)},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": h2d_bytes(probs), "d2h_bytes_per_step": d2h_bytes(probs),
-                "steps": e2e_steps, "host_threads": host_threads, "note": "C-ABI sequence per step: d2ba_reset + set_blocks/add_proj/add_imu/set_prior_info (host buffers) + d2ba_finalize (sort, tile, pinned H2D) + d2ba_solve_fixed + d2ba_get_blocks (D2H), driven by the C++ harness"},
+                "steps": e2e_steps, "host_threads": host_threads, "ms_per_step_breakdown": e2e_breakdown, "note": "C-ABI sequence per step: d2ba_reset + set_blocks/add_proj/add_imu/set_prior_info (host buffers) + d2ba_finalize (sort, tile, pinned H2D) + d2ba_solve_fixed + d2ba_get_blocks (D2H), driven by the C++ harness"},
         "roofline": {"bound": "hbm", "kernel": "k_proj_lin<2,2>", "achieved": proj_gbs, "peak": peak, "unit": "GB/s", "frac": proj_gbs / peak,
                      "traffic": traffic, "peak_source": peak_src, "dominant_kernel_by_time": dom,
                      "algorithmic_bytes_per_launch": int(B * proj_bytes), "kernel_ms_per_iteration": kt,

@@ -31,7 +31,7 @@ struct HWin {
 };
 }  // namespace
 
-struct rp_ctx { std::vector<HWin> win; };
+struct rp_ctx { std::vector<HWin> win; double t_feed = 0, t_finalize = 0, t_solve = 0, t_fetch = 0; };
 
 extern "C" {
 
@@ -83,15 +83,22 @@ double rp_run(rp_ctx *c, d2ba_handle *h, int steps, int iters, int nthreads, d2b
   if (nthreads > nw) nthreads = nw;
   std::vector<d2ba_report> reps(nw);
   auto t0 = std::chrono::steady_clock::now();
+  c->t_feed = c->t_finalize = c->t_solve = c->t_fetch = 0;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   for (int s = 0; s < steps; s++) {
+    auto ta = now();
     if (d2ba_reset(h)) return -2;
     std::atomic<int> next(0), err(0);
     auto work = [&]() { for (;;) { int w = next.fetch_add(1); if (w >= nw) break; int rc = feed_window(h, w, c->win[w]); if (rc) err = rc; } };
     if (nthreads == 1) work();
     else { std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(work); for (auto &t : th) t.join(); }
     if (err) return -100 - err;
+    auto tb = now();
     if (d2ba_finalize(h)) return -3;
+    auto tc = now();
     if (d2ba_solve_fixed(h, iters, reps.data())) return -4;
+    auto td = now();
     std::atomic<int> nx2(0);
     auto fetch = [&]() {
       for (;;) {
@@ -104,11 +111,15 @@ double rp_run(rp_ctx *c, d2ba_handle *h, int steps, int iters, int nthreads, d2b
     };
     if (nthreads == 1) fetch();
     else { std::vector<std::thread> th; for (int t = 0; t < nthreads; t++) th.emplace_back(fetch); for (auto &t : th) t.join(); }
+    auto te = now();
+    c->t_feed += secs(ta, tb); c->t_finalize += secs(tb, tc); c->t_solve += secs(tc, td); c->t_fetch += secs(td, te);
   }
   auto t1 = std::chrono::steady_clock::now();
   if (last_reports) memcpy(last_reports, reps.data(), sizeof(d2ba_report) * nw);
   return std::chrono::duration<double>(t1 - t0).count();
 }
+
+void rp_breakdown(rp_ctx *c, double out[4]) { out[0] = c->t_feed; out[1] = c->t_finalize; out[2] = c->t_solve; out[3] = c->t_fetch; }
 
 int rp_get_outputs(rp_ctx *c, int w, double *pose, double *sb, double *lm) {
   if (!c || w < 0 || w >= (int)c->win.size()) return 1;

@@ -33,6 +33,9 @@ void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_w
 void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s);
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s);
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s);
+size_t chol_smem_need(int n);
+int configure_chol_smem(int max_n);
+void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s);
 void launch_step(const Dev &d, int max_nc, cudaStream_t s);
 void launch_control(const Dev &d, int init, cudaStream_t s);
 void launch_tr_reset(const Dev &d, int first, cudaStream_t s);
@@ -41,6 +44,7 @@ void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream
 void launch_cons_apply(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
 void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_win, const int *lm_win, cudaStream_t s);
 struct SchurTileH { int win, kind, tm, tn; };
+void launch_build_tiles(const void *raw, const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s);
 void launch_prior_from_info(int n_win, int max_m, const int *m_of, const long long *offJ, const long long *offv, const int *is_info,
                             double *A, double *V, double *b, cudaStream_t s);
 }  // namespace d2ba
@@ -49,18 +53,64 @@ using namespace d2ba;
 
 namespace {
 
-struct HObs { int type, pi, pj, ea, eb, lm; double f[kObsFields]; int64_t seq; };
+// open-addressing id -> index map (no per-node allocation; capacity survives clear())
+struct FlatMap {
+  std::vector<int64_t> keys; std::vector<int> vals; size_t n = 0;
+  static uint64_t mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
+  void clear() { std::fill(vals.begin(), vals.end(), -1); n = 0; }
+  int find(int64_t k) const {
+    if (vals.empty()) return -1;
+    size_t m = vals.size() - 1, i = mix((uint64_t)k) & m;
+    while (vals[i] >= 0) { if (keys[i] == k) return vals[i]; i = (i + 1) & m; }
+    return -1;
+  }
+  void grow() {
+    std::vector<int64_t> ok; std::vector<int> ov; ok.swap(keys); ov.swap(vals);
+    size_t cap = ov.empty() ? 64 : ov.size() * 2;
+    keys.assign(cap, 0); vals.assign(cap, -1); n = 0;
+    for (size_t i = 0; i < ov.size(); i++) if (ov[i] >= 0) put(ok[i], ov[i]);
+  }
+  void put(int64_t k, int v) {
+    if ((n + 1) * 2 > vals.size()) grow();
+    size_t m = vals.size() - 1, i = mix((uint64_t)k) & m;
+    while (vals[i] >= 0) { if (keys[i] == k) { vals[i] = v; return; } i = (i + 1) & m; }
+    keys[i] = k; vals[i] = v; n++;
+  }
+};
+
+struct HObs { int type, pi, pj, ea, eb, lm; };   // index form of one residual block (the constants stay in the raw record)
+
+// Per-window pinned buffer of the caller's raw observation records (uploaded as is; the tiled layout and the
+// tangent bases are built on the device by k_build_tiles).  Capacity survives d2ba_reset.
+struct RawObs {
+  d2ba_proj_obs *p = nullptr; size_t cap = 0, n = 0;
+  bool append(const d2ba_proj_obs *src, size_t cnt) {
+    if (n + cnt > cap) {
+      size_t want = std::max<size_t>((n + cnt) * 3 / 2 + 64, 1024);
+      d2ba_proj_obs *q = nullptr;
+      if (cudaHostAlloc((void **)&q, want * sizeof(d2ba_proj_obs), cudaHostAllocDefault) != cudaSuccess) return false;
+      if (n) memcpy(q, p, n * sizeof(d2ba_proj_obs));
+      if (p) cudaFreeHost(p);
+      p = q; cap = want;
+    }
+    memcpy(p + n, src, cnt * sizeof(d2ba_proj_obs));
+    n += cnt;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
+};
 struct HImu { int pi, si, pj, sj; double c[kImuStride]; };
 struct HPriorBlk { int kind, index, off, eff; double x0[9]; };
 
 struct HostWin {
   bool used = false;
   std::vector<int64_t> pose_id, ext_id, sb_id, lm_id;
-  std::unordered_map<int64_t, int> pose_map, ext_map, sb_map, lm_map;
+  FlatMap pose_map, ext_map, sb_map, lm_map;
   std::vector<double> pose, ext, sb, lm;
   std::vector<uint8_t> pose_c, ext_c, sb_c;
   double td = 0; bool has_td = false; uint8_t td_c = 1;
   std::vector<HObs> obs;
+  RawObs raw;
   std::vector<HImu> imu;
   int prior_m = 0; std::vector<double> prior_J, prior_e0; std::vector<HPriorBlk> prior_blk; bool prior_is_info = false;
   std::vector<int> pose_slot, ext_slot; bool admm = false; int n_slots = 0;
@@ -68,7 +118,18 @@ struct HostWin {
   std::vector<int> pose_col, ext_col, sb_col; int td_col = -1, n_lc = 0, n_c = 0;
   std::vector<int> order;            // pair-major order: sorted index -> observation index
   std::vector<int> sorted_pos;       // tile slot (window-local) of the k-th sorted observation
-  void clear() { *this = HostWin(); }
+  void clear() {   // keeps every allocation (the estimator re-adds a similar problem for the next solve)
+    used = false;
+    pose_id.clear(); ext_id.clear(); sb_id.clear(); lm_id.clear();
+    pose_map.clear(); ext_map.clear(); sb_map.clear(); lm_map.clear();
+    pose.clear(); ext.clear(); sb.clear(); lm.clear(); pose_c.clear(); ext_c.clear(); sb_c.clear();
+    td = 0; has_td = false; td_c = 1;
+    obs.clear(); raw.n = 0; imu.clear();
+    prior_m = 0; prior_J.clear(); prior_e0.clear(); prior_blk.clear(); prior_is_info = false;
+    pose_slot.clear(); ext_slot.clear(); admm = false; n_slots = 0;
+    pose_col.clear(); ext_col.clear(); sb_col.clear(); td_col = -1; n_lc = 0; n_c = 0;
+    order.clear(); sorted_pos.clear();
+  }
 };
 
 // ---- minimal NCCL surface resolved with dlopen (torch ships libnccl.so.2; no link-time dependency)
@@ -129,7 +190,7 @@ struct d2ba_handle {
   DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
   DBuf<SchurTileH> d_schur;
-  DBuf<int> d_pr_m, d_pr_info; DBuf<long long> d_pr_oJ, d_pr_ov;
+  DBuf<int> d_pr_m, d_pr_info, d_tile_src; DBuf<long long> d_pr_oJ, d_pr_ov, d_raw_off; DBuf<d2ba_proj_obs> d_raw;
   int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1;
   Dev dev;
   std::vector<WinDesc> h_win;
@@ -139,6 +200,7 @@ struct d2ba_handle {
   int n_used = 0, n6_total = 0, nsb_total = 0, nl_total = 0, n_tiles = 0, n_imu_total = 0, n_schur = 0;
   int job_begin[4] = {0, 0, 0, 0}, job_count[4] = {0, 0, 0, 0};
   int max_rows = 1, max_nc = 1, max_prior_m = 0, max_ldw = 8, n_slots = 0;
+  int max_n_smem = 0, max_rows_glob = 1; bool any_chol_glob = false; int cfg_max_n_smem = -1;
   int64_t totH = 0, totW = 0, totc = 0;
   bool any_admm = false;
   // host mirrors of the solved state
@@ -161,20 +223,7 @@ HostWin *get_win(d2ba_handle *h, int w) {
   return &h->win[w];
 }
 
-void tangent_base(const double *pts_j, double *tb) {
-  // ProjectionTwoFrameOneCamFactor ctor (projectionTwoFrameOneCamFactor.cpp:34-45)
-  double n = sqrt(pts_j[0] * pts_j[0] + pts_j[1] * pts_j[1] + pts_j[2] * pts_j[2]);
-  double a[3] = {pts_j[0] / n, pts_j[1] / n, pts_j[2] / n}, t[3] = {0, 0, 1};
-  if (a[0] == t[0] && a[1] == t[1] && a[2] == t[2]) { t[0] = 1; t[2] = 0; }
-  double dt = a[0] * t[0] + a[1] * t[1] + a[2] * t[2];
-  double b1[3] = {t[0] - a[0] * dt, t[1] - a[1] * dt, t[2] - a[2] * dt};
-  double n1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
-  for (int k = 0; k < 3; k++) b1[k] /= n1;
-  tb[0] = b1[0]; tb[1] = b1[1]; tb[2] = b1[2];
-  tb[3] = a[1] * b1[2] - a[2] * b1[1]; tb[4] = a[2] * b1[0] - a[0] * b1[2]; tb[5] = a[0] * b1[1] - a[1] * b1[0];
-}
-
-int find_in(const std::unordered_map<int64_t, int> &m, int64_t id) { auto it = m.find(id); return it == m.end() ? -1 : it->second; }
+int find_in(const FlatMap &m, int64_t id) { return m.find(id); }
 
 int kind_size(int k) { return (k == D2BA_POSE || k == D2BA_EXTRINSIC) ? 7 : (k == D2BA_SPEED_BIAS ? 9 : 1); }
 int kind_eff(int k) { return (k == D2BA_POSE || k == D2BA_EXTRINSIC) ? 6 : (k == D2BA_SPEED_BIAS ? 9 : 1); }
@@ -253,7 +302,8 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
   h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release();
-  h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release();
+  h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release(); h->d_tile_src.release(); h->d_raw_off.release(); h->d_raw.release();
+  for (auto &w : h->win) w.raw.release();
   d2ba_release_staging(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -282,19 +332,19 @@ int d2ba_set_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, con
     switch (kind) {
       case D2BA_POSE: {
         int k = find_in(w->pose_map, ids[i]);
-        if (k < 0) { k = (int)w->pose_id.size(); w->pose_id.push_back(ids[i]); w->pose_map[ids[i]] = k; w->pose.resize(7 * (k + 1)); w->pose_c.push_back(c); w->pose_slot.push_back(-1); structural = true; }
+        if (k < 0) { k = (int)w->pose_id.size(); w->pose_id.push_back(ids[i]); w->pose_map.put(ids[i], k); w->pose.resize(7 * (k + 1)); w->pose_c.push_back(c); w->pose_slot.push_back(-1); structural = true; }
         else if (w->pose_c[k] != c) structural = true;
         memcpy(&w->pose[7 * k], values + 7 * i, 56); w->pose_c[k] = c; break;
       }
       case D2BA_EXTRINSIC: {
         int k = find_in(w->ext_map, ids[i]);
-        if (k < 0) { k = (int)w->ext_id.size(); w->ext_id.push_back(ids[i]); w->ext_map[ids[i]] = k; w->ext.resize(7 * (k + 1)); w->ext_c.push_back(c); w->ext_slot.push_back(-1); structural = true; }
+        if (k < 0) { k = (int)w->ext_id.size(); w->ext_id.push_back(ids[i]); w->ext_map.put(ids[i], k); w->ext.resize(7 * (k + 1)); w->ext_c.push_back(c); w->ext_slot.push_back(-1); structural = true; }
         else if (w->ext_c[k] != c) structural = true;
         memcpy(&w->ext[7 * k], values + 7 * i, 56); w->ext_c[k] = c; break;
       }
       case D2BA_SPEED_BIAS: {
         int k = find_in(w->sb_map, ids[i]);
-        if (k < 0) { k = (int)w->sb_id.size(); w->sb_id.push_back(ids[i]); w->sb_map[ids[i]] = k; w->sb.resize(9 * (k + 1)); w->sb_c.push_back(c); structural = true; }
+        if (k < 0) { k = (int)w->sb_id.size(); w->sb_id.push_back(ids[i]); w->sb_map.put(ids[i], k); w->sb.resize(9 * (k + 1)); w->sb_c.push_back(c); structural = true; }
         else if (w->sb_c[k] != c) structural = true;
         memcpy(&w->sb[9 * k], values + 9 * i, 72); w->sb_c[k] = c; break;
       }
@@ -303,7 +353,7 @@ int d2ba_set_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, con
         w->td = values[i]; w->td_c = c; w->has_td = true; break;
       case D2BA_LANDMARK: {
         int k = find_in(w->lm_map, ids[i]);
-        if (k < 0) { k = (int)w->lm_id.size(); w->lm_id.push_back(ids[i]); w->lm_map[ids[i]] = k; w->lm.push_back(0); structural = true; }
+        if (k < 0) { k = (int)w->lm_id.size(); w->lm_id.push_back(ids[i]); w->lm_map.put(ids[i], k); w->lm.push_back(0); structural = true; }
         w->lm[k] = values[i]; break;
       }
       default: return fail(h, 2, "unknown block kind");
@@ -317,38 +367,37 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   HostWin *w = get_win(h, window);
   if (!w) return 1;
   w->used = true; h->finalized = false;
-  w->obs.reserve(w->obs.size() + n);
+  if (n <= 0) return 0;
+  const size_t base = w->obs.size();
+  w->obs.resize(base + n);
   // one-entry lookup caches: consecutive residuals of a track share landmark, anchor frame and cameras
   struct Cache { int64_t id = INT64_MIN; int idx = -1; } c_lm, c_fa, c_fb, c_ca, c_cb;
-  auto cached = [](Cache &c, const std::unordered_map<int64_t, int> &m, int64_t id) {
+  auto cached = [](Cache &c, const FlatMap &m, int64_t id) {
     if (c.id != id) { c.id = id; c.idx = find_in(m, id); }
     return c.idx;
   };
   for (int i = 0; i < n; i++) {
     const d2ba_proj_obs &p = in[i];
-    HObs o; memset(&o, 0, sizeof o);
+    HObs o;
     o.type = p.type; o.pi = o.pj = o.ea = o.eb = -1;
     o.lm = cached(c_lm, w->lm_map, p.landmark_id);
-    if (o.lm < 0) return fail(h, 3, "add_proj: unknown landmark id");
-    if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
+    const char *err = nullptr;
+    if (o.lm < 0) err = "add_proj: unknown landmark id";
+    else if (p.type < 0 || p.type > D2BA_PROJ_DEPTH_PRIOR) err = "add_proj: unknown residual type";
+    else if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
       // block lists: ParamResidualInfo.hpp:34-43 (2F1C), :72-82 (2F2C), :107-115 (1F2C)
       o.ea = cached(c_ca, w->ext_map, p.cam_a);
-      if (o.ea < 0) return fail(h, 4, "add_proj: unknown camera id");
-      if (p.type == D2BA_PROJ_2F2C || p.type == D2BA_PROJ_1F2C) { o.eb = cached(c_cb, w->ext_map, p.cam_b); if (o.eb < 0) return fail(h, 4, "add_proj: unknown camera id (b)"); }
-      if (p.type != D2BA_PROJ_1F2C) {
+      if (o.ea < 0) err = "add_proj: unknown camera id";
+      if (!err && (p.type == D2BA_PROJ_2F2C || p.type == D2BA_PROJ_1F2C)) { o.eb = cached(c_cb, w->ext_map, p.cam_b); if (o.eb < 0) err = "add_proj: unknown camera id (b)"; }
+      if (!err && p.type != D2BA_PROJ_1F2C) {
         o.pi = cached(c_fa, w->pose_map, p.frame_a); o.pj = cached(c_fb, w->pose_map, p.frame_b);
-        if (o.pi < 0 || o.pj < 0) return fail(h, 5, "add_proj: unknown frame id");
+        if (o.pi < 0 || o.pj < 0) err = "add_proj: unknown frame id";
       }
-      memcpy(o.f + 0, p.pts_i, 24); memcpy(o.f + 3, p.pts_j, 24); memcpy(o.f + 6, p.vel_i, 24); memcpy(o.f + 9, p.vel_j, 24);
-      o.f[12] = p.td_i; o.f[13] = p.td_j;
-      tangent_base(p.pts_j, o.f + 14);
-      o.f[20] = (p.type == D2BA_PROJ_2F1C_DEPTH) ? 1.0 / p.depth : 0.0;
-    } else {
-      o.f[20] = 1.0 / p.depth;
     }
-    o.seq = (int64_t)w->obs.size();
-    w->obs.push_back(o);
+    if (err) { w->obs.resize(base); return fail(h, 3, err); }
+    w->obs[base + i] = o;
   }
+  if (!w->raw.append(in, (size_t)n)) { w->obs.resize(base); return fail(h, 11, "add_proj: pinned allocation failed"); }
   return 0;
 }
 
@@ -496,8 +545,9 @@ void parallel_for(int n, F f) {
 }
 
 struct Staging {
-  HBuf<WinDesc> win; HBuf<double> x6, xsb, xlm, xtd, obs, imu_c, prior_J, prior_e0;
-  HBuf<int> col6, colsb, tile_grp, tile_win, obs_lm, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
+  HBuf<WinDesc> win; HBuf<double> x6, xsb, xlm, xtd, imu_c, prior_J, prior_e0;
+  HBuf<int> col6, colsb, tile_grp, tile_win, obs_lm, tile_src, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
+  HBuf<long long> raw_off;
   HBuf<long long> pr_offJ, pr_offv;
   HBuf<Group> grp; HBuf<Job> job; HBuf<ImuDesc> imu; HBuf<PriorBlk> pblk; HBuf<SchurTileH> schur;
 };
@@ -527,7 +577,7 @@ void d2ba_release_staging(d2ba_handle *h) {
   auto it = g_staging.find(h);
   if (it == g_staging.end()) return;
   Staging *s = it->second;
-  s->win.release(); s->x6.release(); s->xsb.release(); s->xlm.release(); s->xtd.release(); s->obs.release(); s->imu_c.release();
+  s->win.release(); s->x6.release(); s->xsb.release(); s->xlm.release(); s->xtd.release(); s->imu_c.release(); s->tile_src.release(); s->raw_off.release();
   s->prior_J.release(); s->prior_e0.release(); s->col6.release(); s->colsb.release(); s->tile_grp.release(); s->tile_win.release();
   s->obs_lm.release(); s->lm_ptr.release(); s->lm_obs.release(); s->slot6.release(); s->lm_win.release(); s->blk_win.release();
   s->sb_win.release(); s->pr_m.release(); s->pr_info.release(); s->pr_offJ.release(); s->pr_offv.release(); s->grp.release();
@@ -572,6 +622,7 @@ int d2ba_finalize(d2ba_handle *h) {
     d.td_col = w.td_col; d.n_lc = w.n_lc; d.n_c = w.n_c; d.ldh = std::max(4, roundup(w.n_c, 4));
     d.ldw = roundup(w.n_lc + 1, 8); d.nl_pad = roundup(nl, 32);
     d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
+    d.chol_smem = (w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 32) ? 1 : 0;
     d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size();
     // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order
     const size_t M = w.obs.size();
@@ -630,8 +681,9 @@ int d2ba_finalize(d2ba_handle *h) {
   });
   // ---- serial prefix sums
   h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
+  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false;
   int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0;
-  int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0;
+  int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0; long long off_raw = 0;
   int njobs[4] = {0, 0, 0, 0};
   bool any_info = false;
   for (int wi = 0; wi < nw; wi++) {
@@ -639,6 +691,7 @@ int d2ba_finalize(d2ba_handle *h) {
     d.off6 = off6; off6 += d.n6; d.offsb = offsb; offsb += d.nsb; d.offlm = offlm; offlm += d.nl;
     d.off_tile = off_tile; off_tile += d.n_tile; d.off_rec = off_rec; off_rec += (int64_t)d.n_tile * kTile * d.rec_stride;
     d.off_grp = off_grp; off_grp += d.n_grp; d.off_imu = off_imu; off_imu += d.n_imu;
+    st.raw_off.resize(nw); st.raw_off.p[wi] = off_raw; off_raw += (long long)w.obs.size();
     d.off_lmptr = off_lmptr; off_lmptr += d.nl + 1; d.off_lmobs = off_lmobs; off_lmobs += pl.n_lmobs;
     d.off_prior_blk = off_pblk; off_pblk += d.prior_nblk; d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
     off_pJ += (int64_t)d.prior_m * d.prior_m; off_pv += d.prior_m;
@@ -649,6 +702,7 @@ int d2ba_finalize(d2ba_handle *h) {
     pl.schur_off = n_schur; n_schur += (int)pl.schur.size();
     h->max_rows = std::max(h->max_rows, d.n_c + 1); h->max_nc = std::max(h->max_nc, d.n_c); h->max_ldw = std::max(h->max_ldw, d.ldw);
     h->max_prior_m = std::max(h->max_prior_m, d.prior_m);
+    if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, d.n_c + 1); }
     if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
     if (w.prior_m > 0 && w.prior_is_info) any_info = true;
   }
@@ -660,7 +714,7 @@ int d2ba_finalize(d2ba_handle *h) {
   bool ok = st.win.resize(nw) && st.x6.resize((size_t)off6 * 8) && st.xsb.resize((size_t)offsb * 9) && st.xlm.resize(offlm) && st.xtd.resize(nw) &&
             st.col6.resize(off6) && st.colsb.resize(offsb) && st.slot6.resize(off6) && st.blk_win.resize(off6) && st.sb_win.resize(offsb) &&
             st.lm_win.resize(offlm) && st.tile_grp.resize(off_tile) && st.tile_win.resize(off_tile) && st.obs_lm.resize((size_t)off_tile * kTile) &&
-            st.obs.resize((size_t)off_tile * kTile * kObsFields) && st.lm_ptr.resize(off_lmptr) && st.lm_obs.resize((size_t)off_lmobs) &&
+            st.tile_src.resize((size_t)off_tile * kTile) && st.raw_off.resize(nw) && st.lm_ptr.resize(off_lmptr) && st.lm_obs.resize((size_t)off_lmobs) &&
             st.grp.resize(off_grp) && st.job.resize(n_jobs) && st.imu.resize(off_imu) && st.imu_c.resize((size_t)off_imu * kImuStride) &&
             st.pblk.resize(off_pblk) && st.prior_J.resize((size_t)off_pJ) && st.prior_e0.resize((size_t)off_pv) && st.schur.resize(n_schur) &&
             st.pr_m.resize(nw) && st.pr_info.resize(nw) && st.pr_offJ.resize(nw) && st.pr_offv.resize(nw);
@@ -683,7 +737,8 @@ int d2ba_finalize(d2ba_handle *h) {
     if (d.nl) memcpy(st.xlm.p + d.offlm, w.lm.data(), (size_t)d.nl * 8);
     for (int i = 0; i < d.nl; i++) st.lm_win.p[d.offlm + i] = wi;
     st.xtd.p[wi] = w.td;
-    // observation tiles (AoSoA [field][lane]) + landmark CSR by counting sort
+    // tile tables: source record of every tile slot (the device builds the AoSoA constants from the raw records)
+    // + landmark CSR by counting sort
     int *lmp = st.lm_ptr.p + d.off_lmptr;
     for (int l = 0; l <= d.nl; l++) lmp[l] = 0;
     for (const HObs &o : w.obs) lmp[o.lm + 1]++;
@@ -696,21 +751,15 @@ int d2ba_finalize(d2ba_handle *h) {
       for (int t = 0; t < ntile; t++) {
         const int gt = d.off_tile + t0 + t;
         st.tile_grp.p[gt] = d.off_grp + gi; st.tile_win.p[gt] = wi;
-        double *ob = st.obs.p + (size_t)gt * kObsFields * kTile;
         int *ol = st.obs_lm.p + (size_t)gt * kTile;
+        int *os = st.tile_src.p + (size_t)gt * kTile;
         for (int lane = 0; lane < kTile; lane++) {
           const int idx = t * kTile + lane;
           if (idx < cnt) {
-            const HObs &o = w.obs[w.order[k0 + idx]];
-            for (int f = 0; f < kObsFields; f++) ob[f * kTile + lane] = o.f[f];
-            ol[lane] = o.lm;
-            const int pos = (t0 + t) * kTile + lane;
-            w.sorted_pos[k0 + idx] = pos;
-          } else {
-            for (int f = 0; f < kObsFields; f++) ob[f * kTile + lane] = 0.0;
-            ob[2 * kTile + lane] = 1.0; ob[5 * kTile + lane] = 1.0; ob[14 * kTile + lane] = 1.0; ob[18 * kTile + lane] = 1.0; ob[20 * kTile + lane] = 1.0;
-            ol[lane] = -1;
-          }
+            const int oi = w.order[k0 + idx];
+            ol[lane] = w.obs[oi].lm; os[lane] = oi;
+            w.sorted_pos[k0 + idx] = (t0 + t) * kTile + lane;
+          } else { ol[lane] = -1; os[lane] = -1; }
         }
       }
     }
@@ -754,13 +803,22 @@ int d2ba_finalize(d2ba_handle *h) {
     CK(h->d_H[b].alloc((size_t)offH)); CK(h->d_gc[b].alloc((size_t)offc));
   }
   if ((rc = up(h, h->d_col6, st.col6)) || (rc = up(h, h->d_colsb, st.colsb)) || (rc = up(h, h->d_tile_grp, st.tile_grp)) ||
-      (rc = up(h, h->d_tile_win, st.tile_win)) || (rc = up(h, h->d_obs_lm, st.obs_lm)) || (rc = up(h, h->d_obs, st.obs)) ||
+      (rc = up(h, h->d_tile_win, st.tile_win)) || (rc = up(h, h->d_obs_lm, st.obs_lm)) || (rc = up(h, h->d_tile_src, st.tile_src)) ||
       (rc = up(h, h->d_lm_ptr, st.lm_ptr)) || (rc = up(h, h->d_lm_obs, st.lm_obs)) || (rc = up(h, h->d_slot6, st.slot6)) ||
       (rc = up(h, h->d_lm_win, st.lm_win)) || (rc = up(h, h->d_blk_win, st.blk_win)) || (rc = up(h, h->d_sb_win, st.sb_win)) ||
       (rc = up(h, h->d_grp, st.grp)) || (rc = up(h, h->d_job, st.job)) || (rc = up(h, h->d_imu, st.imu)) || (rc = up(h, h->d_imu_c, st.imu_c)) ||
       (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
       (rc = up(h, h->d_schur, st.schur)))
     return rc;
+  // raw observation records: one async copy per window from its pinned buffer, then the device builds the tiles
+  CK(h->d_raw.alloc((size_t)off_raw)); CK(h->d_obs.alloc((size_t)off_tile * kTile * kObsFields));
+  if ((rc = up(h, h->d_raw_off, st.raw_off))) return rc;
+  for (int wi = 0; wi < nw; wi++) {
+    HostWin &w = h->win[wi];
+    if (w.raw.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
+    if (w.raw.n) CK(cudaMemcpyAsync(h->d_raw.p + st.raw_off.p[wi], w.raw.p, w.raw.n * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->stream));
+  }
+  launch_build_tiles(h->d_raw.p, h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
   CK(h->d_imu_U.alloc((size_t)off_imu * 225)); CK(h->d_prior_A.alloc((size_t)off_pJ));
   CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
   CK(h->d_td_ref.alloc(nw));
@@ -790,6 +848,10 @@ int d2ba_finalize(d2ba_handle *h) {
   if (h->cfg_max_rows != h->max_rows || h->cfg_max_nc != h->max_nc || h->cfg_max_prior != h->max_prior_m) {
     if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
     h->cfg_max_rows = h->max_rows; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
+  }
+  if (h->max_n_smem > 0 && h->cfg_max_n_smem != h->max_n_smem) {
+    if (configure_chol_smem(h->max_n_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_chol_smem) failed");
+    h->cfg_max_n_smem = h->max_n_smem;
   }
   launch_state_prep(D, h->n6_total, 0, h->stream);
   launch_imu_prep(D, h->n_imu_total, h->stream);
@@ -844,7 +906,8 @@ static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
 static void enqueue_iteration(d2ba_handle *h) {
   launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
-  launch_chol(h->dev, h->max_rows, h->stream);
+  if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
+  if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
   launch_step(h->dev, h->max_nc, h->stream);
   enqueue_linearize(h, 0);
   launch_control(h->dev, 0, h->stream);
@@ -992,7 +1055,8 @@ int d2ba_debug_linearize(d2ba_handle *h) {
   // keep an un-factored copy of S in the debug buffer
   CK(h->d_dbg.alloc((size_t)h->totH));
   CK(cudaMemcpyAsync(h->d_dbg.p, h->d_S.p, (size_t)h->totH * 8, cudaMemcpyDeviceToDevice, h->stream));
-  launch_chol(h->dev, h->max_rows, h->stream);
+  if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
+  if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
   launch_step(h->dev, h->max_nc, h->stream);
   CK(cudaMemcpyAsync(h->h_ctl.data(), h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1095,7 +1159,7 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
   for (int it = 0; it < iters; it++) {
     cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
     cudaEventRecord(ev[1], h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
-    cudaEventRecord(ev[2], h->stream); launch_chol(h->dev, h->max_rows, h->stream);
+    cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
     cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);
     cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream);
     cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 4; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);

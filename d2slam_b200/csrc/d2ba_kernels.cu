@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/d2ba.h"
 #include "d2ba_math.cuh"
 #include "d2ba_proj.cuh"
 #include "d2ba_types.cuh"
@@ -802,6 +803,7 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
   Ctl *ctl = d.ctl + wi;
+  if (w.chol_smem) return;
   if (ctl->done || ctl->reuse) return;
   if (ctl->chol_fail) return;
   extern __shared__ double sm[];
@@ -944,6 +946,161 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
         double v = __shfl_sync(0xffffffffu, rhs * myinv, i);
         if (tid == i) xi = v;
         if (tid < i) rhs -= Dg[i * (kNB + 1) + tid] * v;
+      }
+      if (tid < nb) xs[k0 + tid] = xi;
+    }
+    __syncthreads();
+  }
+  double *gn = d.gn_c + w.offc;
+  for (int i = tid; i < n; i += nt) gn[i] = -xs[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory Cholesky for reduced systems that fit one SM (n_c <= ~165: the single-drone window).
+// The whole bordered matrix lives in shared memory (row-major, even leading dimension); 8-column panels:
+//   (1) 8x8 diagonal block in the registers of 8 lanes (shuffle broadcast),
+//   (2) TRSM of the rows below, one row per thread, 8 values in registers,
+//   (3) trailing update with 4x4 register tiles fed from a transposed copy of the panel.
+// Then blocked back substitution, all from shared memory.
+constexpr int kCsThreads = 512;
+constexpr int kCsNB = 8;
+__host__ __device__ inline int chol_smem_ld(int n) { return (n + 1) & ~1; }
+__host__ __device__ inline size_t chol_smem_bytes(int n) {
+  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)n + (size_t)kCsNB * (n + 1)) * 8;
+}
+__global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  if (!w.chol_smem) return;
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse || ctl->chol_fail) return;
+  extern __shared__ double sm[];
+  const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = n + 1;
+  double *A = sm;                         // n1 x ld
+  double *invd = A + (size_t)n1 * ld;     // n
+  double *P = invd + n;                   // kCsNB x ldp transposed panel; later xs / partial sums
+  const double *S = d.S + w.offH;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int fail;
+  if (tid == 0) fail = 0;
+  // load the lower triangle (+ rhs row)
+  for (int r = warp; r < n1; r += (nt >> 5)) {
+    const double *src = S + (size_t)r * ldg;
+    double *dst = A + (size_t)r * ld;
+    const int lim = min(r, n - 1);
+    for (int c = lane; c <= lim; c += 32) dst[c] = src[c];
+  }
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += kCsNB) {
+    const int nb = min(kCsNB, n - k0);
+    // (1) diagonal block
+    if (warp == 0) {
+      double row[kCsNB];
+      const int r = k0 + lane;
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) row[c] = (lane < nb && c <= lane) ? A[(size_t)r * ld + k0 + c] : (c == lane ? 1.0 : 0.0);
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) {
+        const double dcc = __shfl_sync(0xffffffffu, row[c], c);
+        const bool live = c < nb;
+        if (live && (!(dcc > 0.0) || !isfinite(dcc))) bad = true;
+        const double inv = (live && dcc > 0.0) ? rsqrt(dcc) : 1.0;
+        const double lrc = (lane > c && lane < kCsNB) ? row[c] * inv : 0.0;
+        if (lane > c) row[c] = lrc;
+        if (lane == c) { if (live) { row[c] = dcc * inv; invd[k0 + c] = inv; } }
+#pragma unroll
+        for (int c2 = c + 1; c2 < kCsNB; c2++) {
+          const double l2 = __shfl_sync(0xffffffffu, lrc, c2);
+          if (c2 <= lane) row[c2] -= lrc * l2;
+        }
+      }
+      if (bad) fail = 1;
+      if (lane < nb) {
+#pragma unroll
+        for (int c = 0; c < kCsNB; c++) if (c <= lane) A[(size_t)r * ld + k0 + c] = row[c];
+      }
+    }
+    __syncthreads();
+    // (2) rows below: a L_d^T = x, results also into the transposed panel copy P[c][r - k0]
+    for (int r = k0 + nb + tid; r < n1; r += nt) {
+      double a[kCsNB];
+      double *ar = A + (size_t)r * ld + k0;
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) a[c] = (c < nb) ? ar[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) {
+        double s_ = a[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) s_ -= a[k] * A[(size_t)(k0 + c) * ld + k0 + k];
+        a[c] = (c < nb) ? s_ * invd[k0 + c] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) { if (c < nb) ar[c] = a[c]; P[c * ldp + (r - k0)] = a[c]; }
+    }
+    __syncthreads();
+    // (3) trailing update A[i][j] -= sum_c L[i][c] L[j][c] for i >= j >= k0 + nb
+    {
+      const int t0 = nb, ntr = n1 - k0 - nb, nt4 = (ntr + 3) >> 2, ntri = nt4 * (nt4 + 1) / 2;
+      for (int tile = tid; tile < ntri; tile += nt) {
+        int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+        while (ti * (ti + 1) / 2 > tile) ti--;
+        const int tj = tile - ti * (ti + 1) / 2;
+        const int ri = t0 + ti * 4, rj = t0 + tj * 4;       // panel-local rows
+        double acc[4][4] = {};
+        const bool full = (ri + 3 < n1 - k0) && (rj + 3 < n1 - k0);
+#pragma unroll
+        for (int c = 0; c < kCsNB; c++) {
+          const double *pc = P + c * ldp;
+          double vi[4], vj[4];
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { vi[q] = pc[ri + q]; vj[q] = pc[rj + q]; }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { vi[q] = (ri + q < n1 - k0) ? pc[ri + q] : 0.0; vj[q] = (rj + q < n1 - k0) ? pc[rj + q] : 0.0; }
+          }
+#pragma unroll
+          for (int p_ = 0; p_ < 4; p_++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[p_][q] += vi[p_] * vj[q];
+        }
+#pragma unroll
+        for (int p_ = 0; p_ < 4; p_++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int gi = k0 + ri + p_, gj = k0 + rj + q;
+            if (gi < n1 && gj < n && gj <= gi) A[(size_t)gi * ld + gj] -= acc[p_][q];
+          }
+      }
+    }
+    __syncthreads();
+  }
+  if (fail) { if (tid == 0) ctl->chol_fail = 1; return; }
+  // ---- back substitution L^T x = y (y = row n), 32-column blocks from the end
+  double *xs = P;                 // n
+  double *redb = P + n + 1;       // 16 x 32
+  const double *y = A + (size_t)n * ld;
+  const int nblk = (n + 31) / 32;
+  for (int b = nblk - 1; b >= 0; b--) {
+    const int k0 = b * 32, nb = min(32, n - k0);
+    const int col = tid & 31, slice = tid >> 5, nslice = nt >> 5;
+    double s_ = 0;
+    if (col < nb)
+      for (int k = k0 + nb + slice; k < n; k += nslice) s_ += A[(size_t)k * ld + k0 + col] * xs[k];
+    redb[slice * 32 + col] = s_;
+    __syncthreads();
+    if (tid < 32) {
+      double acc = 0;
+      for (int q = 0; q < nslice; q++) acc += redb[q * 32 + tid];
+      double rhs = (tid < nb) ? y[k0 + tid] - acc : 0.0;
+      const double myinv = (tid < nb) ? invd[k0 + tid] : 1.0;
+      double xi = 0;
+      for (int i = nb - 1; i >= 0; i--) {
+        const double v = __shfl_sync(0xffffffffu, rhs * myinv, i);
+        if (tid == i) xi = v;
+        if (tid < i) rhs -= A[(size_t)(k0 + i) * ld + k0 + tid] * v;
       }
       if (tid < nb) xs[k0 + tid] = xi;
     }
@@ -1256,6 +1413,50 @@ __global__ void k_cons_init(Dev d, int n6_total) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Build the 32-observation AoSoA tiles from the caller's raw records (uploaded untouched): gathers the
+// record of every tile slot (pair-major order), computes the unit-sphere tangent base of the factor
+// constructor (projectionTwoFrameOneCamFactor.cpp:34-45) and writes [field][lane] planes.
+__global__ void __launch_bounds__(128) k_build_tiles(const d2ba_proj_obs *raw, const long long *raw_off, const int *tile_src,
+                                                     const int *tile_win, double *obs, int n_tiles) {
+  const int tile = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const int src = tile_src[(size_t)tile * kTile + lane];
+  double f[kObsFields];
+#pragma unroll
+  for (int k = 0; k < kObsFields; k++) f[k] = 0.0;
+  if (src >= 0) {
+    const d2ba_proj_obs &p = raw[raw_off[tile_win[tile]] + src];
+    if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { f[k] = p.pts_i[k]; f[3 + k] = p.pts_j[k]; f[6 + k] = p.vel_i[k]; f[9 + k] = p.vel_j[k]; }
+      f[12] = p.td_i; f[13] = p.td_j;
+      const double n = sqrt(f[3] * f[3] + f[4] * f[4] + f[5] * f[5]);
+      const double a[3] = {f[3] / n, f[4] / n, f[5] / n};
+      double t[3] = {0, 0, 1};
+      if (a[0] == 0.0 && a[1] == 0.0 && a[2] == 1.0) { t[0] = 1; t[2] = 0; }
+      const double dt = a[0] * t[0] + a[1] * t[1] + a[2] * t[2];
+      double b1[3] = {t[0] - a[0] * dt, t[1] - a[1] * dt, t[2] - a[2] * dt};
+      const double n1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+      b1[0] /= n1; b1[1] /= n1; b1[2] /= n1;
+      f[14] = b1[0]; f[15] = b1[1]; f[16] = b1[2];
+      f[17] = a[1] * b1[2] - a[2] * b1[1]; f[18] = a[2] * b1[0] - a[0] * b1[2]; f[19] = a[0] * b1[1] - a[1] * b1[0];
+      f[20] = (p.type == D2BA_PROJ_2F1C_DEPTH) ? 1.0 / p.depth : 0.0;
+    } else {
+      f[2] = 1.0; f[5] = 1.0; f[14] = 1.0; f[18] = 1.0;
+      f[20] = 1.0 / p.depth;
+    }
+  } else {  // padding slot: harmless constants
+    f[2] = 1.0; f[5] = 1.0; f[14] = 1.0; f[18] = 1.0; f[20] = 1.0;
+  }
+  double *ob = obs + (size_t)tile * kObsFields * kTile;
+#pragma unroll
+  for (int k = 0; k < kObsFields; k++) ob[k * kTile + lane] = f[k];
+}
+void launch_build_tiles(const void *raw, const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s) {
+  if (n_tiles > 0) k_build_tiles<<<(n_tiles + 3) / 4, 128, 0, s>>>(reinterpret_cast<const d2ba_proj_obs *>(raw), raw_off, tile_src, tile_win, obs, n_tiles);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launchers (keeps <<<>>> syntax inside this translation unit)
 void launch_state_prep(const Dev &d, int n6_total, int buf, cudaStream_t s) {
   if (n6_total > 0) k_state_prep<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total, buf);
@@ -1311,6 +1512,11 @@ void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_l
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) {
   if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));
 }
+size_t chol_smem_need(int n) { return chol_smem_bytes(n); }
+int configure_chol_smem(int max_n) {
+  return (int)cudaFuncSetAttribute(k_chol_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(max_n));
+}
+void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) { k_chol_smem<<<d.n_win, kCsThreads, chol_smem_bytes(max_n), s>>>(d); }
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
   size_t sm = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   k_chol<<<d.n_win, kCholThreads, sm, s>>>(d, max_rows);

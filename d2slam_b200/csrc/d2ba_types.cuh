@@ -58,6 +58,7 @@ struct WinDesc {
   int64_t off_prior_J, off_prior_v;
   // consensus
   int admm_on;
+  int chol_smem;               // reduced system fits the shared-memory Cholesky
 };
 
 struct PriorBlk {

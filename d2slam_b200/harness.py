@@ -65,6 +65,9 @@ class Replay:
         t = lib().rp_run(self.ctx, solver.h, C.c_int(steps), C.c_int(iters), C.c_int(nthreads), reps)
         if t < 0:
             raise RuntimeError(f"rp_run failed: {t} ({d2ba_lib().d2ba_last_error(solver.h)})")
+        bd = np.zeros(4)
+        lib().rp_breakdown(self.ctx, abi.ptr(bd))
+        self.breakdown = {"feed_s": bd[0], "finalize_s": bd[1], "solve_s": bd[2], "fetch_s": bd[3]}
         return t, list(reps)
 
     def outputs(self, w, n_pose, n_sb, n_lm):
