@@ -101,6 +101,17 @@ def make_batch(B, seed0, n_frames=11, n_landmarks=300):
     return [synth.make_window(seed=seed0 + i, n_frames=n_frames, n_landmarks=n_landmarks) for i in range(B)]
 
 
+def make_swarm_batch(B, seed0, n_agents, agent):
+    """Agent `agent` of B independent n_agents-drone swarms; swarm i uses the slot range [i*S, (i+1)*S)."""
+    out = []
+    for i in range(B):
+        p = synth.make_swarm(seed=seed0 + i, n_agents=n_agents, only_agents=[agent])[0]
+        refs, slots, S = p["consensus"]
+        p["consensus"] = (refs, (slots + i * S).astype(np.int32), S * B)
+        out.append(p)
+    return out
+
+
 def load_all(solver, probs):
     for i, p in enumerate(probs):
         p.load(solver, i)
@@ -141,26 +152,60 @@ def cpu_sample(probs, iters, nthreads, max_windows):
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores: the restated Ceres-equivalent solver
+    (oracle port; the reference itself needs Eigen/Ceres/ROS which this image lacks), one solver thread per
+    window / swarm like ceres num_threads = 1, all host threads busy."""
     if rank != 0:
         return
+    from oracle import orc
     cores = os.cpu_count() or 1
-    n_win = max(cores, min(args.batch, 4 * cores))
-    probs = make_batch(n_win, 1000)
+    n_agents = max(1, args.gpus)
+    iters = args.iters
+    if n_agents == 1:
+        n_units = max(cores, min(args.batch, 4 * cores))
+        probs = make_batch(n_units, 1000)
+        oras = []
+        for p in probs:
+            o = orc.Oracle(max_num_iterations=iters); p.load(o); oras.append(o)
+        run = lambda: orc.solve_many(oras, cores, fixed_iters=iters)
+        workload = f"W1 single-drone 11-frame/300-landmark windows, {iters} trust-region iterations per solve"
+        sample = f"{n_units} windows x {iters} iterations per step, one solver thread per window on {cores} host threads"
+        n_solves = n_units
+    else:
+        n_units = max(2, min(args.batch, max(2, (2 * cores) // n_agents)))
+        swarms = []
+        for i in range(n_units):
+            sw = synth.make_swarm(seed=1000 + i, n_agents=n_agents)
+            ags = []
+            for p in sw:
+                o = orc.Oracle(max_num_iterations=iters, consensus_max_steps=args.admm_steps); p.load(o); ags.append(o)
+            swarms.append(ags)
+        run = lambda: orc.admm_many(swarms, cores, fixed_mode=True)
+        workload = (f"{n_agents}-drone swarm, 11-frame/300-landmark windows + {(n_agents - 1) * 11} remote poses per agent, "
+                    f"ADMM {args.admm_steps} sub-steps x {max(1, iters // args.admm_steps)} iterations")
+        sample = f"{n_units} swarms x {n_agents} agents x {iters} iterations per step, one solver thread per swarm on {cores} host threads"
+        n_solves = n_units * n_agents
     vals = []
     for s in range(args.warmup + args.steps):
-        v, n, dt = cpu_sample(probs, args.iters, cores, n_win)
+        t = time.perf_counter()
+        reps = run()
+        dt = time.perf_counter() - t
+        its = sum(r.total_iterations for r in reps)
         if s >= args.warmup:
-            vals.append((v, dt))
+            vals.append((its / dt, dt))
+        # restore the initial state so that every step does the same work
+        if n_agents == 1:
+            for o, p in zip(oras, probs):
+                o.set_blocks(abi.POSE, p["frame_ids"], p["poses"], p["pose_const"]); o.set_blocks(abi.SPEED_BIAS, p["sb_ids"], p["sb"], None)
+                o.set_blocks(abi.LANDMARK, p["lm_ids"], p["inv_dep"], None)
     value = float(np.mean([v for v, _ in vals])); ms = float(np.mean([dt for _, dt in vals]) * 1e3)
     line = {
         "impl": "reference", "metric": "BA solver iterations/sec", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"W1 single-drone 11-frame/300-landmark windows, {args.iters} trust-region iterations per solve",
-                   "windows_per_step": n_win, "iters_per_solve": args.iters},
+        "config": {"workload": workload, "solves_per_step": n_solves, "iters_per_solve": iters},
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_win} windows x {args.iters} iterations per step, one solver thread per window on {cores} host threads "
-                                   "(restated Ceres-equivalent DENSE_SCHUR+DOGLEG path; the reference itself cannot be built here)"},
+                         "sample": sample + " (restated Ceres-equivalent DENSE_SCHUR+DOGLEG path; the reference itself cannot be built here)"},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -175,10 +220,23 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, iters = args.batch, args.iters
-    probs = make_batch(B, 1000 + rank * 100000)
-    solver = Solver(max_windows=B, device=local_rank, max_num_iterations=iters)
+    swarm = world > 1
+    if swarm:
+        # configs[2]/[3]: N-drone swarm, one agent per GPU, B swarms batched per GPU, ADMM consensus over NCCL
+        probs = make_swarm_batch(B, 1000, world, rank)
+        solver = Solver(max_windows=B, device=local_rank, max_num_iterations=iters, consensus_max_steps=args.admm_steps)
+    else:
+        probs = make_batch(B, 1000 + rank * 100000)
+        solver = Solver(max_windows=B, device=local_rank, max_num_iterations=iters)
     load_all(solver, probs)
     solver.finalize()
+    if swarm:
+        from d2slam_b200.solver import comm_unique_id
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.tensor(list(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        solver.comm_init(bytes(uid.cpu().tolist()), rank, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,8 +313,10 @@ def run_ours(args, rank, world, local_rank):
         "metric": "BA solver iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"W1 single-drone 11-frame/300-landmark windows (configs[1]); batch of {B} independent windows per GPU, "
-                               f"{iters} trust-region iterations per solve, fixed schedule",
+        "config": {"workload": (f"{world}-drone swarm, 11-frame/300-landmark windows + {(world - 1) * 11} remote poses per agent, one agent per GPU, "
+                                f"{B} swarms batched, ADMM {args.admm_steps} sub-steps x {max(1, iters // args.admm_steps)} iterations, NCCL all-reduce consensus" if swarm else
+                                f"W1 single-drone 11-frame/300-landmark windows (configs[1]); batch of {B} independent windows per GPU, "
+                                f"{iters} trust-region iterations per solve, fixed schedule"),
                    "windows_per_gpu": B, "iters_per_solve": iters, "frames": 11, "landmarks": 300, "residual_blocks": len(probs[0]["obs"]) + 11,
                    "l2_policy": "inputs larger than L2 (batch working set >> 126 MB)" if B >= 128 else "batch smaller than L2",
                    "wall_ms_per_step": wall_max * 1e3 / args.steps, "bytes_iter_per_window": int(bi)},
@@ -284,6 +344,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--cpu-windows", type=int, default=96)
+    ap.add_argument("--admm-steps", type=int, default=4)
     ap.add_argument("--impl", default="ours")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -230,6 +230,8 @@ __global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) 
   for (int f0 = 0; f0 < w.n_imu; f0 += kImuChunk) {
     int nf = min(kImuChunk, w.n_imu - f0);
     double *raw = Jr, *fin = Jr + kImuChunk * kF;
+    double *Us = fin + kImuChunk * kF;
+    int *fcols = reinterpret_cast<int *>(Us + kImuChunk * 225);
     for (int e = tid; e < nf * kF; e += nt) raw[e] = 0.0;
     __syncthreads();
     if (tid < nf) {
@@ -238,10 +240,18 @@ __global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) 
               xsb + im.sj * 9, d.prm.gravity, raw + tid * kF + 450, raw + tid * kF);
     }
     __syncthreads();
+    // stage the sqrt-information matrices and the reduced columns of the factor blocks
+    for (int e = tid; e < nf * 225; e += nt) Us[e] = d.imu_U[(size_t)(w.off_imu + f0) * 225 + e];
+    if (tid < nf * 4) {
+      const ImuDesc &im = d.imu[w.off_imu + f0 + tid / 4];
+      const int q = tid & 3;
+      fcols[tid] = q == 0 ? col6[im.pi] : (q == 1 ? colsb[im.si] : (q == 2 ? col6[im.pj] : colsb[im.sj]));
+    }
+    __syncthreads();
     // J = U Jraw, r = U rraw
     for (int e = tid; e < nf * kF; e += nt) {
       int f = e / kF, k = e % kF;
-      const double *U = d.imu_U + (size_t)(w.off_imu + f0 + f) * 225;
+      const double *U = Us + f * 225;
       const double *src = raw + f * kF;
       double s = 0;
       if (k < 450) {
@@ -257,9 +267,8 @@ __global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) 
     // accumulate: 30x30 + gradient per factor
     for (int e = tid; e < nf * 930; e += nt) {
       int f = e / 930, k = e % 930;
-      const ImuDesc &im = d.imu[w.off_imu + f0 + f];
       const double *Jf = fin + f * kF, *rf = Jf + 450;
-      int cols[4] = {col6[im.pi], colsb[im.si], col6[im.pj], colsb[im.sj]};
+      const int *cols = fcols + f * 4;
       auto gcol = [&](int a) -> int {  // local 0..29 -> reduced column
         int b = a < 6 ? 0 : (a < 15 ? 1 : (a < 21 ? 2 : 3));
         int o = a < 6 ? a : (a < 15 ? a - 6 : (a < 21 ? a - 15 : a - 21));
@@ -966,7 +975,8 @@ constexpr int kCsThreads = 512;
 constexpr int kCsNB = 8;
 __host__ __device__ inline int chol_smem_ld(int n) { return (n + 1) & ~1; }
 __host__ __device__ inline size_t chol_smem_bytes(int n) {
-  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)n + (size_t)kCsNB * (n + 1)) * 8;
+  size_t pr = (size_t)kCsNB * (n + 1), need = (size_t)n + 1 + 16 * 32;
+  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)n + (pr > need ? pr : need)) * 8;
 }
 __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   const int wi = blockIdx.x;
@@ -1142,16 +1152,24 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
     // landmark back-substitution and the landmark part of the Cauchy / dogleg dot products
     const double *Wt = d.Wt + w.offW;
     double s_gg = 0, s_uHu = 0, s_nn = 0, s_gdn = 0;
-    for (int l = warp; l < nl; l += nw) {
-      const double *row = Wt + (size_t)l * w.ldw;
-      double a = 0;
-      for (int c = lane; c < nlc; c += 32) a += row[c] * dcs[c];
-      a = warp_sum(a);
-      if (lane == 0) {
-        double di = dinv[l], gt = row[nlc];
-        double gnl = -di * (gt + a);
+    for (int l0 = warp * 4; l0 < nl; l0 += nw * 4) {
+      double a[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (l0 + q < nl) {
+          const double *row = Wt + (size_t)(l0 + q) * w.ldw;
+          for (int c = lane; c < nlc; c += 32) a[q] += row[c] * dcs[c];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) a[q] = warp_sum(a[q]);
+      if (lane < 4 && l0 + lane < nl) {
+        const int l = l0 + lane;
+        const double aq = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
+        const double di = dinv[l], gt = Wt[(size_t)l * w.ldw + nlc];
+        const double gnl = -di * (gt + aq);
         gn_l[l] = gnl;
-        double h = hl[l], g = glv[l], dl2 = D2l[l], ul = g / dl2;
+        const double h = hl[l], g = glv[l], dl2 = D2l[l], ul = g / dl2;
         s_gg += g * ul;
         s_uHu += 2.0 * ul * wuv[l] + h * ul * ul;
         s_nn += gnl * gnl * dl2;
@@ -1467,7 +1485,7 @@ void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s) {
 void launch_prior_prep(const Dev &d, cudaStream_t s) { k_prior_prep<<<d.n_win, 256, 0, s>>>(d); }
 
 size_t misc_smem_bytes(int max_prior_m) {
-  size_t imu = (size_t)(40 + 2 * kMiscImuChunk * (15 * 30 + 15)) * 8;
+  size_t imu = (size_t)(40 + 2 * kMiscImuChunk * (15 * 30 + 15) + kMiscImuChunk * 225 + 2 * kMiscImuChunk + 8) * 8;
   size_t pri = (size_t)(40 + 3 * max_prior_m + 8) * 8;
   return imu > pri ? imu : pri;
 }

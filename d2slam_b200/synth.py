@@ -272,7 +272,7 @@ def _noisy_bearing(rng, b, sigma):
 def make_swarm(seed=0, n_agents=1, n_frames=11, n_landmarks=300, cams="mono", shared_per_pair=50,
                kf_dt=0.1, imu_rate=200, pix_sigma=1.5, pose_noise=(0.05, np.deg2rad(1.0)),
                estimate_extrinsic=False, estimate_td=False, td_offset=0.0, with_prior=True,
-               fix_first_pose=False, consensus=None, main_id=0, room=10.0):
+               fix_first_pose=False, consensus=None, main_id=0, room=10.0, only_agents=None):
     """Build the per-agent problems of an n_agents swarm (n_agents=1 -> W1 / W1s).
 
     cams: "mono" (TUM cam0), "stereo" (TUM cam0+cam1), "quad" (4 corner cameras).
@@ -280,6 +280,8 @@ def make_swarm(seed=0, n_agents=1, n_frames=11, n_landmarks=300, cams="mono", sh
     observed in all own frames; the first ``shared_per_pair`` landmarks per other agent are also
     observed from all frames of that agent (so each local problem holds (n_agents-1)*n_frames
     remote pose blocks without speed-bias, d2vinsstate.cpp:476-485).
+    only_agents: build the problems of these agents only (every rank of a multi-GPU run needs just its own);
+    the random stream is consumed identically, so agent a's problem does not depend on the selection.
     Returns list[Problem].
     """
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -314,7 +316,11 @@ def make_swarm(seed=0, n_agents=1, n_frames=11, n_landmarks=300, cams="mono", sh
     # initial guesses (shared between agents for remote frames = what the remote agent broadcast)
     dpose = np.concatenate([rng.normal(0, pose_noise[0], (n_agents, F, 3)), rng.normal(0, pose_noise[1], (n_agents, F, 3))], axis=-1)
     pose_init = pose_plus(pose_gt, dpose)
+    agent_rngs = [np.random.Generator(np.random.PCG64([seed, 7919, a])) for a in range(n_agents)]
     for a in range(n_agents):
+        if only_agents is not None and a not in only_agents:
+            continue
+        rng = agent_rngs[a]
         tr = trajs[a]
         Rw = tr.R(t_imu)
         acc_m = np.einsum("tji,tj->ti", Rw, tr.acc(t_imu) + g) + ba_gt[a] + rng.normal(0, 0.05, (len(t_imu), 3))

@@ -186,3 +186,13 @@ def solve_many(oracles, nthreads, fixed_iters=0):
     reps = (abi.Report * n)()
     _chk(lib().orc_solve_many(arr, C.c_int32(n), C.c_int32(nthreads), C.c_int32(fixed_iters), reps), "solve_many")
     return list(reps)
+
+
+def admm_many(swarms, nthreads, fixed_mode=True):
+    """swarms: list of lists of Oracle (one list per swarm, same length)."""
+    ns, na = len(swarms), len(swarms[0])
+    flat = [a.h for sw in swarms for a in sw]
+    arr = (C.c_void_p * len(flat))(*flat)
+    reps = (abi.Report * len(flat))()
+    _chk(lib().orc_admm_many(arr, C.c_int32(ns), C.c_int32(na), C.c_int32(nthreads), C.c_int32(1 if fixed_mode else 0), reps), "admm_many")
+    return list(reps)

@@ -97,6 +97,7 @@ int orc_solve_fixed(orc_handle *o, int32_t iters, d2ba_report *report);
 int orc_admm_solve(orc_handle **agents, int32_t n, int32_t fixed_mode, d2ba_report *reports);
 /* n independent windows on nthreads host threads (1 thread per solve, like ceres num_threads=1) */
 int orc_solve_many(orc_handle **hs, int32_t n, int32_t nthreads, int32_t fixed_iters, d2ba_report *reports);
+int orc_admm_many(orc_handle **hs, int32_t n_swarms, int32_t n_agents, int32_t nthreads, int32_t fixed_mode, d2ba_report *reports);
 int orc_get_blocks(orc_handle *o, int32_t kind, int32_t n, const int64_t *ids, double *out);
 int orc_debug_linearize(orc_handle *o);
 int orc_debug_get(orc_handle *o, int32_t item, void *out, int64_t out_bytes, int64_t *needed);

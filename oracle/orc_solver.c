@@ -897,6 +897,32 @@ int orc_admm_solve(orc_handle **ag, int32_t n, int32_t fixed_mode, d2ba_report *
   return 0;
 }
 
+
+/* many independent swarms on nthreads host threads (each swarm = n_agents handles solved by orc_admm_solve) */
+typedef struct { orc_handle **hs; int n_swarms, n_agents, fixed; d2ba_report *reports; volatile int *next; pthread_mutex_t *mu; } swarm_arg_t;
+static void *swarm_worker(void *p) {
+  swarm_arg_t *a = (swarm_arg_t *)p;
+  for (;;) {
+    pthread_mutex_lock(a->mu);
+    int i = (*a->next)++;
+    pthread_mutex_unlock(a->mu);
+    if (i >= a->n_swarms) break;
+    orc_admm_solve(a->hs + (size_t)i * a->n_agents, a->n_agents, a->fixed, a->reports ? a->reports + (size_t)i * a->n_agents : NULL);
+  }
+  return NULL;
+}
+int orc_admm_many(orc_handle **hs, int32_t n_swarms, int32_t n_agents, int32_t nthreads, int32_t fixed_mode, d2ba_report *reports) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  volatile int next = 0;
+  swarm_arg_t a = {hs, n_swarms, n_agents, fixed_mode, reports, &next, &mu};
+  for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, swarm_worker, &a);
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  return 0;
+}
+
 int orc_get_consensus(orc_handle *o, int32_t n, const d2ba_blockref *refs, double *z7, double *tilde6) {
   for (int i = 0; i < n; i++) {
     int k = find_block(o, refs[i].kind, refs[i].id);

@@ -1,0 +1,22 @@
+"""GPU, >= 2 devices: one agent per GPU, NCCL consensus exchange inside libd2ba vs the oracle's ADMM."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_rank_admm_matches_oracle():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(out.stdout[-2000:]); sys.stderr.write(out.stderr[-2000:])
+    assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout
