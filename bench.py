@@ -302,7 +302,10 @@ def run_ours(args, rank, world, local_rank):
     proj_gbs = B * proj_bytes / (kt["proj_lin"] * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("proj_lin_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("proj_lin_bytes_per_launch")
+        if traffic is not None:
+            traffic = float(traffic) * B / float(tj.get("batch", B))   # captured at another batch size: scale per window
     except Exception:
         pass
     # CPU baseline on rank 0, bounded sample, one thread (ceres_options.num_threads = 1)
