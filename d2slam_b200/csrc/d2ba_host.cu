@@ -32,6 +32,8 @@ void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s);
 void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s);
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s);
+void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s);
+int configure_schur_small(int max_ldw);
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s);
 size_t chol_smem_need(int n);
 int configure_chol_smem(int max_n);
@@ -198,9 +200,10 @@ struct d2ba_handle {
   std::vector<Group> h_grp;
   std::vector<int> h_tile_win;
   int n_used = 0, n6_total = 0, nsb_total = 0, nl_total = 0, n_tiles = 0, n_imu_total = 0, n_schur = 0;
-  int job_begin[4] = {0, 0, 0, 0}, job_count[4] = {0, 0, 0, 0};
+  int job_begin[6] = {0, 0, 0, 0, 0, 0}, job_count[6] = {0, 0, 0, 0, 0, 0};
   int max_rows = 1, max_nc = 1, max_prior_m = 0, max_ldw = 8, n_slots = 0;
   int max_n_smem = 0, max_rows_glob = 1; bool any_chol_glob = false; int cfg_max_n_smem = -1;
+  int max_ldw_small = 0, cfg_max_ldw_small = -1;
   int64_t totH = 0, totW = 0, totc = 0;
   bool any_admm = false;
   // host mirrors of the solved state
@@ -349,7 +352,7 @@ int d2ba_set_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, con
         memcpy(&w->sb[9 * k], values + 9 * i, 72); w->sb_c[k] = c; break;
       }
       case D2BA_TD:
-        if (!w->has_td || w->td_c != c) structural = true;
+        if (!w->has_td || w->td_c != c || w->td != values[i]) structural = true;
         w->td = values[i]; w->td_c = c; w->has_td = true; break;
       case D2BA_LANDMARK: {
         int k = find_in(w->lm_map, ids[i]);
@@ -524,10 +527,10 @@ struct WinPlan {
   WinDesc d;
   std::vector<Group> groups;
   std::vector<int> grp_begin, grp_cnt, grp_tile0;   // sorted-obs range and first (window-local) tile of each group
-  std::vector<Job> jobs[4];                         // tile_begin window-local, grp window-local
+  std::vector<Job> jobs[6];                         // tile_begin window-local, grp window-local
   std::vector<SchurTileH> schur;
   int n_tiles = 0, n_lmobs = 0;
-  int job_off[4] = {0, 0, 0, 0};
+  int job_off[6] = {0, 0, 0, 0, 0, 0};
   int schur_off = 0;
 };
 
@@ -657,7 +660,16 @@ int d2ba_finalize(d2ba_handle *h) {
       g.nct = (ns <= 2 && !g.need_td) ? 2 : 4;
       g.rows = o0.type == D2BA_PROJ_2F1C_DEPTH ? 3 : (o0.type == D2BA_PROJ_DEPTH_PRIOR ? 1 : 2);
       if (g.nct == 4) any_wide = true;
-      const int variant = (g.nct == 4 ? 1 : 0) + (g.rows == 3 ? 2 : 0);
+      int variant = (g.nct == 4 ? 1 : 0) + (g.rows == 3 ? 2 : 0);
+      // all shifts zero? (td constant and equal to every observation's stamp)
+      g.shift0 = 0;
+      if (!g.need_td && o0.type != D2BA_PROJ_DEPTH_PRIOR) {
+        bool z = true;
+        for (size_t q = k; q < e && z; q++) { const d2ba_proj_obs &ro = w.raw.p[w.order[q]]; if (w.td - ro.td_i != 0.0 || w.td - ro.td_j != 0.0) z = false; }
+        g.shift0 = z ? 1 : 0;
+      }
+      if (variant == 0 && !g.need_ext && (o0.type == D2BA_PROJ_2F1C || o0.type == D2BA_PROJ_2F2C) && ns == 2 && g.slot_src[0] == 0 && g.slot_src[1] == 1)
+        variant = g.shift0 ? 4 : 5;
       const int cnt = (int)(e - k), ntile = (cnt + kTile - 1) / kTile;
       const int gi = (int)pl.groups.size();
       pl.groups.push_back(g); pl.grp_begin.push_back((int)k); pl.grp_cnt.push_back(cnt); pl.grp_tile0.push_back(tile_run);
@@ -674,17 +686,20 @@ int d2ba_finalize(d2ba_handle *h) {
     pl.n_tiles = tile_run; d.n_tile = tile_run; d.n_grp = (int)pl.groups.size();
     d.rec_stride = any_wide ? 32 : 16;
     pl.n_lmobs = (int)M;
-    int ntw = (d.n_lc + 1 + 31) / 32;
-    if (d.n_lc > 0) for (int tm = 0; tm < ntw; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 0, tm, tn});
-    int t_lo = d.n_lc / 32, t_hi = d.n_c / 32;
-    for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 1, tm, tn});
+    d.schur_small = (d.n_lc + 1 <= 96) ? 1 : 0;
+    if (!d.schur_small) {
+      int ntw = (d.n_lc + 1 + 31) / 32;
+      if (d.n_lc > 0) for (int tm = 0; tm < ntw; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 0, tm, tn});
+      int t_lo = d.n_lc / 32, t_hi = d.n_c / 32;
+      for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 1, tm, tn});
+    }
   });
   // ---- serial prefix sums
   h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
-  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false;
+  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0;
   int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0;
   int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0; long long off_raw = 0;
-  int njobs[4] = {0, 0, 0, 0};
+  int njobs[6] = {0, 0, 0, 0, 0, 0};
   bool any_info = false;
   for (int wi = 0; wi < nw; wi++) {
     HostWin &w = h->win[wi]; WinPlan &pl = plan[wi]; WinDesc &d = pl.d;
@@ -698,16 +713,17 @@ int d2ba_finalize(d2ba_handle *h) {
     d.offH = offH; offH += (int64_t)(d.n_c + 1) * d.ldh;
     d.offW = offW; offW += (int64_t)std::max(d.nl_pad, 32) * d.ldw;
     d.offc = offc; offc += roundup(d.n_c + 1, 4);
-    for (int v = 0; v < 4; v++) { pl.job_off[v] = njobs[v]; njobs[v] += (int)pl.jobs[v].size(); }
+    for (int v = 0; v < 6; v++) { pl.job_off[v] = njobs[v]; njobs[v] += (int)pl.jobs[v].size(); }
     pl.schur_off = n_schur; n_schur += (int)pl.schur.size();
     h->max_rows = std::max(h->max_rows, d.n_c + 1); h->max_nc = std::max(h->max_nc, d.n_c); h->max_ldw = std::max(h->max_ldw, d.ldw);
     h->max_prior_m = std::max(h->max_prior_m, d.prior_m);
+    if (d.schur_small) h->max_ldw_small = std::max(h->max_ldw_small, d.ldw);
     if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, d.n_c + 1); }
     if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
     if (w.prior_m > 0 && w.prior_is_info) any_info = true;
   }
-  int jbase[4]; { int r = 0; for (int v = 0; v < 4; v++) { jbase[v] = r; h->job_begin[v] = r; h->job_count[v] = njobs[v]; r += njobs[v]; } }
-  const int n_jobs = jbase[3] + njobs[3];
+  int jbase[6]; { int r = 0; for (int v = 0; v < 6; v++) { jbase[v] = r; h->job_begin[v] = r; h->job_count[v] = njobs[v]; r += njobs[v]; } }
+  const int n_jobs = jbase[5] + njobs[5];
   h->n6_total = off6; h->nsb_total = offsb; h->nl_total = offlm; h->n_tiles = off_tile; h->n_imu_total = off_imu; h->n_schur = n_schur;
   h->totH = offH; h->totW = offW; h->totc = offc;
   // ---- staging sizes
@@ -765,7 +781,7 @@ int d2ba_finalize(d2ba_handle *h) {
     }
     // CSR entries in ascending position order (deterministic reduction order): positions increase with sorted index
     for (size_t k = 0; k < w.order.size(); k++) { const HObs &o = w.obs[w.order[k]]; lmo[cursor[o.lm]++] = w.sorted_pos[k]; }
-    for (int v = 0; v < 4; v++)
+    for (int v = 0; v < 6; v++)
       for (size_t j = 0; j < pl.jobs[v].size(); j++) {
         Job jb = pl.jobs[v][j]; jb.grp += d.off_grp; jb.tile_begin += d.off_tile;
         st.job.p[jbase[v] + pl.job_off[v] + j] = jb;
@@ -849,6 +865,10 @@ int d2ba_finalize(d2ba_handle *h) {
     if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
     h->cfg_max_rows = h->max_rows; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
   }
+  if (h->max_ldw_small > 0 && h->cfg_max_ldw_small != h->max_ldw_small) {
+    if (configure_schur_small(h->max_ldw_small)) return fail(h, 23, "cudaFuncSetAttribute(k_schur_small) failed");
+    h->cfg_max_ldw_small = h->max_ldw_small;
+  }
   if (h->max_n_smem > 0 && h->cfg_max_n_smem != h->max_n_smem) {
     if (configure_chol_smem(h->max_n_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_chol_smem) failed");
     h->cfg_max_n_smem = h->max_n_smem;
@@ -900,11 +920,12 @@ static int upload_state(d2ba_handle *h) {
 
 static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
   launch_misc_lin(h->dev, eval_cur, h->max_prior_m, h->stream);
-  for (int v = 0; v < 4; v++) launch_proj_lin(h->dev, v, eval_cur, h->job_begin[v], h->job_count[v], h->stream);
+  for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, eval_cur, h->job_begin[v], h->job_count[v], h->stream);
 }
 
 static void enqueue_iteration(d2ba_handle *h) {
   launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+  if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
   if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
   if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
@@ -1051,6 +1072,7 @@ int d2ba_debug_linearize(d2ba_handle *h) {
   enqueue_linearize(h, 1);
   launch_control(h->dev, 1, h->stream);
   launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+  if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
   // keep an un-factored copy of S in the debug buffer
   CK(h->d_dbg.alloc((size_t)h->totH));
@@ -1158,11 +1180,11 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
   for (int i = 0; i < 8; i++) ms_out[i] = 0;
   for (int it = 0; it < iters; it++) {
     cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
-    cudaEventRecord(ev[1], h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+    cudaEventRecord(ev[1], h->stream); if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
     cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
     cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);
     cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream);
-    cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 4; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);
+    cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);
     cudaEventRecord(ev[6], h->stream); launch_control(h->dev, 0, h->stream);
     cudaEventRecord(ev[7], h->stream);
     CK(cudaStreamSynchronize(h->stream));

@@ -197,7 +197,7 @@ D2BA_DEV void prior_dx_pose(const double *x, const double *x0, double *dx) {  //
 // Runs before k_proj_lin (which adds the reprojection blocks with atomics).
 constexpr int kMiscThreads = 256;
 constexpr int kMiscImuChunk = 12;
-__global__ void __launch_bounds__(kMiscThreads) k_misc_lin(Dev d, int eval_cur) {
+__global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cur) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
   Ctl *ctl = d.ctl + wi;
@@ -489,7 +489,11 @@ __global__ void __launch_bounds__(128) k_proj_lin(Dev d, int eval_cur, int job_b
     if (valid) {
       cost += o.cost;
       reinterpret_cast<double2 *>(rec)[0] = make_double2(hl, gl);
-      reinterpret_cast<double2 *>(rec)[1] = make_double2(wtd, 0.0);
+      // rec[3] (and rec[28..29] of wide records) carry the reduced-system columns of the slots, so the
+      // per-landmark gather needs no group lookup
+      reinterpret_cast<double2 *>(rec)[1] = make_double2(wtd, __hiloint2double(g.slot_col[0], g.slot_col[1]));
+      if (NS > 2) reinterpret_cast<double2 *>(rec)[14] = make_double2(__hiloint2double(g.slot_col[2], g.slot_col[3]), __hiloint2double(g.td_col, -1));
+      else if (w.rec_stride == 32) reinterpret_cast<double2 *>(rec)[14] = make_double2(__hiloint2double(-1, -1), __hiloint2double(-1, -1));
     }
     // ---- slots -> staging tile + coupling vector
 #pragma unroll
@@ -595,6 +599,158 @@ template __global__ void k_proj_lin<4, 2>(Dev, int, int, int);
 template __global__ void k_proj_lin<2, 4>(Dev, int, int, int);
 template __global__ void k_proj_lin<4, 4>(Dev, int, int, int);
 
+// ------------------------------------------------------------------------------------------------
+// Fast path of the fused reprojection linearisation for the dominant case: a two-frame factor (2F1C / 2F2C)
+// whose two poses are free and whose extrinsics / td are constant (NCT = 2, KR = 2, slots = {pose_i, pose_j}).
+// Same arithmetic as proj_eval<2,false,false>, but the Jacobian rows are emitted straight into the staging tile
+// and the landmark record, which keeps the live state small enough for 3 CTAs / SM.
+template <bool SHIFT0>
+__global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int job_begin, int job_count) {
+  constexpr int NCOL = 16, LDJ = kTile * 2 + 4, RCOL = 12;
+  constexpr int kWarpDoubles = GC_SIZE + NCOL * LDJ;
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ji = blockIdx.x * 4 + warp;
+  if (ji >= job_count) return;
+  const Job jb = d.job[job_begin + ji];
+  const WinDesc &w = d.win[jb.win];
+  Ctl *ctl = d.ctl + jb.win;
+  if (ctl->done || (!eval_cur && !ctl->step_valid)) return;
+  const int buf = eval_cur ? ctl->cur : 1 - ctl->cur;
+  const Group &g = d.grp[jb.grp];
+  double *gc = sm + warp * kWarpDoubles;
+  double *Js = gc + GC_SIZE;
+  {
+    const double *x6 = d.x6[buf] + (size_t)w.off6 * 8;
+    const double *R6 = d.R6[buf] + (size_t)w.off6 * 12;
+    const int bi = g.blk[0], bj = g.blk[1], ba = g.blk[2], bb = g.blk[3];
+    build_group_consts(g.type, R6 + bi * 12, x6 + bi * 8, R6 + bj * 12, x6 + bj * 8, R6 + ba * 12, x6 + ba * 8,
+                       bb >= 0 ? R6 + bb * 12 : nullptr, bb >= 0 ? x6 + bb * 8 : nullptr, gc);
+  }
+  const double td = d.xtd[buf][jb.win];
+  const double *xlm = d.xlm[buf] + w.offlm;
+  const double s_px = d.prm.sqrt_info_px, huber = d.prm.huber;
+  double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  double cost = 0.0;
+  for (int c = RCOL + 1; c < NCOL; c++) *reinterpret_cast<double2 *>(Js + c * LDJ + lane * 2) = make_double2(0.0, 0.0);
+  const int kq = lane & 3, cr = lane >> 2;
+  for (int t = 0; t < jb.ntiles; t++) {
+    const int tile = jb.tile_begin + t;
+    const double *ob = d.obs + (size_t)tile * kObsFields * kTile + lane;
+    const int lm = d.obs_lm[(size_t)tile * kTile + lane];
+    const bool valid = lm >= 0;
+    const double lam = valid ? xlm[lm] : 1.0;
+    double pi[3] = {ob[0 * kTile], ob[1 * kTile], ob[2 * kTile]};
+    double pj[3] = {ob[3 * kTile], ob[4 * kTile], ob[5 * kTile]};
+    if (!SHIFT0) {
+      const double dti = td - ob[12 * kTile], dtj = td - ob[13 * kTile];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { pi[k] -= dti * ob[(6 + k) * kTile]; pj[k] -= dtj * ob[(9 + k) * kTile]; }
+    }
+    double B[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) B[k] = ob[(14 + k) * kTile];
+    const double il = 1.0 / lam;
+    const double Pci[3] = {pi[0] * il, pi[1] * il, pi[2] * il};
+    double Pmi[3], Pmj[3], Pcj[3], tt[3];
+    mv3(gc + GC_RA, Pci, Pmi);
+    Pmi[0] += gc[GC_TA]; Pmi[1] += gc[GC_TA + 1]; Pmi[2] += gc[GC_TA + 2];
+    mv3(gc + GC_RJI, Pmi, Pmj);
+    Pmj[0] += gc[GC_TJI]; Pmj[1] += gc[GC_TJI + 1]; Pmj[2] += gc[GC_TJI + 2];
+    tt[0] = Pmj[0] - gc[GC_TB]; tt[1] = Pmj[1] - gc[GC_TB + 1]; tt[2] = Pmj[2] - gc[GC_TB + 2];
+    mtv3(gc + GC_RB, tt, Pcj);
+    const double in = rsqrt(dot3(Pcj, Pcj)), inj = rsqrt(dot3(pj, pj));
+    const double ph[3] = {Pcj[0] * in, Pcj[1] * in, Pcj[2] * in};
+    const double e[3] = {ph[0] - pj[0] * inj, ph[1] - pj[1] * inj, ph[2] - pj[2] * inj};
+    double r0 = s_px * dot3(B, e), r1 = s_px * dot3(B + 3, e);
+    const double ss = r0 * r0 + r1 * r1;
+    double sc = 1.0, oc = 0.5 * ss;
+    if (huber > 0 && ss > huber * huber) { const double rs = sqrt(ss); oc = 0.5 * (2.0 * huber * rs - huber * huber); sc = sqrt(huber / rs); }
+    r0 *= sc; r1 *= sc;
+    double red[2][3];
+    {
+      const double b0 = dot3(B, ph), b1 = dot3(B + 3, ph), sn = sc * s_px * in;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { red[0][k] = sn * (B[k] - b0 * ph[k]); red[1][k] = sn * (B[3 + k] - b1 * ph[k]); }
+    }
+    double jl[2], Ji[2][6], Jj[2][6];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      double A[3], Bm[3], Cr[3], Dc[3], c[3];
+      rm3(red[q], gc + GC_JC, Dc);
+      jl[q] = -il * dot3(Dc, Pci);
+      rm3(red[q], gc + GC_JW, A);
+      rm3(red[q], gc + GC_JM, Bm);
+      Cr[0] = red[q][0] * gc[GC_RB + 0] + red[q][1] * gc[GC_RB + 1] + red[q][2] * gc[GC_RB + 2];
+      Cr[1] = red[q][0] * gc[GC_RB + 3] + red[q][1] * gc[GC_RB + 4] + red[q][2] * gc[GC_RB + 5];
+      Cr[2] = red[q][0] * gc[GC_RB + 6] + red[q][1] * gc[GC_RB + 7] + red[q][2] * gc[GC_RB + 8];
+      cross3(Bm, Pmi, c);
+      Ji[q][0] = A[0]; Ji[q][1] = A[1]; Ji[q][2] = A[2]; Ji[q][3] = -c[0]; Ji[q][4] = -c[1]; Ji[q][5] = -c[2];
+      cross3(Cr, Pmj, c);
+      Jj[q][0] = -A[0]; Jj[q][1] = -A[1]; Jj[q][2] = -A[2]; Jj[q][3] = c[0]; Jj[q][4] = c[1]; Jj[q][5] = c[2];
+    }
+    if (!valid) {
+      r0 = 0; r1 = 0; jl[0] = 0; jl[1] = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { Ji[0][k] = 0; Ji[1][k] = 0; Jj[0][k] = 0; Jj[1][k] = 0; }
+    } else cost += oc;
+    // staging tile + landmark record
+    double *rec = d.rec[buf] + (size_t)w.off_rec + ((size_t)(tile - w.off_tile) * kTile + lane) * w.rec_stride;
+    double wi[6], wj[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      *reinterpret_cast<double2 *>(Js + k * LDJ + lane * 2) = make_double2(Ji[0][k], Ji[1][k]);
+      *reinterpret_cast<double2 *>(Js + (6 + k) * LDJ + lane * 2) = make_double2(Jj[0][k], Jj[1][k]);
+      wi[k] = Ji[0][k] * jl[0] + Ji[1][k] * jl[1];
+      wj[k] = Jj[0][k] * jl[0] + Jj[1][k] * jl[1];
+    }
+    *reinterpret_cast<double2 *>(Js + RCOL * LDJ + lane * 2) = make_double2(r0, r1);
+    if (valid) {
+      double2 *r2 = reinterpret_cast<double2 *>(rec);
+      r2[0] = make_double2(jl[0] * jl[0] + jl[1] * jl[1], jl[0] * r0 + jl[1] * r1);
+      r2[1] = make_double2(0.0, __hiloint2double(g.slot_col[0], g.slot_col[1]));
+      r2[2] = make_double2(wi[0], wi[1]); r2[3] = make_double2(wi[2], wi[3]); r2[4] = make_double2(wi[4], wi[5]);
+      r2[5] = make_double2(wj[0], wj[1]); r2[6] = make_double2(wj[2], wj[3]); r2[7] = make_double2(wj[4], wj[5]);
+      if (w.rec_stride == 32) r2[14] = make_double2(__hiloint2double(-1, -1), __hiloint2double(-1, -1));
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int st = 0; st < kTile * 2 / 4; st++) {
+      const double v0 = Js[cr * LDJ + st * 4 + kq], v1 = Js[(8 + cr) * LDJ + st * 4 + kq];
+      dmma(acc[0][0], acc[0][1], v0, v0);
+      dmma(acc[1][0], acc[1][1], v0, v1);
+      dmma(acc[2][0], acc[2][1], v1, v1);
+    }
+    __syncwarp();
+  }
+  cost = warp_sum(cost);
+  if (lane == 0) atomicAdd(&ctl->cand_cost_proj, cost);
+  double *H = d.Hcc[buf] + w.offH;
+  double *gv = d.gc[buf] + w.offc;
+  const int ld = w.ldh, ci = g.slot_col[0], cj = g.slot_col[1];
+  auto l2g = [&](int m) -> int { return m < 6 ? ci + m : (m < 12 ? cj + m - 6 : -1); };
+  const int row = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int cm = p == 2 ? 1 : 0, cn = p == 0 ? 0 : 1;
+    const int m = cm * 8 + row, gm = l2g(m);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int n = cn * 8 + c0 + e;
+      const double v = acc[p][e];
+      if (gm >= 0) {
+        if (n == RCOL) atomicAdd(&gv[gm], v);
+        else {
+          const int gn = l2g(n);
+          if (gn >= 0) { atomicAdd(&H[(size_t)gm * ld + gn], v); if (cm != cn) atomicAdd(&H[(size_t)gn * ld + gm], v); }
+        }
+      }
+    }
+  }
+}
+template __global__ void k_proj_lin_pp<true>(Dev, int, int, int);
+template __global__ void k_proj_lin_pp<false>(Dev, int, int, int);
+
 // debug: raw (un-robustified) residual + full 3x26 Jacobian per observation tile slot
 __global__ void k_proj_debug(Dev d, double *out /*[tiles*32][81]*/, int n_tiles_total, const int *tile_win) {
   const int tile = blockIdx.x;
@@ -671,18 +827,34 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   const int stride = w.rec_stride;
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
   double h = 0, g = 0;
-  for (int k = ptr[l]; k < ptr[l + 1]; k++) {
-    const int pos = lo[k];  // window-local sorted observation position
-    const Group &gr = d.grp[d.tile_grp[w.off_tile + pos / kTile]];
-    const double *rec = recs + (size_t)pos * stride;
-    double v = lane < stride ? rec[lane] : 0.0;
-    if (lane == 0) h += v;
-    if (lane == 1) g += v;
-    int col = -1;
-    if (lane == 2) col = gr.td_col;
-    else if (lane >= 4 && lane < 28) { int s = (lane - 4) / 6; if (lane < 4 + (stride == 16 ? 12 : 24)) { int sc = gr.slot_col[s]; if (gr.slot_src[s] >= 0 && sc >= 0) col = sc + (lane - 4) % 6; } }
-    if (col >= 0) row[col] += v;
-    __syncwarp();
+  const int kb = ptr[l], ke = ptr[l + 1];
+  for (int k0 = kb; k0 < ke; k0 += 32) {
+    const int cnt = min(32, ke - k0);
+    const int mypos = (lane < cnt) ? lo[k0 + lane] : 0;     // coalesced read of the position list
+    for (int q = 0; q < cnt; q += 2) {
+      // two records in flight
+      const int p0 = __shfl_sync(0xffffffffu, mypos, q), p1 = __shfl_sync(0xffffffffu, mypos, min(q + 1, cnt - 1));
+      const bool two = q + 1 < cnt;
+      double v0 = lane < stride ? recs[(size_t)p0 * stride + lane] : 0.0;
+      double v1 = (two && lane < stride) ? recs[(size_t)p1 * stride + lane] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const double v = u == 0 ? v0 : v1;
+        if (u == 1 && !two) break;
+        if (lane == 0) h += v;
+        if (lane == 1) g += v;
+        const double c01 = __shfl_sync(0xffffffffu, v, 3);
+        int col = -1;
+        if (lane >= 4 && lane < 16) { int sc = lane < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (lane - 4) % 6; }
+        if (stride == 32) {
+          const double c23 = __shfl_sync(0xffffffffu, v, 28), ctd = __shfl_sync(0xffffffffu, v, 29);
+          if (lane >= 16 && lane < 28) { int sc = lane < 22 ? __double2hiint(c23) : __double2loint(c23); if (sc >= 0) col = sc + (lane - 4) % 6; }
+          if (lane == 2) col = __double2hiint(ctd);
+        }
+        if (col >= 0) row[col] += v;
+        __syncwarp();
+      }
+    }
   }
   h = __shfl_sync(0xffffffffu, h, 0);
   g = __shfl_sync(0xffffffffu, g, 1);
@@ -796,6 +968,90 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
       }
   uhu = block_sum(uhu, redq);
   if (tid == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-CTA-per-window Schur complement for small landmark-coupled parts (n_lc + 1 <= 96, e.g. the 11-pose
+// single-drone window: 67 columns = 9 blocks of 8 -> 45 lower 8x8 blocks instead of 6 padded 32x32 tiles).
+// The Wt chunk is staged once per 32 landmarks and shared by all blocks; each warp owns up to kSsMaxB blocks.
+constexpr int kSsThreads = 256;
+constexpr int kSsMaxB = 10;   // 12*13/2 = 78 lower blocks over 8 warps
+__global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  if (!w.schur_small) return;
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse) return;
+  const int buf = ctl->cur;
+  const int n = w.n_c, nlc = w.n_lc, ld = w.ldh, ldw = w.ldw;
+  const double mu = ctl->mu;
+  const double *H = d.Hcc[buf] + w.offH;
+  const double *gcv = d.gc[buf] + w.offc;
+  const double *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
+  double *S = d.S + w.offH;
+  const double *Wt = d.Wt + w.offW;
+  extern __shared__ double sm[];
+  double *Ws = sm;                       // 32 x ldws
+  double *redq = sm + 32 * (ldw + 4);    // 40
+  const int ldws = ldw + 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kq = lane & 3, cr = lane >> 2;
+  const int nb8 = ldw >> 3, nblk = nb8 * (nb8 + 1) / 2;
+  int bi[kSsMaxB], bj[kSsMaxB];
+  double acc[kSsMaxB][2];
+#pragma unroll
+  for (int q = 0; q < kSsMaxB; q++) {
+    int t = warp + q * 8;
+    int i = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= t) i++;
+    while (i * (i + 1) / 2 > t) i--;
+    bi[q] = i; bj[q] = t - i * (i + 1) / 2;
+    acc[q][0] = 0.0; acc[q][1] = 0.0;
+  }
+  double uhu = 0.0;
+  if (nlc > 0) {
+    for (int k0 = 0; k0 < w.nl_pad; k0 += 32) {
+      for (int e = tid; e < 32 * ldw; e += kSsThreads) { int k = e / ldw, c = e - k * ldw; Ws[k * ldws + c] = Wt[(size_t)(k0 + k) * ldw + c]; }
+      __syncthreads();
+#pragma unroll 2
+      for (int ks = 0; ks < 32; ks += 4) {
+        const double *wr = Ws + (ks + kq) * ldws + cr;
+#pragma unroll
+        for (int q = 0; q < kSsMaxB; q++)
+          if (warp + q * 8 < nblk) dmma(acc[q][0], acc[q][1], wr[bi[q] * 8], wr[bj[q] * 8]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < kSsMaxB; q++) {
+      if (warp + q * 8 >= nblk) continue;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int m = bi[q] * 8 + cr, c = bj[q] * 8 + kq * 2 + e;
+        const double v = acc[q][e];
+        if (m < nlc && c <= m) {
+          double hv = H[(size_t)m * ld + c];
+          uhu += (m == c ? 1.0 : 2.0) * hv * ucv[m] * ucv[c];
+          if (m == c) hv += mu * D2v[m];
+          S[(size_t)m * ld + c] = hv - v;
+        } else if (m == nlc && c < nlc) {
+          S[(size_t)n * ld + c] = gcv[c] - v;
+        }
+      }
+    }
+  }
+  // rows of the speed-bias part (no landmark coupling) and the rest of the rhs row
+  const int nrow = n - nlc;
+  for (int e = tid; e < nrow * n; e += kSsThreads) {
+    const int i = nlc + e / n, j = e % n;
+    if (j > i) continue;
+    double v = H[(size_t)i * ld + j];
+    uhu += (i == j ? 1.0 : 2.0) * v * ucv[i] * ucv[j];
+    if (i == j) v += mu * D2v[i];
+    S[(size_t)i * ld + j] = v;
+  }
+  for (int j = nlc + tid; j < n; j += kSsThreads) S[(size_t)n * ld + j] = gcv[j];
+  uhu = block_sum(uhu, redq);
+  if (tid == 0) atomicAdd(&ctl->uHu_cam, uhu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1502,6 +1758,8 @@ int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   e = cudaFuncSetAttribute(k_proj_lin<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 2>()); if (e) return e;
   e = cudaFuncSetAttribute(k_proj_lin<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 4>()); if (e) return e;
   e = cudaFuncSetAttribute(k_proj_lin<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 4>()); if (e) return e;
+  e = cudaFuncSetAttribute(k_proj_lin_pp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 2>()); if (e) return e;
+  e = cudaFuncSetAttribute(k_proj_lin_pp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 2>()); if (e) return e;
   size_t chol = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol); if (e) return e;
   size_t st = (size_t)(40 + 3 * max_nc) * 8;
@@ -1518,6 +1776,8 @@ void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int
     case 1: k_proj_lin<4, 2><<<grid, 128, proj_smem<4, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
     case 2: k_proj_lin<2, 4><<<grid, 128, proj_smem<2, 4>(), s>>>(d, eval_cur, job_begin, job_count); break;
     case 3: k_proj_lin<4, 4><<<grid, 128, proj_smem<4, 4>(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 4: k_proj_lin_pp<true><<<grid, 128, proj_smem<2, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 5: k_proj_lin_pp<false><<<grid, 128, proj_smem<2, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
   }
 }
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s) {
@@ -1526,6 +1786,12 @@ void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_w
 void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s) {
   if (n_lm_total <= 0) return;
   k_lm_gather<<<(n_lm_total + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, (size_t)kGatherWarps * max_ldw * 8, s>>>(d, lm_win, n_lm_total, max_ldw);
+}
+void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s) {
+  k_schur_small<<<d.n_win, kSsThreads, (size_t)(32 * (max_ldw + 4) + 40) * 8, s>>>(d);
+}
+int configure_schur_small(int max_ldw) {
+  return (int)cudaFuncSetAttribute(k_schur_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32 * (max_ldw + 4) + 40) * 8));
 }
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) {
   if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));

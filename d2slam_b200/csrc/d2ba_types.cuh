@@ -27,6 +27,7 @@ struct Group {
   int rows;         // residual rows (1, 2 or 3)
   int need_ext;     // any extrinsic Jacobian needed
   int need_td;
+  int shift0;       // every observation has td - td_i == td - td_j == 0 (td constant): velocity terms vanish
 };
 
 struct Job {       // one warp's work: a run of tiles of one group
@@ -59,6 +60,7 @@ struct WinDesc {
   // consensus
   int admm_on;
   int chol_smem;               // reduced system fits the shared-memory Cholesky
+  int schur_small;             // landmark-coupled part <= 127 columns: one-CTA Schur kernel
 };
 
 struct PriorBlk {
