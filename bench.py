@@ -344,7 +344,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=592)   # 4 x 148 SMs: whole waves of the one-CTA-per-window kernels
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--cpu-windows", type=int, default=96)
     ap.add_argument("--admm-steps", type=int, default=4)

@@ -113,6 +113,8 @@ struct HostWin {
   double td = 0; bool has_td = false; uint8_t td_c = 1;
   std::vector<HObs> obs;
   RawObs raw;
+  d2ba_proj_obs *d_raw = nullptr; size_t d_raw_cap = 0;   // device copy of raw (uploaded as it is appended)
+  double td_min = 1e300, td_max = -1e300;
   std::vector<HImu> imu;
   int prior_m = 0; std::vector<double> prior_J, prior_e0; std::vector<HPriorBlk> prior_blk; bool prior_is_info = false;
   std::vector<int> pose_slot, ext_slot; bool admm = false; int n_slots = 0;
@@ -126,7 +128,7 @@ struct HostWin {
     pose_map.clear(); ext_map.clear(); sb_map.clear(); lm_map.clear();
     pose.clear(); ext.clear(); sb.clear(); lm.clear(); pose_c.clear(); ext_c.clear(); sb_c.clear();
     td = 0; has_td = false; td_c = 1;
-    obs.clear(); raw.n = 0; imu.clear();
+    obs.clear(); raw.n = 0; imu.clear(); td_min = 1e300; td_max = -1e300;
     prior_m = 0; prior_J.clear(); prior_e0.clear(); prior_blk.clear(); prior_is_info = false;
     pose_slot.clear(); ext_slot.clear(); admm = false; n_slots = 0;
     pose_col.clear(); ext_col.clear(); sb_col.clear(); td_col = -1; n_lc = 0; n_c = 0;
@@ -181,7 +183,8 @@ struct d2ba_handle {
   d2ba_config cfg;
   std::string err;
   std::vector<HostWin> win;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool finalized = false, state_dirty = false;
   // device arena
@@ -192,7 +195,7 @@ struct d2ba_handle {
   DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
   DBuf<SchurTileH> d_schur;
-  DBuf<int> d_pr_m, d_pr_info, d_tile_src; DBuf<long long> d_pr_oJ, d_pr_ov, d_raw_off; DBuf<d2ba_proj_obs> d_raw;
+  DBuf<int> d_pr_m, d_pr_info, d_tile_src; DBuf<long long> d_pr_oJ, d_pr_ov, d_raw_off;
   int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1;
   Dev dev;
   std::vector<WinDesc> h_win;
@@ -285,6 +288,7 @@ int d2ba_create(const d2ba_config *cfg, d2ba_handle **out) {
   h->win.resize(h->cfg.max_windows);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
   memset(&h->dev, 0, sizeof(h->dev));
   *out = h;
   return 0;
@@ -305,8 +309,10 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
   h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release();
-  h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release(); h->d_tile_src.release(); h->d_raw_off.release(); h->d_raw.release();
-  for (auto &w : h->win) w.raw.release();
+  h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release(); h->d_tile_src.release(); h->d_raw_off.release();
+  cudaStreamSynchronize(h->copy_stream);
+  for (auto &w : h->win) { w.raw.release(); if (w.d_raw) cudaFree(w.d_raw); w.d_raw = nullptr; }
+  cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_copy);
   d2ba_release_staging(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -400,7 +406,26 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
     if (err) { w->obs.resize(base); return fail(h, 3, err); }
     w->obs[base + i] = o;
   }
+  for (int i = 0; i < n; i++) {
+    if (in[i].type == D2BA_PROJ_DEPTH_PRIOR) continue;
+    w->td_min = std::min(w->td_min, std::min(in[i].td_i, in[i].td_j)); w->td_max = std::max(w->td_max, std::max(in[i].td_i, in[i].td_j));
+  }
+  cudaSetDevice(h->cfg.device);   // callers may feed windows from their own threads
+  const bool moved = w->raw.n + (size_t)n > w->raw.cap;
   if (!w->raw.append(in, (size_t)n)) { w->obs.resize(base); return fail(h, 11, "add_proj: pinned allocation failed"); }
+  // start the upload right away (overlaps with the caller preparing the other blocks / windows)
+  if (w->raw.n > w->d_raw_cap) {
+    if (w->d_raw) { cudaStreamSynchronize(h->copy_stream); cudaFree(w->d_raw); }
+    w->d_raw = nullptr; w->d_raw_cap = 0;
+    size_t want = w->raw.cap;
+    if (cudaMalloc((void **)&w->d_raw, want * sizeof(d2ba_proj_obs)) != cudaSuccess) return fail(h, 12, "add_proj: device allocation failed");
+    w->d_raw_cap = want;
+    if (cudaMemcpyAsync(w->d_raw, w->raw.p, w->raw.n * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess) return fail(h, 13, "add_proj: H2D failed");
+  } else {
+    const size_t first = moved ? 0 : base;   // the pinned buffer moved: its old contents were re-copied, re-upload all
+    if (cudaMemcpyAsync(w->d_raw + first, w->raw.p + first, (w->raw.n - first) * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess)
+      return fail(h, 13, "add_proj: H2D failed");
+  }
   return 0;
 }
 
@@ -662,12 +687,7 @@ int d2ba_finalize(d2ba_handle *h) {
       if (g.nct == 4) any_wide = true;
       int variant = (g.nct == 4 ? 1 : 0) + (g.rows == 3 ? 2 : 0);
       // all shifts zero? (td constant and equal to every observation's stamp)
-      g.shift0 = 0;
-      if (!g.need_td && o0.type != D2BA_PROJ_DEPTH_PRIOR) {
-        bool z = true;
-        for (size_t q = k; q < e && z; q++) { const d2ba_proj_obs &ro = w.raw.p[w.order[q]]; if (w.td - ro.td_i != 0.0 || w.td - ro.td_j != 0.0) z = false; }
-        g.shift0 = z ? 1 : 0;
-      }
+      g.shift0 = (!g.need_td && o0.type != D2BA_PROJ_DEPTH_PRIOR && w.td_min == w.td_max && w.td_min == w.td) ? 1 : 0;
       if (variant == 0 && !g.need_ext && (o0.type == D2BA_PROJ_2F1C || o0.type == D2BA_PROJ_2F2C) && ns == 2 && g.slot_src[0] == 0 && g.slot_src[1] == 1)
         variant = g.shift0 ? 4 : 5;
       const int cnt = (int)(e - k), ntile = (cnt + kTile - 1) / kTile;
@@ -706,7 +726,6 @@ int d2ba_finalize(d2ba_handle *h) {
     d.off6 = off6; off6 += d.n6; d.offsb = offsb; offsb += d.nsb; d.offlm = offlm; offlm += d.nl;
     d.off_tile = off_tile; off_tile += d.n_tile; d.off_rec = off_rec; off_rec += (int64_t)d.n_tile * kTile * d.rec_stride;
     d.off_grp = off_grp; off_grp += d.n_grp; d.off_imu = off_imu; off_imu += d.n_imu;
-    st.raw_off.resize(nw); st.raw_off.p[wi] = off_raw; off_raw += (long long)w.obs.size();
     d.off_lmptr = off_lmptr; off_lmptr += d.nl + 1; d.off_lmobs = off_lmobs; off_lmobs += pl.n_lmobs;
     d.off_prior_blk = off_pblk; off_pblk += d.prior_nblk; d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
     off_pJ += (int64_t)d.prior_m * d.prior_m; off_pv += d.prior_m;
@@ -826,15 +845,17 @@ int d2ba_finalize(d2ba_handle *h) {
       (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
       (rc = up(h, h->d_schur, st.schur)))
     return rc;
-  // raw observation records: one async copy per window from its pinned buffer, then the device builds the tiles
-  CK(h->d_raw.alloc((size_t)off_raw)); CK(h->d_obs.alloc((size_t)off_tile * kTile * kObsFields));
-  if ((rc = up(h, h->d_raw_off, st.raw_off))) return rc;
+  // raw observation records were uploaded as they were added (copy stream); the device builds the tiles from them
+  CK(h->d_obs.alloc((size_t)off_tile * kTile * kObsFields));
   for (int wi = 0; wi < nw; wi++) {
     HostWin &w = h->win[wi];
     if (w.raw.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
-    if (w.raw.n) CK(cudaMemcpyAsync(h->d_raw.p + st.raw_off.p[wi], w.raw.p, w.raw.n * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->stream));
+    st.raw_off.p[wi] = (long long)(uintptr_t)w.d_raw;
   }
-  launch_build_tiles(h->d_raw.p, h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
+  if ((rc = up(h, h->d_raw_off, st.raw_off))) return rc;
+  CK(cudaEventRecord(h->ev_copy, h->copy_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+  launch_build_tiles(nullptr, h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
   CK(h->d_imu_U.alloc((size_t)off_imu * 225)); CK(h->d_prior_A.alloc((size_t)off_pJ));
   CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
   CK(h->d_td_ref.alloc(nw));

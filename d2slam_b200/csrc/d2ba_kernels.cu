@@ -991,9 +991,10 @@ __global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
   double *S = d.S + w.offH;
   const double *Wt = d.Wt + w.offW;
   extern __shared__ double sm[];
-  double *Ws = sm;                       // 32 x ldws
-  double *redq = sm + 32 * (ldw + 4);    // 40
   const int ldws = ldw + 4;
+  double *Ws = sm;                            // 2 buffers x 32 x ldws (TMA bulk staged)
+  double *redq = sm + 2 * 32 * ldws;          // 40
+  __shared__ unsigned long long bar[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kq = lane & 3, cr = lane >> 2;
   const int nb8 = ldw >> 3, nblk = nb8 * (nb8 + 1) / 2;
   int bi[kSsMaxB], bj[kSsMaxB];
@@ -1009,17 +1010,31 @@ __global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
   }
   double uhu = 0.0;
   if (nlc > 0) {
-    for (int k0 = 0; k0 < w.nl_pad; k0 += 32) {
-      for (int e = tid; e < 32 * ldw; e += kSsThreads) { int k = e / ldw, c = e - k * ldw; Ws[k * ldws + c] = Wt[(size_t)(k0 + k) * ldw + c]; }
-      __syncthreads();
+    const int nchunk = w.nl_pad / 32;
+    const unsigned row_bytes = (unsigned)ldw * 8u;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    // producer: one thread issues 32 row copies per chunk (rows are padded in shared memory for conflict-free fragments)
+    auto issue = [&](int c, int b) {
+      mbar_expect_tx(&bar[b], 32u * row_bytes);
+      const double *src = Wt + (size_t)c * 32 * ldw;
+      double *dst = Ws + b * 32 * ldws;
+      for (int k = 0; k < 32; k++) bulk_g2s(dst + k * ldws, src + (size_t)k * ldw, row_bytes, &bar[b]);
+    };
+    if (tid == 0) { issue(0, 0); if (nchunk > 1) issue(1, 1); }
+    for (int c = 0; c < nchunk; c++) {
+      const int b = c & 1;
+      mbar_wait(&bar[b], (unsigned)((c >> 1) & 1));
+      const double *Wb = Ws + b * 32 * ldws;
 #pragma unroll 2
       for (int ks = 0; ks < 32; ks += 4) {
-        const double *wr = Ws + (ks + kq) * ldws + cr;
+        const double *wr = Wb + (ks + kq) * ldws + cr;
 #pragma unroll
         for (int q = 0; q < kSsMaxB; q++)
           if (warp + q * 8 < nblk) dmma(acc[q][0], acc[q][1], wr[bi[q] * 8], wr[bj[q] * 8]);
       }
       __syncthreads();
+      if (tid == 0 && c + 2 < nchunk) { fence_proxy_async(); issue(c + 2, b); }
     }
 #pragma unroll
     for (int q = 0; q < kSsMaxB; q++) {
@@ -1699,7 +1714,7 @@ __global__ void __launch_bounds__(128) k_build_tiles(const d2ba_proj_obs *raw, c
 #pragma unroll
   for (int k = 0; k < kObsFields; k++) f[k] = 0.0;
   if (src >= 0) {
-    const d2ba_proj_obs &p = raw[raw_off[tile_win[tile]] + src];
+    const d2ba_proj_obs &p = reinterpret_cast<const d2ba_proj_obs *>((uintptr_t)raw_off[tile_win[tile]])[src];   // per-window base pointer
     if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
 #pragma unroll
       for (int k = 0; k < 3; k++) { f[k] = p.pts_i[k]; f[3 + k] = p.pts_j[k]; f[6 + k] = p.vel_i[k]; f[9 + k] = p.vel_j[k]; }
@@ -1788,10 +1803,10 @@ void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_l
   k_lm_gather<<<(n_lm_total + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, (size_t)kGatherWarps * max_ldw * 8, s>>>(d, lm_win, n_lm_total, max_ldw);
 }
 void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s) {
-  k_schur_small<<<d.n_win, kSsThreads, (size_t)(32 * (max_ldw + 4) + 40) * 8, s>>>(d);
+  k_schur_small<<<d.n_win, kSsThreads, (size_t)(2 * 32 * (max_ldw + 4) + 40) * 8, s>>>(d);
 }
 int configure_schur_small(int max_ldw) {
-  return (int)cudaFuncSetAttribute(k_schur_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32 * (max_ldw + 4) + 40) * 8));
+  return (int)cudaFuncSetAttribute(k_schur_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 32 * (max_ldw + 4) + 40) * 8));
 }
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) {
   if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));
