@@ -46,6 +46,8 @@ void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream
 void launch_cons_apply(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
 void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_win, const int *lm_win, cudaStream_t s);
 struct SchurTileH { int win, kind, tm, tn; };
+int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr, double *A, double *b, int *fail_flag,
+                       cudaStream_t s);
 void launch_build_tiles(const void *raw, const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s);
 void launch_prior_from_info(int n_win, int max_m, const int *m_of, const long long *offJ, const long long *offv, const int *is_info,
                             double *A, double *V, double *b, cudaStream_t s);
@@ -80,7 +82,7 @@ struct FlatMap {
   }
 };
 
-struct HObs { int type, pi, pj, ea, eb, lm; };   // index form of one residual block (the constants stay in the raw record)
+struct HObs { int type, pi, pj, ea, eb, lm, fa; };   // index form of one residual block (constants stay in the raw record); fa = anchor frame
 
 // Per-window pinned buffer of the caller's raw observation records (uploaded as is; the tiled layout and the
 // tangent bases are built on the device by k_build_tiles).  Capacity survives d2ba_reset.
@@ -213,6 +215,8 @@ struct d2ba_handle {
   std::vector<double> h_x6[2], h_xsb[2], h_xlm[2], h_xtd[2];
   // graph cache
   cudaGraphExec_t iter_graph = nullptr; int graph_key = -1;
+  d2ba_handle *marg = nullptr;   // scratch handle of d2ba_marginalize
+  double mu0 = 1e-8;
   // comm
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
 };
@@ -299,6 +303,7 @@ int d2ba_destroy(d2ba_handle *h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   release_graph(h);
+  if (h->marg) { d2ba_destroy(h->marg); h->marg = nullptr; }
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   // DBuf members: release explicitly
   h->d_win.release(); h->d_ctl.release();
@@ -390,6 +395,7 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
     HObs o;
     o.type = p.type; o.pi = o.pj = o.ea = o.eb = -1;
     o.lm = cached(c_lm, w->lm_map, p.landmark_id);
+    o.fa = cached(c_fa, w->pose_map, p.frame_a);
     const char *err = nullptr;
     if (o.lm < 0) err = "add_proj: unknown landmark id";
     else if (p.type < 0 || p.type > D2BA_PROJ_DEPTH_PRIOR) err = "add_proj: unknown residual type";
@@ -881,7 +887,7 @@ int d2ba_finalize(d2ba_handle *h) {
   P.rho_T = h->cfg.rho_frame_T; P.rho_theta = h->cfg.rho_frame_theta; P.rho_landmark = h->cfg.rho_landmark; P.relaxation_alpha = h->cfg.relaxation_alpha;
   P.initial_radius = h->cfg.initial_trust_region_radius; P.max_radius = h->cfg.max_trust_region_radius; P.min_rel_decrease = h->cfg.min_relative_decrease;
   P.ftol = h->cfg.function_tolerance; P.gtol = h->cfg.gradient_tolerance; P.ptol = h->cfg.parameter_tolerance;
-  P.max_iter = h->cfg.max_num_iterations; P.fixed_mode = 0;
+  P.max_iter = h->cfg.max_num_iterations; P.fixed_mode = 0; P.mu0 = h->mu0;
   if (h->cfg_max_rows != h->max_rows || h->cfg_max_nc != h->max_nc || h->cfg_max_prior != h->max_prior_m) {
     if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
     h->cfg_max_rows = h->max_rows; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
@@ -1179,6 +1185,144 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
   }
   if (needed) *needed = (int64_t)buf.size();
   if (out) { if (out_bytes < (int64_t)buf.size()) return 2; memcpy(out, buf.data(), buf.size()); }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ marginalization
+// Marginalizer::marginalize (d2vins/src/estimator/marginalization/marginalization.cpp:173-254) on the device:
+// the relevant residuals (filterResiduals :78-118) form a one-window sub-problem in a scratch handle; its
+// linearisation (k_misc_lin / k_proj_lin, loss-corrected like ResidualInfo::Evaluate), landmark elimination
+// (k_lm_gather + Schur kernel with mu = 0) and a small exact-inverse reduction of the removed pose / speed-bias
+// columns (k_marg_reduce) give the information form (A, b) of the new prior.
+int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove, const int64_t *remove_frame_ids, int32_t *m_out,
+                     int32_t max_m, double *A_out, double *b_out, int32_t *nblk_out, int32_t max_blk, d2ba_blockref *refs_out,
+                     double *x0_out) {
+  HostWin *w = get_win(h, window);
+  if (!w || !w->used) return 1;
+  cudaSetDevice(h->cfg.device);
+  const int np = (int)w->pose_id.size(), ne = (int)w->ext_id.size(), nsb = (int)w->sb_id.size(), nl = (int)w->lm_id.size();
+  std::vector<char> rem_pose(np, 0), rem_sb(nsb, 0), use_pose(np, 0), use_sb(nsb, 0), use_ext(ne, 0), use_lm(nl, 0);
+  bool use_td = false;
+  for (int i = 0; i < np; i++) for (int k = 0; k < n_remove; k++) if (w->pose_id[i] == remove_frame_ids[k]) rem_pose[i] = 1;
+  for (int i = 0; i < nsb; i++) for (int k = 0; k < n_remove; k++) if (w->sb_id[i] == remove_frame_ids[k]) rem_sb[i] = 1;
+  std::vector<d2ba_proj_obs> robs;
+  for (size_t k = 0; k < w->obs.size(); k++) {
+    const HObs &o = w->obs[k];
+    bool r;
+    if (o.type == D2BA_PROJ_DEPTH_PRIOR || o.type == D2BA_PROJ_1F2C) r = o.fa >= 0 && rem_pose[o.fa];   // anchor frame only
+    else r = rem_pose[o.pi] || rem_pose[o.pj];
+    if (!r) continue;
+    robs.push_back(w->raw.p[k]);
+    if (o.pi >= 0) { use_pose[o.pi] = 1; use_pose[o.pj] = 1; }
+    if (o.type != D2BA_PROJ_DEPTH_PRIOR) { use_ext[o.ea] = 1; if (o.eb >= 0) use_ext[o.eb] = 1; use_td = true; }
+    use_lm[o.lm] = 1;
+  }
+  std::vector<d2ba_imu> rimu;
+  for (const HImu &m : w->imu) {
+    if (!(rem_pose[m.pi] || rem_pose[m.pj])) continue;
+    use_pose[m.pi] = use_pose[m.pj] = 1; use_sb[m.si] = use_sb[m.sj] = 1;
+    d2ba_imu r; memset(&r, 0, sizeof r);
+    r.frame_a = w->pose_id[m.pi]; r.frame_b = w->pose_id[m.pj];
+    const double *c = m.c;
+    r.sum_dt = c[0]; memcpy(r.delta_p, c + 1, 24); memcpy(r.delta_q, c + 4, 32); memcpy(r.delta_v, c + 8, 24);
+    memcpy(r.linearized_ba, c + 11, 24); memcpy(r.linearized_bg, c + 14, 24); memcpy(r.jacobian, c + 17, 225 * 8); memcpy(r.covariance, c + 17 + 225, 225 * 8);
+    rimu.push_back(r);
+  }
+  for (const HPriorBlk &b : w->prior_blk) {
+    if (b.kind == D2BA_POSE) use_pose[b.index] = 1; else if (b.kind == D2BA_EXTRINSIC) use_ext[b.index] = 1;
+    else if (b.kind == D2BA_SPEED_BIAS) use_sb[b.index] = 1; else if (b.kind == D2BA_TD) use_td = true; else use_lm[b.index] = 1;
+  }
+  // scratch handle
+  if (!h->marg) {
+    d2ba_config c = h->cfg; c.max_windows = 1; c.consensus_max_steps = 0; c.use_cuda_graph = 0;
+    int rc = d2ba_create(&c, &h->marg);
+    if (rc) return fail(h, 60, "marginalize: cannot create scratch handle");
+    h->marg->mu0 = 0.0;
+  }
+  d2ba_handle *t = h->marg;
+  d2ba_reset(t);
+  // blocks: kept poses, removed poses | extrinsics | td | kept speed-bias, removed speed-bias | landmarks (all free)
+  std::vector<int> keep_cols, rem_cols;
+  int nblk = 0, xo = 0, nk = 0, col = 0;
+  std::vector<int64_t> ids; std::vector<double> vals; std::vector<uint8_t> cst;
+  auto flush = [&](int kind, int sz) { int rc = ids.empty() ? 0 : d2ba_set_blocks(t, 0, kind, (int)ids.size(), ids.data(), vals.data(), cst.data()); ids.clear(); vals.clear(); cst.clear(); (void)sz; return rc; };
+  auto emit = [&](int kind, int64_t id, const double *v, int sz) {
+    if (nblk >= max_blk) return false;
+    refs_out[nblk].kind = kind; refs_out[nblk].pad = 0; refs_out[nblk].id = id;
+    if (x0_out) memcpy(x0_out + xo, v, 8 * sz);
+    xo += sz; nblk++; return true;
+  };
+  int rc = 0;
+  // tmp column order = [poses | ext | td | sb]; remember which reduced columns are kept / removed
+  std::vector<int> pose_col(np, -1), sb_col(nsb, -1), ext_col(ne, -1);
+  for (int pass = 0; pass < 2; pass++)
+    for (int i = 0; i < np; i++) if (use_pose[i] && rem_pose[i] == pass) { ids.push_back(w->pose_id[i]); vals.insert(vals.end(), &w->pose[7 * i], &w->pose[7 * i] + 7); cst.push_back(0); pose_col[i] = col; col += 6; }
+  if ((rc = flush(D2BA_POSE, 7))) return rc;
+  for (int i = 0; i < ne; i++) if (use_ext[i]) { ids.push_back(w->ext_id[i]); vals.insert(vals.end(), &w->ext[7 * i], &w->ext[7 * i] + 7); cst.push_back(0); ext_col[i] = col; col += 6; }
+  if ((rc = flush(D2BA_EXTRINSIC, 7))) return rc;
+  int td_col = -1;
+  { int64_t z = 0; uint8_t c0 = use_td ? 0 : 1; double tdv = w->td; if ((rc = d2ba_set_blocks(t, 0, D2BA_TD, 1, &z, &tdv, &c0))) return rc; if (use_td) { td_col = col; col += 1; } }
+  for (int pass = 0; pass < 2; pass++)
+    for (int i = 0; i < nsb; i++) if (use_sb[i] && rem_sb[i] == pass) { ids.push_back(w->sb_id[i]); vals.insert(vals.end(), &w->sb[9 * i], &w->sb[9 * i] + 9); cst.push_back(0); sb_col[i] = col; col += 9; }
+  if ((rc = flush(D2BA_SPEED_BIAS, 9))) return rc;
+  for (int i = 0; i < nl; i++) if (use_lm[i]) { ids.push_back(w->lm_id[i]); vals.push_back(w->lm[i]); cst.push_back(0); }
+  if ((rc = flush(D2BA_LANDMARK, 1))) return rc;
+  // kept blocks in the reference's type order (sortParams :262-270): POSE, SPEED_BIAS, EXTRINSIC, TD
+  bool ok = true;
+  for (int i = 0; i < np; i++) if (use_pose[i] && !rem_pose[i]) { ok = ok && emit(D2BA_POSE, w->pose_id[i], &w->pose[7 * i], 7); for (int q = 0; q < 6; q++) keep_cols.push_back(pose_col[i] + q); }
+  for (int i = 0; i < nsb; i++) if (use_sb[i] && !rem_sb[i]) { ok = ok && emit(D2BA_SPEED_BIAS, w->sb_id[i], &w->sb[9 * i], 9); for (int q = 0; q < 9; q++) keep_cols.push_back(sb_col[i] + q); }
+  for (int i = 0; i < ne; i++) if (use_ext[i]) { ok = ok && emit(D2BA_EXTRINSIC, w->ext_id[i], &w->ext[7 * i], 7); for (int q = 0; q < 6; q++) keep_cols.push_back(ext_col[i] + q); }
+  if (use_td) { ok = ok && emit(D2BA_TD, 0, &w->td, 1); keep_cols.push_back(td_col); }
+  if (!ok) return fail(h, 61, "marginalize: refs_out too small");
+  for (int i = 0; i < np; i++) if (use_pose[i] && rem_pose[i]) for (int q = 0; q < 6; q++) rem_cols.push_back(pose_col[i] + q);
+  for (int i = 0; i < nsb; i++) if (use_sb[i] && rem_sb[i]) for (int q = 0; q < 9; q++) rem_cols.push_back(sb_col[i] + q);
+  nk = (int)keep_cols.size();
+  const int nr = (int)rem_cols.size();
+  if (nk > max_m) return fail(h, 62, "marginalize: A_out too small");
+  if (nk == 0 || nr == 0) return fail(h, 63, "marginalize: nothing to keep or nothing to remove (reference returns nullptr)");
+  if ((rc = d2ba_add_proj(t, 0, (int)robs.size(), robs.data()))) return fail(h, rc, std::string("marginalize/add_proj: ") + t->err);
+  if (!rimu.empty() && (rc = d2ba_add_imu(t, 0, (int)rimu.size(), rimu.data()))) return fail(h, rc, std::string("marginalize/add_imu: ") + t->err);
+  if (w->prior_m > 0) {
+    std::vector<d2ba_blockref> pr; std::vector<double> px0;
+    for (const HPriorBlk &b : w->prior_blk) {
+      d2ba_blockref r; r.kind = b.kind; r.pad = 0;
+      r.id = b.kind == D2BA_POSE ? w->pose_id[b.index] : b.kind == D2BA_EXTRINSIC ? w->ext_id[b.index] : b.kind == D2BA_SPEED_BIAS ? w->sb_id[b.index]
+             : b.kind == D2BA_LANDMARK ? w->lm_id[b.index] : 0;
+      pr.push_back(r); px0.insert(px0.end(), b.x0, b.x0 + kind_size(b.kind));
+    }
+    if ((rc = set_prior_common(t, 0, w->prior_m, w->prior_J.data(), w->prior_e0.data(), (int)pr.size(), pr.data(), px0.data(), w->prior_is_info)))
+      return fail(h, rc, std::string("marginalize/prior: ") + t->err);
+  }
+  if ((rc = d2ba_finalize(t))) return fail(h, rc, std::string("marginalize/finalize: ") + t->err);
+  if (t->h_win[0].n_c != col) return fail(h, 64, "marginalize: internal column count mismatch");
+  // linearise and eliminate the landmarks (mu = 0)
+  t->dev.prm.fixed_mode = 1; t->dev.prm.max_iter = 1;
+  launch_tr_reset(t->dev, 1, t->stream);
+  enqueue_linearize(t, 1);
+  launch_control(t->dev, 1, t->stream);
+  launch_lm_gather(t->dev, t->d_lm_win.p, t->nl_total, t->max_ldw, t->stream);
+  if (t->max_ldw_small > 0) launch_schur_small(t->dev, t->max_ldw_small, t->stream);
+  launch_schur(t->dev, t->d_schur.p, t->n_schur, t->stream);
+  // eliminate the removed camera columns
+  DBuf<int> d_keep, d_rem, d_flag; DBuf<double> d_A, d_b;
+  cudaError_t ce;
+  if ((ce = d_keep.alloc(nk)) || (ce = d_rem.alloc(nr)) || (ce = d_flag.alloc(1)) || (ce = d_A.alloc((size_t)nk * nk)) || (ce = d_b.alloc(nk)))
+    return fail(h, 65, "marginalize: device allocation failed");
+  cudaMemcpyAsync(d_keep.p, keep_cols.data(), nk * sizeof(int), cudaMemcpyHostToDevice, t->stream);
+  cudaMemcpyAsync(d_rem.p, rem_cols.data(), nr * sizeof(int), cudaMemcpyHostToDevice, t->stream);
+  cudaMemsetAsync(d_flag.p, 0, sizeof(int), t->stream);
+  const WinDesc &td_ = t->h_win[0];
+  if (launch_marg_reduce(t->d_S.p + td_.offH, td_.ldh, td_.n_c, d_keep.p, nk, d_rem.p, nr, d_A.p, d_b.p, d_flag.p, t->stream))
+    return fail(h, 66, "marginalize: reduce kernel needs more shared memory than available");
+  int flag = 0;
+  cudaMemcpyAsync(A_out, d_A.p, (size_t)nk * nk * 8, cudaMemcpyDeviceToHost, t->stream);
+  cudaMemcpyAsync(b_out, d_b.p, (size_t)nk * 8, cudaMemcpyDeviceToHost, t->stream);
+  cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, t->stream);
+  ce = cudaStreamSynchronize(t->stream);
+  d_keep.release(); d_rem.release(); d_flag.release(); d_A.release(); d_b.release();
+  if (ce != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(h, 67, std::string("marginalize: ") + cudaGetErrorString(ce));
+  if (flag) return fail(h, 68, "marginalize: removed block is not positive definite");
+  *m_out = nk; *nblk_out = nblk;
   return 0;
 }
 

@@ -828,31 +828,59 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
   double h = 0, g = 0;
   const int kb = ptr[l], ke = ptr[l + 1];
-  for (int k0 = kb; k0 < ke; k0 += 32) {
-    const int cnt = min(32, ke - k0);
-    const int mypos = (lane < cnt) ? lo[k0 + lane] : 0;     // coalesced read of the position list
-    for (int q = 0; q < cnt; q += 2) {
-      // two records in flight
-      const int p0 = __shfl_sync(0xffffffffu, mypos, q), p1 = __shfl_sync(0xffffffffu, mypos, min(q + 1, cnt - 1));
-      const bool two = q + 1 < cnt;
-      double v0 = lane < stride ? recs[(size_t)p0 * stride + lane] : 0.0;
-      double v1 = (two && lane < stride) ? recs[(size_t)p1 * stride + lane] : 0.0;
+  if (stride == 16) {
+    // compact records (128 B): two per warp load (half-warp each), up to 8 loads = 16 records in flight
+    const int half = lane >> 4, sub = lane & 15;
+    for (int k0 = kb; k0 < ke; k0 += 16) {
+      const int cnt = min(16, ke - k0);
+      const int mypos = (lane < cnt) ? lo[k0 + lane] : 0;
+      double v[8];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const double v = u == 0 ? v0 : v1;
-        if (u == 1 && !two) break;
-        if (lane == 0) h += v;
-        if (lane == 1) g += v;
-        const double c01 = __shfl_sync(0xffffffffu, v, 3);
+      for (int q = 0; q < 8; q++) {
+        const int o = 2 * q + half;
+        const int p = __shfl_sync(0xffffffffu, mypos, o < cnt ? o : 0);
+        v[q] = (o < cnt) ? recs[(size_t)p * 16 + sub] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (2 * q >= cnt) break;
+        const double c01 = __shfl_sync(0xffffffffu, v[q], (lane & 16) | 3);   // columns word of this half's record
         int col = -1;
-        if (lane >= 4 && lane < 16) { int sc = lane < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (lane - 4) % 6; }
-        if (stride == 32) {
-          const double c23 = __shfl_sync(0xffffffffu, v, 28), ctd = __shfl_sync(0xffffffffu, v, 29);
+        if (sub >= 4) { int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
+        if (sub == 0) h += v[q];
+        if (sub == 1) g += v[q];
+        // the two halves may hit the same columns (anchor pose): apply them one after the other
+        if (half == 0 && col >= 0) row[col] += v[q];
+        __syncwarp();
+        if (half == 1 && col >= 0 && 2 * q + 1 < cnt) row[col] += v[q];
+        __syncwarp();
+      }
+    }
+    h += __shfl_xor_sync(0xffffffffu, h, 16);
+    g += __shfl_xor_sync(0xffffffffu, g, 16);
+  } else {
+    for (int k0 = kb; k0 < ke; k0 += 32) {
+      const int cnt = min(32, ke - k0);
+      const int mypos = (lane < cnt) ? lo[k0 + lane] : 0;     // coalesced read of the position list
+      for (int q = 0; q < cnt; q += 2) {
+        const int p0 = __shfl_sync(0xffffffffu, mypos, q), p1 = __shfl_sync(0xffffffffu, mypos, min(q + 1, cnt - 1));
+        const bool two = q + 1 < cnt;
+        double v0 = recs[(size_t)p0 * 32 + lane];
+        double v1 = two ? recs[(size_t)p1 * 32 + lane] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const double v = u == 0 ? v0 : v1;
+          if (u == 1 && !two) break;
+          if (lane == 0) h += v;
+          if (lane == 1) g += v;
+          const double c01 = __shfl_sync(0xffffffffu, v, 3), c23 = __shfl_sync(0xffffffffu, v, 28), ctd = __shfl_sync(0xffffffffu, v, 29);
+          int col = -1;
+          if (lane >= 4 && lane < 16) { int sc = lane < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (lane - 4) % 6; }
           if (lane >= 16 && lane < 28) { int sc = lane < 22 ? __double2hiint(c23) : __double2loint(c23); if (sc >= 0) col = sc + (lane - 4) % 6; }
           if (lane == 2) col = __double2hiint(ctd);
+          if (col >= 0) row[col] += v;
+          __syncwarp();
         }
-        if (col >= 0) row[col] += v;
-        __syncwarp();
       }
     }
   }
@@ -1602,7 +1630,7 @@ __global__ void k_tr_reset(Dev d, int first) {
   const int wi = blockIdx.x * blockDim.x + threadIdx.x;
   if (wi >= d.n_win) return;
   Ctl *c = d.ctl + wi;
-  c->radius = d.prm.initial_radius; c->mu = 1e-8; c->reuse = 0; c->done = 0; c->term = 0; c->step_valid = 1;
+  c->radius = d.prm.initial_radius; c->mu = d.prm.mu0; c->reuse = 0; c->done = 0; c->term = 0; c->step_valid = 1;
   c->invalid_run = 0; c->iter = 0; c->chol_fail = 0; c->gmax_l_bits = 0ull;
   c->cand_cost_misc = 0; c->cand_cost_proj = 0;
   if (first) { c->cur = 0; c->succ = 0; c->lin_count = 0; }
@@ -1743,6 +1771,59 @@ __global__ void __launch_bounds__(128) k_build_tiles(const d2ba_proj_obs *raw, c
 }
 void launch_build_tiles(const void *raw, const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s) {
   if (n_tiles > 0) k_build_tiles<<<(n_tiles + 3) / 4, 128, 0, s>>>(reinterpret_cast<const d2ba_proj_obs *>(raw), raw_off, tile_src, tile_win, obs, n_tiles);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second stage of the marginalization: S (landmarks already eliminated) is split into kept / removed camera
+// columns and the removed ones are eliminated with the exact inverse (Cholesky), Utility::schurComplement
+// (d2common/include/d2common/utils.hpp:131-141):  A = S11 - S12 S22^-1 S21,  b = g1 - S12 S22^-1 g2.
+__global__ void __launch_bounds__(256) k_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr,
+                                                     double *A, double *b, int *fail_flag) {
+  extern __shared__ double sm[];
+  double *R = sm;                 // nr x nr (lower Cholesky of S22)
+  double *X = sm + nr * nr;       // nr x (nk+1)
+  const int tid = threadIdx.x, nt = blockDim.x, nk1 = nk + 1;
+  auto Sat = [&](int i, int j) { return i >= j ? S[(size_t)i * ld + j] : S[(size_t)j * ld + i]; };
+  for (int e = tid; e < nr * nr; e += nt) { int i = e / nr, j = e % nr; R[e] = Sat(rem_idx[i], rem_idx[j]); }
+  for (int e = tid; e < nr * nk1; e += nt) { int i = e / nk1, j = e % nk1; X[e] = j < nk ? Sat(rem_idx[i], keep_idx[j]) : S[(size_t)n * ld + rem_idx[i]]; }
+  __syncthreads();
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int c = 0; c < nr; c++) {
+    __syncthreads();
+    const double dcc = R[c * nr + c];
+    if (!(dcc > 0.0)) { if (tid == 0) bad = 1; }
+    const double inv = 1.0 / sqrt(dcc > 0.0 ? dcc : 1.0);
+    __syncthreads();
+    for (int r = c + tid; r < nr; r += nt) R[r * nr + c] = (r == c) ? dcc * inv : R[r * nr + c] * inv;
+    __syncthreads();
+    for (int e = tid; e < (nr - c - 1) * (nr - c - 1); e += nt) {
+      int r = c + 1 + e / (nr - c - 1), c2 = c + 1 + e % (nr - c - 1);
+      if (c2 <= r) R[r * nr + c2] -= R[r * nr + c] * R[c2 * nr + c];
+    }
+  }
+  __syncthreads();
+  // X <- S22^-1 X, one right-hand-side column per thread
+  for (int j = tid; j < nk1; j += nt) {
+    for (int i = 0; i < nr; i++) { double s_ = X[i * nk1 + j]; for (int k = 0; k < i; k++) s_ -= R[i * nr + k] * X[k * nk1 + j]; X[i * nk1 + j] = s_ / R[i * nr + i]; }
+    for (int i = nr - 1; i >= 0; i--) { double s_ = X[i * nk1 + j]; for (int k = i + 1; k < nr; k++) s_ -= R[k * nr + i] * X[k * nk1 + j]; X[i * nk1 + j] = s_ / R[i * nr + i]; }
+  }
+  __syncthreads();
+  for (int e = tid; e < nk * nk1; e += nt) {
+    int i = e / nk1, j = e % nk1;
+    double s_ = j < nk ? Sat(keep_idx[i], keep_idx[j]) : S[(size_t)n * ld + keep_idx[i]];
+    for (int k = 0; k < nr; k++) s_ -= Sat(keep_idx[i], rem_idx[k]) * X[k * nk1 + j];
+    if (j < nk) A[(size_t)i * nk + j] = s_; else b[i] = s_;
+  }
+  if (tid == 0 && bad) *fail_flag = 1;
+}
+int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr, double *A, double *b, int *fail_flag,
+                       cudaStream_t s) {
+  size_t smb = ((size_t)nr * nr + (size_t)nr * (nk + 1)) * 8;
+  cudaError_t e = cudaFuncSetAttribute(k_marg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+  if (e != cudaSuccess) return (int)e;
+  k_marg_reduce<<<1, 256, smb, s>>>(S, ld, n, keep_idx, nk, rem_idx, nr, A, b, fail_flag);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

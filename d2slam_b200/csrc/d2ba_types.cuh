@@ -94,6 +94,7 @@ struct SolverParams {
   double rho_T, rho_theta, rho_landmark, relaxation_alpha;
   double initial_radius, max_radius, min_rel_decrease, ftol, gtol, ptol;
   int max_iter, fixed_mode;
+  double mu0;   // initial LM regularisation of the dogleg GN solve (1e-8; 0 for marginalization)
 };
 
 // All device pointers of a handle (passed to kernels by value).

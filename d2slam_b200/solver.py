@@ -158,6 +158,19 @@ class Solver:
                   "get_blocks")
         return out
 
+    def marginalize(self, window, remove_frame_ids, max_m=1024, max_blk=256):
+        """-> (A [m,m], b [m], refs, x0) of the new prior (information form)."""
+        rem = np.ascontiguousarray(remove_frame_ids, dtype=np.int64)
+        A = np.zeros((max_m, max_m)); b = np.zeros(max_m); refs = np.zeros(max_blk, dtype=abi.blockref_dtype); x0 = np.zeros(max_blk * 9)
+        m = C.c_int32(); nb = C.c_int32()
+        Aflat = np.zeros(max_m * max_m)
+        self._chk(lib().d2ba_marginalize(self.h, C.c_int32(window), C.c_int32(len(rem)), abi.ptr(rem), C.byref(m), C.c_int32(max_m), abi.ptr(Aflat),
+                                         abi.ptr(b), C.byref(nb), C.c_int32(max_blk), abi.ptr(refs), abi.ptr(x0)), "marginalize")
+        mm = m.value
+        refs = refs[: nb.value].copy()
+        nx = int(sum(abi.KIND_SIZE[int(k)] for k in refs["kind"]))
+        return Aflat[: mm * mm].reshape(mm, mm).copy(), b[:mm].copy(), refs, x0[:nx].copy()
+
     def kernel_times(self, iters):
         out = np.zeros(8)
         self._chk(lib().d2ba_debug_kernel_times(self.h, C.c_int32(iters), abi.ptr(out)), "kernel_times")

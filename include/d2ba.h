@@ -247,13 +247,16 @@ int d2ba_get_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n,
 int d2ba_num_windows(const d2ba_handle *h);
 
 /* ---------------------------------------------------------------- marginalization (next row, 8f-1) */
-/* Marginalize the listed frames out of window `window` using the residuals currently in the
- * problem; the new prior replaces the window's prior and is also returned in information
- * form.  A_out is m_out x m_out row-major; refs_out lists the kept blocks. */
+/* Marginalize the listed frames out of window `window` using the residuals currently added to it
+ * (Marginalizer::marginalize with remove_base_when_margin_remote = 2, margin_enable_fej = 0, exact-inverse Schur
+ * complement: config/tum/tum_single.yaml:87-94).  Returns the new prior in information form: A_out is
+ * m_out x m_out row-major, b_out has m_out entries, refs_out lists the kept blocks (POSE, SPEED_BIAS, EXTRINSIC, TD
+ * order, tangent sizes 6/9/6/1) and x0_out their linearisation points (concatenated nominal sizes 7/9/7/1).
+ * Hand it back with d2ba_set_prior_info after the window has been rebuilt without the removed frames. */
 int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove,
                      const int64_t *remove_frame_ids, int32_t *m_out, int32_t max_m,
                      double *A_out, double *b_out, int32_t *nblk_out, int32_t max_blk,
-                     d2ba_blockref *refs_out);
+                     d2ba_blockref *refs_out, double *x0_out);
 
 /* ---------------------------------------------------------------- introspection (parity tests) */
 enum d2ba_debug_item {

@@ -161,6 +161,17 @@ class Oracle:
         _chk(lib().orc_get_consensus(self.h, C.c_int32(len(refs)), abi.ptr(refs), abi.ptr(z), abi.ptr(t)), "get_consensus")
         return z, t
 
+    def marginalize(self, remove_frame_ids, max_m=1024, max_blk=256):
+        rem = np.ascontiguousarray(remove_frame_ids, dtype=np.int64)
+        Aflat = np.zeros(max_m * max_m); b = np.zeros(max_m); refs = np.zeros(max_blk, dtype=abi.blockref_dtype); x0 = np.zeros(max_blk * 9)
+        m = C.c_int32(); nb = C.c_int32()
+        _chk(lib().orc_marginalize_x0(self.h, C.c_int32(len(rem)), abi.ptr(rem), C.byref(m), C.c_int32(max_m), abi.ptr(Aflat), abi.ptr(b),
+                                      C.byref(nb), C.c_int32(max_blk), abi.ptr(refs), abi.ptr(x0)), "marginalize")
+        mm = m.value
+        refs = refs[: nb.value].copy()
+        nx = int(sum(abi.KIND_SIZE[int(k)] for k in refs["kind"]))
+        return Aflat[: mm * mm].reshape(mm, mm).copy(), b[:mm].copy(), refs, x0[:nx].copy()
+
     def debug_linearize(self):
         _chk(lib().orc_debug_linearize(self.h), "debug_linearize")
 

@@ -101,9 +101,9 @@ int orc_admm_many(orc_handle **hs, int32_t n_swarms, int32_t n_agents, int32_t n
 int orc_get_blocks(orc_handle *o, int32_t kind, int32_t n, const int64_t *ids, double *out);
 int orc_debug_linearize(orc_handle *o);
 int orc_debug_get(orc_handle *o, int32_t item, void *out, int64_t out_bytes, int64_t *needed);
-int orc_marginalize(orc_handle *o, int32_t n_remove, const int64_t *remove_frame_ids, int32_t *m_out,
-                    int32_t max_m, double *A_out, double *b_out, int32_t *nblk_out, int32_t max_blk,
-                    d2ba_blockref *refs_out);
+int orc_marginalize_x0(orc_handle *o, int32_t n_remove, const int64_t *remove_frame_ids, int32_t *m_out,
+                       int32_t max_m, double *A_out, double *b_out, int32_t *nblk_out, int32_t max_blk,
+                       d2ba_blockref *refs_out, double *x0_out);
 /* consensus state access for tests */
 int orc_get_consensus(orc_handle *o, int32_t n, const d2ba_blockref *refs, double *z7_out, double *tilde6_out);
 

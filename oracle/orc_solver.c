@@ -30,7 +30,7 @@
 #include <time.h>
 #include <pthread.h>
 
-typedef struct { int type, pi, pj, ea, eb, lm; orc_obs_const c; double depth; int64_t seq; } obs_t;
+typedef struct { int type, pi, pj, ea, eb, lm, fa; orc_obs_const c; double depth; int64_t seq; } obs_t;   /* fa: anchor frame (relevance in marginalization) */
 typedef struct { int pi, si, pj, sj; orc_imu_const c; } imu_t;
 
 typedef struct { int64_t *keys; int *vals; int cap, n; } imap_t;
@@ -209,6 +209,7 @@ int orc_add_proj(orc_handle *o, int32_t n, const d2ba_proj_obs *in) {
     t.type = p->type; t.pi = t.pj = t.ea = t.eb = -1;
     t.lm = imap_get(&o->lm_map, p->landmark_id);
     if (t.lm < 0) return 2;
+    t.fa = imap_get(&o->pose_map, p->frame_a);
     if (p->type != D2BA_PROJ_DEPTH_PRIOR) {
       /* parameter lists: ParamResidualInfo.hpp:34-43 (2F1C), :72-82 (2F2C), :107-115 (1F2C) */
       t.ea = imap_get(&o->ext_map, p->cam_a);
@@ -1050,10 +1051,150 @@ int orc_debug_get(orc_handle *o, int32_t item, void *out, int64_t out_bytes, int
   return rc;
 }
 
-int orc_marginalize_stub_unused(orc_handle *o, int32_t n_remove, const int64_t *remove_frame_ids, int32_t *m_out,
-                    int32_t max_m, double *A_out, double *b_out, int32_t *nblk_out, int32_t max_blk,
-                    d2ba_blockref *refs_out) {
-  (void)o; (void)n_remove; (void)remove_frame_ids; (void)m_out; (void)max_m; (void)A_out; (void)b_out;
-  (void)nblk_out; (void)max_blk; (void)refs_out;
-  return 100; /* implemented in orc_margin.c when the 8f-1 row is built */
+/* ------------------------------------------------------------------ marginalization
+ * Marginalizer::marginalize, d2vins/src/estimator/marginalization/marginalization.cpp:173-254, with
+ * filterResiduals (:78-118), sortParams (:256-285), evaluate (:17-76) and the exact-inverse Schur complement of
+ * Utility::schurComplement (d2common/include/d2common/utils.hpp:131-141, margin_sparse_solver: 1).
+ * Configuration restated: remove_base_when_margin_remote = 2 (every landmark of a relevant residual is
+ * marginalised, config/tum/tum_single.yaml:89), margin_enable_fej = 0 (:94) -> evaluation at the current state.
+ * Kept blocks are ordered by ParamsType like sortParams (POSE, SPEED_BIAS, EXTRINSIC, TD); ties (std::sort over a
+ * pointer-keyed map in the reference) are resolved by block insertion order here. Output: A dx = b information
+ * form ("Ignore -b", :203-204), kept-block refs and their linearisation points x0. */
+int orc_marginalize_x0(orc_handle *o, int32_t n_remove, const int64_t *remove_frame_ids, int32_t *m_out, int32_t max_m,
+                       double *A_out, double *b_out, int32_t *nblk_out, int32_t max_blk, d2ba_blockref *refs_out,
+                       double *x0_out) {
+  if (!o->cols_valid) assign_cols(o);
+  const state_t *x = &o->x;
+  char *rem_pose = (char *)calloc(o->np + 1, 1), *rem_sb = (char *)calloc(o->nsb + 1, 1);
+  for (int i = 0; i < o->np; i++) for (int k = 0; k < n_remove; k++) if (o->pose_id[i] == remove_frame_ids[k]) rem_pose[i] = 1;
+  for (int i = 0; i < o->nsb; i++) for (int k = 0; k < n_remove; k++) if (o->sb_id[i] == remove_frame_ids[k]) rem_sb[i] = 1;
+  /* relevant residuals (ParamResidualInfo.hpp relavant()) */
+  char *rel_obs = (char *)calloc(o->nobs + 1, 1), *rel_imu = (char *)calloc(o->nimu + 1, 1);
+  char *use_pose = (char *)calloc(o->np + 1, 1), *use_sb = (char *)calloc(o->nsb + 1, 1), *use_ext = (char *)calloc(o->ne + 1, 1),
+       *use_lm = (char *)calloc(o->nl + 1, 1);
+  int use_td = 0;
+  for (int k = 0; k < o->nobs; k++) {
+    const obs_t *t = o->obs + k;
+    int r = 0;
+    if (t->type == ORC_PROJ_DEPTH_PRIOR || t->type == ORC_PROJ_1F2C) {
+      /* DepthResInfo / LandmarkOneFrameTwoCamResInfo::relavant: the anchor frame only (ParamResidualInfo.hpp:104-106,160-162) */
+      r = t->fa >= 0 ? rem_pose[t->fa] : 0;
+    } else r = rem_pose[t->pi] || rem_pose[t->pj];
+    rel_obs[k] = (char)r;
+    if (!r) continue;
+    if (t->pi >= 0) { use_pose[t->pi] = 1; use_pose[t->pj] = 1; }
+    if (t->type != ORC_PROJ_DEPTH_PRIOR) { use_ext[t->ea] = 1; if (t->eb >= 0) use_ext[t->eb] = 1; use_td = 1; }
+    use_lm[t->lm] = 1;
+  }
+  for (int k = 0; k < o->nimu; k++) {
+    const imu_t *t = o->imu + k;
+    if (rem_pose[t->pi] || rem_pose[t->pj]) { rel_imu[k] = 1; use_pose[t->pi] = use_pose[t->pj] = 1; use_sb[t->si] = use_sb[t->sj] = 1; }
+  }
+  if (o->pm > 0)
+    for (int i = 0; i < o->pnblk; i++) {
+      int kind = o->pkind[i], idx = o->pindex[i];
+      if (kind == D2BA_POSE) use_pose[idx] = 1; else if (kind == D2BA_EXTRINSIC) use_ext[idx] = 1; else if (kind == D2BA_SPEED_BIAS) use_sb[idx] = 1;
+      else if (kind == D2BA_TD) use_td = 1; else use_lm[idx] = 1;
+    }
+  /* column layout: keep [POSE, SPEED_BIAS, EXTRINSIC, TD] | remove [POSE, SPEED_BIAS, LANDMARK] */
+  int *cp = (int *)malloc(sizeof(int) * (o->np + 1)), *cs = (int *)malloc(sizeof(int) * (o->nsb + 1)), *ce = (int *)malloc(sizeof(int) * (o->ne + 1)),
+      *cl = (int *)malloc(sizeof(int) * (o->nl + 1));
+  int ctd = -1, c = 0, nblk = 0, xo = 0, rc = 0;
+  for (int i = 0; i < o->np; i++) cp[i] = -1;
+  for (int i = 0; i < o->nsb; i++) cs[i] = -1;
+  for (int i = 0; i < o->ne; i++) ce[i] = -1;
+  for (int i = 0; i < o->nl; i++) cl[i] = -1;
+#define EMIT(kind_, id_, ptr_, sz_) do { if (nblk >= max_blk) { rc = 3; } else { refs_out[nblk].kind = kind_; refs_out[nblk].pad = 0; refs_out[nblk].id = id_; \
+    if (x0_out) memcpy(x0_out + xo, ptr_, sizeof(double) * (sz_)); xo += (sz_); nblk++; } } while (0)
+  for (int i = 0; i < o->np; i++) if (use_pose[i] && !rem_pose[i]) { cp[i] = c; c += 6; EMIT(D2BA_POSE, o->pose_id[i], x->pose + 7 * i, 7); }
+  for (int i = 0; i < o->nsb; i++) if (use_sb[i] && !rem_sb[i]) { cs[i] = c; c += 9; EMIT(D2BA_SPEED_BIAS, o->sb_id[i], x->sb + 9 * i, 9); }
+  for (int i = 0; i < o->ne; i++) if (use_ext[i]) { ce[i] = c; c += 6; EMIT(D2BA_EXTRINSIC, o->ext_id[i], x->ext + 7 * i, 7); }
+  if (use_td) { ctd = c; c += 1; EMIT(D2BA_TD, 0, &x->td, 1); }
+  const int nk = c;
+  for (int i = 0; i < o->np; i++) if (use_pose[i] && rem_pose[i]) { cp[i] = c; c += 6; }
+  for (int i = 0; i < o->nsb; i++) if (use_sb[i] && rem_sb[i]) { cs[i] = c; c += 9; }
+  for (int i = 0; i < o->nl; i++) if (use_lm[i]) { cl[i] = c; c += 1; }
+  const int N = c, nr = N - nk;
+  if (rc == 0 && (nk > max_m)) rc = 4;
+  if (rc == 0 && (nk == 0 || nr == 0)) rc = 5;   /* reference returns nullptr (:190-196) */
+  if (rc) goto cleanup;
+  {
+    double *H = (double *)calloc((size_t)N * N, 8), *g = (double *)calloc(N, 8);
+#define ACCJ(rows_, nb_, cols_, widths_, lds_, Js_, r_) do { \
+      for (int a_ = 0; a_ < (nb_); a_++) { if ((cols_)[a_] < 0) continue; \
+        for (int i_ = 0; i_ < (widths_)[a_]; i_++) { double gs_ = 0; for (int q_ = 0; q_ < (rows_); q_++) gs_ += (Js_)[a_][q_ * (lds_)[a_] + i_] * (r_)[q_]; g[(cols_)[a_] + i_] += gs_; } \
+        for (int b_ = 0; b_ < (nb_); b_++) { if ((cols_)[b_] < 0) continue; \
+          for (int i_ = 0; i_ < (widths_)[a_]; i_++) for (int j_ = 0; j_ < (widths_)[b_]; j_++) { double s_ = 0; \
+            for (int q_ = 0; q_ < (rows_); q_++) s_ += (Js_)[a_][q_ * (lds_)[a_] + i_] * (Js_)[b_][q_ * (lds_)[b_] + j_]; \
+            H[(size_t)((cols_)[a_] + i_) * N + (cols_)[b_] + j_] += s_; } } } } while (0)
+    for (int k = 0; k < o->nobs; k++) {
+      if (!rel_obs[k]) continue;
+      const obs_t *t = o->obs + k;
+      double r[3], Ji[21] = {0}, Jj[21] = {0}, Ja[21] = {0}, Jb[21] = {0}, Jl[3] = {0}, Jtd[3] = {0};
+      int rows;
+      eval_proj(o, x, t, 1, r, Ji, Jj, Ja, Jb, Jl, Jtd, &rows);
+      int cols[6] = {t->pi >= 0 ? cp[t->pi] : -1, t->pj >= 0 ? cp[t->pj] : -1, t->ea >= 0 ? ce[t->ea] : -1, t->eb >= 0 ? ce[t->eb] : -1, cl[t->lm],
+                     t->type == ORC_PROJ_DEPTH_PRIOR ? -1 : ctd};
+      int widths[6] = {6, 6, 6, 6, 1, 1}, lds[6] = {7, 7, 7, 7, 1, 1};
+      const double *Js[6] = {Ji, Jj, Ja, Jb, Jl, Jtd};
+      ACCJ(rows, 6, cols, widths, lds, Js, r);
+    }
+    for (int k = 0; k < o->nimu; k++) {
+      if (!rel_imu[k]) continue;
+      const imu_t *t = o->imu + k;
+      double r[15], Jpi[105], Jsi[135], Jpj[105], Jsj[135];
+      orc_imu_eval(&t->c, o->cfg.gravity_norm, x->pose + 7 * t->pi, x->sb + 9 * t->si, x->pose + 7 * t->pj, x->sb + 9 * t->sj, r, Jpi, Jsi, Jpj, Jsj);
+      int cols[4] = {cp[t->pi], cs[t->si], cp[t->pj], cs[t->sj]}, widths[4] = {6, 9, 6, 9}, lds[4] = {7, 9, 7, 9};
+      const double *Js[4] = {Jpi, Jsi, Jpj, Jsj};
+      ACCJ(15, 4, cols, widths, lds, Js, r);
+    }
+    if (o->pm > 0) {
+      int m = o->pm;
+      double *dx = (double *)malloc(8 * m), *r = (double *)malloc(8 * m);
+      int *pc = (int *)malloc(sizeof(int) * o->pnblk), *pw = (int *)malloc(sizeof(int) * o->pnblk), *pl = (int *)malloc(sizeof(int) * o->pnblk);
+      const double **pj = (const double **)malloc(sizeof(double *) * o->pnblk);
+      for (int i = 0; i < o->pnblk; i++) {
+        int kind = o->pkind[i], idx = o->pindex[i], off = o->poff[i];
+        const double *x0 = o->px0 + 9 * i;
+        if (kind == D2BA_POSE) { orc_prior_dx_pose(x->pose + 7 * idx, x0, dx + off); pc[i] = cp[idx]; }
+        else if (kind == D2BA_EXTRINSIC) { orc_prior_dx_pose(x->ext + 7 * idx, x0, dx + off); pc[i] = ce[idx]; }
+        else if (kind == D2BA_SPEED_BIAS) { for (int q = 0; q < 9; q++) dx[off + q] = x->sb[9 * idx + q] - x0[q]; pc[i] = cs[idx]; }
+        else if (kind == D2BA_TD) { dx[off] = x->td - x0[0]; pc[i] = ctd; }
+        else { dx[off] = x->lm[idx] - x0[0]; pc[i] = cl[idx]; }
+        pw[i] = o->peff[i]; pl[i] = m; pj[i] = o->pJ + off;
+      }
+      for (int i = 0; i < m; i++) { double a = o->pe0[i]; for (int j = 0; j < m; j++) a += o->pJ[(size_t)i * m + j] * dx[j]; r[i] = a; }
+      ACCJ(m, o->pnblk, pc, pw, pl, pj, r);
+      free(dx); free(r); free(pc); free(pw); free(pl); free(pj);
+    }
+    /* A = H11 - H12 H22^-1 H21, b = g1 - H12 H22^-1 g2 with the exact inverse (Cholesky solve) */
+    double *H22 = (double *)malloc(8 * (size_t)nr * nr), *X = (double *)malloc(8 * (size_t)nr * (nk + 1));
+    for (int i = 0; i < nr; i++) for (int j = 0; j < nr; j++) H22[(size_t)i * nr + j] = H[(size_t)(nk + i) * N + nk + j];
+    if (chol_inplace(H22, nr)) rc = 6;
+    else {
+      double *col = (double *)malloc(8 * nr);
+      for (int j = 0; j <= nk; j++) {
+        for (int i = 0; i < nr; i++) col[i] = j < nk ? H[(size_t)(nk + i) * N + j] : g[nk + i];
+        chol_solve(H22, nr, col);
+        for (int i = 0; i < nr; i++) X[(size_t)i * (nk + 1) + j] = col[i];
+      }
+      free(col);
+      for (int i = 0; i < nk; i++) {
+        for (int j = 0; j < nk; j++) {
+          double s_ = H[(size_t)i * N + j];
+          for (int k = 0; k < nr; k++) s_ -= H[(size_t)i * N + nk + k] * X[(size_t)k * (nk + 1) + j];
+          A_out[(size_t)i * nk + j] = s_;
+        }
+        double s_ = g[i];
+        for (int k = 0; k < nr; k++) s_ -= H[(size_t)i * N + nk + k] * X[(size_t)k * (nk + 1) + nk];
+        b_out[i] = s_;
+      }
+      *m_out = nk; *nblk_out = nblk;
+    }
+    free(H22); free(X); free(H); free(g);
+  }
+cleanup:
+  free(rem_pose); free(rem_sb); free(rel_obs); free(rel_imu); free(use_pose); free(use_sb); free(use_ext); free(use_lm);
+  free(cp); free(cs); free(ce); free(cl);
+  return rc;
 }
