@@ -1147,6 +1147,17 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
     case D2BA_DBG_S: {
       if (h->d_dbg.n < (size_t)h->totH) return fail(h, 4, "debug_get(S): call d2ba_debug_linearize first");
       auto S = fetch(h->d_dbg.p + d.offH, (size_t)n * ld);
+      if (d.schur_small && d.chol_smem) {
+        // the speed-bias rows of such windows never pass through S (k_chol_smem reads them from Hcc): rebuild them
+        // for the debug view exactly as that kernel does (H + mu D^2 on the diagonal, mu = 1e-8 after tr_reset)
+        auto H = fetch(h->d_H[cur].p + d.offH, (size_t)n * ld);
+        for (int i = nlc; i < n; i++)
+          for (int j = 0; j <= i; j++) {
+            double v = H[(size_t)i * ld + j];
+            if (i == j) { double dd = sqrt(v); dd = dd < 1e-6 ? 1e-6 : (dd > 1e32 ? 1e32 : dd); v += h->mu0 * dd * dd; }
+            S[(size_t)i * ld + j] = v;
+          }
+      }
       std::vector<double> o((size_t)n * n);
       for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { o[(size_t)i * n + j] = S[(size_t)i * ld + j]; o[(size_t)j * n + i] = S[(size_t)i * ld + j]; }
       put_d(o); break;

@@ -232,20 +232,20 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
     double *raw = Jr, *fin = Jr + kImuChunk * kF;
     double *Us = fin + kImuChunk * kF;
     int *fcols = reinterpret_cast<int *>(Us + kImuChunk * 225);
+
+    for (int e = tid; e < nf * 225; e += nt) Us[e] = d.imu_U[(size_t)(w.off_imu + f0) * 225 + e];
+    if (tid >= 32 && tid < 32 + nf * 4) {
+      const int t4 = tid - 32;
+      const ImuDesc &im = d.imu[w.off_imu + f0 + t4 / 4];
+      const int q = t4 & 3;
+      fcols[t4] = q == 0 ? col6[im.pi] : (q == 1 ? colsb[im.si] : (q == 2 ? col6[im.pj] : colsb[im.sj]));
+    }
     for (int e = tid; e < nf * kF; e += nt) raw[e] = 0.0;
     __syncthreads();
     if (tid < nf) {
       const ImuDesc &im = d.imu[w.off_imu + f0 + tid];
       imu_raw(d.imu_c + (size_t)(w.off_imu + f0 + tid) * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8,
               xsb + im.sj * 9, d.prm.gravity, raw + tid * kF + 450, raw + tid * kF);
-    }
-    __syncthreads();
-    // stage the sqrt-information matrices and the reduced columns of the factor blocks
-    for (int e = tid; e < nf * 225; e += nt) Us[e] = d.imu_U[(size_t)(w.off_imu + f0) * 225 + e];
-    if (tid < nf * 4) {
-      const ImuDesc &im = d.imu[w.off_imu + f0 + tid / 4];
-      const int q = tid & 3;
-      fcols[tid] = q == 0 ? col6[im.pi] : (q == 1 ? colsb[im.si] : (q == 2 ? col6[im.pj] : colsb[im.sj]));
     }
     __syncthreads();
     // J = U Jraw, r = U rraw
@@ -1082,8 +1082,9 @@ __global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
       }
     }
   }
-  // rows of the speed-bias part (no landmark coupling) and the rest of the rhs row
-  const int nrow = n - nlc;
+  // rows of the speed-bias part (no landmark coupling) and the rest of the rhs row; when the shared-memory
+  // Cholesky owns this window it reads them straight from Hcc instead (saves the copy through S)
+  const int nrow = w.chol_smem ? 0 : n - nlc;
   for (int e = tid; e < nrow * n; e += kSsThreads) {
     const int i = nlc + e / n, j = e % n;
     if (j > i) continue;
@@ -1092,7 +1093,7 @@ __global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
     if (i == j) v += mu * D2v[i];
     S[(size_t)i * ld + j] = v;
   }
-  for (int j = nlc + tid; j < n; j += kSsThreads) S[(size_t)n * ld + j] = gcv[j];
+  if (!w.chol_smem) for (int j = nlc + tid; j < n; j += kSsThreads) S[(size_t)n * ld + j] = gcv[j];
   uhu = block_sum(uhu, redq);
   if (tid == 0) atomicAdd(&ctl->uHu_cam, uhu);
 }
@@ -1275,8 +1276,39 @@ constexpr int kCsNB = 8;
 __host__ __device__ inline int chol_smem_ld(int n) { return (n + 1) & ~1; }
 __host__ __device__ inline size_t chol_smem_bytes(int n) {
   size_t pr = (size_t)kCsNB * (n + 1), need = (size_t)n + 1 + 16 * 32;
-  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)n + (pr > need ? pr : need)) * 8;
+  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)((n + 1) & ~1) + (pr > need ? pr : need)) * 8;   // invd padded to even: P stays 16 B aligned
 }
+// 8x8 diagonal block at (k0, k0): lanes 0..7 of one warp hold one row each in registers, columns are broadcast with
+// shuffles; writes L_d back and the reciprocal diagonal into invd.  Returns true if a pivot is not positive.
+D2BA_DEV bool chol_diag8(double *A, int ld, double *invd, int k0, int nb, int lane) {
+  double row[kCsNB];
+  const int r = k0 + lane;
+#pragma unroll
+  for (int c = 0; c < kCsNB; c++) row[c] = (lane < nb && c <= lane) ? A[(size_t)r * ld + k0 + c] : (c == lane ? 1.0 : 0.0);
+  bool bad = false;
+#pragma unroll
+  for (int c = 0; c < kCsNB; c++) {
+    const double dcc = __shfl_sync(0xffffffffu, row[c], c);
+    const bool live = c < nb;
+    const bool pos = dcc > 0.0 && dcc < 1e300;
+    if (live && !pos) bad = true;
+    const double inv = (live && pos) ? ((dcc > 1e-30 && dcc < 1e30) ? fast_rsqrt(dcc) : rsqrt(dcc)) : 1.0;
+    const double lrc = (lane > c && lane < kCsNB) ? row[c] * inv : 0.0;
+    if (lane > c) row[c] = lrc;
+    if (lane == c && live) { row[c] = dcc * inv; invd[k0 + c] = inv; }
+#pragma unroll
+    for (int c2 = c + 1; c2 < kCsNB; c2++) {
+      const double l2 = __shfl_sync(0xffffffffu, lrc, c2);
+      if (c2 <= lane) row[c2] -= lrc * l2;
+    }
+  }
+  if (lane < nb) {
+#pragma unroll
+    for (int c = 0; c < kCsNB; c++) if (c <= lane) A[(size_t)r * ld + k0 + c] = row[c];
+  }
+  return bad;
+}
+
 __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
@@ -1286,53 +1318,50 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   extern __shared__ double sm[];
   const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = n + 1;
   double *A = sm;                         // n1 x ld
-  double *invd = A + (size_t)n1 * ld;     // n
-  double *P = invd + n;                   // kCsNB x ldp transposed panel; later xs / partial sums
+  double *invd = A + (size_t)n1 * ld;     // n (padded to even)
+  double *P = invd + ((n + 1) & ~1);      // kCsNB x ldp transposed panel; later xs / partial sums
   const double *S = d.S + w.offH;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int fail;
   if (tid == 0) fail = 0;
-  // load the lower triangle (+ rhs row)
-  for (int r = warp; r < n1; r += (nt >> 5)) {
-    const double *src = S + (size_t)r * ldg;
-    double *dst = A + (size_t)r * ld;
-    const int lim = min(r, n - 1);
-    for (int c = lane; c <= lim; c += 32) dst[c] = src[c];
-  }
-  __syncthreads();
-  for (int k0 = 0; k0 < n; k0 += kCsNB) {
-    const int nb = min(kCsNB, n - k0);
-    // (1) diagonal block
-    if (warp == 0) {
-      double row[kCsNB];
-      const int r = k0 + lane;
-#pragma unroll
-      for (int c = 0; c < kCsNB; c++) row[c] = (lane < nb && c <= lane) ? A[(size_t)r * ld + k0 + c] : (c == lane ? 1.0 : 0.0);
-      bool bad = false;
-#pragma unroll
-      for (int c = 0; c < kCsNB; c++) {
-        const double dcc = __shfl_sync(0xffffffffu, row[c], c);
-        const bool live = c < nb;
-        if (live && (!(dcc > 0.0) || !isfinite(dcc))) bad = true;
-        const double inv = (live && dcc > 0.0) ? rsqrt(dcc) : 1.0;
-        const double lrc = (lane > c && lane < kCsNB) ? row[c] * inv : 0.0;
-        if (lane > c) row[c] = lrc;
-        if (lane == c) { if (live) { row[c] = dcc * inv; invd[k0 + c] = inv; } }
-#pragma unroll
-        for (int c2 = c + 1; c2 < kCsNB; c2++) {
-          const double l2 = __shfl_sync(0xffffffffu, lrc, c2);
-          if (c2 <= lane) row[c2] -= lrc * l2;
+  // load the lower triangle (+ rhs row).  Rows of the landmark-coupled part come from the Schur kernel's S; when that
+  // was the one-CTA kernel the speed-bias rows are taken from Hcc directly (+ mu D^2 on the diagonal) and their
+  // share of u^T H u is accumulated here.
+  {
+    const int nlc = w.n_lc, cur = ctl->cur;
+    const bool direct = w.schur_small != 0;
+    const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
+    const double mu = ctl->mu;
+    double uhu = 0.0;
+    for (int r = warp; r < n1; r += (nt >> 5)) {
+      double *dst = A + (size_t)r * ld;
+      const int lim = min(r, n - 1);
+      if (direct && r >= nlc && r < n) {
+        const double *src = H + (size_t)r * ldg;
+        const double ur = ucv[r];
+        for (int c = lane; c <= lim; c += 32) {
+          double v = src[c];
+          uhu += (c == r ? 1.0 : 2.0) * v * ur * ucv[c];
+          if (c == r) v += mu * D2v[r];
+          dst[c] = v;
         }
-      }
-      if (bad) fail = 1;
-      if (lane < nb) {
-#pragma unroll
-        for (int c = 0; c < kCsNB; c++) if (c <= lane) A[(size_t)r * ld + k0 + c] = row[c];
+      } else if (direct && r == n) {
+        const double *src = S + (size_t)r * ldg;
+        for (int c = lane; c <= lim; c += 32) dst[c] = c < nlc ? src[c] : gcv[c];
+      } else {
+        const double *src = S + (size_t)r * ldg;
+        for (int c = lane; c <= lim; c += 32) dst[c] = src[c];
       }
     }
-    __syncthreads();
-    // (2) rows below: a L_d^T = x, results also into the transposed panel copy P[c][r - k0]
-    for (int r = k0 + nb + tid; r < n1; r += nt) {
+    if (direct) { uhu = warp_sum(uhu); if (lane == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu); }
+  }
+  __syncthreads();
+  if (warp == 0) { if (chol_diag8(A, ld, invd, 0, min(kCsNB, n), lane)) fail = 1; }
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += kCsNB) {
+    const int nb = min(kCsNB, n - k0), nxt = k0 + nb;
+    // (2) rows below the (already factored) diagonal block: a L_d^T = x; results also into the transposed copy P[c][r - k0]
+    for (int r = nxt + tid; r < n1; r += nt) {
       double a[kCsNB];
       double *ar = A + (size_t)r * ld + k0;
 #pragma unroll
@@ -1348,40 +1377,83 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
       for (int c = 0; c < kCsNB; c++) { if (c < nb) ar[c] = a[c]; P[c * ldp + (r - k0)] = a[c]; }
     }
     __syncthreads();
-    // (3) trailing update A[i][j] -= sum_c L[i][c] L[j][c] for i >= j >= k0 + nb
-    {
-      const int t0 = nb, ntr = n1 - k0 - nb, nt4 = (ntr + 3) >> 2, ntri = nt4 * (nt4 + 1) / 2;
-      for (int tile = tid; tile < ntri; tile += nt) {
-        int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
-        while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-        while (ti * (ti + 1) / 2 > tile) ti--;
-        const int tj = tile - ti * (ti + 1) / 2;
-        const int ri = t0 + ti * 4, rj = t0 + tj * 4;       // panel-local rows
-        double acc[4][4] = {};
-        const bool full = (ri + 3 < n1 - k0) && (rj + 3 < n1 - k0);
+    if (nxt >= n) break;
+    const int nb2 = min(kCsNB, n - nxt);
+    // (3a) look-ahead: bring the next panel's columns [nxt, nxt+nb2) up to date, one row per thread
+    for (int r = nxt + tid; r < n1; r += nt) {
+      double acc[kCsNB];
 #pragma unroll
-        for (int c = 0; c < kCsNB; c++) {
-          const double *pc = P + c * ldp;
-          double vi[4], vj[4];
+      for (int j = 0; j < kCsNB; j++) acc[j] = 0.0;
+      const int rl = r - k0;
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) {
+        const double *pc = P + c * ldp;
+        const double vr = pc[rl];
+#pragma unroll
+        for (int j = 0; j < kCsNB; j++) acc[j] += vr * pc[nb + j];   // P[c][nxt + j - k0] (zero padded beyond the matrix)
+      }
+      double *ar = A + (size_t)r * ld + nxt;
+#pragma unroll
+      for (int j = 0; j < kCsNB; j++) if (j < nb2 && nxt + j <= r) ar[j] -= acc[j];
+    }
+    __syncthreads();
+    // (3b) warp 0 factors the next diagonal block while the other warps update the rest of the trailing matrix
+    if (warp == 0) {
+      if (chol_diag8(A, ld, invd, nxt, nb2, lane)) fail = 1;
+    } else {
+      const int o = nxt + kCsNB;                     // first row / column of the remaining trailing matrix
+      const int ntr = n1 - o;
+      if (ntr > 0) {
+        const int nt4 = (ntr + 3) >> 2, ntri = nt4 * (nt4 + 1) / 2, wt = nt - 32, wtid = tid - 32;
+        for (int tile = wtid; tile < ntri; tile += wt) {
+          int ti = (int)((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+          while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+          while (ti * (ti + 1) / 2 > tile) ti--;
+          const int tj = tile - ti * (ti + 1) / 2;
+          const int gi0 = o + ti * 4, gj0 = o + tj * 4;   // global row / col of the tile
+          const int ri = gi0 - k0, rj = gj0 - k0;         // panel-local
+          double acc[4][4] = {};
+          const bool full = (gi0 + 3 < n1) && (gj0 + 3 < n) && (tj < ti);
           if (full) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) { vi[q] = pc[ri + q]; vj[q] = pc[rj + q]; }
+            for (int c = 0; c < kCsNB; c++) {
+              const double *pc = P + c * ldp;
+              const double2 i01 = *reinterpret_cast<const double2 *>(pc + ri), i23 = *reinterpret_cast<const double2 *>(pc + ri + 2);
+              const double2 j01 = *reinterpret_cast<const double2 *>(pc + rj), j23 = *reinterpret_cast<const double2 *>(pc + rj + 2);
+              const double vi[4] = {i01.x, i01.y, i23.x, i23.y}, vj[4] = {j01.x, j01.y, j23.x, j23.y};
+#pragma unroll
+              for (int p_ = 0; p_ < 4; p_++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[p_][q] += vi[p_] * vj[q];
+            }
+#pragma unroll
+            for (int p_ = 0; p_ < 4; p_++) {
+              double2 *dst = reinterpret_cast<double2 *>(A + (size_t)(gi0 + p_) * ld + gj0);
+              double2 v0 = dst[0], v1 = dst[1];
+              v0.x -= acc[p_][0]; v0.y -= acc[p_][1]; v1.x -= acc[p_][2]; v1.y -= acc[p_][3];
+              dst[0] = v0; dst[1] = v1;
+            }
           } else {
 #pragma unroll
-            for (int q = 0; q < 4; q++) { vi[q] = (ri + q < n1 - k0) ? pc[ri + q] : 0.0; vj[q] = (rj + q < n1 - k0) ? pc[rj + q] : 0.0; }
+            for (int c = 0; c < kCsNB; c++) {
+              const double *pc = P + c * ldp;
+              double vi[4], vj[4];
+#pragma unroll
+              for (int q = 0; q < 4; q++) { vi[q] = (gi0 + q < n1) ? pc[ri + q] : 0.0; vj[q] = (gj0 + q < n1) ? pc[rj + q] : 0.0; }
+#pragma unroll
+              for (int p_ = 0; p_ < 4; p_++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[p_][q] += vi[p_] * vj[q];
+            }
+#pragma unroll
+            for (int p_ = 0; p_ < 4; p_++)
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const int gi = gi0 + p_, gj = gj0 + q;
+                if (gi < n1 && gj < n && gj <= gi) A[(size_t)gi * ld + gj] -= acc[p_][q];
+              }
           }
-#pragma unroll
-          for (int p_ = 0; p_ < 4; p_++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) acc[p_][q] += vi[p_] * vj[q];
         }
-#pragma unroll
-        for (int p_ = 0; p_ < 4; p_++)
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int gi = k0 + ri + p_, gj = k0 + rj + q;
-            if (gi < n1 && gj < n && gj <= gi) A[(size_t)gi * ld + gj] -= acc[p_][q];
-          }
       }
     }
     __syncthreads();
@@ -1451,20 +1523,23 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
     // landmark back-substitution and the landmark part of the Cauchy / dogleg dot products
     const double *Wt = d.Wt + w.offW;
     double s_gg = 0, s_uHu = 0, s_nn = 0, s_gdn = 0;
-    for (int l0 = warp * 4; l0 < nl; l0 += nw * 4) {
-      double a[4] = {0, 0, 0, 0};
+    for (int l0 = warp * 8; l0 < nl; l0 += nw * 8) {
+      double a[8];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
+      for (int q = 0; q < 8; q++) {
+        a[q] = 0.0;
         if (l0 + q < nl) {
           const double *row = Wt + (size_t)(l0 + q) * w.ldw;
           for (int c = lane; c < nlc; c += 32) a[q] += row[c] * dcs[c];
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++) a[q] = warp_sum(a[q]);
-      if (lane < 4 && l0 + lane < nl) {
+      for (int q = 0; q < 8; q++) a[q] = warp_sum(a[q]);
+      if (lane < 8 && l0 + lane < nl) {
         const int l = l0 + lane;
-        const double aq = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
+        double aq = a[0];
+#pragma unroll
+        for (int q = 1; q < 8; q++) if (lane == q) aq = a[q];
         const double di = dinv[l], gt = Wt[(size_t)l * w.ldw + nlc];
         const double gnl = -di * (gt + aq);
         gn_l[l] = gnl;

@@ -87,6 +87,16 @@ D2BA_DEV double d2_of(double h) {
   return d * d;
 }
 
+// 1/sqrt(d) to full double precision: fp32 MUFU seed + two Newton steps (22 -> 44 -> 88 bits); d must be a normal
+// positive number in the float range (true for the pivots of the scaled normal equations)
+D2BA_DEV double fast_rsqrt(double d) {
+  double y = (double)rsqrtf((float)d);
+  const double hd = 0.5 * d;
+  y = y * (1.5 - hd * y * y);
+  y = y * (1.5 - hd * y * y);
+  return y;
+}
+
 D2BA_DEV double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
