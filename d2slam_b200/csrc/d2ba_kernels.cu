@@ -1275,7 +1275,7 @@ constexpr int kCsThreads = 512;
 constexpr int kCsNB = 8;
 __host__ __device__ inline int chol_smem_ld(int n) { return (n + 1) & ~1; }
 __host__ __device__ inline size_t chol_smem_bytes(int n) {
-  size_t pr = (size_t)kCsNB * (n + 1), need = (size_t)n + 1 + 16 * 32;
+  size_t pr = (size_t)kCsNB * ((n + 2) & ~1), need = (size_t)n + 1 + 16 * 32;
   return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)((n + 1) & ~1) + (pr > need ? pr : need)) * 8;   // invd padded to even: P stays 16 B aligned
 }
 // 8x8 diagonal block at (k0, k0): lanes 0..7 of one warp hold one row each in registers, columns are broadcast with
@@ -1316,7 +1316,7 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ double sm[];
-  const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = n + 1;
+  const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;   // even: double2 panel loads
   double *A = sm;                         // n1 x ld
   double *invd = A + (size_t)n1 * ld;     // n (padded to even)
   double *P = invd + ((n + 1) & ~1);      // kCsNB x ldp transposed panel; later xs / partial sums
