@@ -217,6 +217,7 @@ struct d2ba_handle {
   cudaGraphExec_t iter_graph = nullptr; int graph_key = -1;
   d2ba_handle *marg = nullptr;   // scratch handle of d2ba_marginalize
   double mu0 = 1e-8;
+  bool force_full_S = false;     // the Schur kernels must write the complete reduced system (marginalization reads it)
   // comm
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
 };
@@ -656,7 +657,7 @@ int d2ba_finalize(d2ba_handle *h) {
     d.td_col = w.td_col; d.n_lc = w.n_lc; d.n_c = w.n_c; d.ldh = std::max(4, roundup(w.n_c, 4));
     d.ldw = roundup(w.n_lc + 1, 8); d.nl_pad = roundup(nl, 32);
     d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
-    d.chol_smem = (w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 32) ? 1 : 0;
+    d.chol_smem = (!h->force_full_S && w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 32) ? 1 : 0;
     d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size();
     // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order
     const size_t M = w.obs.size();
@@ -1248,7 +1249,7 @@ int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove, const int
     d2ba_config c = h->cfg; c.max_windows = 1; c.consensus_max_steps = 0; c.use_cuda_graph = 0;
     int rc = d2ba_create(&c, &h->marg);
     if (rc) return fail(h, 60, "marginalize: cannot create scratch handle");
-    h->marg->mu0 = 0.0;
+    h->marg->mu0 = 0.0; h->marg->force_full_S = true;
   }
   d2ba_handle *t = h->marg;
   d2ba_reset(t);
