@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -168,7 +169,10 @@ Nccl g_nccl;
 template <typename T>
 struct DBuf {
   T *p = nullptr; size_t n = 0;
+  bool view = false;   // p points into the handle's upload arena (not owned)
+  void bind(void *base, size_t byte_off, size_t count) { if (p && !view) cudaFree(p); p = (T *)((char *)base + byte_off); n = count; view = true; }
   cudaError_t alloc(size_t count) {
+    if (view) { p = nullptr; n = 0; view = false; }
     if (count <= n && p) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; n = 0;
@@ -176,7 +180,26 @@ struct DBuf {
     if (e == cudaSuccess) n = count;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
+};
+
+}  // namespace
+
+namespace {
+template <typename T>
+struct HBuf {   // pinned host staging buffer (grows, never shrinks)
+  T *p = nullptr; size_t cap = 0, n = 0;
+  bool resize(size_t count) {
+    n = count;
+    if (count <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = count + count / 4 + 16;
+    if (cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
 };
 
 }  // namespace
@@ -188,8 +211,10 @@ struct d2ba_handle {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evf0 = nullptr, evf1 = nullptr, evf2 = nullptr;   // device span of the last finalize: uploads | tile build + prep kernels
   bool finalized = false, state_dirty = false;
   // device arena
+  DBuf<char> d_arena;   // device image of the pinned staging arena (one H2D copy per finalize); the DBufs it backs are views
   DBuf<WinDesc> d_win; DBuf<Ctl> d_ctl;
   DBuf<double> d_x6[2], d_R6[2], d_xsb[2], d_xlm[2], d_xtd[2];
   DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_lm_obs, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
@@ -201,7 +226,7 @@ struct d2ba_handle {
   int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1;
   Dev dev;
   std::vector<WinDesc> h_win;
-  std::vector<Ctl> h_ctl;
+  HBuf<Ctl> h_ctl;   // pinned: D2H target of every solve
   std::vector<Group> h_grp;
   std::vector<int> h_tile_win;
   int n_used = 0, n6_total = 0, nsb_total = 0, nl_total = 0, n_tiles = 0, n_imu_total = 0, n_schur = 0;
@@ -212,12 +237,16 @@ struct d2ba_handle {
   int64_t totH = 0, totW = 0, totc = 0;
   bool any_admm = false;
   // host mirrors of the solved state
-  std::vector<double> h_x6[2], h_xsb[2], h_xlm[2], h_xtd[2];
+  HBuf<double> h_x6[2], h_xsb[2], h_xlm[2], h_xtd[2];   // pinned D2H targets
   // graph cache
   cudaGraphExec_t iter_graph = nullptr; int graph_key = -1;
+  int solves_since_finalize = 0;   // the iteration graph is captured from the second solve of an unchanged structure on
   d2ba_handle *marg = nullptr;   // scratch handle of d2ba_marginalize
   double mu0 = 1e-8;
   bool force_full_S = false;     // the Schur kernels must write the complete reduced system (marginalization reads it)
+  double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wall-clock phases of the last d2ba_finalize (d2ba_debug_host_times)
+  double solve_ms[4] = {0, 0, 0, 0};             // host wall-clock of the last solve: enqueue, wait for the device, write-back
+  std::atomic<long long> add_ns[4];              // thread-summed ns inside d2ba_add_proj since the last reset: index, stamps, staging copy, CUDA calls
   // comm
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
 };
@@ -292,7 +321,7 @@ int d2ba_create(const d2ba_config *cfg, d2ba_handle **out) {
   if (h->cfg.parameter_tolerance <= 0) h->cfg.parameter_tolerance = 1e-8;
   h->win.resize(h->cfg.max_windows);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
-  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evf0); cudaEventCreate(&h->evf1); cudaEventCreate(&h->evf2);
   cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
   memset(&h->dev, 0, sizeof(h->dev));
   *out = h;
@@ -307,7 +336,8 @@ int d2ba_destroy(d2ba_handle *h) {
   if (h->marg) { d2ba_destroy(h->marg); h->marg = nullptr; }
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   // DBuf members: release explicitly
-  h->d_win.release(); h->d_ctl.release();
+  h->d_win.release(); h->d_ctl.release(); h->h_ctl.release(); h->d_arena.release();
+  for (int b = 0; b < 2; b++) { h->h_x6[b].release(); h->h_xsb[b].release(); h->h_xlm[b].release(); h->h_xtd[b].release(); }
   for (int b = 0; b < 2; b++) { h->d_x6[b].release(); h->d_R6[b].release(); h->d_xsb[b].release(); h->d_xlm[b].release(); h->d_xtd[b].release(); h->d_rec[b].release(); h->d_H[b].release(); h->d_gc[b].release(); }
   h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_lm_obs.release();
   h->d_slot6.release(); h->d_lm_win.release(); h->d_blk_win.release(); h->d_sb_win.release(); h->d_tile_win.release();
@@ -320,7 +350,7 @@ int d2ba_destroy(d2ba_handle *h) {
   for (auto &w : h->win) { w.raw.release(); if (w.d_raw) cudaFree(w.d_raw); w.d_raw = nullptr; }
   cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_copy);
   d2ba_release_staging(h);
-  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evf0); cudaEventDestroy(h->evf1); cudaEventDestroy(h->evf2);
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -330,6 +360,7 @@ int d2ba_reset(d2ba_handle *h) {
   if (!h) return 1;
   for (auto &w : h->win) w.clear();
   h->finalized = false;
+  for (auto &a : h->add_ns) a = 0;
   return 0;
 }
 
@@ -384,6 +415,8 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   w->used = true; h->finalized = false;
   if (n <= 0) return 0;
   const size_t base = w->obs.size();
+  auto tq = std::chrono::steady_clock::now();
+  auto lap = [&](int k) { auto t = std::chrono::steady_clock::now(); h->add_ns[k] += std::chrono::duration_cast<std::chrono::nanoseconds>(t - tq).count(); tq = t; };
   w->obs.resize(base + n);
   // one-entry lookup caches: consecutive residuals of a track share landmark, anchor frame and cameras
   struct Cache { int64_t id = INT64_MIN; int idx = -1; } c_lm, c_fa, c_fb, c_ca, c_cb;
@@ -413,13 +446,16 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
     if (err) { w->obs.resize(base); return fail(h, 3, err); }
     w->obs[base + i] = o;
   }
+  lap(0);
   for (int i = 0; i < n; i++) {
     if (in[i].type == D2BA_PROJ_DEPTH_PRIOR) continue;
     w->td_min = std::min(w->td_min, std::min(in[i].td_i, in[i].td_j)); w->td_max = std::max(w->td_max, std::max(in[i].td_i, in[i].td_j));
   }
+  lap(1);
   cudaSetDevice(h->cfg.device);   // callers may feed windows from their own threads
   const bool moved = w->raw.n + (size_t)n > w->raw.cap;
   if (!w->raw.append(in, (size_t)n)) { w->obs.resize(base); return fail(h, 11, "add_proj: pinned allocation failed"); }
+  lap(2);
   // start the upload right away (overlaps with the caller preparing the other blocks / windows)
   if (w->raw.n > w->d_raw_cap) {
     if (w->d_raw) { cudaStreamSynchronize(h->copy_stream); cudaFree(w->d_raw); }
@@ -433,6 +469,7 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
     if (cudaMemcpyAsync(w->d_raw + first, w->raw.p + first, (w->raw.n - first) * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess)
       return fail(h, 13, "add_proj: H2D failed");
   }
+  lap(3);
   return 0;
 }
 
@@ -539,22 +576,6 @@ int d2ba_set_consensus(d2ba_handle *h, int32_t window, int32_t n, const d2ba_blo
 
 namespace {
 
-template <typename T>
-struct HBuf {   // pinned host staging buffer (grows, never shrinks)
-  T *p = nullptr; size_t cap = 0, n = 0;
-  bool resize(size_t count) {
-    n = count;
-    if (count <= cap) return true;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    size_t want = count + count / 4 + 16;
-    if (cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
-    cap = want;
-    return true;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
-};
-
 struct WinPlan {
   WinDesc d;
   std::vector<Group> groups;
@@ -579,12 +600,19 @@ void parallel_for(int n, F f) {
   for (auto &t : th) t.join();
 }
 
-struct Staging {
-  HBuf<WinDesc> win; HBuf<double> x6, xsb, xlm, xtd, imu_c, prior_J, prior_e0;
-  HBuf<int> col6, colsb, tile_grp, tile_win, obs_lm, tile_src, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
-  HBuf<long long> raw_off;
-  HBuf<long long> pr_offJ, pr_offv;
-  HBuf<Group> grp; HBuf<Job> job; HBuf<ImuDesc> imu; HBuf<PriorBlk> pblk; HBuf<SchurTileH> schur;
+template <typename T>
+struct HView {   // typed slice of the pinned staging arena
+  T *p = nullptr; size_t n = 0, off = 0;
+};
+struct Staging {   // every array finalize uploads lives in ONE pinned arena -> one H2D copy into one device arena
+  HBuf<char> arena; size_t cursor = 0;
+  HView<WinDesc> win; HView<double> x6, xsb, xlm, xtd, imu_c, prior_J, prior_e0;
+  HView<int> col6, colsb, tile_grp, tile_win, obs_lm, tile_src, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
+  HView<long long> raw_off;
+  HView<long long> pr_offJ, pr_offv;
+  HView<Group> grp; HView<Job> job; HView<ImuDesc> imu; HView<PriorBlk> pblk; HView<SchurTileH> schur;
+  template <typename T> void reserve(HView<T> &v, size_t count) { v.n = count; v.off = cursor; cursor += (count * sizeof(T) + 255) & ~(size_t)255; }
+  template <typename T> void place(HView<T> &v) { v.p = (T *)(arena.p + v.off); }
 };
 std::map<d2ba_handle *, Staging *> g_staging;   // owned per handle, freed in d2ba_destroy
 std::mutex g_staging_mu;
@@ -599,9 +627,8 @@ Staging *staging_of(d2ba_handle *h) {
 }
 
 template <typename T>
-int up(d2ba_handle *h, DBuf<T> &b, const HBuf<T> &v) {
-  CK(b.alloc(v.n));
-  if (v.n) CK(cudaMemcpyAsync(b.p, v.p, v.n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+int up(d2ba_handle *h, DBuf<T> &b, const HView<T> &v) {   // the data travels with the single arena copy
+  b.bind(h->d_arena.p, v.off, v.n);
   return 0;
 }
 
@@ -612,11 +639,7 @@ void d2ba_release_staging(d2ba_handle *h) {
   auto it = g_staging.find(h);
   if (it == g_staging.end()) return;
   Staging *s = it->second;
-  s->win.release(); s->x6.release(); s->xsb.release(); s->xlm.release(); s->xtd.release(); s->imu_c.release(); s->tile_src.release(); s->raw_off.release();
-  s->prior_J.release(); s->prior_e0.release(); s->col6.release(); s->colsb.release(); s->tile_grp.release(); s->tile_win.release();
-  s->obs_lm.release(); s->lm_ptr.release(); s->lm_obs.release(); s->slot6.release(); s->lm_win.release(); s->blk_win.release();
-  s->sb_win.release(); s->pr_m.release(); s->pr_info.release(); s->pr_offJ.release(); s->pr_offv.release(); s->grp.release();
-  s->job.release(); s->imu.release(); s->pblk.release(); s->schur.release();
+  s->arena.release();
   delete s;
   g_staging.erase(it);
 }
@@ -633,6 +656,11 @@ int d2ba_finalize(d2ba_handle *h) {
   }
   if (nw == 0) return fail(h, 22, "finalize: no window in use");
   Staging &st = *staging_of(h);
+  // the pinned staging buffers are rewritten below: wait for the uploads of the previous finalize of this handle
+  // (normally long complete -- a solve synchronises the stream); the uploads enqueued by THIS call are not waited for
+  CK(cudaStreamSynchronize(h->stream));
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](int slot) { auto t = std::chrono::steady_clock::now(); h->host_ms[slot] = std::chrono::duration<double, std::milli>(t - tp0).count(); tp0 = t; };
   std::vector<WinPlan> plan(nw);
   size_t total_obs = 0;
   for (int i = 0; i < nw; i++) total_obs += h->win[i].obs.size();
@@ -659,16 +687,36 @@ int d2ba_finalize(d2ba_handle *h) {
     d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
     d.chol_smem = (!h->force_full_S && w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 32) ? 1 : 0;
     d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size();
-    // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order
+    // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order.  The number of distinct
+    // keys is small (<= a few hundred), so this is a counting sort: key -> bucket via a flat hash, buckets ordered by key.
     const size_t M = w.obs.size();
-    std::vector<std::pair<uint64_t, uint32_t>> keys(M);
-    for (size_t k = 0; k < M; k++) {
-      const HObs &o = w.obs[k];
-      uint64_t key = ((uint64_t)(o.type & 0xF) << 60) | ((uint64_t)((o.pi + 1) & 0x7FFF) << 45) | ((uint64_t)((o.pj + 1) & 0x7FFF) << 30) |
-                     ((uint64_t)((o.ea + 1) & 0x7FFF) << 15) | (uint64_t)((o.eb + 1) & 0x7FFF);
-      keys[k] = {key, (uint32_t)k};
+    std::vector<std::pair<uint64_t, uint32_t>> keys(M);   // (key, bucket) then reused as (key, obs index) in sorted order
+    {
+      FlatMap bucket_of;                                     // key -> bucket id
+      std::vector<uint64_t> bkey; std::vector<uint32_t> bcount;
+      std::vector<uint32_t> ob(M);
+      uint64_t last_key = ~0ull; int last_b = -1;
+      for (size_t k = 0; k < M; k++) {
+        const HObs &o = w.obs[k];
+        const uint64_t key = ((uint64_t)(o.type & 0xF) << 60) | ((uint64_t)((o.pi + 1) & 0x7FFF) << 45) | ((uint64_t)((o.pj + 1) & 0x7FFF) << 30) |
+                             ((uint64_t)((o.ea + 1) & 0x7FFF) << 15) | (uint64_t)((o.eb + 1) & 0x7FFF);
+        int b;
+        if (key == last_key) b = last_b;
+        else {
+          b = bucket_of.find((int64_t)key);
+          if (b < 0) { b = (int)bkey.size(); bucket_of.put((int64_t)key, b); bkey.push_back(key); bcount.push_back(0); }
+          last_key = key; last_b = b;
+        }
+        ob[k] = (uint32_t)b; bcount[b]++;
+      }
+      std::vector<uint32_t> border(bkey.size());
+      for (size_t i = 0; i < border.size(); i++) border[i] = (uint32_t)i;
+      std::sort(border.begin(), border.end(), [&](uint32_t a, uint32_t b) { return bkey[a] < bkey[b]; });
+      std::vector<uint32_t> start(bkey.size());
+      uint32_t run = 0;
+      for (uint32_t bi : border) { start[bi] = run; run += bcount[bi]; }
+      for (size_t k = 0; k < M; k++) { const uint32_t b = ob[k]; keys[start[b]++] = {bkey[b], (uint32_t)k}; }   // stable within a bucket
     }
-    std::sort(keys.begin(), keys.end());
     w.order.resize(M); w.sorted_pos.assign(M, -1);
     for (size_t k = 0; k < M; k++) w.order[k] = (int)keys[k].second;
     bool any_wide = false;
@@ -721,6 +769,7 @@ int d2ba_finalize(d2ba_handle *h) {
       for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 1, tm, tn});
     }
   });
+  lap(0);
   // ---- serial prefix sums
   h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
   h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0;
@@ -753,14 +802,23 @@ int d2ba_finalize(d2ba_handle *h) {
   h->n6_total = off6; h->nsb_total = offsb; h->nl_total = offlm; h->n_tiles = off_tile; h->n_imu_total = off_imu; h->n_schur = n_schur;
   h->totH = offH; h->totW = offW; h->totc = offc;
   // ---- staging sizes
-  bool ok = st.win.resize(nw) && st.x6.resize((size_t)off6 * 8) && st.xsb.resize((size_t)offsb * 9) && st.xlm.resize(offlm) && st.xtd.resize(nw) &&
-            st.col6.resize(off6) && st.colsb.resize(offsb) && st.slot6.resize(off6) && st.blk_win.resize(off6) && st.sb_win.resize(offsb) &&
-            st.lm_win.resize(offlm) && st.tile_grp.resize(off_tile) && st.tile_win.resize(off_tile) && st.obs_lm.resize((size_t)off_tile * kTile) &&
-            st.tile_src.resize((size_t)off_tile * kTile) && st.raw_off.resize(nw) && st.lm_ptr.resize(off_lmptr) && st.lm_obs.resize((size_t)off_lmobs) &&
-            st.grp.resize(off_grp) && st.job.resize(n_jobs) && st.imu.resize(off_imu) && st.imu_c.resize((size_t)off_imu * kImuStride) &&
-            st.pblk.resize(off_pblk) && st.prior_J.resize((size_t)off_pJ) && st.prior_e0.resize((size_t)off_pv) && st.schur.resize(n_schur) &&
-            st.pr_m.resize(nw) && st.pr_info.resize(nw) && st.pr_offJ.resize(nw) && st.pr_offv.resize(nw);
+  st.cursor = 0;
+  st.reserve(st.win, nw); st.reserve(st.x6, (size_t)off6 * 8); st.reserve(st.xsb, (size_t)offsb * 9); st.reserve(st.xlm, offlm); st.reserve(st.xtd, nw);
+  st.reserve(st.col6, off6); st.reserve(st.colsb, offsb); st.reserve(st.slot6, off6); st.reserve(st.blk_win, off6); st.reserve(st.sb_win, offsb);
+  st.reserve(st.lm_win, offlm); st.reserve(st.tile_grp, off_tile); st.reserve(st.tile_win, off_tile); st.reserve(st.obs_lm, (size_t)off_tile * kTile);
+  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.lm_obs, (size_t)off_lmobs);
+  st.reserve(st.grp, off_grp); st.reserve(st.job, n_jobs); st.reserve(st.imu, off_imu); st.reserve(st.imu_c, (size_t)off_imu * kImuStride);
+  st.reserve(st.pblk, off_pblk); st.reserve(st.prior_J, (size_t)off_pJ); st.reserve(st.prior_e0, (size_t)off_pv); st.reserve(st.schur, n_schur);
+  st.reserve(st.pr_m, nw); st.reserve(st.pr_info, nw); st.reserve(st.pr_offJ, nw); st.reserve(st.pr_offv, nw);
+  bool ok = st.arena.resize(st.cursor + 256);
+  if (ok) {
+    st.place(st.win); st.place(st.x6); st.place(st.xsb); st.place(st.xlm); st.place(st.xtd); st.place(st.col6); st.place(st.colsb); st.place(st.slot6);
+    st.place(st.blk_win); st.place(st.sb_win); st.place(st.lm_win); st.place(st.tile_grp); st.place(st.tile_win); st.place(st.obs_lm); st.place(st.tile_src);
+    st.place(st.raw_off); st.place(st.lm_ptr); st.place(st.lm_obs); st.place(st.grp); st.place(st.job); st.place(st.imu); st.place(st.imu_c); st.place(st.pblk);
+    st.place(st.prior_J); st.place(st.prior_e0); st.place(st.schur); st.place(st.pr_m); st.place(st.pr_info); st.place(st.pr_offJ); st.place(st.pr_offv);
+  }
   if (!ok) return fail(h, 24, "pinned staging allocation failed");
+  lap(1);
   // ---- pass B (parallel): fill the staging buffers
   parallel_for(nw, [&](int wi) {
     HostWin &w = h->win[wi]; WinPlan &pl = plan[wi]; const WinDesc &d = pl.d;
@@ -831,10 +889,23 @@ int d2ba_finalize(d2ba_handle *h) {
       }
     }
   });
+  lap(2);
   h->h_win.assign(st.win.p, st.win.p + nw);
   h->h_grp.assign(st.grp.p, st.grp.p + off_grp);
   // ---- uploads (pinned -> device, async on the solver stream)
   int rc;
+  CK(cudaEventRecord(h->evf0, h->stream));
+  // raw observation records were uploaded as they were added (copy stream); their device addresses ride in the arena
+  for (int wi = 0; wi < nw; wi++) {
+    HostWin &w = h->win[wi];
+    if (w.raw.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
+    st.raw_off.p[wi] = (long long)(uintptr_t)w.d_raw;
+  }
+  if (st.cursor > h->d_arena.n) {   // growing: views of the old arena die with it
+    CK(cudaStreamSynchronize(h->stream));
+    CK(h->d_arena.alloc(st.cursor + st.cursor / 4 + 256));
+  }
+  CK(cudaMemcpyAsync(h->d_arena.p, st.arena.p, st.cursor, cudaMemcpyHostToDevice, h->stream));
   if ((rc = up(h, h->d_win, st.win))) return rc;
   CK(h->d_ctl.alloc(nw)); CK(cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Ctl) * nw, h->stream));
   if ((rc = up(h, h->d_x6[0], st.x6)) || (rc = up(h, h->d_xsb[0], st.xsb)) || (rc = up(h, h->d_xlm[0], st.xlm)) || (rc = up(h, h->d_xtd[0], st.xtd))) return rc;
@@ -852,16 +923,12 @@ int d2ba_finalize(d2ba_handle *h) {
       (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
       (rc = up(h, h->d_schur, st.schur)))
     return rc;
-  // raw observation records were uploaded as they were added (copy stream); the device builds the tiles from them
+  // the device builds the tiles from the raw records
   CK(h->d_obs.alloc((size_t)off_tile * kTile * kObsFields));
-  for (int wi = 0; wi < nw; wi++) {
-    HostWin &w = h->win[wi];
-    if (w.raw.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
-    st.raw_off.p[wi] = (long long)(uintptr_t)w.d_raw;
-  }
   if ((rc = up(h, h->d_raw_off, st.raw_off))) return rc;
   CK(cudaEventRecord(h->ev_copy, h->copy_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+  CK(cudaEventRecord(h->evf1, h->stream));
   launch_build_tiles(nullptr, h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
   CK(h->d_imu_U.alloc((size_t)off_imu * 225)); CK(h->d_prior_A.alloc((size_t)off_pJ));
   CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
@@ -908,14 +975,28 @@ int d2ba_finalize(d2ba_handle *h) {
     launch_prior_from_info(nw, h->max_prior_m, h->d_pr_m.p, h->d_pr_oJ.p, h->d_pr_ov.p, h->d_pr_info.p, h->d_prior_J.p, h->d_prior_A.p, h->d_prior_e0.p, h->stream);
   }
   launch_prior_prep(D, h->stream);
-  CK(cudaStreamSynchronize(h->stream));   // staging buffers are reused by the next finalize
+  CK(cudaEventRecord(h->evf2, h->stream));
+  lap(3);
   CK(cudaGetLastError());
-  h->h_ctl.assign(nw, Ctl());
-  for (int b = 0; b < 2; b++) {
-    h->h_x6[b].assign(st.x6.p, st.x6.p + st.x6.n); h->h_xsb[b].assign(st.xsb.p, st.xsb.p + st.xsb.n);
-    h->h_xlm[b].assign(st.xlm.p, st.xlm.p + st.xlm.n); h->h_xtd[b].assign(st.xtd.p, st.xtd.p + st.xtd.n);
+  lap(4);
+  bool okm = h->h_ctl.resize(nw);
+  for (int b = 0; b < 2; b++) okm = okm && h->h_x6[b].resize(st.x6.n) && h->h_xsb[b].resize(st.xsb.n) && h->h_xlm[b].resize(st.xlm.n) && h->h_xtd[b].resize(st.xtd.n);
+  if (!okm) return fail(h, 24, "pinned read-back allocation failed");
+  memset(h->h_ctl.p, 0, sizeof(Ctl) * nw);
+  h->finalized = true; h->state_dirty = false; h->solves_since_finalize = 0;
+  lap(5);
+  return 0;
+}
+
+int d2ba_debug_host_times(d2ba_handle *h, double *ms_out) {
+  if (!h || !ms_out) return 1;
+  memcpy(ms_out, h->host_ms, sizeof h->host_ms);
+  if (h->finalized && cudaEventSynchronize(h->evf2) == cudaSuccess) {
+    float a = 0, b = 0; cudaEventElapsedTime(&a, h->evf0, h->evf1); cudaEventElapsedTime(&b, h->evf1, h->evf2);
+    ms_out[6] = a; ms_out[7] = b;
   }
-  h->finalized = true; h->state_dirty = false;
+  for (int k = 0; k < 4; k++) ms_out[8 + k] = 1e-6 * (double)h->add_ns[k].load();
+  for (int k = 0; k < 3; k++) ms_out[12 + k] = h->solve_ms[k];
   return 0;
 }
 
@@ -986,6 +1067,8 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
   h->dev.prm.fixed_mode = fixed ? 1 : 0; h->dev.prm.max_iter = iters;
   const int key = (fixed ? 1 : 0) * 100000 + iters;
   if (h->graph_key != key) release_graph(h);
+  auto tq = std::chrono::steady_clock::now();
+  auto lap = [&](int k) { auto t = std::chrono::steady_clock::now(); h->solve_ms[k] = std::chrono::duration<double, std::milli>(t - tq).count(); tq = t; };
   CK(cudaEventRecord(h->ev0, h->stream));
   launch_tr_reset(h->dev, 1, h->stream);
   if (h->any_admm) launch_cons_init(h->dev, h->n6_total, h->stream);
@@ -994,7 +1077,9 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
     if (h->any_admm) { int rc = consensus_exchange(h); if (rc) return rc; }
     enqueue_linearize(h, 1);
     launch_control(h->dev, st == 0 ? 1 : 2, h->stream);
-    if (h->cfg.use_cuda_graph) {
+    // A graph pays off when the same structure is solved repeatedly (ADMM sub-steps, re-solves, the device-resident
+    // benchmark); the reference-style reset -> add -> finalize -> solve cycle launches directly and skips the instantiation.
+    if (h->cfg.use_cuda_graph && (h->iter_graph || h->solves_since_finalize > 0 || st > 0)) {
       if (!h->iter_graph) {
         cudaGraph_t g;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1011,28 +1096,30 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   // read back control blocks and both state buffers (the accepted buffer differs per window)
-  CK(cudaMemcpyAsync(h->h_ctl.data(), h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_ctl.p, h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
   for (int b = 0; b < 2; b++) {
-    CK(cudaMemcpyAsync(h->h_x6[b].data(), h->d_x6[b].p, h->h_x6[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (!h->h_xsb[b].empty()) CK(cudaMemcpyAsync(h->h_xsb[b].data(), h->d_xsb[b].p, h->h_xsb[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (!h->h_xlm[b].empty()) CK(cudaMemcpyAsync(h->h_xlm[b].data(), h->d_xlm[b].p, h->h_xlm[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_xtd[b].data(), h->d_xtd[b].p, h->h_xtd[b].size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_x6[b].p, h->d_x6[b].p, h->h_x6[b].n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h->h_xsb[b].n) CK(cudaMemcpyAsync(h->h_xsb[b].p, h->d_xsb[b].p, h->h_xsb[b].n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (h->h_xlm[b].n) CK(cudaMemcpyAsync(h->h_xlm[b].p, h->d_xlm[b].p, h->h_xlm[b].n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_xtd[b].p, h->d_xtd[b].p, h->h_xtd[b].n * 8, cudaMemcpyDeviceToHost, h->stream));
   }
+  lap(0);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
+  lap(1);
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   // write the solved state back into the host windows (so a following solve starts from it)
   int wi = 0;
   for (auto &w : h->win) {
     if (!w.used) continue;
-    const WinDesc &d = h->h_win[wi]; const int cur = h->h_ctl[wi].cur;
-    for (int i = 0; i < d.np; i++) memcpy(&w.pose[7 * i], &h->h_x6[cur][(size_t)(d.off6 + i) * 8], 56);
-    for (int i = 0; i < d.ne; i++) memcpy(&w.ext[7 * i], &h->h_x6[cur][(size_t)(d.off6 + d.np + i) * 8], 56);
-    if (d.nsb) memcpy(w.sb.data(), &h->h_xsb[cur][(size_t)d.offsb * 9], (size_t)d.nsb * 72);
-    if (d.nl) memcpy(w.lm.data(), &h->h_xlm[cur][d.offlm], (size_t)d.nl * 8);
-    w.td = h->h_xtd[cur][wi];
+    const WinDesc &d = h->h_win[wi]; const int cur = h->h_ctl.p[wi].cur;
+    for (int i = 0; i < d.np; i++) memcpy(&w.pose[7 * i], &h->h_x6[cur].p[(size_t)(d.off6 + i) * 8], 56);
+    for (int i = 0; i < d.ne; i++) memcpy(&w.ext[7 * i], &h->h_x6[cur].p[(size_t)(d.off6 + d.np + i) * 8], 56);
+    if (d.nsb) memcpy(w.sb.data(), &h->h_xsb[cur].p[(size_t)d.offsb * 9], (size_t)d.nsb * 72);
+    if (d.nl) memcpy(w.lm.data(), &h->h_xlm[cur].p[d.offlm], (size_t)d.nl * 8);
+    w.td = h->h_xtd[cur].p[wi];
     if (reports) {
-      const Ctl &c = h->h_ctl[wi]; d2ba_report &r = reports[wi];
+      const Ctl &c = h->h_ctl.p[wi]; d2ba_report &r = reports[wi];
       r.total_iterations = c.lin_count; r.successful_steps = c.succ; r.termination = c.term; r.succ = c.term != 4;
       r.total_time = ms * 1e-3; r.initial_cost = c.initial_cost; r.final_cost = c.cost; r.state_changes = 0;
       r.final_gradient_max_norm = c.gmax_c; r.final_radius = c.radius;
@@ -1040,6 +1127,8 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
     wi++;
   }
   h->state_dirty = true;   // device buffer 0 no longer holds the accepted state of every window
+  h->solves_since_finalize++;
+  lap(2);
   return 0;
 }
 
@@ -1108,7 +1197,7 @@ int d2ba_debug_linearize(d2ba_handle *h) {
   if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
   if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
   launch_step(h->dev, h->max_nc, h->stream);
-  CK(cudaMemcpyAsync(h->h_ctl.data(), h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_ctl.p, h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   release_graph(h);
@@ -1124,7 +1213,7 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
   std::vector<uint8_t> buf;
   auto put_d = [&](const std::vector<double> &v) { buf.resize(v.size() * 8); memcpy(buf.data(), v.data(), buf.size()); };
   auto fetch = [&](const double *src, size_t cnt) { std::vector<double> v(cnt); if (cnt) cudaMemcpy(v.data(), src, cnt * 8, cudaMemcpyDeviceToHost); return v; };
-  const int cur = h->h_ctl[window].cur;
+  const int cur = h->h_ctl.p[window].cur;
   switch (item) {
     case D2BA_DBG_N_CAM: { int64_t v = n; buf.resize(8); memcpy(buf.data(), &v, 8); break; }
     case D2BA_DBG_N_LC: { int64_t v = nlc; buf.resize(8); memcpy(buf.data(), &v, 8); break; }
@@ -1144,7 +1233,7 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
       for (int l = 0; l < nl; l++) for (int c = 0; c < nlc; c++) o[(size_t)l * nlc + c] = Wt[(size_t)l * d.ldw + c] / di[l];
       put_d(o); break;
     }
-    case D2BA_DBG_COST: { std::vector<double> v(1, h->h_ctl[window].cost); put_d(v); break; }
+    case D2BA_DBG_COST: { std::vector<double> v(1, h->h_ctl.p[window].cost); put_d(v); break; }
     case D2BA_DBG_S: {
       if (h->d_dbg.n < (size_t)h->totH) return fail(h, 4, "debug_get(S): call d2ba_debug_linearize first");
       auto S = fetch(h->d_dbg.p + d.offH, (size_t)n * ld);

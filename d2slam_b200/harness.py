@@ -22,6 +22,7 @@ def lib():
         _LIB = C.CDLL(p)
         _LIB.rp_create.restype = C.c_void_p
         _LIB.rp_run.restype = C.c_double
+        _LIB.rp_run_pipelined.restype = C.c_double
     return _LIB
 
 
@@ -65,9 +66,23 @@ class Replay:
         t = lib().rp_run(self.ctx, solver.h, C.c_int(steps), C.c_int(iters), C.c_int(nthreads), reps)
         if t < 0:
             raise RuntimeError(f"rp_run failed: {t} ({d2ba_lib().d2ba_last_error(solver.h)})")
-        bd = np.zeros(4)
+        bd = np.zeros(8)
         lib().rp_breakdown(self.ctx, abi.ptr(bd))
         self.breakdown = {"feed_s": bd[0], "finalize_s": bd[1], "solve_s": bd[2], "fetch_s": bd[3]}
+        # thread-summed seconds inside each group of C-ABI calls of the feed phase (diagnostics)
+        self.feed_calls = {"set_blocks_s": bd[4], "add_proj_s": bd[5], "add_imu_s": bd[6], "prior_cons_s": bd[7]}
+        return t, list(reps)
+
+    def run_pipelined(self, solvers, steps, iters, nthreads):
+        """Same per-step sequence with consecutive steps overlapped across ``len(solvers)`` handles (feed | finalize | solve+fetch)."""
+        reps = (abi.Report * self.n)()
+        hs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+        t = lib().rp_run_pipelined(self.ctx, hs, C.c_int(len(solvers)), C.c_int(steps), C.c_int(iters), C.c_int(nthreads), reps)
+        if t < 0:
+            raise RuntimeError(f"rp_run_pipelined failed: {t} " + " | ".join(str(d2ba_lib().d2ba_last_error(s.h)) for s in solvers))
+        bd = np.zeros(8)
+        lib().rp_breakdown(self.ctx, abi.ptr(bd))
+        self.breakdown = {"feed_s": bd[0], "finalize_s": bd[1], "solve_s": bd[2], "fetch_s": bd[3]}   # stage busy times; stages overlap
         return t, list(reps)
 
     def outputs(self, w, n_pose, n_sb, n_lm):

@@ -48,7 +48,7 @@ EXPORTED = [
     "d2ba_add_proj", "d2ba_add_landmark_tracks", "d2ba_add_imu", "d2ba_set_prior", "d2ba_set_prior_info",
     "d2ba_set_consensus", "d2ba_comm_unique_id", "d2ba_comm_init", "d2ba_consensus_buffer", "d2ba_finalize",
     "d2ba_solve", "d2ba_solve_fixed", "d2ba_get_blocks", "d2ba_num_windows", "d2ba_marginalize",
-    "d2ba_debug_linearize", "d2ba_debug_get", "d2ba_debug_kernel_times",
+    "d2ba_debug_linearize", "d2ba_debug_get", "d2ba_debug_kernel_times", "d2ba_debug_host_times",
 ]
 
 
@@ -175,6 +175,16 @@ class Solver:
         out = np.zeros(8)
         self._chk(lib().d2ba_debug_kernel_times(self.h, C.c_int32(iters), abi.ptr(out)), "kernel_times")
         return {k: out[i] / max(out[7], 1) for i, k in enumerate(KERNEL_NAMES)}
+
+    def host_times(self):
+        """Wall-clock ms of the phases of the last finalize()."""
+        out = np.zeros(16)
+        self._chk(lib().d2ba_debug_host_times(self.h, abi.ptr(out)), "host_times")
+        d = dict(zip(("plan", "prefix", "fill", "enqueue", "wait", "mirror"), out[:6].round(3).tolist()))
+        d.update(zip(("dev_upload", "dev_prep"), out[6:8].round(3).tolist()))
+        d.update(zip(("solve_enqueue", "solve_wait", "solve_writeback"), out[12:15].round(3).tolist()))
+        d.update(zip(("add_lookup", "add_stamps", "add_copy", "add_cuda"), out[8:12].round(3).tolist()))
+        return d
 
     def debug_linearize(self):
         self._chk(lib().d2ba_debug_linearize(self.h), "debug_linearize")
