@@ -685,7 +685,7 @@ int d2ba_finalize(d2ba_handle *h) {
     d.td_col = w.td_col; d.n_lc = w.n_lc; d.n_c = w.n_c; d.ldh = std::max(4, roundup(w.n_c, 4));
     d.ldw = roundup(w.n_lc + 1, 8); d.nl_pad = roundup(nl, 32);
     d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
-    d.chol_smem = (!h->force_full_S && w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 32) ? 1 : 0;
+    d.chol_smem = (!h->force_full_S && w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 16) ? 1 : 0;   // 16 B of static shared memory (fail flag + mbarrier)
     d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size();
     // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order.  The number of distinct
     // keys is small (<= a few hundred), so this is a counting sort: key -> bucket via a flat hash, buckets ordered by key.

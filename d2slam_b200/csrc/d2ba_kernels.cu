@@ -12,6 +12,7 @@
 //   k_control         accept / reject, radius, convergence
 //   k_cons_*          ADMM consensus pack / apply
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <stdint.h>
 
 #include "../../include/d2ba.h"
@@ -1267,46 +1268,95 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
 // ------------------------------------------------------------------------------------------------
 // Shared-memory Cholesky for reduced systems that fit one SM (n_c <= ~165: the single-drone window).
 // The whole bordered matrix lives in shared memory (row-major, even leading dimension); 8-column panels:
-//   (1) 8x8 diagonal block in the registers of 8 lanes (shuffle broadcast),
-//   (2) TRSM of the rows below, one row per thread, 8 values in registers,
-//   (3) trailing update with 4x4 register tiles fed from a transposed copy of the panel.
-// Then blocked back substitution, all from shared memory.
+//   (1) 8x8 diagonal block in the registers of 8 lanes: unscaled elimination whose per-column dependency chain is
+//       shuffle -> reciprocal -> one DFMA, columns scaled by 1/sqrt(d) afterwards,
+//   (2) TRSM of the rows below, one row per thread, against the row-scaled block (one DFMA per step on the chain),
+//   (3) trailing update on the fp64 tensor cores: 8x8 output tiles, two DMMA m8n8k4 per tile, operands from a
+//       transposed copy of the panel; the tile column of the next panel first, then warp 0 factors the next
+//       diagonal block while the other warps update the rest.
+// Then blocked back substitution, all from shared memory.  (Measured on B200: DFMA latency 8.7 cycles, DMMA 26,
+// shuffle 30, dependent LDS ~30; DMMA and DFMA have the same peak, so the tensor-core form wins on issue slots.)
 constexpr int kCsThreads = 512;
 constexpr int kCsNB = 8;
 __host__ __device__ inline int chol_smem_ld(int n) { return (n + 1) & ~1; }
 __host__ __device__ inline size_t chol_smem_bytes(int n) {
   size_t pr = (size_t)kCsNB * ((n + 2) & ~1), need = (size_t)n + 1 + 16 * 32;
-  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)((n + 1) & ~1) + (pr > need ? pr : need)) * 8;   // invd padded to even: P stays 16 B aligned
+  return ((size_t)(n + 1) * chol_smem_ld(n) + (size_t)((n + 1) & ~1) + (pr > need ? pr : need)) * 8 + 32;   // invd padded to even: P stays 16 B aligned
 }
-// 8x8 diagonal block at (k0, k0): lanes 0..7 of one warp hold one row each in registers, columns are broadcast with
-// shuffles; writes L_d back and the reciprocal diagonal into invd.  Returns true if a pivot is not positive.
-D2BA_DEV bool chol_diag8(double *A, int ld, double *invd, int k0, int nb, int lane) {
+// 1/d to full double precision: fp32 MUFU seed + two Newton steps; d must be a normal positive number in float range
+D2BA_DEV double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));   // MUFU.RCP64H: ~20 good bits, no fp32 round trip
+  double e = fma(-d, r, 1.0); r = fma(r, e, r);
+  e = fma(-d, r, 1.0); r = fma(r, e, r);
+  e = fma(-d, r, 1.0); r = fma(r, e, r);   // third step: the seed is only guaranteed to ~2^-19, keep a safety margin
+  return r;
+}
+// 8x8 diagonal block at (k0, k0): lanes 0..7 of one warp hold one row each in registers.  Writes L_d back, 1/L_cc
+// into invd and the row-scaled block M[c][k] = L[c][k] / L[c][c] (k < c) into Ms.  Returns true on a bad pivot.
+D2BA_DEV bool chol_diag8(double *A, int ld, double *invd, double *Ms, int msld, int k0, int nb, int lane) {
   double row[kCsNB];
   const int r = k0 + lane;
 #pragma unroll
   for (int c = 0; c < kCsNB; c++) row[c] = (lane < nb && c <= lane) ? A[(size_t)r * ld + k0 + c] : (c == lane ? 1.0 : 0.0);
   bool bad = false;
+  double dmine = 1.0;   // pivot of this lane's own column
 #pragma unroll
   for (int c = 0; c < kCsNB; c++) {
     const double dcc = __shfl_sync(0xffffffffu, row[c], c);
     const bool live = c < nb;
-    const bool pos = dcc > 0.0 && dcc < 1e300;
+    const bool pos = dcc > 1e-30 && dcc < 1e30;
     if (live && !pos) bad = true;
-    const double inv = (live && pos) ? ((dcc > 1e-30 && dcc < 1e30) ? fast_rsqrt(dcc) : rsqrt(dcc)) : 1.0;
-    const double lrc = (lane > c && lane < kCsNB) ? row[c] * inv : 0.0;
-    if (lane > c) row[c] = lrc;
-    if (lane == c && live) { row[c] = dcc * inv; invd[k0 + c] = inv; }
+    if (lane == c) dmine = dcc;
+    const double uc = row[c];   // unscaled entry of this lane in column c
+    double pr[kCsNB];
 #pragma unroll
-    for (int c2 = c + 1; c2 < kCsNB; c2++) {
-      const double l2 = __shfl_sync(0xffffffffu, lrc, c2);
-      if (c2 <= lane) row[c2] -= lrc * l2;
-    }
+    for (int c2 = c + 1; c2 < kCsNB; c2++) pr[c2] = uc * __shfl_sync(0xffffffffu, uc, c2);   // independent of the reciprocal
+    const double rc = (live && pos) ? fast_rcp(dcc) : 0.0;
+#pragma unroll
+    for (int c2 = c + 1; c2 < kCsNB; c2++)
+      if (c2 <= lane) row[c2] = fma(-pr[c2], rc, row[c2]);
   }
-  if (lane < nb) {
+  // scale: L[r][c] = U[r][c] / sqrt(d_c)
+  const double smine = (lane < nb && dmine > 1e-30 && dmine < 1e30) ? fast_rsqrt(dmine) : 1.0;
+  double sc[kCsNB];
 #pragma unroll
-    for (int c = 0; c < kCsNB; c++) if (c <= lane) A[(size_t)r * ld + k0 + c] = row[c];
+  for (int c = 0; c < kCsNB; c++) sc[c] = __shfl_sync(0xffffffffu, smine, c);
+  if (lane < nb) {
+    invd[k0 + lane] = smine;
+#pragma unroll
+    for (int c = 0; c < kCsNB; c++) {
+      const double l = row[c] * sc[c];
+      if (c <= lane) A[(size_t)r * ld + k0 + c] = l;
+      Ms[lane * msld + c] = (c < lane) ? l * smine : 0.0;
+    }
+  } else if (lane < kCsNB) {
+#pragma unroll
+    for (int c = 0; c < kCsNB; c++) Ms[lane * msld + c] = 0.0;
   }
   return bad;
+}
+
+// C(8x8 at rows gi0.., cols gj0..) -= P^T P over the 8 panel columns; rows >= n1 and the strict upper part of a
+// diagonal tile are not stored.  pmax = last readable index of a row of the panel copy.
+D2BA_DEV void chol_tile8(double *A, int ld, const double *P, int ldp, int gi0, int gj0, int ri, int rj, int pmax, int n1, bool diag_tile, int lane) {
+  const int q = lane & 3, g = lane >> 2;
+  const int ia = min(ri + g, pmax), ib = min(rj + g, pmax);
+  const double a0 = -P[q * ldp + ia], a1 = -P[(q + 4) * ldp + ia];
+  const double b0 = P[q * ldp + ib], b1 = P[(q + 4) * ldp + ib];
+  const int gi = gi0 + g, gj = gj0 + 2 * q;
+  const bool rowok = gi < n1;
+  double2 *dst = reinterpret_cast<double2 *>(A + (size_t)gi * ld + gj);
+  double2 c = rowok ? *dst : make_double2(0.0, 0.0);
+  dmma(c.x, c.y, a0, b0);
+  dmma(c.x, c.y, a1, b1);
+  if (rowok) {
+    if (!diag_tile && gj0 + 8 <= n1 - 1) *dst = c;   // interior tile: all 8 columns are matrix columns below the diagonal
+    else {
+      if (gj <= gi && gj < n1 - 1) A[(size_t)gi * ld + gj] = c.x;
+      if (gj + 1 <= gi && gj + 1 < n1 - 1) A[(size_t)gi * ld + gj + 1] = c.y;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
@@ -1315,49 +1365,74 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   if (!w.chol_smem) return;
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
-  extern __shared__ double sm[];
-  const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;   // even: double2 panel loads
+  extern __shared__ __align__(16) double sm[];
+  const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;
   double *A = sm;                         // n1 x ld
   double *invd = A + (size_t)n1 * ld;     // n (padded to even)
   double *P = invd + ((n + 1) & ~1);      // kCsNB x ldp transposed panel; later xs / partial sums
   const double *S = d.S + w.offH;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   __shared__ int fail;
+  // row-scaled diagonal block for the TRSM: parked in the (never touched) upper-right corner of A, or behind the panel
+  // copy when the matrix is too small to have one
+  double *Ms = n >= 32 ? A + (ld - kCsNB) : P + (size_t)kCsNB * ldp;
+  const int msld = n >= 32 ? ld : kCsNB;
   if (tid == 0) fail = 0;
-  // load the lower triangle (+ rhs row).  Rows of the landmark-coupled part come from the Schur kernel's S; when that
-  // was the one-CTA kernel the speed-bias rows are taken from Hcc directly (+ mu D^2 on the diagonal) and their
-  // share of u^T H u is accumulated here.
+#ifdef D2BA_CHOL_TIMING
+  long long tk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tq = clock64();
+#define TLAP(k) do { long long t_ = clock64(); tk[k] += t_ - tq; tq = t_; } while (0)
+#else
+#define TLAP(k) do { } while (0)
+#endif
+  // load the lower triangle (+ rhs row) with one TMA bulk copy per row, all in flight at once.  Rows of the
+  // landmark-coupled part come from the Schur kernel's S; when that was the one-CTA kernel the speed-bias rows are
+  // taken from Hcc directly (+ mu D^2 on the diagonal, added below) and their share of u^T H u is accumulated here.
   {
+    __shared__ __align__(8) unsigned long long bar;
     const int nlc = w.n_lc, cur = ctl->cur;
     const bool direct = w.schur_small != 0;
     const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
-    const double mu = ctl->mu;
-    double uhu = 0.0;
-    for (int r = warp; r < n1; r += (nt >> 5)) {
-      double *dst = A + (size_t)r * ld;
-      const int lim = min(r, n - 1);
-      if (direct && r >= nlc && r < n) {
-        const double *src = H + (size_t)r * ldg;
-        const double ur = ucv[r];
-        for (int c = lane; c <= lim; c += 32) {
-          double v = src[c];
-          uhu += (c == r ? 1.0 : 2.0) * v * ur * ucv[c];
-          if (c == r) v += mu * D2v[r];
-          dst[c] = v;
-        }
-      } else if (direct && r == n) {
-        const double *src = S + (size_t)r * ldg;
-        for (int c = lane; c <= lim; c += 32) dst[c] = c < nlc ? src[c] : gcv[c];
-      } else {
-        const double *src = S + (size_t)r * ldg;
-        for (int c = lane; c <= lim; c += 32) dst[c] = src[c];
+    const int nbulk = direct ? n : n1;               // rows copied by TMA; the rhs row of the direct case is stitched by hand
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) {
+        unsigned total = 0;
+        for (int r = 0; r < nbulk; r++) total += (unsigned)(((min(r, n - 1) + 2) & ~1) * 8);
+        mbar_expect_tx(&bar, total);
+      }
+      __syncwarp();
+      for (int r = lane; r < nbulk; r += 32) {
+        const double *src = ((direct && r >= nlc) ? H : S) + (size_t)r * ldg;
+        bulk_g2s(A + (size_t)r * ld, src, (unsigned)(((min(r, n - 1) + 2) & ~1) * 8), &bar);
       }
     }
-    if (direct) { uhu = warp_sum(uhu); if (lane == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu); }
+    if (direct) {
+      const double *src = S + (size_t)n * ldg;
+      double *dst = A + (size_t)n * ld;
+      for (int c = tid; c < n; c += nt) dst[c] = c < nlc ? src[c] : gcv[c];
+    }
+    mbar_wait(&bar, 0);
+    if (direct) {
+      const double mu = ctl->mu;
+      double uhu = 0.0;
+      for (int r = nlc + warp; r < n; r += nwarp) {
+        const double *row = A + (size_t)r * ld;
+        const double ur = ucv[r];
+        double acc = 0.0;
+        for (int c = lane; c < r; c += 32) acc += row[c] * ucv[c];
+        uhu += 2.0 * acc * ur;
+        if (lane == 0) { const double v = row[r]; uhu += v * ur * ur; A[(size_t)r * ld + r] = v + mu * D2v[r]; }
+      }
+      uhu = warp_sum(uhu);
+      if (lane == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
+    }
   }
   __syncthreads();
-  if (warp == 0) { if (chol_diag8(A, ld, invd, 0, min(kCsNB, n), lane)) fail = 1; }
+  TLAP(0);
+  if (warp == 0) { if (chol_diag8(A, ld, invd, Ms, msld, 0, min(kCsNB, n), lane)) fail = 1; }
   __syncthreads();
+  TLAP(1);
   for (int k0 = 0; k0 < n; k0 += kCsNB) {
     const int nb = min(kCsNB, n - k0), nxt = k0 + nb;
     // (2) rows below the (already factored) diagonal block: a L_d^T = x; results also into the transposed copy P[c][r - k0]
@@ -1365,98 +1440,52 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
       double a[kCsNB];
       double *ar = A + (size_t)r * ld + k0;
 #pragma unroll
-      for (int c = 0; c < kCsNB; c++) a[c] = (c < nb) ? ar[c] : 0.0;
+      for (int c = 0; c < kCsNB; c++) a[c] = (c < nb) ? ar[c] * invd[k0 + c] : 0.0;
 #pragma unroll
-      for (int c = 0; c < kCsNB; c++) {
+      for (int c = 1; c < kCsNB; c++) {
         double s_ = a[c];
 #pragma unroll
-        for (int k = 0; k < c; k++) s_ -= a[k] * A[(size_t)(k0 + c) * ld + k0 + k];
-        a[c] = (c < nb) ? s_ * invd[k0 + c] : 0.0;
+        for (int k = 0; k < c; k++) s_ = fma(-a[k], Ms[c * msld + k], s_);
+        a[c] = s_;
       }
 #pragma unroll
       for (int c = 0; c < kCsNB; c++) { if (c < nb) ar[c] = a[c]; P[c * ldp + (r - k0)] = a[c]; }
     }
+    TLAP(2);
     __syncthreads();
+    TLAP(3);
     if (nxt >= n) break;
     const int nb2 = min(kCsNB, n - nxt);
-    // (3a) look-ahead: bring the next panel's columns [nxt, nxt+nb2) up to date, one row per thread
-    for (int r = nxt + tid; r < n1; r += nt) {
-      double acc[kCsNB];
-#pragma unroll
-      for (int j = 0; j < kCsNB; j++) acc[j] = 0.0;
-      const int rl = r - k0;
-#pragma unroll
-      for (int c = 0; c < kCsNB; c++) {
-        const double *pc = P + c * ldp;
-        const double vr = pc[rl];
-#pragma unroll
-        for (int j = 0; j < kCsNB; j++) acc[j] += vr * pc[nb + j];   // P[c][nxt + j - k0] (zero padded beyond the matrix)
-      }
-      double *ar = A + (size_t)r * ld + nxt;
-#pragma unroll
-      for (int j = 0; j < kCsNB; j++) if (j < nb2 && nxt + j <= r) ar[j] -= acc[j];
-    }
+    const int pmax = n - k0;                           // P rows hold indices [nb, n1 - 1 - k0]
+    const int T8 = (n1 - nxt + 7) >> 3;                // 8-row tiles of the trailing matrix (rows / cols from nxt)
+    // (3a) look-ahead: the tile column of the next panel, all warps
+    for (int ti = warp; ti < T8; ti += nwarp)
+      chol_tile8(A, ld, P, ldp, nxt + 8 * ti, nxt, nb + 8 * ti, nb, pmax, n1, ti == 0, lane);
     __syncthreads();
+    TLAP(4);
     // (3b) warp 0 factors the next diagonal block while the other warps update the rest of the trailing matrix
     if (warp == 0) {
-      if (chol_diag8(A, ld, invd, nxt, nb2, lane)) fail = 1;
+      if (chol_diag8(A, ld, invd, Ms, msld, nxt, nb2, lane)) fail = 1;
     } else {
-      const int o = nxt + kCsNB;                     // first row / column of the remaining trailing matrix
-      const int ntr = n1 - o;
-      if (ntr > 0) {
-        const int nt4 = (ntr + 3) >> 2, ntri = nt4 * (nt4 + 1) / 2, wt = nt - 32, wtid = tid - 32;
-        for (int tile = wtid; tile < ntri; tile += wt) {
-          int ti = (int)((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
-          while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-          while (ti * (ti + 1) / 2 > tile) ti--;
-          const int tj = tile - ti * (ti + 1) / 2;
-          const int gi0 = o + ti * 4, gj0 = o + tj * 4;   // global row / col of the tile
-          const int ri = gi0 - k0, rj = gj0 - k0;         // panel-local
-          double acc[4][4] = {};
-          const bool full = (gi0 + 3 < n1) && (gj0 + 3 < n) && (tj < ti);
-          if (full) {
-#pragma unroll
-            for (int c = 0; c < kCsNB; c++) {
-              const double *pc = P + c * ldp;
-              const double2 i01 = *reinterpret_cast<const double2 *>(pc + ri), i23 = *reinterpret_cast<const double2 *>(pc + ri + 2);
-              const double2 j01 = *reinterpret_cast<const double2 *>(pc + rj), j23 = *reinterpret_cast<const double2 *>(pc + rj + 2);
-              const double vi[4] = {i01.x, i01.y, i23.x, i23.y}, vj[4] = {j01.x, j01.y, j23.x, j23.y};
-#pragma unroll
-              for (int p_ = 0; p_ < 4; p_++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[p_][q] += vi[p_] * vj[q];
-            }
-#pragma unroll
-            for (int p_ = 0; p_ < 4; p_++) {
-              double2 *dst = reinterpret_cast<double2 *>(A + (size_t)(gi0 + p_) * ld + gj0);
-              double2 v0 = dst[0], v1 = dst[1];
-              v0.x -= acc[p_][0]; v0.y -= acc[p_][1]; v1.x -= acc[p_][2]; v1.y -= acc[p_][3];
-              dst[0] = v0; dst[1] = v1;
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < kCsNB; c++) {
-              const double *pc = P + c * ldp;
-              double vi[4], vj[4];
-#pragma unroll
-              for (int q = 0; q < 4; q++) { vi[q] = (gi0 + q < n1) ? pc[ri + q] : 0.0; vj[q] = (gj0 + q < n1) ? pc[rj + q] : 0.0; }
-#pragma unroll
-              for (int p_ = 0; p_ < 4; p_++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[p_][q] += vi[p_] * vj[q];
-            }
-#pragma unroll
-            for (int p_ = 0; p_ < 4; p_++)
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const int gi = gi0 + p_, gj = gj0 + q;
-                if (gi < n1 && gj < n && gj <= gi) A[(size_t)gi * ld + gj] -= acc[p_][q];
-              }
-          }
+      // warps 4, 8, 12 share warp 0's scheduler / fp64 pipe: they sit this phase out once the trailing matrix is
+      // small enough that the diagonal block (a pure latency chain) is the longer of the two jobs
+      const int T = T8 - 1;                            // tiles per side without the first tile column
+      const int ntile = T * (T + 1) / 2;
+      const bool spare = ntile <= 140;
+      if (!(spare && (warp & 3) == 0)) {
+        const int wslot = spare ? (warp - 1 - (warp >> 2)) : (warp - 1), nslot = spare ? nwarp - (nwarp >> 2) : nwarp - 1;
+        int ti = 0, tj = wslot;                        // tile (ti, tj) of the lower triangle, row-major enumeration
+        while (tj > ti) { tj -= ti + 1; ti++; }
+        while (ti < T) {
+          chol_tile8(A, ld, P, ldp, nxt + 8 * (ti + 1), nxt + 8 * (tj + 1), nb + 8 * (ti + 1), nb + 8 * (tj + 1), pmax, n1, ti == tj, lane);
+          tj += nslot;
+          while (tj > ti) { tj -= ti + 1; ti++; }
         }
       }
     }
+    TLAP(5);
     __syncthreads();
+    TLAP(6);
   }
   if (fail) { if (tid == 0) ctl->chol_fail = 1; return; }
   // ---- back substitution L^T x = y (y = row n), 32-column blocks from the end
@@ -1471,24 +1500,37 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
     if (col < nb)
       for (int k = k0 + nb + slice; k < n; k += nslice) s_ += A[(size_t)k * ld + k0 + col] * xs[k];
     redb[slice * 32 + col] = s_;
+    TLAP(7);
     __syncthreads();
     if (tid < 32) {
       double acc = 0;
+#pragma unroll 4
       for (int q = 0; q < nslice; q++) acc += redb[q * 32 + tid];
       double rhs = (tid < nb) ? y[k0 + tid] - acc : 0.0;
       const double myinv = (tid < nb) ? invd[k0 + tid] : 1.0;
+      double lcol[32];   // L[k0 + i][k0 + tid] for i > tid: the triangular solve below then runs register / shuffle only
+#pragma unroll
+      for (int i = 0; i < 32; i++) lcol[i] = (i < nb && tid < i) ? A[(size_t)(k0 + i) * ld + k0 + tid] : 0.0;
       double xi = 0;
-      for (int i = nb - 1; i >= 0; i--) {
+#pragma unroll
+      for (int i = 31; i >= 0; i--) {
         const double v = __shfl_sync(0xffffffffu, rhs * myinv, i);
         if (tid == i) xi = v;
-        if (tid < i) rhs -= A[(size_t)(k0 + i) * ld + k0 + tid] * v;
+        rhs -= lcol[i] * v;
       }
       if (tid < nb) xs[k0 + tid] = xi;
     }
+    TLAP(8);
     __syncthreads();
   }
   double *gn = d.gn_c + w.offc;
   for (int i = tid; i < n; i += nt) gn[i] = -xs[i];
+#ifdef D2BA_CHOL_TIMING
+  TLAP(9);
+  if (wi == 0 && (tid == 0 || tid == 32 || tid == 480))
+    printf("chol timing tid %d n %d: load %lld diag0 %lld trsm %lld trsm_bar %lld look+bar %lld work3b %lld bar3b %lld back_partial %lld back_tri %lld tail %lld\n", tid, n,
+           tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[7], tk[8], tk[9]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

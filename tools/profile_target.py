@@ -8,7 +8,8 @@ from d2slam_b200.solver import Solver
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-probs = [synth.make_window(seed=500 + i) for i in range(B)]
+base = [synth.make_window(seed=500 + i) for i in range(min(B, 16))]   # distinct device copies of 16 distinct windows
+probs = [base[i % len(base)] for i in range(B)]
 s = Solver(max_windows=B, use_cuda_graph=0)
 for i, p in enumerate(probs):
     p.load(s, i)
