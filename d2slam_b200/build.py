@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libd2ba.so")
+OUT = os.environ.get("D2BA_OUT") or os.path.join(HERE, "libd2ba.so")
 SOURCES = ["d2ba_kernels.cu", "d2ba_host.cu", "d2ba_margin.cu"]
 EXTRA_DEPS = ["d2ba_harness.cpp"]
 HEADERS = ["d2ba_types.cuh", "d2ba_math.cuh", "d2ba_proj.cuh", os.path.join("..", "..", "include", "d2ba.h")]
@@ -27,9 +27,10 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objdir = "build_side" if os.environ.get("D2BA_OUT") else "build"
+    os.makedirs(os.path.join(HERE, objdir), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(HERE, objdir, s.replace(".cu", ".o"))
         objs.append(o)
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("D2BA_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -44,6 +45,8 @@ def build(force=False, verbose=False):
     subprocess.check_call(link)
     # host-side harness (C++ stand-in for the D2Estimator call sequence), links against libd2ba.so
     harness = os.path.join(HERE, "libd2ba_harness.so")
+    if os.environ.get("D2BA_OUT"):
+        return OUT   # instrumented side build: library only
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", os.path.join(CSRC, "d2ba_harness.cpp"), "-o", harness,
                            "-L" + HERE, "-ld2ba", "-Wl,-rpath,$ORIGIN"])
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:

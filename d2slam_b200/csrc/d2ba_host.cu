@@ -31,7 +31,7 @@ void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s
 int configure_kernels(int max_rows, int max_nc, int max_prior_m);
 void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int job_count, cudaStream_t s);
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s);
-void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s);
+void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, int any_compact, int any_wide, cudaStream_t s);
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s);
 void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s);
 int configure_schur_small(int max_ldw);
@@ -49,7 +49,7 @@ void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_w
 struct SchurTileH { int win, kind, tm, tn; };
 int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr, double *A, double *b, int *fail_flag,
                        cudaStream_t s);
-void launch_build_tiles(const void *raw, const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s);
+void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s);
 void launch_prior_from_info(int n_win, int max_m, const int *m_of, const long long *offJ, const long long *offv, const int *is_info,
                             double *A, double *V, double *b, cudaStream_t s);
 }  // namespace d2ba
@@ -85,26 +85,35 @@ struct FlatMap {
 
 struct HObs { int type, pi, pj, ea, eb, lm, fa; };   // index form of one residual block (constants stay in the raw record); fa = anchor frame
 
-// Per-window pinned buffer of the caller's raw observation records (uploaded as is; the tiled layout and the
-// tangent bases are built on the device by k_build_tiles).  Capacity survives d2ba_reset.
-struct RawObs {
-  d2ba_proj_obs *p = nullptr; size_t cap = 0, n = 0;
-  bool append(const d2ba_proj_obs *src, size_t cnt) {
-    if (n + cnt > cap) {
-      size_t want = std::max<size_t>((n + cnt) * 3 / 2 + 64, 1024);
-      d2ba_proj_obs *q = nullptr;
-      if (cudaHostAlloc((void **)&q, want * sizeof(d2ba_proj_obs), cudaHostAllocDefault) != cudaSuccess) return false;
-      if (n) memcpy(q, p, n * sizeof(d2ba_proj_obs));
-      if (p) cudaFreeHost(p);
-      p = q; cap = want;
-    }
-    memcpy(p + n, src, cnt * sizeof(d2ba_proj_obs));
-    n += cnt;
+// Per-window pinned staging of the observation constants in the compact upload format (d2ba_types.cuh: ObsJ /
+// ObsAnchor): the anchor half of a reprojection record (pts_i, vel_i, td_i) repeats for every observation of a
+// landmark, so it is stored once per run of identical anchors -- less than half the bytes of the caller's 160-byte
+// records cross PCIe.  The tiled layout and the tangent bases are built on the device by k_build_tiles.
+// Capacity survives d2ba_reset.
+template <typename T>
+struct PinArr {
+  T *p = nullptr; size_t cap = 0, n = 0;
+  bool moved = false;   // the last reserve() re-allocated (the whole array must be uploaded again)
+  bool reserve(size_t extra) {
+    moved = false;
+    if (n + extra <= cap) return true;
+    size_t want = std::max<size_t>((n + extra) * 3 / 2 + 64, 1024);
+    T *q = nullptr;
+    if (cudaHostAlloc((void **)&q, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+    if (n) memcpy(q, p, n * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = q; cap = want; moved = true;
     return true;
   }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
 };
+template <typename T>
+struct DevArr {   // device mirror of a PinArr, filled as the host side is appended
+  T *p = nullptr; size_t cap = 0;
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
 struct HImu { int pi, si, pj, sj; double c[kImuStride]; };
+constexpr int kMiscImuChunkHost = 12;   // == kMiscImuChunk of k_misc_lin
 struct HPriorBlk { int kind, index, off, eff; double x0[9]; };
 
 struct HostWin {
@@ -115,8 +124,8 @@ struct HostWin {
   std::vector<uint8_t> pose_c, ext_c, sb_c;
   double td = 0; bool has_td = false; uint8_t td_c = 1;
   std::vector<HObs> obs;
-  RawObs raw;
-  d2ba_proj_obs *d_raw = nullptr; size_t d_raw_cap = 0;   // device copy of raw (uploaded as it is appended)
+  PinArr<ObsJ> rawj; PinArr<ObsAnchor> anch;              // compact observation constants (pinned)
+  DevArr<ObsJ> d_rawj; DevArr<ObsAnchor> d_anch;          // device copies (uploaded as they are appended)
   double td_min = 1e300, td_max = -1e300;
   std::vector<HImu> imu;
   int prior_m = 0; std::vector<double> prior_J, prior_e0; std::vector<HPriorBlk> prior_blk; bool prior_is_info = false;
@@ -131,7 +140,7 @@ struct HostWin {
     pose_map.clear(); ext_map.clear(); sb_map.clear(); lm_map.clear();
     pose.clear(); ext.clear(); sb.clear(); lm.clear(); pose_c.clear(); ext_c.clear(); sb_c.clear();
     td = 0; has_td = false; td_c = 1;
-    obs.clear(); raw.n = 0; imu.clear(); td_min = 1e300; td_max = -1e300;
+    obs.clear(); rawj.n = 0; anch.n = 0; imu.clear(); td_min = 1e300; td_max = -1e300;
     prior_m = 0; prior_J.clear(); prior_e0.clear(); prior_blk.clear(); prior_is_info = false;
     pose_slot.clear(); ext_slot.clear(); admm = false; n_slots = 0;
     pose_col.clear(); ext_col.clear(); sb_col.clear(); td_col = -1; n_lc = 0; n_c = 0;
@@ -234,6 +243,7 @@ struct d2ba_handle {
   int max_rows = 1, max_nc = 1, max_prior_m = 0, max_ldw = 8, n_slots = 0;
   int max_n_smem = 0, max_rows_glob = 1; bool any_chol_glob = false; int cfg_max_n_smem = -1;
   int max_ldw_small = 0, cfg_max_ldw_small = -1;
+  int any_compact = 0, any_wide = 0;   // record widths present (which gather kernels to launch)
   int64_t totH = 0, totW = 0, totc = 0;
   bool any_admm = false;
   // host mirrors of the solved state
@@ -246,6 +256,8 @@ struct d2ba_handle {
   bool force_full_S = false;     // the Schur kernels must write the complete reduced system (marginalization reads it)
   double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wall-clock phases of the last d2ba_finalize (d2ba_debug_host_times)
   double solve_ms[4] = {0, 0, 0, 0};             // host wall-clock of the last solve: enqueue, wait for the device, write-back
+  std::atomic<long long> h2d_bytes_add;          // bytes d2ba_add_proj put on the copy stream since the last reset
+  long long h2d_bytes_fin = 0;                   // bytes of the last finalize's arena upload
   std::atomic<long long> add_ns[4];              // thread-summed ns inside d2ba_add_proj since the last reset: index, stamps, staging copy, CUDA calls
   // comm
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
@@ -347,7 +359,7 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release();
   h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release(); h->d_tile_src.release(); h->d_raw_off.release();
   cudaStreamSynchronize(h->copy_stream);
-  for (auto &w : h->win) { w.raw.release(); if (w.d_raw) cudaFree(w.d_raw); w.d_raw = nullptr; }
+  for (auto &w : h->win) { w.rawj.release(); w.anch.release(); w.d_rawj.release(); w.d_anch.release(); }
   cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_copy);
   d2ba_release_staging(h);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evf0); cudaEventDestroy(h->evf1); cudaEventDestroy(h->evf2);
@@ -361,6 +373,7 @@ int d2ba_reset(d2ba_handle *h) {
   for (auto &w : h->win) w.clear();
   h->finalized = false;
   for (auto &a : h->add_ns) a = 0;
+  h->h2d_bytes_add = 0;
   return 0;
 }
 
@@ -409,21 +422,52 @@ int d2ba_set_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, con
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+// append-range upload of a pinned array into its device mirror (copy stream)
+template <typename T>
+int push_range(d2ba_handle *h, PinArr<T> &host, DevArr<T> &dev, size_t first_new) {
+  if (host.n > dev.cap) {
+    if (dev.p) { cudaStreamSynchronize(h->copy_stream); cudaFree(dev.p); }
+    dev.p = nullptr; dev.cap = 0;
+    if (cudaMalloc((void **)&dev.p, host.cap * sizeof(T)) != cudaSuccess) return fail(h, 12, "add_proj: device allocation failed");
+    dev.cap = host.cap; first_new = 0;
+  }
+  if (host.moved) first_new = 0;   // the pinned array moved: everything before was re-copied on the host, upload it all again
+  if (host.n > first_new &&
+      cudaMemcpyAsync(dev.p + first_new, host.p + first_new, (host.n - first_new) * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess)
+    return fail(h, 13, "add_proj: H2D failed");
+  h->h2d_bytes_add += (long long)((host.n - first_new) * sizeof(T));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs *in) {
   HostWin *w = get_win(h, window);
   if (!w) return 1;
   w->used = true; h->finalized = false;
   if (n <= 0) return 0;
-  const size_t base = w->obs.size();
+  const size_t base = w->obs.size(), base_a = w->anch.n;
   auto tq = std::chrono::steady_clock::now();
   auto lap = [&](int k) { auto t = std::chrono::steady_clock::now(); h->add_ns[k] += std::chrono::duration_cast<std::chrono::nanoseconds>(t - tq).count(); tq = t; };
+  cudaSetDevice(h->cfg.device);   // callers may feed windows from their own threads
+  if (!w->rawj.reserve((size_t)n) || !w->anch.reserve((size_t)n)) return fail(h, 11, "add_proj: pinned allocation failed");
   w->obs.resize(base + n);
-  // one-entry lookup caches: consecutive residuals of a track share landmark, anchor frame and cameras
+  lap(3);
+  // one pass over the caller's records: ids -> block indices (one-entry caches: consecutive residuals of a track share
+  // landmark, anchor frame and cameras), stamps, and the compact upload records written straight into pinned memory
   struct Cache { int64_t id = INT64_MIN; int idx = -1; } c_lm, c_fa, c_fb, c_ca, c_cb;
   auto cached = [](Cache &c, const FlatMap &m, int64_t id) {
     if (c.id != id) { c.id = id; c.idx = find_in(m, id); }
     return c.idx;
   };
+  ObsJ *oj = w->rawj.p + w->rawj.n;
+  ObsAnchor *an = w->anch.p;
+  size_t na = w->anch.n;
+  double tmin = w->td_min, tmax = w->td_max;
   for (int i = 0; i < n; i++) {
     const d2ba_proj_obs &p = in[i];
     HObs o;
@@ -443,33 +487,31 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
         if (o.pi < 0 || o.pj < 0) err = "add_proj: unknown frame id";
       }
     }
-    if (err) { w->obs.resize(base); return fail(h, 3, err); }
+    if (err) { w->obs.resize(base); w->anch.n = base_a; return fail(h, 3, err); }
     w->obs[base + i] = o;
+    ObsJ &r = oj[i];
+    if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
+      tmin = std::min(tmin, std::min(p.td_i, p.td_j)); tmax = std::max(tmax, std::max(p.td_i, p.td_j));
+      // anchor half: bitwise identical to the previous anchor -> share it
+      if (na == base_a || memcmp(an[na - 1].pts_i, p.pts_i, 24) != 0 || memcmp(an[na - 1].vel_i, p.vel_i, 24) != 0 || memcmp(&an[na - 1].td_i, &p.td_i, 8) != 0) {
+        ObsAnchor &a = an[na++];
+        memcpy(a.pts_i, p.pts_i, 24); memcpy(a.vel_i, p.vel_i, 24); a.td_i = p.td_i; a.pad = 0.0;
+      }
+      memcpy(r.pts_j, p.pts_j, 24); memcpy(r.vel_j, p.vel_j, 24); r.td_j = p.td_j;
+      r.depth = p.type == D2BA_PROJ_2F1C_DEPTH ? p.depth : 0.0;
+      r.anchor = (int32_t)(na - 1); r.type = p.type;
+    } else {
+      memset(&r, 0, sizeof r);
+      r.depth = p.depth; r.anchor = 0; r.type = p.type;
+    }
   }
+  w->td_min = tmin; w->td_max = tmax;
+  w->rawj.n += (size_t)n; w->anch.n = na;
   lap(0);
-  for (int i = 0; i < n; i++) {
-    if (in[i].type == D2BA_PROJ_DEPTH_PRIOR) continue;
-    w->td_min = std::min(w->td_min, std::min(in[i].td_i, in[i].td_j)); w->td_max = std::max(w->td_max, std::max(in[i].td_i, in[i].td_j));
-  }
-  lap(1);
-  cudaSetDevice(h->cfg.device);   // callers may feed windows from their own threads
-  const bool moved = w->raw.n + (size_t)n > w->raw.cap;
-  if (!w->raw.append(in, (size_t)n)) { w->obs.resize(base); return fail(h, 11, "add_proj: pinned allocation failed"); }
+  // start the uploads right away (they overlap with the caller preparing the other blocks / windows)
+  int rc;
+  if ((rc = push_range(h, w->rawj, w->d_rawj, base)) || (rc = push_range(h, w->anch, w->d_anch, base_a))) return rc;
   lap(2);
-  // start the upload right away (overlaps with the caller preparing the other blocks / windows)
-  if (w->raw.n > w->d_raw_cap) {
-    if (w->d_raw) { cudaStreamSynchronize(h->copy_stream); cudaFree(w->d_raw); }
-    w->d_raw = nullptr; w->d_raw_cap = 0;
-    size_t want = w->raw.cap;
-    if (cudaMalloc((void **)&w->d_raw, want * sizeof(d2ba_proj_obs)) != cudaSuccess) return fail(h, 12, "add_proj: device allocation failed");
-    w->d_raw_cap = want;
-    if (cudaMemcpyAsync(w->d_raw, w->raw.p, w->raw.n * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess) return fail(h, 13, "add_proj: H2D failed");
-  } else {
-    const size_t first = moved ? 0 : base;   // the pinned buffer moved: its old contents were re-copied, re-upload all
-    if (cudaMemcpyAsync(w->d_raw + first, w->raw.p + first, (w->raw.n - first) * sizeof(d2ba_proj_obs), cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess)
-      return fail(h, 13, "add_proj: H2D failed");
-  }
-  lap(3);
   return 0;
 }
 
@@ -687,6 +729,21 @@ int d2ba_finalize(d2ba_handle *h) {
     d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
     d.chol_smem = (!h->force_full_S && w.n_c >= 1 && chol_smem_need(w.n_c) <= (size_t)232448 - 16) ? 1 : 0;   // 16 B of static shared memory (fail flag + mbarrier)
     d.prior_m = w.prior_m; d.prior_nblk = (int)w.prior_blk.size();
+    {   // chronological pre-integration chain?  (anything else accumulates with atomics)
+      const int ni = (int)w.imu.size();
+      bool ok = ni >= 1 && ni <= kMiscImuChunkHost;
+      for (int a = 0; a < ni && ok; a++) {
+        const HImu &x = w.imu[a];
+        if (x.pi == x.pj || x.si == x.sj) ok = false;
+        if (a > 0 && (x.pi != w.imu[a - 1].pj || x.si != w.imu[a - 1].sj)) ok = false;
+        for (int b = 0; b < a - 1 && ok; b++) {   // no sharing with non-neighbours
+          const HImu &y = w.imu[b];
+          if (x.pi == y.pi || x.pi == y.pj || x.pj == y.pi || x.pj == y.pj || x.si == y.si || x.si == y.sj || x.sj == y.si || x.sj == y.sj) ok = false;
+        }
+        if (a > 0 && (x.pj == w.imu[a - 1].pi || x.sj == w.imu[a - 1].si)) ok = false;
+      }
+      d.imu_chain_ok = ok ? 1 : 0;
+    }
     // pair-major order: key = (type, pose_i, pose_j, ext_a, ext_b), ties by insertion order.  The number of distinct
     // keys is small (<= a few hundred), so this is a counting sort: key -> bucket via a flat hash, buckets ordered by key.
     const size_t M = w.obs.size();
@@ -772,7 +829,7 @@ int d2ba_finalize(d2ba_handle *h) {
   lap(0);
   // ---- serial prefix sums
   h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
-  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0;
+  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0; h->any_compact = h->any_wide = 0;
   int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0;
   int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0; long long off_raw = 0;
   int njobs[6] = {0, 0, 0, 0, 0, 0};
@@ -793,6 +850,7 @@ int d2ba_finalize(d2ba_handle *h) {
     h->max_rows = std::max(h->max_rows, d.n_c + 1); h->max_nc = std::max(h->max_nc, d.n_c); h->max_ldw = std::max(h->max_ldw, d.ldw);
     h->max_prior_m = std::max(h->max_prior_m, d.prior_m);
     if (d.schur_small) h->max_ldw_small = std::max(h->max_ldw_small, d.ldw);
+    if (d.rec_stride == 16) h->any_compact = 1; else h->any_wide = 1;
     if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, d.n_c + 1); }
     if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
     if (w.prior_m > 0 && w.prior_is_info) any_info = true;
@@ -806,7 +864,7 @@ int d2ba_finalize(d2ba_handle *h) {
   st.reserve(st.win, nw); st.reserve(st.x6, (size_t)off6 * 8); st.reserve(st.xsb, (size_t)offsb * 9); st.reserve(st.xlm, offlm); st.reserve(st.xtd, nw);
   st.reserve(st.col6, off6); st.reserve(st.colsb, offsb); st.reserve(st.slot6, off6); st.reserve(st.blk_win, off6); st.reserve(st.sb_win, offsb);
   st.reserve(st.lm_win, offlm); st.reserve(st.tile_grp, off_tile); st.reserve(st.tile_win, off_tile); st.reserve(st.obs_lm, (size_t)off_tile * kTile);
-  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.lm_obs, (size_t)off_lmobs);
+  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, 2 * (size_t)nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.lm_obs, (size_t)off_lmobs);
   st.reserve(st.grp, off_grp); st.reserve(st.job, n_jobs); st.reserve(st.imu, off_imu); st.reserve(st.imu_c, (size_t)off_imu * kImuStride);
   st.reserve(st.pblk, off_pblk); st.reserve(st.prior_J, (size_t)off_pJ); st.reserve(st.prior_e0, (size_t)off_pv); st.reserve(st.schur, n_schur);
   st.reserve(st.pr_m, nw); st.reserve(st.pr_info, nw); st.reserve(st.pr_offJ, nw); st.reserve(st.pr_offv, nw);
@@ -898,14 +956,15 @@ int d2ba_finalize(d2ba_handle *h) {
   // raw observation records were uploaded as they were added (copy stream); their device addresses ride in the arena
   for (int wi = 0; wi < nw; wi++) {
     HostWin &w = h->win[wi];
-    if (w.raw.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
-    st.raw_off.p[wi] = (long long)(uintptr_t)w.d_raw;
+    if (w.rawj.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
+    st.raw_off.p[2 * wi] = (long long)(uintptr_t)w.d_rawj.p; st.raw_off.p[2 * wi + 1] = (long long)(uintptr_t)w.d_anch.p;
   }
   if (st.cursor > h->d_arena.n) {   // growing: views of the old arena die with it
     CK(cudaStreamSynchronize(h->stream));
     CK(h->d_arena.alloc(st.cursor + st.cursor / 4 + 256));
   }
   CK(cudaMemcpyAsync(h->d_arena.p, st.arena.p, st.cursor, cudaMemcpyHostToDevice, h->stream));
+  h->h2d_bytes_fin = (long long)st.cursor;
   if ((rc = up(h, h->d_win, st.win))) return rc;
   CK(h->d_ctl.alloc(nw)); CK(cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Ctl) * nw, h->stream));
   if ((rc = up(h, h->d_x6[0], st.x6)) || (rc = up(h, h->d_xsb[0], st.xsb)) || (rc = up(h, h->d_xlm[0], st.xlm)) || (rc = up(h, h->d_xtd[0], st.xtd))) return rc;
@@ -929,7 +988,7 @@ int d2ba_finalize(d2ba_handle *h) {
   CK(cudaEventRecord(h->ev_copy, h->copy_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
   CK(cudaEventRecord(h->evf1, h->stream));
-  launch_build_tiles(nullptr, h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
+  launch_build_tiles(h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
   CK(h->d_imu_U.alloc((size_t)off_imu * 225)); CK(h->d_prior_A.alloc((size_t)off_pJ));
   CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
   CK(h->d_td_ref.alloc(nw));
@@ -997,6 +1056,7 @@ int d2ba_debug_host_times(d2ba_handle *h, double *ms_out) {
   }
   for (int k = 0; k < 4; k++) ms_out[8 + k] = 1e-6 * (double)h->add_ns[k].load();
   for (int k = 0; k < 3; k++) ms_out[12 + k] = h->solve_ms[k];
+  ms_out[15] = (double)(h->h2d_bytes_add.load() + h->h2d_bytes_fin);
   return 0;
 }
 
@@ -1033,7 +1093,7 @@ static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
 }
 
 static void enqueue_iteration(d2ba_handle *h) {
-  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
   if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
   if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
@@ -1188,7 +1248,7 @@ int d2ba_debug_linearize(d2ba_handle *h) {
   launch_tr_reset(h->dev, 1, h->stream);
   enqueue_linearize(h, 1);
   launch_control(h->dev, 1, h->stream);
-  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
   if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
   // keep an un-factored copy of S in the debug buffer
@@ -1313,7 +1373,20 @@ int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove, const int
     if (o.type == D2BA_PROJ_DEPTH_PRIOR || o.type == D2BA_PROJ_1F2C) r = o.fa >= 0 && rem_pose[o.fa];   // anchor frame only
     else r = rem_pose[o.pi] || rem_pose[o.pj];
     if (!r) continue;
-    robs.push_back(w->raw.p[k]);
+    {   // back to the caller's record format from the compact constants + block indices
+      d2ba_proj_obs p; memset(&p, 0, sizeof p);
+      const ObsJ &r = w->rawj.p[k];
+      p.type = o.type; p.landmark_id = w->lm_id[o.lm];
+      p.frame_a = o.fa >= 0 ? w->pose_id[o.fa] : 0; p.frame_b = o.pj >= 0 ? w->pose_id[o.pj] : p.frame_a;
+      p.cam_a = o.ea >= 0 ? (int32_t)w->ext_id[o.ea] : 0; p.cam_b = o.eb >= 0 ? (int32_t)w->ext_id[o.eb] : 0;
+      if (o.type != D2BA_PROJ_DEPTH_PRIOR) {
+        const ObsAnchor &a = w->anch.p[r.anchor];
+        memcpy(p.pts_i, a.pts_i, 24); memcpy(p.vel_i, a.vel_i, 24); p.td_i = a.td_i;
+        memcpy(p.pts_j, r.pts_j, 24); memcpy(p.vel_j, r.vel_j, 24); p.td_j = r.td_j;
+      }
+      p.depth = r.depth;
+      robs.push_back(p);
+    }
     if (o.pi >= 0) { use_pose[o.pi] = 1; use_pose[o.pj] = 1; }
     if (o.type != D2BA_PROJ_DEPTH_PRIOR) { use_ext[o.ea] = 1; if (o.eb >= 0) use_ext[o.eb] = 1; use_td = true; }
     use_lm[o.lm] = 1;
@@ -1401,7 +1474,7 @@ int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove, const int
   launch_tr_reset(t->dev, 1, t->stream);
   enqueue_linearize(t, 1);
   launch_control(t->dev, 1, t->stream);
-  launch_lm_gather(t->dev, t->d_lm_win.p, t->nl_total, t->max_ldw, t->stream);
+  launch_lm_gather(t->dev, t->d_lm_win.p, t->nl_total, t->max_ldw, t->any_compact, t->any_wide, t->stream);
   if (t->max_ldw_small > 0) launch_schur_small(t->dev, t->max_ldw_small, t->stream);
   launch_schur(t->dev, t->d_schur.p, t->n_schur, t->stream);
   // eliminate the removed camera columns
@@ -1445,7 +1518,7 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
   for (int i = 0; i < 8; i++) cudaEventCreate(&ev[i]);
   for (int i = 0; i < 8; i++) ms_out[i] = 0;
   for (int it = 0; it < iters; it++) {
-    cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->stream);
+    cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
     cudaEventRecord(ev[1], h->stream); if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
     cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
     cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);

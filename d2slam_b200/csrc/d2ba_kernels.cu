@@ -216,81 +216,135 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
   const double *xlm = d.xlm[buf] + w.offlm;
   const int *col6 = d.col6 + w.off6;
   const int *colsb = d.colsb + w.offsb;
-  // ---- zero
-  {
-    double2 *H2 = reinterpret_cast<double2 *>(H);
-    size_t tot2 = ((size_t)(n + 1) * ld) / 2;  // ld is a multiple of 4
-    for (size_t e = tid; e < tot2; e += nt) H2[e] = make_double2(0.0, 0.0);
-    for (int e = tid; e < n; e += nt) g[e] = 0.0;
-  }
-  __syncthreads();
-  double cost = 0.0;
-  // ---- IMU factors, processed in chunks of kImuChunk to bound shared memory
+#ifdef D2BA_MISC_TIMING
+  long long mk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long mq = clock64();
+#define MLAP(k) do { __syncthreads(); long long t_ = clock64(); mk[k] += t_ - mq; mq = t_; } while (0)
+#else
+#define MLAP(k) do { } while (0)
+#endif
+  // ---- zero + IMU factors.  The raw residual / Jacobian of a factor is one long dependent chain (one lane per
+  //      factor, all in warp 0); the other warps zero H / g and stage the sqrt-information meanwhile.  U J and
+  //      [J r]^T [J r] then run on the fp64 tensor cores (m8n8k4), 8x8 output tiles spread over the warps.
   constexpr int kImuChunk = kMiscImuChunk;
   constexpr int kF = 15 * 30 + 15;  // doubles per factor for (J, r)
+  const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+  double cost = 0.0;
+  bool zeroed = false;
+  auto zero_H = [&](int t0, int tn) {
+    double2 *H2 = reinterpret_cast<double2 *>(H);
+    const size_t tot2 = ((size_t)(n + 1) * ld) / 2;  // ld is a multiple of 4
+    for (size_t e = t0; e < tot2; e += tn) H2[e] = make_double2(0.0, 0.0);
+    for (int e = t0; e < n; e += tn) g[e] = 0.0;
+  };
   for (int f0 = 0; f0 < w.n_imu; f0 += kImuChunk) {
-    int nf = min(kImuChunk, w.n_imu - f0);
+    const int nf = min(kImuChunk, w.n_imu - f0);
     double *raw = Jr, *fin = Jr + kImuChunk * kF;
     double *Us = fin + kImuChunk * kF;
     int *fcols = reinterpret_cast<int *>(Us + kImuChunk * 225);
-
-    for (int e = tid; e < nf * 225; e += nt) Us[e] = d.imu_U[(size_t)(w.off_imu + f0) * 225 + e];
-    if (tid >= 32 && tid < 32 + nf * 4) {
-      const int t4 = tid - 32;
-      const ImuDesc &im = d.imu[w.off_imu + f0 + t4 / 4];
-      const int q = t4 & 3;
-      fcols[t4] = q == 0 ? col6[im.pi] : (q == 1 ? colsb[im.si] : (q == 2 ? col6[im.pj] : colsb[im.sj]));
-    }
     for (int e = tid; e < nf * kF; e += nt) raw[e] = 0.0;
     __syncthreads();
-    if (tid < nf) {
-      const ImuDesc &im = d.imu[w.off_imu + f0 + tid];
-      imu_raw(d.imu_c + (size_t)(w.off_imu + f0 + tid) * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8,
-              xsb + im.sj * 9, d.prm.gravity, raw + tid * kF + 450, raw + tid * kF);
-    }
-    __syncthreads();
-    // J = U Jraw, r = U rraw
-    for (int e = tid; e < nf * kF; e += nt) {
-      int f = e / kF, k = e % kF;
-      const double *U = Us + f * 225;
-      const double *src = raw + f * kF;
-      double s = 0;
-      if (k < 450) {
-        int i = k / 30, j = k % 30;
-        for (int q = i; q < 15; q++) s += U[i * 15 + q] * src[q * 30 + j];  // U is upper triangular
-      } else {
-        int i = k - 450;
-        for (int q = i; q < 15; q++) s += U[i * 15 + q] * src[450 + q];
+    if (warp == 0) {
+      if (lane < nf) {
+        const ImuDesc &im = d.imu[w.off_imu + f0 + lane];
+        imu_raw(d.imu_c + (size_t)(w.off_imu + f0 + lane) * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8,
+                xsb + im.sj * 9, d.prm.gravity, raw + lane * kF + 450, raw + lane * kF);
       }
-      fin[e] = s;
+    } else {
+      const int t0 = tid - 32, tn = nt - 32;
+      for (int e = t0; e < nf * 225; e += tn) Us[e] = d.imu_U[(size_t)(w.off_imu + f0) * 225 + e];
+      if (t0 < nf * 4) {
+        const ImuDesc &im = d.imu[w.off_imu + f0 + t0 / 4];
+        const int q = t0 & 3;
+        fcols[t0] = q == 0 ? col6[im.pi] : (q == 1 ? colsb[im.si] : (q == 2 ? col6[im.pj] : colsb[im.sj]));
+      }
+      if (!zeroed) zero_H(t0, tn);
+    }
+    zeroed = true;
+    __syncthreads();
+    MLAP(2);
+    // fin = U [Jraw | rraw]: per factor 2 x 4 output tiles, K = 15 (4 k-steps, the 16th masked)
+    {
+      const int g4 = lane >> 2, q4 = lane & 3;
+      for (int job = warp; job < nf * 8; job += nwarp) {
+        const int f = job >> 3, ti = (job >> 2) & 1, tj = job & 3;
+        const double *U = Us + f * 225, *src = raw + f * kF;
+        const int i = 8 * ti + g4, bc = 8 * tj + g4;
+        double c0 = 0.0, c1 = 0.0, av[4], bv[4];   // operands first: the (volatile) MMAs then issue back to back
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const int kq = 4 * kk + q4;
+          const bool kok = kq < 15;
+          av[kk] = (kok && i < 15) ? U[i * 15 + kq] : 0.0;
+          bv[kk] = !kok ? 0.0 : (bc < 30 ? src[kq * 30 + bc] : (bc == 30 ? src[450 + kq] : 0.0));
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
+        if (i < 15) {
+          double *dst = fin + f * kF;
+          const int j0 = 8 * tj + 2 * q4;
+          if (j0 < 30) { dst[i * 30 + j0] = c0; dst[i * 30 + j0 + 1] = c1; }
+          else if (j0 == 30) dst[450 + i] = c0;
+        }
+      }
     }
     __syncthreads();
-    // accumulate: 30x30 + gradient per factor
-    for (int e = tid; e < nf * 930; e += nt) {
-      int f = e / 930, k = e % 930;
-      const double *Jf = fin + f * kF, *rf = Jf + 450;
-      const int *cols = fcols + f * 4;
-      auto gcol = [&](int a) -> int {  // local 0..29 -> reduced column
-        int b = a < 6 ? 0 : (a < 15 ? 1 : (a < 21 ? 2 : 3));
-        int o = a < 6 ? a : (a < 15 ? a - 6 : (a < 21 ? a - 15 : a - 21));
-        return cols[b] < 0 ? -1 : cols[b] + o;
-      };
-      if (k < 900) {
-        int a = k / 30, b = k % 30;
-        int ga = gcol(a), gb = gcol(b);
-        if (ga < 0 || gb < 0) continue;
-        double s = 0;
+    MLAP(3);
+    // accumulate [J r]^T [J r]: per factor 4 x 4 output tiles (rows a < 30; column 30 is the gradient).
+    // Chronological chain (the normal case): local rows / cols 0..14 of factor f are the same parameters as 15..29
+    // of factor f-1, so the tile of factor f also sums factor f-1's shifted block and every Hessian entry has exactly
+    // one writer: plain stores into the freshly zeroed H instead of ~900 L2 atomics per factor.
+    {
+      const bool chain = w.imu_chain_ok != 0;
+      const int g4 = lane >> 2, q4 = lane & 3;
+      for (int job = warp; job < nf * 16; job += nwarp) {
+        const int f = job >> 4, ta = (job >> 2) & 3, tb = job & 3;
+        const double *Jf = fin + f * kF;
+        const int *cols = fcols + f * 4;
+        auto gcol = [&](int a) -> int {  // local 0..29 -> reduced column
+          const int b = a < 6 ? 0 : (a < 15 ? 1 : (a < 21 ? 2 : 3));
+          const int o = a < 6 ? a : (a < 15 ? a - 6 : (a < 21 ? a - 15 : a - 21));
+          return cols[b] < 0 ? -1 : cols[b] + o;
+        };
+        const int ar = 8 * ta + g4, bc = 8 * tb + g4;
+        const bool with_prev = chain && f > 0 && ta < 2 && (tb < 2 || tb == 3);
+        const double *Jp = Jf - kF;   // factor f-1: rows / cols shifted by 15 (dereferenced only when with_prev)
+        double c0 = 0.0, c1 = 0.0, av[8], bv[8];   // operands first: the (volatile) MMAs then issue back to back
 #pragma unroll
-        for (int q = 0; q < 15; q++) s += Jf[q * 30 + a] * Jf[q * 30 + b];
-        if (s != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], s);
-      } else {
-        int a = k - 900;
-        int ga = gcol(a);
-        if (ga < 0) continue;
-        double s = 0;
+        for (int kk = 0; kk < 4; kk++) {
+          const int kq = 4 * kk + q4;
+          const bool kok = kq < 15;
+          av[kk] = (kok && ar < 30) ? Jf[kq * 30 + ar] : 0.0;
+          bv[kk] = !kok ? 0.0 : (bc < 30 ? Jf[kq * 30 + bc] : (bc == 30 ? Jf[450 + kq] : 0.0));
+          av[4 + kk] = (with_prev && kok && ar < 15) ? Jp[kq * 30 + ar + 15] : 0.0;
+          bv[4 + kk] = (!with_prev || !kok) ? 0.0 : (bc < 15 ? Jp[kq * 30 + bc + 15] : (bc == 30 ? Jp[450 + kq] : 0.0));
+        }
 #pragma unroll
-        for (int q = 0; q < 15; q++) s += Jf[q * 30 + a] * rf[q];
-        atomicAdd(&g[ga], s);
+        for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
+        if (with_prev) {
+#pragma unroll
+          for (int kk = 4; kk < 8; kk++) dmma(c0, c1, av[kk], bv[kk]);
+        }
+        if (ar < 30) {
+          const int ga = gcol(ar);
+          if (ga >= 0) {
+            const bool last = f == nf - 1;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+              const int bo = 8 * tb + 2 * q4 + u;
+              const double v = u == 0 ? c0 : c1;
+              if (bo < 30) {
+                const int gb = gcol(bo);
+                if (gb >= 0) {
+                  if (!chain) { if (v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }
+                  else if (!(ar >= 15 && bo >= 15) || last) H[(size_t)ga * ld + gb] = v;
+                }
+              } else if (bo == 30) {
+                if (!chain) atomicAdd(&g[ga], v);
+                else if (ar < 15 || last) g[ga] = v;
+              }
+            }
+          }
+        }
       }
     }
     if (tid < nf) {
@@ -300,7 +354,9 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
       cost += 0.5 * s;
     }
     __syncthreads();
+    MLAP(4);
   }
+  if (!zeroed) { zero_H(tid, nt); __syncthreads(); }
   // ---- prior: r = e0 + J dx ; H += J^T J ; g += J^T r
   if (w.prior_m > 0) {
     const int m = w.prior_m;
@@ -345,6 +401,7 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
     }
     __syncthreads();
   }
+  MLAP(5);
   // ---- ADMM terms (ConsensusSolver::updateTilde, ConsensusSolver.cpp:108-164)
   if (w.admm_on) {
     const int *slot = d.slot6 + w.off6;
@@ -400,6 +457,10 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
   }
   cost = block_sum(cost, red);
   if (tid == 0) { ctl->cand_cost_misc = cost; }
+#ifdef D2BA_MISC_TIMING
+  MLAP(6);
+  if (wi == 0 && tid == 0) printf("misc timing: zero %lld uload %lld imu_raw %lld UJ %lld JtJ %lld prior %lld tail %lld\n", mk[0], mk[1], mk[2], mk[3], mk[4], mk[5], mk[6]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -815,6 +876,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   if (gl_idx >= n_lm_total) return;
   const int wi = lm_win[gl_idx];
   const WinDesc &w = d.win[wi];
+  if (w.rec_stride == 16) return;   // compact windows: k_lm_gather16
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse) return;
   const int buf = ctl->cur;
@@ -905,6 +967,79 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   }
   wu = warp_sum(wu);
   if (lane == 0) {
+    d.hl[w.offlm + l] = h; d.gl[w.offlm + l] = g; d.dinv[w.offlm + l] = di; d.wu[w.offlm + l] = wu; d.D2l[w.offlm + l] = dl2;
+    if (!(hp > 0.0)) ctl->chol_fail = 1;
+    atomicMax(&ctl->gmax_l_bits, (unsigned long long)__double_as_longlong(fabs(g)));
+  }
+}
+
+// Compact-record windows (rec_stride == 16): one HALF-warp per landmark -- a 128-byte record is exactly one 16-lane
+// load, so the two halves of a warp work on two landmarks independently (no cross-half ordering, half-warp masks).
+constexpr int kG16Lm = 16;   // landmarks per 256-thread CTA
+__global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *lm_win, int n_lm_total, int max_ldw) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, hw = threadIdx.x >> 4, sub = lane & 15, hbase = lane & 16;
+  const unsigned hmask = 0xffffu << hbase;
+  const int gl_idx = blockIdx.x * kG16Lm + hw;
+  if (gl_idx >= n_lm_total) return;
+  const int wi = lm_win[gl_idx];
+  const WinDesc &w = d.win[wi];
+  if (w.rec_stride != 16) return;
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse) return;
+  const int buf = ctl->cur;
+  const int l = gl_idx - w.offlm;
+  double *row = sm + hw * max_ldw;
+  const int nlc = w.n_lc;
+  for (int c = sub; c <= nlc; c += 16) row[c] = 0.0;
+  __syncwarp(hmask);
+  const int *ptr = d.lm_ptr + w.off_lmptr;
+  const int *lo = d.lm_obs + w.off_lmobs;
+  const double *recs = d.rec[buf] + (size_t)w.off_rec;
+  double h = 0, g = 0;
+  const int kb = ptr[l], ke = ptr[l + 1];
+  for (int k0 = kb; k0 < ke; k0 += 8) {
+    const int cnt = min(8, ke - k0);
+    const int mypos = (sub < cnt) ? lo[k0 + sub] : 0;
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int p = __shfl_sync(hmask, mypos, hbase | (q < cnt ? q : 0));
+      v[q] = (q < cnt) ? recs[(size_t)p * 16 + sub] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      if (q >= cnt) break;
+      const double c01 = __shfl_sync(hmask, v[q], hbase | 3);   // packed column word of the record
+      int col = -1;
+      if (sub >= 4) { const int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
+      if (sub == 0) h += v[q];
+      if (sub == 1) g += v[q];
+      if (col >= 0) row[col] += v[q];
+      __syncwarp(hmask);   // the two slots of different records may name the same column block
+    }
+  }
+  h = __shfl_sync(hmask, h, hbase);
+  g = __shfl_sync(hmask, g, hbase | 1);
+  if (w.admm_on) {
+    const double rl = d.prm.rho_landmark;
+    h += rl * rl;
+    g += rl * rl * (d.xlm[buf][w.offlm + l] - d.lm_ref[w.offlm + l]);
+  }
+  const double dl2 = d2_of(h);
+  const double hp = h + ctl->mu * dl2;
+  const double di = 1.0 / sqrt(hp);
+  double *Wt = d.Wt + w.offW + (size_t)l * w.ldw;
+  const double *uc = d.uc + w.offc;
+  double wu = 0;
+  for (int c = sub; c < w.ldw; c += 16) {
+    const double rv = (c < nlc) ? row[c] : 0.0;
+    Wt[c] = (c < nlc) ? rv * di : (c == nlc ? g * di : 0.0);
+    if (c < nlc) wu += rv * uc[c];
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) wu += __shfl_xor_sync(hmask, wu, o);
+  if (sub == 0) {
     d.hl[w.offlm + l] = h; d.gl[w.offlm + l] = g; d.dinv[w.offlm + l] = di; d.wu[w.offlm + l] = wu; d.D2l[w.offlm + l] = dl2;
     if (!(hp > 0.0)) ctl->chol_fail = 1;
     atomicMax(&ctl->gmax_l_bits, (unsigned long long)__double_as_longlong(fabs(g)));
@@ -1847,11 +1982,10 @@ __global__ void k_cons_init(Dev d, int n6_total) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Build the 32-observation AoSoA tiles from the caller's raw records (uploaded untouched): gathers the
+// Build the 32-observation AoSoA tiles from the compact upload records (ObsJ + shared ObsAnchor): gathers the
 // record of every tile slot (pair-major order), computes the unit-sphere tangent base of the factor
 // constructor (projectionTwoFrameOneCamFactor.cpp:34-45) and writes [field][lane] planes.
-__global__ void __launch_bounds__(128) k_build_tiles(const d2ba_proj_obs *raw, const long long *raw_off, const int *tile_src,
-                                                     const int *tile_win, double *obs, int n_tiles) {
+__global__ void __launch_bounds__(128) k_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles) {
   const int tile = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   const int src = tile_src[(size_t)tile * kTile + lane];
@@ -1859,11 +1993,13 @@ __global__ void __launch_bounds__(128) k_build_tiles(const d2ba_proj_obs *raw, c
 #pragma unroll
   for (int k = 0; k < kObsFields; k++) f[k] = 0.0;
   if (src >= 0) {
-    const d2ba_proj_obs &p = reinterpret_cast<const d2ba_proj_obs *>((uintptr_t)raw_off[tile_win[tile]])[src];   // per-window base pointer
+    const int wi = tile_win[tile];
+    const ObsJ &p = reinterpret_cast<const ObsJ *>((uintptr_t)raw_off[2 * wi])[src];   // per-window base pointers
     if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
+      const ObsAnchor &a0 = reinterpret_cast<const ObsAnchor *>((uintptr_t)raw_off[2 * wi + 1])[p.anchor];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { f[k] = p.pts_i[k]; f[3 + k] = p.pts_j[k]; f[6 + k] = p.vel_i[k]; f[9 + k] = p.vel_j[k]; }
-      f[12] = p.td_i; f[13] = p.td_j;
+      for (int k = 0; k < 3; k++) { f[k] = a0.pts_i[k]; f[3 + k] = p.pts_j[k]; f[6 + k] = a0.vel_i[k]; f[9 + k] = p.vel_j[k]; }
+      f[12] = a0.td_i; f[13] = p.td_j;
       const double n = sqrt(f[3] * f[3] + f[4] * f[4] + f[5] * f[5]);
       const double a[3] = {f[3] / n, f[4] / n, f[5] / n};
       double t[3] = {0, 0, 1};
@@ -1886,8 +2022,8 @@ __global__ void __launch_bounds__(128) k_build_tiles(const d2ba_proj_obs *raw, c
 #pragma unroll
   for (int k = 0; k < kObsFields; k++) ob[k * kTile + lane] = f[k];
 }
-void launch_build_tiles(const void *raw, const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s) {
-  if (n_tiles > 0) k_build_tiles<<<(n_tiles + 3) / 4, 128, 0, s>>>(reinterpret_cast<const d2ba_proj_obs *>(raw), raw_off, tile_src, tile_win, obs, n_tiles);
+void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s) {
+  if (n_tiles > 0) k_build_tiles<<<(n_tiles + 3) / 4, 128, 0, s>>>(raw_off, tile_src, tile_win, obs, n_tiles);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1996,9 +2132,12 @@ void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s) {
   if (n_tiles > 0) k_proj_debug<<<n_tiles, 32, 0, s>>>(d, out, n_tiles, tile_win);
 }
-void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, cudaStream_t s) {
+void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, int any_compact, int any_wide, cudaStream_t s) {
   if (n_lm_total <= 0) return;
-  k_lm_gather<<<(n_lm_total + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, (size_t)kGatherWarps * max_ldw * 8, s>>>(d, lm_win, n_lm_total, max_ldw);
+  if (any_wide)
+    k_lm_gather<<<(n_lm_total + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, (size_t)kGatherWarps * max_ldw * 8, s>>>(d, lm_win, n_lm_total, max_ldw);
+  if (any_compact)
+    k_lm_gather16<<<(n_lm_total + kG16Lm - 1) / kG16Lm, kG16Lm * 16, (size_t)kG16Lm * max_ldw * 8, s>>>(d, lm_win, n_lm_total, max_ldw);
 }
 void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s) {
   k_schur_small<<<d.n_win, kSsThreads, (size_t)(2 * 32 * (max_ldw + 4) + 40) * 8, s>>>(d);

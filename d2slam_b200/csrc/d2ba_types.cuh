@@ -34,6 +34,17 @@ struct Job {       // one warp's work: a run of tiles of one group
   int win, grp, tile_begin, ntiles;
 };
 
+// Compact upload format of the observation constants (built by d2ba_add_proj, consumed by k_build_tiles).
+struct ObsJ {        // per residual block: the observing half of a reprojection record (72 bytes)
+  double pts_j[3], vel_j[3], td_j;
+  double depth;      // measured depth (2F1C_DEPTH, DEPTH_PRIOR), else 0
+  int32_t anchor;    // index into the window's ObsAnchor table
+  int32_t type;      // d2ba_proj_type
+};
+struct ObsAnchor {   // the anchor half, stored once per run of residual blocks that share it (64 bytes)
+  double pts_i[3], vel_i[3], td_i, pad;
+};
+
 struct ImuDesc {
   int pi, si, pj, sj;  // window-local indices (six-dof table / speed-bias table)
 };
@@ -61,6 +72,8 @@ struct WinDesc {
   int admm_on;
   int chol_smem;               // reduced system fits the shared-memory Cholesky
   int schur_small;             // landmark-coupled part <= 127 columns: one-CTA Schur kernel
+  int imu_chain_ok;            // IMU factors form one chronological chain (factor f starts at the frame factor f-1 ends at, no other
+                               // sharing, at most one chunk): their Hessian blocks are owned by one writer each, stored without atomics
 };
 
 struct PriorBlk {

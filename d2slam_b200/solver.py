@@ -16,7 +16,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(_HERE, "libd2ba.so")
+    # D2BA_LIB: developer override (instrumented builds); the product always loads the in-tree library
+    return os.environ.get("D2BA_LIB") or os.path.join(_HERE, "libd2ba.so")
 
 
 def lib():
@@ -183,6 +184,7 @@ class Solver:
         d = dict(zip(("plan", "prefix", "fill", "enqueue", "wait", "mirror"), out[:6].round(3).tolist()))
         d.update(zip(("dev_upload", "dev_prep"), out[6:8].round(3).tolist()))
         d.update(zip(("solve_enqueue", "solve_wait", "solve_writeback"), out[12:15].round(3).tolist()))
+        d["h2d_bytes"] = int(out[15])
         d.update(zip(("add_lookup", "add_stamps", "add_copy", "add_cuda"), out[8:12].round(3).tolist()))
         return d
 

@@ -285,7 +285,8 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out /* [8]
 /* Host wall-clock (ms) of the phases of the last d2ba_finalize: [plan (pair-major order, groups, jobs), prefix sums +
  * staging resize, staging fill, upload enqueue, error check, read-back buffers, device ms of the uploads, device ms of tile build + prep kernels], followed by
  * the thread-summed ms spent inside d2ba_add_proj since the last d2ba_reset: [id lookup, stamp scan, staging copy,
- * CUDA calls], then the host wall-clock ms of the last solve: [enqueue, wait for the device, write-back, 0]. */
+ * CUDA calls], then the host wall-clock ms of the last solve: [enqueue, wait for the device, write-back] and, in [15], the
+ * host-to-device BYTES of the last reset -> add -> finalize cycle (observation records + staging arena). */
 int d2ba_debug_host_times(d2ba_handle *h, double *ms_out /* [16] */);
 
 #ifdef __cplusplus
