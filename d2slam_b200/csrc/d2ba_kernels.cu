@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/d2ba.h"
 #include "d2ba_math.cuh"
@@ -289,12 +290,9 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
     }
     __syncthreads();
     MLAP(3);
-    // accumulate [J r]^T [J r]: per factor 4 x 4 output tiles (rows a < 30; column 30 is the gradient).
-    // Chronological chain (the normal case): local rows / cols 0..14 of factor f are the same parameters as 15..29
-    // of factor f-1, so the tile of factor f also sums factor f-1's shifted block and every Hessian entry has exactly
-    // one writer: plain stores into the freshly zeroed H instead of ~900 L2 atomics per factor.
+    // accumulate [J r]^T [J r]: per factor 4 x 4 output tiles (rows a < 30; column 30 is the gradient), flushed with
+    // L2 reductions (measured: faster than single-writer plain stores or read-modify-write passes here)
     {
-      const bool chain = w.imu_chain_ok != 0;
       const int g4 = lane >> 2, q4 = lane & 3;
       for (int job = warp; job < nf * 16; job += nwarp) {
         const int f = job >> 4, ta = (job >> 2) & 3, tb = job & 3;
@@ -306,42 +304,25 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
           return cols[b] < 0 ? -1 : cols[b] + o;
         };
         const int ar = 8 * ta + g4, bc = 8 * tb + g4;
-        const bool with_prev = chain && f > 0 && ta < 2 && (tb < 2 || tb == 3);
-        const double *Jp = Jf - kF;   // factor f-1: rows / cols shifted by 15 (dereferenced only when with_prev)
-        double c0 = 0.0, c1 = 0.0, av[8], bv[8];   // operands first: the (volatile) MMAs then issue back to back
+        double c0 = 0.0, c1 = 0.0, av[4], bv[4];   // operands first: the (volatile) MMAs then issue back to back
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
           const int kq = 4 * kk + q4;
           const bool kok = kq < 15;
           av[kk] = (kok && ar < 30) ? Jf[kq * 30 + ar] : 0.0;
           bv[kk] = !kok ? 0.0 : (bc < 30 ? Jf[kq * 30 + bc] : (bc == 30 ? Jf[450 + kq] : 0.0));
-          av[4 + kk] = (with_prev && kok && ar < 15) ? Jp[kq * 30 + ar + 15] : 0.0;
-          bv[4 + kk] = (!with_prev || !kok) ? 0.0 : (bc < 15 ? Jp[kq * 30 + bc + 15] : (bc == 30 ? Jp[450 + kq] : 0.0));
         }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
-        if (with_prev) {
-#pragma unroll
-          for (int kk = 4; kk < 8; kk++) dmma(c0, c1, av[kk], bv[kk]);
-        }
         if (ar < 30) {
           const int ga = gcol(ar);
           if (ga >= 0) {
-            const bool last = f == nf - 1;
 #pragma unroll
             for (int u = 0; u < 2; u++) {
               const int bo = 8 * tb + 2 * q4 + u;
               const double v = u == 0 ? c0 : c1;
-              if (bo < 30) {
-                const int gb = gcol(bo);
-                if (gb >= 0) {
-                  if (!chain) { if (v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }
-                  else if (!(ar >= 15 && bo >= 15) || last) H[(size_t)ga * ld + gb] = v;
-                }
-              } else if (bo == 30) {
-                if (!chain) atomicAdd(&g[ga], v);
-                else if (ar < 15 || last) g[ga] = v;
-              }
+              if (bo < 30) { const int gb = gcol(bo); if (gb >= 0 && v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }
+              else if (bo == 30) atomicAdd(&g[ga], v);
             }
           }
         }
@@ -1140,7 +1121,7 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
 // The Wt chunk is staged once per 32 landmarks and shared by all blocks; each warp owns up to kSsMaxB blocks.
 constexpr int kSsThreads = 256;
 constexpr int kSsMaxB = 10;   // 12*13/2 = 78 lower blocks over 8 warps
-__global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
+__global__ void __launch_bounds__(kSsThreads, 2) k_schur_small(Dev d) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
   if (!w.schur_small) return;
@@ -1172,6 +1153,7 @@ __global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
     bi[q] = i; bj[q] = t - i * (i + 1) / 2;
     acc[q][0] = 0.0; acc[q][1] = 0.0;
   }
+  const int nq = warp < nblk ? (nblk - 1 - warp) / 8 + 1 : 0;   // blocks owned by this warp (t = warp, warp + 8, ...)
   double uhu = 0.0;
   if (nlc > 0) {
     const int nchunk = w.nl_pad / 32;
@@ -1190,12 +1172,32 @@ __global__ void __launch_bounds__(kSsThreads) k_schur_small(Dev d) {
       const int b = c & 1;
       mbar_wait(&bar[b], (unsigned)((c >> 1) & 1));
       const double *Wb = Ws + b * 32 * ldws;
+      // the number of blocks this warp owns is warp-uniform: dispatch once per chunk to a fully unrolled body whose MMAs
+      // are unconditional (a predicated mma.sync costs a WARPSYNC each); operands first, then the MMAs back to back
+      auto body = [&](auto NQ) {
+        constexpr int nq_c = decltype(NQ)::value;
 #pragma unroll 2
-      for (int ks = 0; ks < 32; ks += 4) {
-        const double *wr = Wb + (ks + kq) * ldws + cr;
+        for (int ks = 0; ks < 32; ks += 4) {
+          const double *wr = Wb + (ks + kq) * ldws + cr;
+          double fa[nq_c > 0 ? nq_c : 1], fb[nq_c > 0 ? nq_c : 1];
 #pragma unroll
-        for (int q = 0; q < kSsMaxB; q++)
-          if (warp + q * 8 < nblk) dmma(acc[q][0], acc[q][1], wr[bi[q] * 8], wr[bj[q] * 8]);
+          for (int q = 0; q < nq_c; q++) { fa[q] = wr[bi[q] * 8]; fb[q] = wr[bj[q] * 8]; }
+#pragma unroll
+          for (int q = 0; q < nq_c; q++) dmma(acc[q][0], acc[q][1], fa[q], fb[q]);
+        }
+      };
+      switch (nq) {
+        case 1: body(std::integral_constant<int, 1>()); break;
+        case 2: body(std::integral_constant<int, 2>()); break;
+        case 3: body(std::integral_constant<int, 3>()); break;
+        case 4: body(std::integral_constant<int, 4>()); break;
+        case 5: body(std::integral_constant<int, 5>()); break;
+        case 6: body(std::integral_constant<int, 6>()); break;
+        case 7: body(std::integral_constant<int, 7>()); break;
+        case 8: body(std::integral_constant<int, 8>()); break;
+        case 9: body(std::integral_constant<int, 9>()); break;
+        case 10: body(std::integral_constant<int, 10>()); break;
+        default: break;
       }
       __syncthreads();
       if (tid == 0 && c + 2 < nchunk) { fence_proxy_async(); issue(c + 2, b); }
@@ -1501,11 +1503,13 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ __align__(16) double sm[];
-  const int n = w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;
+  // after the speed-bias elimination (k_sb_elim) only the landmark-coupled part is left, read from Sr
+  const bool reduced = w.sb_elim != 0;
+  const int n = reduced ? w.n_lc : w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = reduced ? w.ldr : w.ldh, ldp = (n + 2) & ~1;
   double *A = sm;                         // n1 x ld
   double *invd = A + (size_t)n1 * ld;     // n (padded to even)
   double *P = invd + ((n + 1) & ~1);      // kCsNB x ldp transposed panel; later xs / partial sums
-  const double *S = d.S + w.offH;
+  const double *S = reduced ? d.Sr + w.offSr : d.S + w.offH;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   __shared__ int fail;
   // row-scaled diagonal block for the TRSM: parked in the (never touched) upper-right corner of A, or behind the panel
@@ -1525,7 +1529,7 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   {
     __shared__ __align__(8) unsigned long long bar;
     const int nlc = w.n_lc, cur = ctl->cur;
-    const bool direct = w.schur_small != 0;
+    const bool direct = !reduced && w.schur_small != 0;
     const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
     const int nbulk = direct ? n : n1;               // rows copied by TMA; the rhs row of the direct case is stitched by hand
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -1666,6 +1670,381 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
     printf("chol timing tid %d n %d: load %lld diag0 %lld trsm %lld trsm_bar %lld look+bar %lld work3b %lld bar3b %lld back_partial %lld back_tri %lld tail %lld\n", tid, n,
            tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[7], tk[8], tk[9]);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Speed-bias elimination (arrow structure of the visual-inertial reduced system).
+// Columns are ordered [poses / extrinsics / td | speed-bias blocks]; the speed-bias block S_ss is block tridiagonal
+// (IMU factors couple consecutive frames only) while its coupling B to the landmark-coupled part is dense.  Instead of
+// one dense Cholesky of all n_c columns (a chain of n_c dependent column steps on a matrix that fills one SM's shared
+// memory), the speed-bias blocks are eliminated first with a block-bidiagonal Cholesky
+//     L_kk L_kk^T = D_k - E'_{k-1} E'_{k-1}^T,   E'_k = E_k L_kk^-T,   Y_k = L_kk^-1 (B_k - E'_{k-1} Y_{k-1})
+// ([B | g_s] carries the right-hand side as its last column), the dense part shrinks to
+//     Sr = S_pp - Y^T Y,  rhs_r = g_p - Y^T z_s            (n_lc x n_lc, tensor-core SYRK)
+// which k_chol_smem factors with several windows per SM, and k_sb_back recovers the speed-bias step from
+//     L_kk^T x_k = z_k - Y_k x_p - E'_k^T x_{k+1}.
+// Same normal equations, another (equally stable) elimination order than the reference's dense LLT.
+// (constants and the kernel follow chol_block9)
+// Cholesky of one 9x9 block held in shared memory (row stride 9), lanes 0..8 own one row each.  Unscaled elimination
+// with the reciprocal chain of chol_diag8; L overwrites the lower part, 1/L_ii goes to invd.  Returns true on a bad pivot.
+D2BA_DEV bool chol_block9(double *Dk, double *invd, int lane) {
+  constexpr int NB = 9;
+  double row[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) row[c] = (lane < NB && c <= lane) ? Dk[lane * NB + c] : 0.0;
+  bool bad = false;
+  double dmine = 1.0;
+#pragma unroll
+  for (int c = 0; c < NB; c++) {
+    const double dcc = __shfl_sync(0xffffffffu, row[c], c);
+    const bool pos = dcc > 1e-30 && dcc < 1e30;
+    if (!pos) bad = true;
+    if (lane == c) dmine = dcc;
+    const double uc = row[c];
+    double pr[NB];
+#pragma unroll
+    for (int c2 = c + 1; c2 < NB; c2++) pr[c2] = uc * __shfl_sync(0xffffffffu, uc, c2);
+    const double rc = pos ? fast_rcp(dcc) : 0.0;
+#pragma unroll
+    for (int c2 = c + 1; c2 < NB; c2++)
+      if (c2 <= lane) row[c2] = fma(-pr[c2], rc, row[c2]);
+  }
+  const double smine = (lane < NB && dmine > 1e-30 && dmine < 1e30) ? fast_rsqrt(dmine) : 1.0;
+  double sc[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c++) sc[c] = __shfl_sync(0xffffffffu, smine, c);
+  if (lane < NB) {
+    invd[lane] = smine;
+#pragma unroll
+    for (int c = 0; c < NB; c++) if (c <= lane) Dk[lane * NB + c] = row[c] * sc[c];
+  }
+  return bad;
+}
+
+constexpr int kSeThreads = 128;    // warp 0: D / E chain, warps 1..3: Y rows, SYRK, stores
+constexpr int kSeMaxBlocks = 32;   // speed-bias blocks per window (mbarrier table)
+constexpr int kSeSlotRows = 12;    // a block's 9 Y rows padded to three MMA k-steps
+__host__ __device__ inline int sbe_ldys(int nlc) { return (nlc + 1 + 7) & ~7; }                 // smem row stride of Y
+__host__ __device__ inline size_t sbe_smem_bytes(int nlc, int nb) {
+  return ((size_t)3 * kSeSlotRows * sbe_ldys(nlc) + (size_t)nb * 2 * 81 + (size_t)nb * 9 + (size_t)(nlc + 9 * nb) + (size_t)9 * nb + 16) * 8;
+}
+
+__global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  if (!w.sb_elim) return;
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse || ctl->chol_fail) return;
+  extern __shared__ __align__(16) double sm[];
+  const int nlc = w.n_lc, nb = w.n_sbe, n = w.n_c, ld = w.ldh, cur = ctl->cur;
+  const int ldys = sbe_ldys(nlc), ncol = nlc + 1, slot_sz = kSeSlotRows * ldys;
+  double *Yr = sm;                                  // ring of 3 slots x 12 rows x ldys: [B_k | g_k] -> Y_k (rows 9..11 stay zero)
+  double *Dk = Yr + (size_t)3 * slot_sz;            // nb x 81 : D_k -> L_kk
+  double *Ek = Dk + (size_t)nb * 81;                // nb x 81 : E_k (rows: block k+1, cols: block k) -> E'_k
+  double *invd = Ek + (size_t)nb * 81;              // nb x 9
+  double *us = invd + (size_t)nb * 9;               // n : u = g / D^2 of the accepted linearisation
+  double *gs = us + n;                              // 9 nb : speed-bias part of the gradient
+  const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
+  const double *S = d.S + w.offH;
+  const double mu = ctl->mu;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int fail;
+  __shared__ __align__(8) unsigned long long bar_B[kSeMaxBlocks], bar_L[kSeMaxBlocks], bar_E[kSeMaxBlocks];
+  if (tid == 0) {
+    fail = 0;
+    for (int k = 0; k < nb; k++) { mbar_init(&bar_B[k], 1); mbar_init(&bar_L[k], 1); mbar_init(&bar_E[k], 1); }
+    mbar_fence_init();
+  }
+#ifdef D2BA_SBE_TIMING
+  long long sk[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long sq = clock64();
+#define SLAP(k) do { long long t_ = clock64(); sk[k] += t_ - sq; sq = t_; } while (0)
+#else
+#define SLAP(k) do { } while (0)
+#endif
+  __syncthreads();
+  // B rows of a block: one TMA bulk copy per row into ring slot k % 3 (issued by one follower lane, two blocks ahead)
+  const unsigned row_bytes = (unsigned)(((nlc + 1) & ~1) * 8);
+  auto issue_rows = [&](int k) {
+    mbar_expect_tx(&bar_B[k], 9u * row_bytes);
+    double *dst = Yr + (size_t)(k % 3) * slot_sz;
+    for (int i = 0; i < 9; i++) bulk_g2s(dst + (size_t)i * ldys, H + (size_t)(nlc + 9 * k + i) * ld, row_bytes, &bar_B[k]);
+  };
+  if (tid == 32) { issue_rows(0); if (nb > 1) issue_rows(1); }
+  // ---- the 9x9 blocks, u, zero padding rows of the ring; the blocks' share of u^T H u; mu D^2 onto the diagonals
+  // (8-byte cp.async: every element is in flight at once instead of one dependent load -> store pair per iteration)
+  for (int e = tid; e < n; e += nt) cp_async8(us + e, ucv + e);
+  for (int e = tid; e < 9 * nb * 18; e += nt) {
+    const int r = e / 18, q = e - 18 * r, k = r / 9, i = r - 9 * k, j = q % 9;
+    const double *hr = H + (size_t)(nlc + r) * ld;
+    if (q < 9) { if (k > 0) cp_async8(Ek + (size_t)(k - 1) * 81 + i * 9 + j, hr + nlc + 9 * (k - 1) + j); }
+    else cp_async8(Dk + (size_t)k * 81 + i * 9 + j, hr + nlc + 9 * k + j);
+  }
+  for (int e = tid; e < 9 * nb; e += nt) cp_async8(gs + e, gcv + nlc + e);
+  cp_async_wait_all();
+  for (int e = tid; e < 3 * 3 * ldys; e += nt) { const int s3 = e / (3 * ldys), rem = e - s3 * 3 * ldys; Yr[(size_t)s3 * slot_sz + 9 * ldys + rem] = 0.0; }
+  __syncthreads();
+  double uhu = 0.0;
+  for (int e = tid; e < 9 * nb * 18; e += nt) {
+    const int r = e / 18, q = e - 18 * r, k = r / 9, i = r - 9 * k, j = q % 9;
+    const double ur = us[nlc + r];
+    if (q < 9) { if (k > 0) uhu += 2.0 * ur * Ek[(size_t)(k - 1) * 81 + i * 9 + j] * us[nlc + 9 * (k - 1) + j]; }
+    else if (j < i) uhu += 2.0 * ur * Dk[(size_t)k * 81 + i * 9 + j] * us[nlc + 9 * k + j];
+    else if (j == i) uhu += Dk[(size_t)k * 81 + i * 9 + i] * ur * ur;
+  }
+  __syncthreads();
+  for (int e = tid; e < 9 * nb; e += nt) Dk[(size_t)(e / 9) * 81 + (e % 9) * 10] += mu * D2v[nlc + e];
+  __syncthreads();
+  SLAP(0);
+  if (warp == 0) {
+    // ---- the D / E chain: chol(D_k) -> E'_k = E_k L_kk^-T -> D_{k+1} -= E'_k E'_k^T, each block published by an mbarrier
+    for (int k = 0; k < nb; k++) {
+      double *Lk = Dk + (size_t)k * 81, *iv = invd + k * 9;
+      if (chol_block9(Lk, iv, lane)) fail = 1;
+      SLAP(1);
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_L[k]);
+      if (k + 1 < nb) {
+        double *Ep = Ek + (size_t)k * 81;
+        if (lane < 9) {
+          double *er = Ep + lane * 9;
+          double a[9];
+#pragma unroll
+          for (int c = 0; c < 9; c++) a[c] = er[c];
+#pragma unroll
+          for (int c = 0; c < 9; c++) {
+            double s_ = a[c];
+#pragma unroll
+            for (int j = 0; j < c; j++) s_ = fma(-a[j], Lk[c * 9 + j], s_);
+            a[c] = s_ * iv[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 9; c++) er[c] = a[c];
+        }
+        __syncwarp();
+        double *Dn = Dk + (size_t)(k + 1) * 81;
+        for (int e = lane; e < 81; e += 32) {
+          const int i = e / 9, j = e - 9 * i;
+          double s_ = 0.0;
+#pragma unroll
+          for (int m = 0; m < 9; m++) s_ += Ep[i * 9 + m] * Ep[j * 9 + m];
+          Dn[e] -= s_;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_E[k]);
+        SLAP(2);
+      }
+    }
+  } else {
+    // ---- followers: per block  [B_k | g_k] - E'_{k-1} Y_{k-1} -> L_kk^-1 (.) = Y_k (one column per thread, registers),
+    //      Sr accumulators -= Y_k^T Y_k on the tensor cores, Y_k to global for the back substitution, next rows prefetched
+    const int t1 = tid - 32, n1t = nt - 32, fw = warp - 1, nfw = (nt >> 5) - 1;
+    const int kq = lane & 3, cr = lane >> 2;
+    const int nb8 = (ncol + 7) >> 3;
+    // output blocks of Sr are owned by block ROW: follower warp fw owns rows fw, fw + 3, fw + 6 (n_lc + 1 <= 72), so one
+    // k-step needs the nine column fragments once plus its own three row fragments, all MMAs of a k-step independent
+    // row fw + 3 ri has at most 3 (ri + 1) blocks on or below the diagonal: 3 + 6 + 9 accumulator pairs
+    double acc0[3][2], acc1[6][2], acc2[9][2];
+#pragma unroll
+    for (int bj = 0; bj < 3; bj++) { acc0[bj][0] = 0.0; acc0[bj][1] = 0.0; }
+#pragma unroll
+    for (int bj = 0; bj < 6; bj++) { acc1[bj][0] = 0.0; acc1[bj][1] = 0.0; }
+#pragma unroll
+    for (int bj = 0; bj < 9; bj++) { acc2[bj][0] = 0.0; acc2[bj][1] = 0.0; }
+    double *Yg = d.sbY + w.offY;
+    const int ldy = w.ldy;
+    for (int k = 0; k < nb; k++) {
+      double *Yk = Yr + (size_t)(k % 3) * slot_sz;
+      const double *Yp = Yr + (size_t)((k + 2) % 3) * slot_sz;   // slot of block k-1
+      mbar_wait(&bar_B[k], 0);
+      if (k > 0) mbar_wait(&bar_E[k - 1], 0);
+      mbar_wait(&bar_L[k], 0);
+      SLAP(1);
+      const double *Lk = Dk + (size_t)k * 81, *iv = invd + k * 9, *Ep = Ek + (size_t)(k > 0 ? k - 1 : 0) * 81;
+      for (int c = t1; c < ldys; c += n1t) {
+        double y[9];
+        if (c < nlc) {
+          double ub = 0.0;
+#pragma unroll
+          for (int i = 0; i < 9; i++) { y[i] = Yk[(size_t)i * ldys + c]; ub += y[i] * us[nlc + 9 * k + i]; }
+          uhu += 2.0 * ub * us[c];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 9; i++) y[i] = c == nlc ? gs[9 * k + i] : 0.0;
+        }
+        if (c < ncol) {
+          if (k > 0) {
+            double yp[9];
+#pragma unroll
+            for (int m = 0; m < 9; m++) yp[m] = Yp[(size_t)m * ldys + c];
+#pragma unroll
+            for (int i = 0; i < 9; i++)
+#pragma unroll
+              for (int m = 0; m < 9; m++) y[i] = fma(-Ep[i * 9 + m], yp[m], y[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 9; i++) {
+            double s_ = y[i];
+#pragma unroll
+            for (int j = 0; j < i; j++) s_ = fma(-Lk[i * 9 + j], y[j], s_);
+            y[i] = s_ * iv[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) Yk[(size_t)i * ldys + c] = y[i];
+        if (c < ldy) {
+#pragma unroll
+          for (int i = 0; i < 9; i++) Yg[(size_t)(9 * k + i) * ldy + c] = y[i];
+        }
+      }
+      SLAP(2);
+      asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");
+      SLAP(3);
+      // rank-9 update of the owned output blocks (three k-steps over the 12 padded rows of the slot)
+      {
+        const double *yb = Yk + (size_t)kq * ldys + cr;
+#pragma unroll
+        for (int st = 0; st < 3; st++) {
+          const double *yr = yb + (size_t)(4 * st) * ldys;
+          double f[9], fa[3];
+#pragma unroll
+          for (int bj = 0; bj < 9; bj++) f[bj] = bj < nb8 ? yr[bj * 8] : 0.0;
+#pragma unroll
+          for (int ri = 0; ri < 3; ri++) fa[ri] = (fw + 3 * ri < nb8) ? yr[(fw + 3 * ri) * 8] : 0.0;
+          // unconditional MMAs (a predicated mma.sync costs a WARPSYNC each): blocks above the diagonal or beyond the
+          // matrix accumulate into entries that are never stored
+#pragma unroll
+          for (int bj = 0; bj < 3; bj++) dmma(acc0[bj][0], acc0[bj][1], fa[0], f[bj]);
+#pragma unroll
+          for (int bj = 0; bj < 6; bj++) dmma(acc1[bj][0], acc1[bj][1], fa[1], f[bj]);
+#pragma unroll
+          for (int bj = 0; bj < 9; bj++) dmma(acc2[bj][0], acc2[bj][1], fa[2], f[bj]);
+        }
+      }
+      SLAP(4);
+      asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");   // slot (k+2) % 3 == slot of block k-1 is dead now
+      if (t1 == 0 && k + 2 < nb) { fence_proxy_async(); issue_rows(k + 2); }
+      SLAP(5);
+    }
+    // ---- Sr = S_pp - sum_k Y_k^T Y_k (lower), rhs row Sr[nlc][c] = g_p[c] - (Y^T z)[c]: all loads of S first
+    {
+      const int ldr = w.ldr;
+      double *Sr = d.Sr + w.offSr;
+      auto src_of = [&](int bi, int bj, int e) -> const double * {
+        const int m = bi * 8 + cr, c = bj * 8 + kq * 2 + e;
+        if (bi >= nb8 || bj > bi) return nullptr;
+        if (m < nlc && c <= m) return S + (size_t)m * ld + c;
+        if (m == nlc && c < nlc) return S + (size_t)n * ld + c;
+        return nullptr;
+      };
+      auto dst_of = [&](int bi, int bj, int e) -> double * {
+        const int m = bi * 8 + cr, c = bj * 8 + kq * 2 + e;
+        if (bi >= nb8 || bj > bi) return nullptr;
+        if (m < nlc && c <= m) return Sr + (size_t)m * ldr + c;
+        if (m == nlc && c < nlc) return Sr + (size_t)nlc * ldr + c;
+        return nullptr;
+      };
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+#pragma unroll
+        for (int bj = 0; bj < 3; bj++) { const double *p_ = src_of(fw, bj, e); acc0[bj][e] = (p_ ? *p_ : 0.0) - acc0[bj][e]; }
+#pragma unroll
+        for (int bj = 0; bj < 6; bj++) { const double *p_ = src_of(fw + 3, bj, e); acc1[bj][e] = (p_ ? *p_ : 0.0) - acc1[bj][e]; }
+#pragma unroll
+        for (int bj = 0; bj < 9; bj++) { const double *p_ = src_of(fw + 6, bj, e); acc2[bj][e] = (p_ ? *p_ : 0.0) - acc2[bj][e]; }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+#pragma unroll
+        for (int bj = 0; bj < 3; bj++) { double *p_ = dst_of(fw, bj, e); if (p_) *p_ = acc0[bj][e]; }
+#pragma unroll
+        for (int bj = 0; bj < 6; bj++) { double *p_ = dst_of(fw + 3, bj, e); if (p_) *p_ = acc1[bj][e]; }
+#pragma unroll
+        for (int bj = 0; bj < 9; bj++) { double *p_ = dst_of(fw + 6, bj, e); if (p_) *p_ = acc2[bj][e]; }
+      }
+    }
+  }
+  SLAP(6);
+  uhu = warp_sum(uhu);
+  if (lane == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
+  __syncthreads();
+  if (fail) { if (tid == 0) ctl->chol_fail = 1; return; }
+  double *LE = d.sbLE + w.offLE;
+  for (int e = tid; e < nb * 81; e += nt) { LE[e] = Dk[e]; LE[(size_t)nb * 81 + e] = Ek[e]; }
+  for (int e = tid; e < nb * 9; e += nt) LE[(size_t)nb * 162 + e] = invd[e];
+#ifdef D2BA_SBE_TIMING
+  SLAP(7);
+  if (wi == 0 && (tid == 0 || tid == 32 || tid == 64)) printf("sbe timing tid %d: init %lld a %lld b %lld c %lld d %lld e %lld tailwork %lld end %lld\n", tid, sk[0], sk[1], sk[2], sk[3], sk[4], sk[5], sk[6], sk[7]);
+#endif
+}
+
+// Speed-bias part of the Gauss-Newton step: L_kk^T x_k = z_k - Y_k x_p - E'_k^T x_{k+1}, blocks from the last to the
+// first.  One CTA per window: all warps form v = Y x_p (coalesced, many loads in flight) and stage the small blocks,
+// warp 0 then runs the short recursion out of shared memory.
+constexpr int kSbBackThreads = 256;
+__global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
+  const int wi = blockIdx.x;
+  const WinDesc &w = d.win[wi];
+  if (!w.sb_elim) return;
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || ctl->reuse || ctl->chol_fail) return;
+  extern __shared__ double sm[];
+  const int nlc = w.n_lc, nb = w.n_sbe, ldy = w.ldy;
+  double *xp = sm;                       // nlc (padded to 96)
+  double *rhs = sm + 96;                 // 9 nb : z - Y x_p
+  double *LE = rhs + 9 * nb;             // nb x 171
+  const double *Yg = d.sbY + w.offY, *LEg = d.sbLE + w.offLE;
+  double *gn = d.gn_c + w.offc;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  for (int c = tid; c < 96; c += nt) xp[c] = c < nlc ? -gn[c] : 0.0;
+  for (int e = tid; e < nb * 171; e += nt) cp_async8(LE + e, LEg + e);   // needed only by the recursion: lands during the products
+  __syncthreads();
+  for (int r0 = warp * 4; r0 < 9 * nb; r0 += nwarp * 4) {
+    double s_[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (r0 + q >= 9 * nb) break;
+      const double *yr = Yg + (size_t)(r0 + q) * ldy;
+      for (int c = lane; c < nlc; c += 32) s_[q] += yr[c] * xp[c];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double t = warp_sum(s_[q]);
+      if (lane == 0 && r0 + q < 9 * nb) rhs[r0 + q] = Yg[(size_t)(r0 + q) * ldy + nlc] - t;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (warp != 0) return;
+  const double *Lg = LE, *Eg = LE + (size_t)nb * 81, *ivg = LE + (size_t)nb * 162;
+  double xn = 0.0;   // lane i < 9 holds x_{k+1}[i]
+  for (int k = nb - 1; k >= 0; k--) {
+    double t = lane < 9 ? rhs[9 * k + lane] : 0.0;
+    if (k + 1 < nb) {   // - E'_k^T x_{k+1}: entry i = sum_m E'_k[m][i] x_{k+1}[m]
+      const double *E = Eg + (size_t)k * 81;
+#pragma unroll
+      for (int m = 0; m < 9; m++) {
+        const double xm = __shfl_sync(0xffffffffu, xn, m);
+        if (lane < 9) t -= E[m * 9 + lane] * xm;
+      }
+    }
+    // L_kk^T x = t, from the last entry up
+    const double *L = Lg + (size_t)k * 81;
+    const double myinv = lane < 9 ? ivg[k * 9 + lane] : 1.0;
+    double lcol[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) lcol[i] = lane < i ? L[i * 9 + lane] : 0.0;
+    double x = 0.0;
+#pragma unroll
+    for (int i = 8; i >= 0; i--) {
+      const double v = __shfl_sync(0xffffffffu, t * myinv, i);
+      if (lane == i) x = v;
+      t -= lcol[i] * v;
+    }
+    xn = x;
+    if (lane < 9) gn[nlc + 9 * k + lane] = -x;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2152,7 +2531,17 @@ size_t chol_smem_need(int n) { return chol_smem_bytes(n); }
 int configure_chol_smem(int max_n) {
   return (int)cudaFuncSetAttribute(k_chol_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(max_n));
 }
-void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) { k_chol_smem<<<d.n_win, kCsThreads, chol_smem_bytes(max_n), s>>>(d); }
+void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) {
+  // small systems (after the speed-bias elimination): 4 warps per window so that several windows share an SM
+  const int threads = max_n <= 96 ? 128 : kCsThreads;
+  k_chol_smem<<<d.n_win, threads, chol_smem_bytes(max_n), s>>>(d);
+}
+size_t sb_elim_smem(int nlc, int nb) { return sbe_smem_bytes(nlc, nb); }
+int configure_sb_elim(size_t smem) { return (int)cudaFuncSetAttribute(k_sb_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
+void launch_sb_elim(const Dev &d, size_t smem, cudaStream_t s) { k_sb_elim<<<d.n_win, kSeThreads, smem, s>>>(d); }
+size_t sb_back_smem(int nb) { return (size_t)(96 + 9 * nb + 171 * nb) * 8; }
+int sb_max_blocks() { return kSeMaxBlocks; }
+void launch_sb_back(const Dev &d, int max_nb, cudaStream_t s) { k_sb_back<<<d.n_win, kSbBackThreads, sb_back_smem(max_nb), s>>>(d); }
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
   size_t sm = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   k_chol<<<d.n_win, kCholThreads, sm, s>>>(d, max_rows);

@@ -153,6 +153,14 @@ D2BA_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;
 D2BA_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register round trip, any number in flight
+D2BA_DEV void cp_async8(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+D2BA_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+D2BA_DEV void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 D2BA_DEV void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                "r"(bytes), "r"(smem_u32(bar))

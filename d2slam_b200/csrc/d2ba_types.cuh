@@ -72,8 +72,10 @@ struct WinDesc {
   int admm_on;
   int chol_smem;               // reduced system fits the shared-memory Cholesky
   int schur_small;             // landmark-coupled part <= 127 columns: one-CTA Schur kernel
-  int imu_chain_ok;            // IMU factors form one chronological chain (factor f starts at the frame factor f-1 ends at, no other
-                               // sharing, at most one chunk): their Hessian blocks are owned by one writer each, stored without atomics
+  // speed-bias elimination (k_sb_elim): block-tridiagonal speed-bias part eliminated before the dense Cholesky
+  int sb_elim, n_sbe;          // enabled, number of (non-constant) speed-bias blocks
+  int ldy, ldr;                // row stride of the stored Y rows / of the reduced system Sr
+  int64_t offY, offLE, offSr;  // offsets (doubles) into Dev::sbY, sbLE, Sr
 };
 
 struct PriorBlk {
@@ -158,6 +160,8 @@ struct Dev {
   double *dinv;         // [NL] 1/sqrt(h + mu d^2)
   double *hl, *gl;      // [NL]
   double *S;            // reduced system (lower) per window
+  double *Sr;           // after the speed-bias elimination: (n_lc + 1) x ldr per window
+  double *sbY, *sbLE;   // L_ss^-1 [B | g_s] rows; L_kk, E'_k, 1/diag(L_kk) blocks
   double *gred;         // n_c
   double *D2c;          // n_c
   double *gn_c, *gn_l;  // Gauss-Newton step

@@ -173,9 +173,11 @@ class Solver:
         return Aflat[: mm * mm].reshape(mm, mm).copy(), b[:mm].copy(), refs, x0[:nx].copy()
 
     def kernel_times(self, iters):
-        out = np.zeros(8)
+        out = np.zeros(10)
         self._chk(lib().d2ba_debug_kernel_times(self.h, C.c_int32(iters), abi.ptr(out)), "kernel_times")
-        return {k: out[i] / max(out[7], 1) for i, k in enumerate(KERNEL_NAMES)}
+        kt = {k: out[i] / max(out[7], 1) for i, k in enumerate(KERNEL_NAMES)}
+        self.chol_split = {"sb_elim": out[8] / max(out[7], 1), "sb_back": out[9] / max(out[7], 1)}   # shares of kt["chol"]
+        return kt
 
     def host_times(self):
         """Wall-clock ms of the phases of the last finalize()."""

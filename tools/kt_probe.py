@@ -15,4 +15,4 @@ for i in range(B):
     from d2slam_b200 import abi
     s.set_blocks(i, abi.POSE, p["frame_ids"], p["poses"], p["pose_const"]); s.set_blocks(i, abi.SPEED_BIAS, p["sb_ids"], p["sb"], None); s.set_blocks(i, abi.LANDMARK, p["lm_ids"], p["inv_dep"], None)
 kt = s.kernel_times(8)
-print(json.dumps({k: round(v * 1e3, 1) for k, v in kt.items()}), "sum_us", round(sum(kt.values()) * 1e3, 1))
+print(json.dumps({k: round(v * 1e3, 1) for k, v in kt.items()}), "sum_us", round(sum(kt.values()) * 1e3, 1), {k: round(v * 1e3, 1) for k, v in s.chol_split.items()})
