@@ -230,7 +230,7 @@ struct d2ba_handle {
   DBuf<char> d_arena;   // device image of the pinned staging arena (one H2D copy per finalize); the DBufs it backs are views
   DBuf<WinDesc> d_win; DBuf<Ctl> d_ctl;
   DBuf<double> d_x6[2], d_R6[2], d_xsb[2], d_xlm[2], d_xtd[2];
-  DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_lm_obs, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
+  DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_obs_slot, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
   DBuf<Group> d_grp; DBuf<Job> d_job; DBuf<ImuDesc> d_imu; DBuf<PriorBlk> d_prior_blk;
   DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
@@ -361,7 +361,7 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_win.release(); h->d_ctl.release(); h->h_ctl.release(); h->d_arena.release(); h->d_sbY.release(); h->d_sbLE.release(); h->d_Sr.release();
   for (int b = 0; b < 2; b++) { h->h_x6[b].release(); h->h_xsb[b].release(); h->h_xlm[b].release(); h->h_xtd[b].release(); }
   for (int b = 0; b < 2; b++) { h->d_x6[b].release(); h->d_R6[b].release(); h->d_xsb[b].release(); h->d_xlm[b].release(); h->d_xtd[b].release(); h->d_rec[b].release(); h->d_H[b].release(); h->d_gc[b].release(); }
-  h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_lm_obs.release();
+  h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_obs_slot.release();
   h->d_slot6.release(); h->d_lm_win.release(); h->d_blk_win.release(); h->d_sb_win.release(); h->d_tile_win.release();
   h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release();
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
@@ -659,7 +659,7 @@ struct HView {   // typed slice of the pinned staging arena
 struct Staging {   // every array finalize uploads lives in ONE pinned arena -> one H2D copy into one device arena
   HBuf<char> arena; size_t cursor = 0;
   HView<WinDesc> win; HView<double> x6, xsb, xlm, xtd, imu_c, prior_J, prior_e0;
-  HView<int> col6, colsb, tile_grp, tile_win, obs_lm, tile_src, lm_ptr, lm_obs, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
+  HView<int> col6, colsb, tile_grp, tile_win, obs_lm, tile_src, lm_ptr, obs_slot, slot6, lm_win, blk_win, sb_win, pr_m, pr_info;
   HView<long long> raw_off;
   HView<long long> pr_offJ, pr_offv;
   HView<Group> grp; HView<Job> job; HView<ImuDesc> imu; HView<PriorBlk> pblk; HView<SchurTileH> schur;
@@ -850,7 +850,7 @@ int d2ba_finalize(d2ba_handle *h) {
   for (int wi = 0; wi < nw; wi++) {
     HostWin &w = h->win[wi]; WinPlan &pl = plan[wi]; WinDesc &d = pl.d;
     d.off6 = off6; off6 += d.n6; d.offsb = offsb; offsb += d.nsb; d.offlm = offlm; offlm += d.nl;
-    d.off_tile = off_tile; off_tile += d.n_tile; d.off_rec = off_rec; off_rec += (int64_t)d.n_tile * kTile * d.rec_stride;
+    d.off_tile = off_tile; off_tile += d.n_tile; d.off_rec = off_rec; off_rec += (int64_t)std::max(pl.n_lmobs, 1) * d.rec_stride;
     d.off_grp = off_grp; off_grp += d.n_grp; d.off_imu = off_imu; off_imu += d.n_imu;
     d.off_lmptr = off_lmptr; off_lmptr += d.nl + 1; d.off_lmobs = off_lmobs; off_lmobs += pl.n_lmobs;
     d.off_prior_blk = off_pblk; off_pblk += d.prior_nblk; d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
@@ -881,7 +881,7 @@ int d2ba_finalize(d2ba_handle *h) {
   st.reserve(st.win, nw); st.reserve(st.x6, (size_t)off6 * 8); st.reserve(st.xsb, (size_t)offsb * 9); st.reserve(st.xlm, offlm); st.reserve(st.xtd, nw);
   st.reserve(st.col6, off6); st.reserve(st.colsb, offsb); st.reserve(st.slot6, off6); st.reserve(st.blk_win, off6); st.reserve(st.sb_win, offsb);
   st.reserve(st.lm_win, offlm); st.reserve(st.tile_grp, off_tile); st.reserve(st.tile_win, off_tile); st.reserve(st.obs_lm, (size_t)off_tile * kTile);
-  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, 2 * (size_t)nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.lm_obs, (size_t)off_lmobs);
+  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, 2 * (size_t)nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.obs_slot, (size_t)off_tile * kTile);
   st.reserve(st.grp, off_grp); st.reserve(st.job, n_jobs); st.reserve(st.imu, off_imu); st.reserve(st.imu_c, (size_t)off_imu * kImuStride);
   st.reserve(st.pblk, off_pblk); st.reserve(st.prior_J, (size_t)off_pJ); st.reserve(st.prior_e0, (size_t)off_pv); st.reserve(st.schur, n_schur);
   st.reserve(st.pr_m, nw); st.reserve(st.pr_info, nw); st.reserve(st.pr_offJ, nw); st.reserve(st.pr_offv, nw);
@@ -889,7 +889,7 @@ int d2ba_finalize(d2ba_handle *h) {
   if (ok) {
     st.place(st.win); st.place(st.x6); st.place(st.xsb); st.place(st.xlm); st.place(st.xtd); st.place(st.col6); st.place(st.colsb); st.place(st.slot6);
     st.place(st.blk_win); st.place(st.sb_win); st.place(st.lm_win); st.place(st.tile_grp); st.place(st.tile_win); st.place(st.obs_lm); st.place(st.tile_src);
-    st.place(st.raw_off); st.place(st.lm_ptr); st.place(st.lm_obs); st.place(st.grp); st.place(st.job); st.place(st.imu); st.place(st.imu_c); st.place(st.pblk);
+    st.place(st.raw_off); st.place(st.lm_ptr); st.place(st.obs_slot); st.place(st.grp); st.place(st.job); st.place(st.imu); st.place(st.imu_c); st.place(st.pblk);
     st.place(st.prior_J); st.place(st.prior_e0); st.place(st.schur); st.place(st.pr_m); st.place(st.pr_info); st.place(st.pr_offJ); st.place(st.pr_offv);
   }
   if (!ok) return fail(h, 24, "pinned staging allocation failed");
@@ -919,7 +919,7 @@ int d2ba_finalize(d2ba_handle *h) {
     for (const HObs &o : w.obs) lmp[o.lm + 1]++;
     for (int l = 0; l < d.nl; l++) lmp[l + 1] += lmp[l];
     std::vector<int> cursor(lmp, lmp + d.nl);
-    int *lmo = st.lm_obs.p + d.off_lmobs;
+    int *oslot = st.obs_slot.p + (size_t)d.off_tile * kTile;   // tile slot -> record position (landmark-major), -1 = padding
     for (int gi = 0; gi < (int)pl.groups.size(); gi++) {
       st.grp.p[d.off_grp + gi] = pl.groups[gi];
       const int cnt = pl.grp_cnt[gi], ntile = (cnt + kTile - 1) / kTile, k0 = pl.grp_begin[gi], t0 = pl.grp_tile0[gi];
@@ -934,12 +934,12 @@ int d2ba_finalize(d2ba_handle *h) {
             const int oi = w.order[k0 + idx];
             ol[lane] = w.obs[oi].lm; os[lane] = oi;
             w.sorted_pos[k0 + idx] = (t0 + t) * kTile + lane;
-          } else { ol[lane] = -1; os[lane] = -1; }
+          } else { ol[lane] = -1; os[lane] = -1; oslot[(size_t)(t0 + t) * kTile + lane] = -1; }
         }
       }
     }
-    // CSR entries in ascending position order (deterministic reduction order): positions increase with sorted index
-    for (size_t k = 0; k < w.order.size(); k++) { const HObs &o = w.obs[w.order[k]]; lmo[cursor[o.lm]++] = w.sorted_pos[k]; }
+    // a landmark's records in ascending tile-position order (deterministic reduction order): positions increase with sorted index
+    for (size_t k = 0; k < w.order.size(); k++) { const HObs &o = w.obs[w.order[k]]; oslot[w.sorted_pos[k]] = cursor[o.lm]++; }
     for (int v = 0; v < 6; v++)
       for (size_t j = 0; j < pl.jobs[v].size(); j++) {
         Job jb = pl.jobs[v][j]; jb.grp += d.off_grp; jb.tile_begin += d.off_tile;
@@ -993,7 +993,7 @@ int d2ba_finalize(d2ba_handle *h) {
   }
   if ((rc = up(h, h->d_col6, st.col6)) || (rc = up(h, h->d_colsb, st.colsb)) || (rc = up(h, h->d_tile_grp, st.tile_grp)) ||
       (rc = up(h, h->d_tile_win, st.tile_win)) || (rc = up(h, h->d_obs_lm, st.obs_lm)) || (rc = up(h, h->d_tile_src, st.tile_src)) ||
-      (rc = up(h, h->d_lm_ptr, st.lm_ptr)) || (rc = up(h, h->d_lm_obs, st.lm_obs)) || (rc = up(h, h->d_slot6, st.slot6)) ||
+      (rc = up(h, h->d_lm_ptr, st.lm_ptr)) || (rc = up(h, h->d_obs_slot, st.obs_slot)) || (rc = up(h, h->d_slot6, st.slot6)) ||
       (rc = up(h, h->d_lm_win, st.lm_win)) || (rc = up(h, h->d_blk_win, st.blk_win)) || (rc = up(h, h->d_sb_win, st.sb_win)) ||
       (rc = up(h, h->d_grp, st.grp)) || (rc = up(h, h->d_job, st.job)) || (rc = up(h, h->d_imu, st.imu)) || (rc = up(h, h->d_imu_c, st.imu_c)) ||
       (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
@@ -1021,7 +1021,7 @@ int d2ba_finalize(d2ba_handle *h) {
   D.win = h->d_win.p; D.ctl = h->d_ctl.p; D.n_win = nw;
   for (int b = 0; b < 2; b++) { D.x6[b] = h->d_x6[b].p; D.R6[b] = h->d_R6[b].p; D.xsb[b] = h->d_xsb[b].p; D.xlm[b] = h->d_xlm[b].p; D.xtd[b] = h->d_xtd[b].p; D.rec[b] = h->d_rec[b].p; D.Hcc[b] = h->d_H[b].p; D.gc[b] = h->d_gc[b].p; }
   D.col6 = h->d_col6.p; D.colsb = h->d_colsb.p; D.grp = h->d_grp.p; D.job = h->d_job.p; D.n_job = n_jobs;
-  D.tile_grp = h->d_tile_grp.p; D.obs = h->d_obs.p; D.obs_lm = h->d_obs_lm.p; D.lm_ptr = h->d_lm_ptr.p; D.lm_obs = h->d_lm_obs.p;
+  D.tile_grp = h->d_tile_grp.p; D.obs = h->d_obs.p; D.obs_lm = h->d_obs_lm.p; D.lm_ptr = h->d_lm_ptr.p; D.obs_slot = h->d_obs_slot.p;
   D.imu = h->d_imu.p; D.imu_c = h->d_imu_c.p; D.imu_U = h->d_imu_U.p; D.prior_blk = h->d_prior_blk.p; D.prior_J = h->d_prior_J.p;
   D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
   D.lm_ref = h->d_lm_ref.p; D.sb_ref = h->d_sb_ref.p; D.td_ref = h->d_td_ref.p; D.cons_buf = h->d_cons.p; D.n_slots = h->n_slots;

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <stdint.h>
+#include <map>
+#include <mutex>
 #include <type_traits>
 
 #include "../../include/d2ba.h"
@@ -528,7 +530,10 @@ __global__ void __launch_bounds__(128) k_proj_lin(Dev d, int eval_cur, int job_b
     double hl = 0, gl = 0, wtd = 0;
 #pragma unroll
     for (int q = 0; q < ROWS; q++) { hl += o.jl[q] * o.jl[q]; gl += o.jl[q] * o.r[q]; if (NS > 2 && need_td) wtd += o.jt[q] * o.jl[q]; }
-    double *rec = d.rec[buf] + (size_t)w.off_rec + ((size_t)(tile - w.off_tile) * kTile + lane) * w.rec_stride;
+    // records are stored landmark-major (obs_slot: tile slot -> position in the landmark's run), so the per-landmark
+    // reduction streams them; padding lanes (slot -1) never write
+    const int rslot = d.obs_slot[(size_t)tile * kTile + lane];
+    double *rec = d.rec[buf] + (size_t)w.off_rec + (size_t)(rslot < 0 ? 0 : rslot) * w.rec_stride;
     if (valid) {
       cost += o.cost;
       reinterpret_cast<double2 *>(rec)[0] = make_double2(hl, gl);
@@ -738,7 +743,10 @@ __global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int
       for (int k = 0; k < 6; k++) { Ji[0][k] = 0; Ji[1][k] = 0; Jj[0][k] = 0; Jj[1][k] = 0; }
     } else cost += oc;
     // staging tile + landmark record
-    double *rec = d.rec[buf] + (size_t)w.off_rec + ((size_t)(tile - w.off_tile) * kTile + lane) * w.rec_stride;
+    // records are stored landmark-major (obs_slot: tile slot -> position in the landmark's run), so the per-landmark
+    // reduction streams them; padding lanes (slot -1) never write
+    const int rslot = d.obs_slot[(size_t)tile * kTile + lane];
+    double *rec = d.rec[buf] + (size_t)w.off_rec + (size_t)(rslot < 0 ? 0 : rslot) * w.rec_stride;
     double wi[6], wj[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -867,7 +875,6 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   for (int c = lane; c <= nlc; c += 32) row[c] = 0.0;
   __syncwarp();
   const int *ptr = d.lm_ptr + w.off_lmptr;
-  const int *lo = d.lm_obs + w.off_lmobs;
   const int stride = w.rec_stride;
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
   double h = 0, g = 0;
@@ -877,13 +884,11 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
     const int half = lane >> 4, sub = lane & 15;
     for (int k0 = kb; k0 < ke; k0 += 16) {
       const int cnt = min(16, ke - k0);
-      const int mypos = (lane < cnt) ? lo[k0 + lane] : 0;
       double v[8];
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         const int o = 2 * q + half;
-        const int p = __shfl_sync(0xffffffffu, mypos, o < cnt ? o : 0);
-        v[q] = (o < cnt) ? recs[(size_t)p * 16 + sub] : 0.0;
+        v[q] = (o < cnt) ? recs[(size_t)(k0 + o) * 16 + sub] : 0.0;
       }
 #pragma unroll
       for (int q = 0; q < 8; q++) {
@@ -905,9 +910,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   } else {
     for (int k0 = kb; k0 < ke; k0 += 32) {
       const int cnt = min(32, ke - k0);
-      const int mypos = (lane < cnt) ? lo[k0 + lane] : 0;     // coalesced read of the position list
       for (int q = 0; q < cnt; q += 2) {
-        const int p0 = __shfl_sync(0xffffffffu, mypos, q), p1 = __shfl_sync(0xffffffffu, mypos, min(q + 1, cnt - 1));
+        const int p0 = k0 + q, p1 = k0 + min(q + 1, cnt - 1);
         const bool two = q + 1 < cnt;
         double v0 = recs[(size_t)p0 * 32 + lane];
         double v1 = two ? recs[(size_t)p1 * 32 + lane] : 0.0;
@@ -975,19 +979,14 @@ __global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *l
   for (int c = sub; c <= nlc; c += 16) row[c] = 0.0;
   __syncwarp(hmask);
   const int *ptr = d.lm_ptr + w.off_lmptr;
-  const int *lo = d.lm_obs + w.off_lmobs;
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
   double h = 0, g = 0;
   const int kb = ptr[l], ke = ptr[l + 1];
-  for (int k0 = kb; k0 < ke; k0 += 8) {
+  for (int k0 = kb; k0 < ke; k0 += 8) {   // the landmark's records are contiguous (landmark-major store of k_proj_lin)
     const int cnt = min(8, ke - k0);
-    const int mypos = (sub < cnt) ? lo[k0 + sub] : 0;
     double v[8];
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int p = __shfl_sync(hmask, mypos, hbase | (q < cnt ? q : 0));
-      v[q] = (q < cnt) ? recs[(size_t)p * 16 + sub] : 0.0;
-    }
+    for (int q = 0; q < 8; q++) v[q] = (q < cnt) ? recs[(size_t)(k0 + q) * 16 + sub] : 0.0;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       if (q >= cnt) break;
@@ -2449,10 +2448,26 @@ __global__ void __launch_bounds__(256) k_marg_reduce(const double *S, int ld, in
   }
   if (tid == 0 && bad) *fail_flag = 1;
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-process property of the kernel, while every handle asks for what
+// ITS windows need: only ever raise it, so a handle with small windows cannot pull the limit from under a live handle
+// with large ones.
+template <typename K>
+cudaError_t raise_smem_limit(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<const void *, size_t> cur;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &c = cur[(const void *)kernel];
+  if (bytes <= c) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) c = bytes;
+  return e;
+}
+
 int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr, double *A, double *b, int *fail_flag,
                        cudaStream_t s) {
   size_t smb = ((size_t)nr * nr + (size_t)nr * (nk + 1)) * 8;
-  cudaError_t e = cudaFuncSetAttribute(k_marg_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+  cudaError_t e = raise_smem_limit(k_marg_reduce, (size_t)(smb));
   if (e != cudaSuccess) return (int)e;
   k_marg_reduce<<<1, 256, smb, s>>>(S, ld, n, keep_idx, nk, rem_idx, nr, A, b, fail_flag);
   return 0;
@@ -2482,17 +2497,17 @@ static size_t proj_smem() { return (size_t)4 * (GC_SIZE + NCT * 8 * (kTile * KR 
 
 int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_proj_lin<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 2>()); if (e) return e;
-  e = cudaFuncSetAttribute(k_proj_lin<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 2>()); if (e) return e;
-  e = cudaFuncSetAttribute(k_proj_lin<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 4>()); if (e) return e;
-  e = cudaFuncSetAttribute(k_proj_lin<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<4, 4>()); if (e) return e;
-  e = cudaFuncSetAttribute(k_proj_lin_pp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 2>()); if (e) return e;
-  e = cudaFuncSetAttribute(k_proj_lin_pp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem<2, 2>()); if (e) return e;
+  e = raise_smem_limit(k_proj_lin<2, 2>, (size_t)(proj_smem<2, 2>())); if (e) return e;
+  e = raise_smem_limit(k_proj_lin<4, 2>, (size_t)(proj_smem<4, 2>())); if (e) return e;
+  e = raise_smem_limit(k_proj_lin<2, 4>, (size_t)(proj_smem<2, 4>())); if (e) return e;
+  e = raise_smem_limit(k_proj_lin<4, 4>, (size_t)(proj_smem<4, 4>())); if (e) return e;
+  e = raise_smem_limit(k_proj_lin_pp<true>, (size_t)(proj_smem<2, 2>())); if (e) return e;
+  e = raise_smem_limit(k_proj_lin_pp<false>, (size_t)(proj_smem<2, 2>())); if (e) return e;
   size_t chol = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
-  e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol); if (e) return e;
+  e = raise_smem_limit(k_chol, (size_t)(chol)); if (e) return e;
   size_t st = (size_t)(40 + 3 * max_nc) * 8;
-  e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st); if (e) return e;
-  e = cudaFuncSetAttribute(k_misc_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)misc_smem_bytes(max_prior_m)); if (e) return e;
+  e = raise_smem_limit(k_step, (size_t)(st)); if (e) return e;
+  e = raise_smem_limit(k_misc_lin, (size_t)(misc_smem_bytes(max_prior_m))); if (e) return e;
   return 0;
 }
 
@@ -2522,14 +2537,14 @@ void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s) {
   k_schur_small<<<d.n_win, kSsThreads, (size_t)(2 * 32 * (max_ldw + 4) + 40) * 8, s>>>(d);
 }
 int configure_schur_small(int max_ldw) {
-  return (int)cudaFuncSetAttribute(k_schur_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * 32 * (max_ldw + 4) + 40) * 8));
+  return (int)raise_smem_limit(k_schur_small, (size_t)((2 * 32 * (max_ldw + 4) + 40) * 8));
 }
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) {
   if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));
 }
 size_t chol_smem_need(int n) { return chol_smem_bytes(n); }
 int configure_chol_smem(int max_n) {
-  return (int)cudaFuncSetAttribute(k_chol_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem_bytes(max_n));
+  return (int)raise_smem_limit(k_chol_smem, (size_t)(chol_smem_bytes(max_n)));
 }
 void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) {
   // small systems (after the speed-bias elimination): 4 warps per window so that several windows share an SM
@@ -2537,7 +2552,7 @@ void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) {
   k_chol_smem<<<d.n_win, threads, chol_smem_bytes(max_n), s>>>(d);
 }
 size_t sb_elim_smem(int nlc, int nb) { return sbe_smem_bytes(nlc, nb); }
-int configure_sb_elim(size_t smem) { return (int)cudaFuncSetAttribute(k_sb_elim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
+int configure_sb_elim(size_t smem) { return (int)raise_smem_limit(k_sb_elim, (size_t)(smem)); }
 void launch_sb_elim(const Dev &d, size_t smem, cudaStream_t s) { k_sb_elim<<<d.n_win, kSeThreads, smem, s>>>(d); }
 size_t sb_back_smem(int nb) { return (size_t)(96 + 9 * nb + 171 * nb) * 8; }
 int sb_max_blocks() { return kSeMaxBlocks; }

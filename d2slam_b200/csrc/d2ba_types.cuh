@@ -135,7 +135,7 @@ struct Dev {
   double *rec[2];       // landmark-side per-observation records
   // landmark CSR
   const int *lm_ptr;
-  const int *lm_obs;
+  const int *obs_slot;  // [T][32] position of the observation's record in its landmark's run (window-local), -1 = padding
   // imu
   const ImuDesc *imu;
   const double *imu_c;  // [NIMU][kImuStride]

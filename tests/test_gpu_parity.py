@@ -242,3 +242,35 @@ def test_rho_swap_quirk_visible():
     for i, p in enumerate(sw):
         d = state_diff(state_of(s, p, i), state_of(ags[i], p))
         assert d["pos"] <= 1e-6 and d["rot"] <= 1e-6, d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["w1_mono", "w1_stereo", "stereo_free_ext_td", "small"])
+def test_speed_bias_elimination_equals_dense_cholesky(name, monkeypatch):
+    """The arrow-structure path (k_sb_elim -> k_chol_smem on the pose part -> k_sb_back) and the dense Cholesky of
+    the whole reduced system are two elimination orders of the same normal equations: same Gauss-Newton step, same
+    trajectory, both within the oracle tolerances."""
+    from d2slam_b200.solver import Solver
+    from oracle import orc
+    pr = synth.make_window(**CASES[name])
+    o = orc.Oracle(); pr.load(o)
+    out = {}
+    for tag, env in (("elim", "0"), ("dense", "1")):
+        monkeypatch.setenv("D2BA_NO_SB_ELIM", env)     # read by d2ba_create
+        s = Solver(); pr.load(s, 0); s.finalize()
+        s.debug_linearize()
+        out[tag + "_gn"] = s.debug_get(0, abi.DBG_GN_STEP).copy()
+        s2 = Solver(); pr.load(s2, 0); s2.finalize()
+        rep = s2.solve_fixed(8)[0]
+        out[tag] = state_of(s2, pr, 0); out[tag + "_cost"] = rep.final_cost
+    o.debug_linearize()
+    gn_ref = o.debug_get(abi.DBG_GN_STEP)
+    assert relerr(out["elim_gn"], out["dense_gn"]) <= 1e-6   # 1e10-conditioned system, atomics reorder the sums run to run
+    assert relerr(out["elim_gn"], gn_ref) <= 1e-6 and relerr(out["dense_gn"], gn_ref) <= 1e-6
+    d = state_diff(out["elim"], out["dense"])
+    assert d["pos"] <= 1e-6 and d["rot"] <= 1e-6 and d["sb"] <= 1e-6 and d["lm_rel"] <= 1e-5, d
+    assert abs(out["elim_cost"] - out["dense_cost"]) <= 1e-7 * max(1.0, abs(out["dense_cost"]))
+    ro = o.solve_fixed(8)
+    d = state_diff(out["elim"], state_of(o, pr))
+    assert d["pos"] <= 1e-6 and d["rot"] <= 1e-6 and d["sb"] <= 1e-6, d
+    assert abs(out["elim_cost"] - ro.final_cost) <= 1e-7 * max(1.0, abs(ro.final_cost))
