@@ -104,7 +104,9 @@ struct PinArr {
     if (n + extra <= cap) return true;
     size_t want = std::max<size_t>((n + extra) * 3 / 2 + 64, 1024);
     T *q = nullptr;
-    if (cudaHostAlloc((void **)&q, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) return false;
+    // write-combined: the feeding threads only ever append (no read-for-ownership, no cache pollution) and the DMA engine
+    // does not have to snoop the CPU caches; reading it back (marginalization, growth) is slow but rare
+    if (cudaHostAlloc((void **)&q, want * sizeof(T), cudaHostAllocWriteCombined) != cudaSuccess) return false;
     if (n) memcpy(q, p, n * sizeof(T));
     if (p) cudaFreeHost(p);
     p = q; cap = want; moved = true;
@@ -477,6 +479,7 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   ObsJ *oj = w->rawj.p + w->rawj.n;
   ObsAnchor *an = w->anch.p;
   size_t na = w->anch.n;
+  ObsAnchor last; memset(&last, 0, sizeof last);   // cached copy of an[na - 1]: the pinned arrays are write-only for this loop
   double tmin = w->td_min, tmax = w->td_max;
   for (int i = 0; i < n; i++) {
     const d2ba_proj_obs &p = in[i];
@@ -503,16 +506,19 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
     if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
       tmin = std::min(tmin, std::min(p.td_i, p.td_j)); tmax = std::max(tmax, std::max(p.td_i, p.td_j));
       // anchor half: bitwise identical to the previous anchor -> share it
-      if (na == base_a || memcmp(an[na - 1].pts_i, p.pts_i, 24) != 0 || memcmp(an[na - 1].vel_i, p.vel_i, 24) != 0 || memcmp(&an[na - 1].td_i, &p.td_i, 8) != 0) {
-        ObsAnchor &a = an[na++];
-        memcpy(a.pts_i, p.pts_i, 24); memcpy(a.vel_i, p.vel_i, 24); a.td_i = p.td_i; a.pad = 0.0;
+      if (na == base_a || memcmp(last.pts_i, p.pts_i, 24) != 0 || memcmp(last.vel_i, p.vel_i, 24) != 0 || memcmp(&last.td_i, &p.td_i, 8) != 0) {
+        memcpy(last.pts_i, p.pts_i, 24); memcpy(last.vel_i, p.vel_i, 24); last.td_i = p.td_i; last.pad = 0.0;
+        an[na++] = last;
       }
-      memcpy(r.pts_j, p.pts_j, 24); memcpy(r.vel_j, p.vel_j, 24); r.td_j = p.td_j;
-      r.depth = p.type == D2BA_PROJ_2F1C_DEPTH ? p.depth : 0.0;
-      r.anchor = (int32_t)(na - 1); r.type = p.type;
+      ObsJ t;
+      memcpy(t.pts_j, p.pts_j, 24); memcpy(t.vel_j, p.vel_j, 24); t.td_j = p.td_j;
+      t.depth = p.type == D2BA_PROJ_2F1C_DEPTH ? p.depth : 0.0;
+      t.anchor = (int32_t)(na - 1); t.type = p.type;
+      r = t;   // one sequential 72-byte store burst
     } else {
-      memset(&r, 0, sizeof r);
-      r.depth = p.depth; r.anchor = 0; r.type = p.type;
+      ObsJ t; memset(&t, 0, sizeof t);
+      t.depth = p.depth; t.anchor = 0; t.type = p.type;
+      r = t;
     }
   }
   w->td_min = tmin; w->td_max = tmax;

@@ -24,9 +24,9 @@ for nt in (16,):
     print(json.dumps({"threads": nt, "ms_step": round(t / 5 * 1e3, 2), **{k: round(v / 5 * 1e3, 2) for k, v in rp.breakdown.items()},
                       **{k: round(v / 5 * 1e3, 2) for k, v in rp.feed_calls.items()}, "finalize_phases": s.host_times()}), flush=True)
 extra = [Solver(max_windows=B, max_num_iterations=iters) for _ in range(5)]
-for nh in (4, 5):
+for nh in (4,):
     hs = ([s] + extra)[:nh]
-    for nt in (12, 16, 24):
+    for nt in (12, 16, 20):
         rp.run_pipelined(hs, 8, iters, nt)
         t, reps = rp.run_pipelined(hs, 12, iters, nt)
         print(json.dumps({"pipelined_handles": nh, "threads": nt, "ms_step": round(t / 12 * 1e3, 2), "iter_per_s": round(B * iters * 12 / t), "dev_solve_ms": round(reps[0].total_time * 1e3, 2),

@@ -35,7 +35,7 @@ if os.path.exists(launch):
 traffic = {}
 for f in sorted(os.listdir(G)):
     m = re.match(rf"prof_(\w+)_B{B}\.ncu-rep", f)
-    if not m:
+    if not m or m.group(1) in ("multi", "chol2"):
         continue
     kn = m.group(1)
     raw = subprocess.run(["ncu", "-i", os.path.join(G, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
