@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int
     const int tile = jb.tile_begin + t;
     const double *ob = d.obs + (size_t)tile * kObsFields * kTile + lane;
     const int lm = d.obs_lm[(size_t)tile * kTile + lane];
+    const int rslot = d.obs_slot[(size_t)tile * kTile + lane];   // needed only for the record store: in flight with the rest
     const bool valid = lm >= 0;
     const double lam = valid ? xlm[lm] : 1.0;
     double pi[3] = {ob[0 * kTile], ob[1 * kTile], ob[2 * kTile]};
@@ -745,7 +746,6 @@ __global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int
     // staging tile + landmark record
     // records are stored landmark-major (obs_slot: tile slot -> position in the landmark's run), so the per-landmark
     // reduction streams them; padding lanes (slot -1) never write
-    const int rslot = d.obs_slot[(size_t)tile * kTile + lane];
     double *rec = d.rec[buf] + (size_t)w.off_rec + (size_t)(rslot < 0 ? 0 : rslot) * w.rec_stride;
     double wi[6], wj[6];
 #pragma unroll
