@@ -39,10 +39,13 @@ void launch_chol(const Dev &d, int max_rows, cudaStream_t s);
 size_t chol_smem_need(int n);
 int configure_chol_smem(int max_n);
 void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s);
-size_t sb_elim_smem(int nlc, int nb);
+size_t sb_elim_smem(int ldw, int n_c, int nb);
+size_t sb_back_smem(int nlc, int nb);
+int configure_sb_back(size_t smem);
+void launch_zero_sb_rows(const Dev &d, cudaStream_t s);
 int configure_sb_elim(size_t smem);
 void launch_sb_elim(const Dev &d, size_t smem, cudaStream_t s);
-void launch_sb_back(const Dev &d, int max_nb, cudaStream_t s);
+void launch_sb_back(const Dev &d, size_t smem, cudaStream_t s);
 int sb_max_blocks();
 void launch_step(const Dev &d, int max_nc, cudaStream_t s);
 void launch_control(const Dev &d, int init, cudaStream_t s);
@@ -250,10 +253,10 @@ struct d2ba_handle {
   int max_n_smem = 0, max_rows_glob = 1; bool any_chol_glob = false; int cfg_max_n_smem = -1;
   int max_ldw_small = 0, cfg_max_ldw_small = -1;
   int any_compact = 0, any_wide = 0;   // record widths present (which gather kernels to launch)
-  int sbe_max_nb = 0;
+  size_t sbb_smem = 0, cfg_sbb_smem = 0;   // k_sb_back dynamic shared memory
   size_t sbe_smem = 0, cfg_sbe_smem = 0;   // speed-bias elimination: dynamic shared memory of k_sb_elim (0 = no window uses it)
-  int64_t totY = 0, totLE = 0, totSr = 0;
-  DBuf<double> d_sbY, d_sbLE, d_Sr;
+  int64_t totLE = 0;
+  DBuf<double> d_sbLE;
   int64_t totH = 0, totW = 0, totc = 0;
   bool any_admm = false;
   // host mirrors of the solved state
@@ -360,7 +363,7 @@ int d2ba_destroy(d2ba_handle *h) {
   if (h->marg) { d2ba_destroy(h->marg); h->marg = nullptr; }
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   // DBuf members: release explicitly
-  h->d_win.release(); h->d_ctl.release(); h->h_ctl.release(); h->d_arena.release(); h->d_sbY.release(); h->d_sbLE.release(); h->d_Sr.release();
+  h->d_win.release(); h->d_ctl.release(); h->h_ctl.release(); h->d_arena.release(); h->d_sbLE.release();
   for (int b = 0; b < 2; b++) { h->h_x6[b].release(); h->h_xsb[b].release(); h->h_xlm[b].release(); h->h_xtd[b].release(); }
   for (int b = 0; b < 2; b++) { h->d_x6[b].release(); h->d_R6[b].release(); h->d_xsb[b].release(); h->d_xlm[b].release(); h->d_xtd[b].release(); h->d_rec[b].release(); h->d_H[b].release(); h->d_gc[b].release(); }
   h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_obs_slot.release();
@@ -820,12 +823,12 @@ int d2ba_finalize(d2ba_handle *h) {
     d.rec_stride = any_wide ? 32 : 16;
     pl.n_lmobs = (int)M;
     d.schur_small = (d.n_lc + 1 <= 96) ? 1 : 0;
-    {   // speed-bias elimination: needs the one-CTA Schur + shared-memory Cholesky path and a block-tridiagonal
-        // speed-bias part (IMU factors / prior blocks only between neighbouring speed-bias blocks)
+    {   // speed-bias elimination: needs a block-tridiagonal speed-bias part (IMU factors / prior blocks only between
+        // neighbouring speed-bias blocks)
       std::vector<int> pos(nsb, -1);
       int nb = 0;
       for (int i = 0; i < nsb; i++) if (w.sb_col[i] >= 0) pos[i] = nb++;
-      bool ok = !h->force_full_S && !h->no_sb_elim && d.chol_smem && d.schur_small && nb >= 1 && d.n_lc >= 1 && d.n_lc + 1 <= 72 && w.n_c == w.n_lc + 9 * nb;
+      bool ok = !h->force_full_S && !h->no_sb_elim && nb >= 1 && d.n_lc >= 1 && w.n_c == w.n_lc + 9 * nb;
       for (size_t a = 0; a < w.imu.size() && ok; a++) {
         const int pa = pos[w.imu[a].si], pb = pos[w.imu[a].sj];
         if (pa >= 0 && pb >= 0 && std::abs(pa - pb) > 1) ok = false;
@@ -833,9 +836,11 @@ int d2ba_finalize(d2ba_handle *h) {
       int pmin = 1 << 30, pmax = -1;
       for (const HPriorBlk &b : w.prior_blk) if (b.kind == D2BA_SPEED_BIAS && pos[b.index] >= 0) { pmin = std::min(pmin, pos[b.index]); pmax = std::max(pmax, pos[b.index]); }
       if (pmax - pmin > 1) ok = false;
-      if (ok && (sb_elim_smem(d.n_lc, nb) > (size_t)200 * 1024 || nb > sb_max_blocks() || nb * 180 * 8 > 40 * 1024)) ok = false;
+      if (ok && (sb_elim_smem(d.ldw, d.n_c, nb) > (size_t)200 * 1024 || nb > sb_max_blocks() || sb_back_smem(d.n_lc, nb) > (size_t)200 * 1024)) ok = false;
       d.sb_elim = ok ? 1 : 0; d.n_sbe = nb;
-      d.ldy = roundup(d.n_lc + 1, 4); d.ldr = roundup(d.n_lc + 1, 4);
+      // the dense Cholesky only sees the pose part then: decide its kernel with that size
+      if (ok) d.chol_smem = (chol_smem_need(d.n_lc) <= (size_t)232448 - 16) ? 1 : 0;
+      d.wt_rows = d.nl_pad + (ok ? roundup(9 * nb, 32) : 0);
     }
     if (!d.schur_small) {
       int ntw = (d.n_lc + 1 + 31) / 32;
@@ -847,8 +852,8 @@ int d2ba_finalize(d2ba_handle *h) {
   lap(0);
   // ---- serial prefix sums
   h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
-  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0; h->any_compact = h->any_wide = 0; h->sbe_smem = 0; h->sbe_max_nb = 0;
-  int64_t offY = 0, offLE = 0, offSr = 0;
+  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0; h->any_compact = h->any_wide = 0; h->sbe_smem = 0; h->sbb_smem = 0;
+  int64_t offLE = 0;
   int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0;
   int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0; long long off_raw = 0;
   int njobs[6] = {0, 0, 0, 0, 0, 0};
@@ -862,7 +867,7 @@ int d2ba_finalize(d2ba_handle *h) {
     d.off_prior_blk = off_pblk; off_pblk += d.prior_nblk; d.off_prior_J = off_pJ; d.off_prior_v = off_pv;
     off_pJ += (int64_t)d.prior_m * d.prior_m; off_pv += d.prior_m;
     d.offH = offH; offH += (int64_t)(d.n_c + 1) * d.ldh;
-    d.offW = offW; offW += (int64_t)std::max(d.nl_pad, 32) * d.ldw;
+    d.offW = offW; offW += (int64_t)std::max(d.wt_rows, 32) * d.ldw;
     d.offc = offc; offc += roundup(d.n_c + 1, 4);
     for (int v = 0; v < 6; v++) { pl.job_off[v] = njobs[v]; njobs[v] += (int)pl.jobs[v].size(); }
     pl.schur_off = n_schur; n_schur += (int)pl.schur.size();
@@ -871,17 +876,17 @@ int d2ba_finalize(d2ba_handle *h) {
     if (d.schur_small) h->max_ldw_small = std::max(h->max_ldw_small, d.ldw);
     if (d.rec_stride == 16) h->any_compact = 1; else h->any_wide = 1;
     if (d.sb_elim) {
-      d.offY = offY; offY += (int64_t)9 * d.n_sbe * d.ldy; d.offLE = offLE; offLE += (int64_t)d.n_sbe * 171; d.offSr = offSr; offSr += (int64_t)(d.n_lc + 1) * d.ldr;
-      h->sbe_smem = std::max(h->sbe_smem, sb_elim_smem(d.n_lc, d.n_sbe)); h->sbe_max_nb = std::max(h->sbe_max_nb, d.n_sbe);
+      d.offLE = offLE; offLE += (int64_t)d.n_sbe * 171;
+      h->sbe_smem = std::max(h->sbe_smem, sb_elim_smem(d.ldw, d.n_c, d.n_sbe)); h->sbb_smem = std::max(h->sbb_smem, sb_back_smem(d.n_lc, d.n_sbe));
     }
-    if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.sb_elim ? d.n_lc : d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, d.n_c + 1); }
+    if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.sb_elim ? d.n_lc : d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, (d.sb_elim ? d.n_lc : d.n_c) + 1); }
     if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
     if (w.prior_m > 0 && w.prior_is_info) any_info = true;
   }
   int jbase[6]; { int r = 0; for (int v = 0; v < 6; v++) { jbase[v] = r; h->job_begin[v] = r; h->job_count[v] = njobs[v]; r += njobs[v]; } }
   const int n_jobs = jbase[5] + njobs[5];
   h->n6_total = off6; h->nsb_total = offsb; h->nl_total = offlm; h->n_tiles = off_tile; h->n_imu_total = off_imu; h->n_schur = n_schur;
-  h->totH = offH; h->totW = offW; h->totc = offc; h->totY = offY; h->totLE = offLE; h->totSr = offSr;
+  h->totH = offH; h->totW = offW; h->totc = offc; h->totLE = offLE;
   // ---- staging sizes
   st.cursor = 0;
   st.reserve(st.win, nw); st.reserve(st.x6, (size_t)off6 * 8); st.reserve(st.xsb, (size_t)offsb * 9); st.reserve(st.xlm, offlm); st.reserve(st.xtd, nw);
@@ -1019,7 +1024,7 @@ int d2ba_finalize(d2ba_handle *h) {
   if ((rc = alloc_zero(h, h->d_Wt, (size_t)offW))) return rc;   // padding rows / columns must be zero
   CK(h->d_dinv.alloc(offlm)); CK(h->d_hl.alloc(offlm)); CK(h->d_gl.alloc(offlm)); CK(h->d_S.alloc((size_t)offH));
   CK(h->d_gred.alloc((size_t)offc)); CK(h->d_D2c.alloc((size_t)offc)); CK(h->d_gn_c.alloc((size_t)offc)); CK(h->d_gn_l.alloc(offlm));
-  CK(h->d_sbY.alloc((size_t)std::max<int64_t>(offY, 1))); CK(h->d_sbLE.alloc((size_t)std::max<int64_t>(offLE, 1))); CK(h->d_Sr.alloc((size_t)std::max<int64_t>(offSr, 1)));
+  CK(h->d_sbLE.alloc((size_t)std::max<int64_t>(offLE, 1)));
   CK(h->d_step_c.alloc((size_t)offc)); CK(h->d_step_l.alloc(offlm)); CK(h->d_wu.alloc(offlm)); CK(h->d_uc.alloc((size_t)offc)); CK(h->d_D2l.alloc(offlm));
   // ---- device view
   Dev &D = h->dev;
@@ -1032,7 +1037,7 @@ int d2ba_finalize(d2ba_handle *h) {
   D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
   D.lm_ref = h->d_lm_ref.p; D.sb_ref = h->d_sb_ref.p; D.td_ref = h->d_td_ref.p; D.cons_buf = h->d_cons.p; D.n_slots = h->n_slots;
   D.Wt = h->d_Wt.p; D.dinv = h->d_dinv.p; D.hl = h->d_hl.p; D.gl = h->d_gl.p; D.S = h->d_S.p; D.gred = h->d_gred.p; D.D2c = h->d_D2c.p;
-  D.sbY = h->d_sbY.p; D.sbLE = h->d_sbLE.p; D.Sr = h->d_Sr.p;
+  D.sbLE = h->d_sbLE.p;
   D.gn_c = h->d_gn_c.p; D.gn_l = h->d_gn_l.p; D.step_c = h->d_step_c.p; D.step_l = h->d_step_l.p; D.wu = h->d_wu.p; D.uc = h->d_uc.p; D.D2l = h->d_D2l.p;
   SolverParams &P = D.prm;
   P.sqrt_info_px = h->cfg.focal_length / 1.5; P.depth_sqrt_inf = h->cfg.depth_sqrt_inf; P.gravity = h->cfg.gravity_norm; P.huber = h->cfg.huber_delta;
@@ -1051,6 +1056,10 @@ int d2ba_finalize(d2ba_handle *h) {
   if (h->sbe_smem > 0 && h->cfg_sbe_smem < h->sbe_smem) {
     if (configure_sb_elim(h->sbe_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_sb_elim) failed");
     h->cfg_sbe_smem = h->sbe_smem;
+  }
+  if (h->sbb_smem > 0 && h->cfg_sbb_smem < h->sbb_smem) {
+    if (configure_sb_back(h->sbb_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_sb_back) failed");
+    h->cfg_sbb_smem = h->sbb_smem;
   }
   if (h->max_n_smem > 0 && h->cfg_max_n_smem != h->max_n_smem) {
     if (configure_chol_smem(h->max_n_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_chol_smem) failed");
@@ -1123,12 +1132,12 @@ static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
 
 static void enqueue_iteration(d2ba_handle *h) {
   launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
+  if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);   // Y rows into Wt: the Schur kernels subtract them too
   if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
-  if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);
   if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
-  if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbe_max_nb, h->stream);
   if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
+  if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
   launch_step(h->dev, h->max_nc, h->stream);
   enqueue_linearize(h, 0);
   launch_control(h->dev, 0, h->stream);
@@ -1280,15 +1289,20 @@ int d2ba_debug_linearize(d2ba_handle *h) {
   enqueue_linearize(h, 1);
   launch_control(h->dev, 1, h->stream);
   launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
+  // debug view: the landmark-only Schur complement (eliminated speed-bias rows zeroed), kept un-factored in d_dbg
+  if (h->sbe_smem > 0) launch_zero_sb_rows(h->dev, h->stream);
   if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
   launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
-  // keep an un-factored copy of S in the debug buffer
   CK(h->d_dbg.alloc((size_t)h->totH));
   CK(cudaMemcpyAsync(h->d_dbg.p, h->d_S.p, (size_t)h->totH * 8, cudaMemcpyDeviceToDevice, h->stream));
-  if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);
+  if (h->sbe_smem > 0) {   // now the system the solver factors: Y rows in place, Schur again
+    launch_sb_elim(h->dev, h->sbe_smem, h->stream);
+    if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
+    launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+  }
   if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
-  if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbe_max_nb, h->stream);
   if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
+  if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
   launch_step(h->dev, h->max_nc, h->stream);
   CK(cudaMemcpyAsync(h->h_ctl.p, h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1554,8 +1568,9 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
   for (int i = 0; i < 10; i++) ms_out[i] = 0;
   for (int it = 0; it < iters; it++) {
     cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
+    cudaEventRecord(evs[0], h->stream); if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);
     cudaEventRecord(ev[1], h->stream); if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
-    cudaEventRecord(ev[2], h->stream); if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream); cudaEventRecord(evs[0], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); cudaEventRecord(evs[1], h->stream); if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbe_max_nb, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
+    cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream); cudaEventRecord(evs[1], h->stream); if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
     cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);
     cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream);
     cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);
@@ -1563,7 +1578,7 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
     cudaEventRecord(ev[7], h->stream);
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); ms_out[i] += ms; }
-    { float ms = 0; cudaEventElapsedTime(&ms, ev[2], evs[0]); ms_out[8] += ms; cudaEventElapsedTime(&ms, evs[1], ev[3]); ms_out[9] += ms; }
+    { float ms = 0; cudaEventElapsedTime(&ms, evs[0], ev[1]); ms_out[8] += ms; cudaEventElapsedTime(&ms, evs[1], ev[3]); ms_out[9] += ms; }
   }
   ms_out[7] = iters;
   for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);

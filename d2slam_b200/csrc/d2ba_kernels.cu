@@ -1051,6 +1051,7 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
   double uhu = 0.0;   // this tile's share of u^T Hcc u (lower elements, off-diagonal counted twice)
   if (t.kind == 1) {
     // plain copy region: S[i][j] = H[i][j] + mu D^2 (i == j) for i in [nlc, n), j <= i; rhs row j in [nlc, n)
+    if (w.sb_elim) return;   // the speed-bias rows were eliminated by k_sb_elim (which also took their share of u^T H u)
     const int i0 = t.tm * 32, j0 = t.tn * 32;
     for (int e = tid; e < 1024; e += 128) {
       int i = i0 + e / 32, j = j0 + e % 32;
@@ -1073,7 +1074,7 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
   const double *Wt = d.Wt + w.offW;
   const int ldw = w.ldw;
   const int kq = lane & 3, cr = lane >> 2;
-  for (int k0 = 0; k0 < w.nl_pad; k0 += kSyrkK) {
+  for (int k0 = 0; k0 < w.wt_rows; k0 += kSyrkK) {   // landmark rows, then the eliminated speed-bias rows Y
     for (int e = tid; e < kSyrkK * 32; e += 128) {
       int k = e / 32, c = e % 32;
       const double *rowp = Wt + (size_t)(k0 + k) * ldw;
@@ -1107,7 +1108,7 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
           if (m == c) hv += mu * D2v[m];
           S[(size_t)m * ld + c] = hv - v;
         } else if (m == nlc && c < nlc) {
-          S[(size_t)n * ld + c] = gcv[c] - v;
+          S[(size_t)(w.sb_elim ? nlc : n) * ld + c] = gcv[c] - v;   // rhs row of the system the Cholesky will see
         }
       }
   uhu = block_sum(uhu, redq);
@@ -1155,7 +1156,7 @@ __global__ void __launch_bounds__(kSsThreads, 2) k_schur_small(Dev d) {
   const int nq = warp < nblk ? (nblk - 1 - warp) / 8 + 1 : 0;   // blocks owned by this warp (t = warp, warp + 8, ...)
   double uhu = 0.0;
   if (nlc > 0) {
-    const int nchunk = w.nl_pad / 32;
+    const int nchunk = w.wt_rows / 32;   // landmark rows, then the eliminated speed-bias rows Y
     const unsigned row_bytes = (unsigned)ldw * 8u;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -1214,14 +1215,14 @@ __global__ void __launch_bounds__(kSsThreads, 2) k_schur_small(Dev d) {
           if (m == c) hv += mu * D2v[m];
           S[(size_t)m * ld + c] = hv - v;
         } else if (m == nlc && c < nlc) {
-          S[(size_t)n * ld + c] = gcv[c] - v;
+          S[(size_t)(w.sb_elim ? nlc : n) * ld + c] = gcv[c] - v;   // rhs row of the system the Cholesky will see
         }
       }
     }
   }
   // rows of the speed-bias part (no landmark coupling) and the rest of the rhs row; when the shared-memory
   // Cholesky owns this window it reads them straight from Hcc instead (saves the copy through S)
-  const int nrow = w.chol_smem ? 0 : n - nlc;
+  const int nrow = (w.chol_smem || w.sb_elim) ? 0 : n - nlc;
   for (int e = tid; e < nrow * n; e += kSsThreads) {
     const int i = nlc + e / n, j = e % n;
     if (j > i) continue;
@@ -1230,7 +1231,7 @@ __global__ void __launch_bounds__(kSsThreads, 2) k_schur_small(Dev d) {
     if (i == j) v += mu * D2v[i];
     S[(size_t)i * ld + j] = v;
   }
-  if (!w.chol_smem) for (int j = nlc + tid; j < n; j += kSsThreads) S[(size_t)n * ld + j] = gcv[j];
+  if (!w.chol_smem && !w.sb_elim) for (int j = nlc + tid; j < n; j += kSsThreads) S[(size_t)n * ld + j] = gcv[j];
   uhu = block_sum(uhu, redq);
   if (tid == 0) atomicAdd(&ctl->uHu_cam, uhu);
 }
@@ -1260,7 +1261,7 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
   double *Dg = redb + 16 * 32;      // kNB x (kNB+1) diagonal block (row-major, lower)
   double *invd = Dg + kNB * (kNB + 1);  // reciprocal diagonal of L, all n columns
   __shared__ int fail;
-  const int n = w.n_c, n1 = n + 1, ld = w.ldh;
+  const int n = w.sb_elim ? w.n_lc : w.n_c, n1 = n + 1, ld = w.ldh;   // speed-bias blocks eliminated beforehand: pose part only
   double *S = d.S + w.offH;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) fail = 0;
@@ -1502,13 +1503,13 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ __align__(16) double sm[];
-  // after the speed-bias elimination (k_sb_elim) only the landmark-coupled part is left, read from Sr
+  // after the speed-bias elimination (k_sb_elim + Schur) only the landmark-coupled part is left: S rows 0..n_lc (rhs)
   const bool reduced = w.sb_elim != 0;
-  const int n = reduced ? w.n_lc : w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = reduced ? w.ldr : w.ldh, ldp = (n + 2) & ~1;
+  const int n = reduced ? w.n_lc : w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;
   double *A = sm;                         // n1 x ld
   double *invd = A + (size_t)n1 * ld;     // n (padded to even)
   double *P = invd + ((n + 1) & ~1);      // kCsNB x ldp transposed panel; later xs / partial sums
-  const double *S = reduced ? d.Sr + w.offSr : d.S + w.offH;
+  const double *S = d.S + w.offH;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   __shared__ int fail;
   // row-scaled diagonal block for the TRSM: parked in the (never touched) upper-right corner of A, or behind the panel
@@ -1678,9 +1679,10 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
 // one dense Cholesky of all n_c columns (a chain of n_c dependent column steps on a matrix that fills one SM's shared
 // memory), the speed-bias blocks are eliminated first with a block-bidiagonal Cholesky
 //     L_kk L_kk^T = D_k - E'_{k-1} E'_{k-1}^T,   E'_k = E_k L_kk^-T,   Y_k = L_kk^-1 (B_k - E'_{k-1} Y_{k-1})
-// ([B | g_s] carries the right-hand side as its last column), the dense part shrinks to
-//     Sr = S_pp - Y^T Y,  rhs_r = g_p - Y^T z_s            (n_lc x n_lc, tensor-core SYRK)
-// which k_chol_smem factors with several windows per SM, and k_sb_back recovers the speed-bias step from
+// ([B | g_s] carries the right-hand side as its last column).  The rows Y are appended to the scaled landmark rows Wt,
+// so the Schur kernel that runs next forms  S_pp + mu D^2 - Wt^T Wt - Y^T Y  and  g_p - Wt^T g~ - Y^T z_s  in one
+// tensor-core SYRK: the dense part shrinks to n_lc x n_lc, which k_chol_smem factors with several windows per SM (or
+// k_chol for multi-agent windows), and k_sb_back recovers the speed-bias step from
 //     L_kk^T x_k = z_k - Y_k x_p - E'_k^T x_{k+1}.
 // Same normal equations, another (equally stable) elimination order than the reference's dense LLT.
 // (constants and the kernel follow chol_block9)
@@ -1720,12 +1722,11 @@ D2BA_DEV bool chol_block9(double *Dk, double *invd, int lane) {
   return bad;
 }
 
-constexpr int kSeThreads = 128;    // warp 0: D / E chain, warps 1..3: Y rows, SYRK, stores
+constexpr int kSeThreads = 128;    // warp 0: D / E chain, warps 1..3: Y rows
 constexpr int kSeMaxBlocks = 32;   // speed-bias blocks per window (mbarrier table)
-constexpr int kSeSlotRows = 12;    // a block's 9 Y rows padded to three MMA k-steps
-__host__ __device__ inline int sbe_ldys(int nlc) { return (nlc + 1 + 7) & ~7; }                 // smem row stride of Y
-__host__ __device__ inline size_t sbe_smem_bytes(int nlc, int nb) {
-  return ((size_t)3 * kSeSlotRows * sbe_ldys(nlc) + (size_t)nb * 2 * 81 + (size_t)nb * 9 + (size_t)(nlc + 9 * nb) + (size_t)9 * nb + 16) * 8;
+constexpr int kSeSlotRows = 9;
+__host__ __device__ inline size_t sbe_smem_bytes(int ldw, int n_c, int nb) {
+  return ((size_t)3 * kSeSlotRows * ldw + (size_t)nb * 2 * 81 + (size_t)nb * 9 + (size_t)n_c + (size_t)9 * nb + 16) * 8;
 }
 
 __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
@@ -1736,15 +1737,15 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ __align__(16) double sm[];
   const int nlc = w.n_lc, nb = w.n_sbe, n = w.n_c, ld = w.ldh, cur = ctl->cur;
-  const int ldys = sbe_ldys(nlc), ncol = nlc + 1, slot_sz = kSeSlotRows * ldys;
-  double *Yr = sm;                                  // ring of 3 slots x 12 rows x ldys: [B_k | g_k] -> Y_k (rows 9..11 stay zero)
+  const int ldys = w.ldw, ncol = nlc + 1, slot_sz = kSeSlotRows * ldys;   // ldw: multiple of 8, >= n_lc + 1
+  double *Yr = sm;                                  // ring of 3 slots x 9 rows x ldw: [B_k | g_k] -> Y_k
   double *Dk = Yr + (size_t)3 * slot_sz;            // nb x 81 : D_k -> L_kk
   double *Ek = Dk + (size_t)nb * 81;                // nb x 81 : E_k (rows: block k+1, cols: block k) -> E'_k
   double *invd = Ek + (size_t)nb * 81;              // nb x 9
   double *us = invd + (size_t)nb * 9;               // n : u = g / D^2 of the accepted linearisation
   double *gs = us + n;                              // 9 nb : speed-bias part of the gradient
   const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
-  const double *S = d.S + w.offH;
+  double *Yg = d.Wt + w.offW + (size_t)w.nl_pad * w.ldw;   // the eliminated rows follow the landmark rows of Wt
   const double mu = ctl->mu;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int fail;
@@ -1754,12 +1755,6 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
     for (int k = 0; k < nb; k++) { mbar_init(&bar_B[k], 1); mbar_init(&bar_L[k], 1); mbar_init(&bar_E[k], 1); }
     mbar_fence_init();
   }
-#ifdef D2BA_SBE_TIMING
-  long long sk[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long sq = clock64();
-#define SLAP(k) do { long long t_ = clock64(); sk[k] += t_ - sq; sq = t_; } while (0)
-#else
-#define SLAP(k) do { } while (0)
-#endif
   __syncthreads();
   // B rows of a block: one TMA bulk copy per row into ring slot k % 3 (issued by one follower lane, two blocks ahead)
   const unsigned row_bytes = (unsigned)(((nlc + 1) & ~1) * 8);
@@ -1769,8 +1764,7 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
     for (int i = 0; i < 9; i++) bulk_g2s(dst + (size_t)i * ldys, H + (size_t)(nlc + 9 * k + i) * ld, row_bytes, &bar_B[k]);
   };
   if (tid == 32) { issue_rows(0); if (nb > 1) issue_rows(1); }
-  // ---- the 9x9 blocks, u, zero padding rows of the ring; the blocks' share of u^T H u; mu D^2 onto the diagonals
-  // (8-byte cp.async: every element is in flight at once instead of one dependent load -> store pair per iteration)
+  // ---- the 9x9 blocks, u, g_s (8-byte cp.async: everything in flight at once); the blocks' share of u^T H u; mu D^2
   for (int e = tid; e < n; e += nt) cp_async8(us + e, ucv + e);
   for (int e = tid; e < 9 * nb * 18; e += nt) {
     const int r = e / 18, q = e - 18 * r, k = r / 9, i = r - 9 * k, j = q % 9;
@@ -1780,7 +1774,6 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   }
   for (int e = tid; e < 9 * nb; e += nt) cp_async8(gs + e, gcv + nlc + e);
   cp_async_wait_all();
-  for (int e = tid; e < 3 * 3 * ldys; e += nt) { const int s3 = e / (3 * ldys), rem = e - s3 * 3 * ldys; Yr[(size_t)s3 * slot_sz + 9 * ldys + rem] = 0.0; }
   __syncthreads();
   double uhu = 0.0;
   for (int e = tid; e < 9 * nb * 18; e += nt) {
@@ -1793,13 +1786,11 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   __syncthreads();
   for (int e = tid; e < 9 * nb; e += nt) Dk[(size_t)(e / 9) * 81 + (e % 9) * 10] += mu * D2v[nlc + e];
   __syncthreads();
-  SLAP(0);
   if (warp == 0) {
     // ---- the D / E chain: chol(D_k) -> E'_k = E_k L_kk^-T -> D_{k+1} -= E'_k E'_k^T, each block published by an mbarrier
     for (int k = 0; k < nb; k++) {
       double *Lk = Dk + (size_t)k * 81, *iv = invd + k * 9;
       if (chol_block9(Lk, iv, lane)) fail = 1;
-      SLAP(1);
       __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_L[k]);
@@ -1832,34 +1823,19 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
         __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_E[k]);
-        SLAP(2);
       }
     }
   } else {
-    // ---- followers: per block  [B_k | g_k] - E'_{k-1} Y_{k-1} -> L_kk^-1 (.) = Y_k (one column per thread, registers),
-    //      Sr accumulators -= Y_k^T Y_k on the tensor cores, Y_k to global for the back substitution, next rows prefetched
-    const int t1 = tid - 32, n1t = nt - 32, fw = warp - 1, nfw = (nt >> 5) - 1;
-    const int kq = lane & 3, cr = lane >> 2;
-    const int nb8 = (ncol + 7) >> 3;
-    // output blocks of Sr are owned by block ROW: follower warp fw owns rows fw, fw + 3, fw + 6 (n_lc + 1 <= 72), so one
-    // k-step needs the nine column fragments once plus its own three row fragments, all MMAs of a k-step independent
-    // row fw + 3 ri has at most 3 (ri + 1) blocks on or below the diagonal: 3 + 6 + 9 accumulator pairs
-    double acc0[3][2], acc1[6][2], acc2[9][2];
-#pragma unroll
-    for (int bj = 0; bj < 3; bj++) { acc0[bj][0] = 0.0; acc0[bj][1] = 0.0; }
-#pragma unroll
-    for (int bj = 0; bj < 6; bj++) { acc1[bj][0] = 0.0; acc1[bj][1] = 0.0; }
-#pragma unroll
-    for (int bj = 0; bj < 9; bj++) { acc2[bj][0] = 0.0; acc2[bj][1] = 0.0; }
-    double *Yg = d.sbY + w.offY;
-    const int ldy = w.ldy;
+    // ---- followers: per block  Y_k = L_kk^-1 ([B_k | g_k] - E'_{k-1} Y_{k-1}), one column per thread in registers;
+    //      the rows go to Wt (behind the landmark rows), so the Schur kernel that follows subtracts Y^T Y together with
+    //      the landmark terms and k_sb_back finds them there
+    const int t1 = tid - 32, n1t = nt - 32;
     for (int k = 0; k < nb; k++) {
       double *Yk = Yr + (size_t)(k % 3) * slot_sz;
       const double *Yp = Yr + (size_t)((k + 2) % 3) * slot_sz;   // slot of block k-1
       mbar_wait(&bar_B[k], 0);
       if (k > 0) mbar_wait(&bar_E[k - 1], 0);
       mbar_wait(&bar_L[k], 0);
-      SLAP(1);
       const double *Lk = Dk + (size_t)k * 81, *iv = invd + k * 9, *Ep = Ek + (size_t)(k > 0 ? k - 1 : 0) * 81;
       for (int c = t1; c < ldys; c += n1t) {
         double y[9];
@@ -1891,80 +1867,12 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
           }
         }
 #pragma unroll
-        for (int i = 0; i < 9; i++) Yk[(size_t)i * ldys + c] = y[i];
-        if (c < ldy) {
-#pragma unroll
-          for (int i = 0; i < 9; i++) Yg[(size_t)(9 * k + i) * ldy + c] = y[i];
-        }
+        for (int i = 0; i < 9; i++) { Yk[(size_t)i * ldys + c] = y[i]; Yg[(size_t)(9 * k + i) * ldys + c] = y[i]; }
       }
-      SLAP(2);
-      asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");
-      SLAP(3);
-      // rank-9 update of the owned output blocks (three k-steps over the 12 padded rows of the slot)
-      {
-        const double *yb = Yk + (size_t)kq * ldys + cr;
-#pragma unroll
-        for (int st = 0; st < 3; st++) {
-          const double *yr = yb + (size_t)(4 * st) * ldys;
-          double f[9], fa[3];
-#pragma unroll
-          for (int bj = 0; bj < 9; bj++) f[bj] = bj < nb8 ? yr[bj * 8] : 0.0;
-#pragma unroll
-          for (int ri = 0; ri < 3; ri++) fa[ri] = (fw + 3 * ri < nb8) ? yr[(fw + 3 * ri) * 8] : 0.0;
-          // unconditional MMAs (a predicated mma.sync costs a WARPSYNC each): blocks above the diagonal or beyond the
-          // matrix accumulate into entries that are never stored
-#pragma unroll
-          for (int bj = 0; bj < 3; bj++) dmma(acc0[bj][0], acc0[bj][1], fa[0], f[bj]);
-#pragma unroll
-          for (int bj = 0; bj < 6; bj++) dmma(acc1[bj][0], acc1[bj][1], fa[1], f[bj]);
-#pragma unroll
-          for (int bj = 0; bj < 9; bj++) dmma(acc2[bj][0], acc2[bj][1], fa[2], f[bj]);
-        }
-      }
-      SLAP(4);
       asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");   // slot (k+2) % 3 == slot of block k-1 is dead now
       if (t1 == 0 && k + 2 < nb) { fence_proxy_async(); issue_rows(k + 2); }
-      SLAP(5);
-    }
-    // ---- Sr = S_pp - sum_k Y_k^T Y_k (lower), rhs row Sr[nlc][c] = g_p[c] - (Y^T z)[c]: all loads of S first
-    {
-      const int ldr = w.ldr;
-      double *Sr = d.Sr + w.offSr;
-      auto src_of = [&](int bi, int bj, int e) -> const double * {
-        const int m = bi * 8 + cr, c = bj * 8 + kq * 2 + e;
-        if (bi >= nb8 || bj > bi) return nullptr;
-        if (m < nlc && c <= m) return S + (size_t)m * ld + c;
-        if (m == nlc && c < nlc) return S + (size_t)n * ld + c;
-        return nullptr;
-      };
-      auto dst_of = [&](int bi, int bj, int e) -> double * {
-        const int m = bi * 8 + cr, c = bj * 8 + kq * 2 + e;
-        if (bi >= nb8 || bj > bi) return nullptr;
-        if (m < nlc && c <= m) return Sr + (size_t)m * ldr + c;
-        if (m == nlc && c < nlc) return Sr + (size_t)nlc * ldr + c;
-        return nullptr;
-      };
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-#pragma unroll
-        for (int bj = 0; bj < 3; bj++) { const double *p_ = src_of(fw, bj, e); acc0[bj][e] = (p_ ? *p_ : 0.0) - acc0[bj][e]; }
-#pragma unroll
-        for (int bj = 0; bj < 6; bj++) { const double *p_ = src_of(fw + 3, bj, e); acc1[bj][e] = (p_ ? *p_ : 0.0) - acc1[bj][e]; }
-#pragma unroll
-        for (int bj = 0; bj < 9; bj++) { const double *p_ = src_of(fw + 6, bj, e); acc2[bj][e] = (p_ ? *p_ : 0.0) - acc2[bj][e]; }
-      }
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-#pragma unroll
-        for (int bj = 0; bj < 3; bj++) { double *p_ = dst_of(fw, bj, e); if (p_) *p_ = acc0[bj][e]; }
-#pragma unroll
-        for (int bj = 0; bj < 6; bj++) { double *p_ = dst_of(fw + 3, bj, e); if (p_) *p_ = acc1[bj][e]; }
-#pragma unroll
-        for (int bj = 0; bj < 9; bj++) { double *p_ = dst_of(fw + 6, bj, e); if (p_) *p_ = acc2[bj][e]; }
-      }
     }
   }
-  SLAP(6);
   uhu = warp_sum(uhu);
   if (lane == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
   __syncthreads();
@@ -1972,16 +1880,13 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   double *LE = d.sbLE + w.offLE;
   for (int e = tid; e < nb * 81; e += nt) { LE[e] = Dk[e]; LE[(size_t)nb * 81 + e] = Ek[e]; }
   for (int e = tid; e < nb * 9; e += nt) LE[(size_t)nb * 162 + e] = invd[e];
-#ifdef D2BA_SBE_TIMING
-  SLAP(7);
-  if (wi == 0 && (tid == 0 || tid == 32 || tid == 64)) printf("sbe timing tid %d: init %lld a %lld b %lld c %lld d %lld e %lld tailwork %lld end %lld\n", tid, sk[0], sk[1], sk[2], sk[3], sk[4], sk[5], sk[6], sk[7]);
-#endif
 }
 
 // Speed-bias part of the Gauss-Newton step: L_kk^T x_k = z_k - Y_k x_p - E'_k^T x_{k+1}, blocks from the last to the
 // first.  One CTA per window: all warps form v = Y x_p (coalesced, many loads in flight) and stage the small blocks,
 // warp 0 then runs the short recursion out of shared memory.
 constexpr int kSbBackThreads = 256;
+__host__ __device__ inline size_t sb_back_smem_bytes(int nlc, int nb) { return (size_t)(((nlc + 31) & ~31) + 9 * nb + 171 * nb) * 8; }
 __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
@@ -1989,14 +1894,14 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ double sm[];
-  const int nlc = w.n_lc, nb = w.n_sbe, ldy = w.ldy;
-  double *xp = sm;                       // nlc (padded to 96)
-  double *rhs = sm + 96;                 // 9 nb : z - Y x_p
+  const int nlc = w.n_lc, nb = w.n_sbe, ldy = w.ldw;
+  double *xp = sm;                       // nlc (padded to 32)
+  double *rhs = sm + ((nlc + 31) & ~31); // 9 nb : z - Y x_p
   double *LE = rhs + 9 * nb;             // nb x 171
-  const double *Yg = d.sbY + w.offY, *LEg = d.sbLE + w.offLE;
+  const double *Yg = d.Wt + w.offW + (size_t)w.nl_pad * w.ldw, *LEg = d.sbLE + w.offLE;
   double *gn = d.gn_c + w.offc;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  for (int c = tid; c < 96; c += nt) xp[c] = c < nlc ? -gn[c] : 0.0;
+  for (int c = tid; c < nlc; c += nt) xp[c] = -gn[c];
   for (int e = tid; e < nb * 171; e += nt) cp_async8(LE + e, LEg + e);   // needed only by the recursion: lands during the products
   __syncthreads();
   for (int r0 = warp * 4; r0 < 9 * nb; r0 += nwarp * 4) {
@@ -2551,12 +2456,21 @@ void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) {
   const int threads = max_n <= 96 ? 128 : kCsThreads;
   k_chol_smem<<<d.n_win, threads, chol_smem_bytes(max_n), s>>>(d);
 }
-size_t sb_elim_smem(int nlc, int nb) { return sbe_smem_bytes(nlc, nb); }
+__global__ void k_zero_sb_rows(Dev d) {
+  const WinDesc &w = d.win[blockIdx.x];
+  if (!w.sb_elim) return;
+  double *Yg = d.Wt + w.offW + (size_t)w.nl_pad * w.ldw;
+  const size_t tot = (size_t)(w.wt_rows - w.nl_pad) * w.ldw;
+  for (size_t e = threadIdx.x; e < tot; e += blockDim.x) Yg[e] = 0.0;
+}
+void launch_zero_sb_rows(const Dev &d, cudaStream_t s) { k_zero_sb_rows<<<d.n_win, 256, 0, s>>>(d); }
+size_t sb_elim_smem(int ldw, int n_c, int nb) { return sbe_smem_bytes(ldw, n_c, nb); }
 int configure_sb_elim(size_t smem) { return (int)raise_smem_limit(k_sb_elim, (size_t)(smem)); }
 void launch_sb_elim(const Dev &d, size_t smem, cudaStream_t s) { k_sb_elim<<<d.n_win, kSeThreads, smem, s>>>(d); }
-size_t sb_back_smem(int nb) { return (size_t)(96 + 9 * nb + 171 * nb) * 8; }
+size_t sb_back_smem(int nlc, int nb) { return sb_back_smem_bytes(nlc, nb); }
 int sb_max_blocks() { return kSeMaxBlocks; }
-void launch_sb_back(const Dev &d, int max_nb, cudaStream_t s) { k_sb_back<<<d.n_win, kSbBackThreads, sb_back_smem(max_nb), s>>>(d); }
+void launch_sb_back(const Dev &d, size_t smem, cudaStream_t s) { k_sb_back<<<d.n_win, kSbBackThreads, smem, s>>>(d); }
+int configure_sb_back(size_t smem) { return (int)raise_smem_limit(k_sb_back, smem); }
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
   size_t sm = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   k_chol<<<d.n_win, kCholThreads, sm, s>>>(d, max_rows);

@@ -74,8 +74,8 @@ struct WinDesc {
   int schur_small;             // landmark-coupled part <= 127 columns: one-CTA Schur kernel
   // speed-bias elimination (k_sb_elim): block-tridiagonal speed-bias part eliminated before the dense Cholesky
   int sb_elim, n_sbe;          // enabled, number of (non-constant) speed-bias blocks
-  int ldy, ldr;                // row stride of the stored Y rows / of the reduced system Sr
-  int64_t offY, offLE, offSr;  // offsets (doubles) into Dev::sbY, sbLE, Sr
+  int wt_rows;                 // rows of Wt the Schur kernels sum over: nl_pad landmark rows (+ the eliminated speed-bias rows, padded to 32)
+  int64_t offLE;               // offset (doubles) into Dev::sbLE
 };
 
 struct PriorBlk {
@@ -160,8 +160,7 @@ struct Dev {
   double *dinv;         // [NL] 1/sqrt(h + mu d^2)
   double *hl, *gl;      // [NL]
   double *S;            // reduced system (lower) per window
-  double *Sr;           // after the speed-bias elimination: (n_lc + 1) x ldr per window
-  double *sbY, *sbLE;   // L_ss^-1 [B | g_s] rows; L_kk, E'_k, 1/diag(L_kk) blocks
+  double *sbLE;         // speed-bias elimination: L_kk, E'_k, 1/diag(L_kk) blocks (the rows Y live behind the landmark rows of Wt)
   double *gred;         // n_c
   double *D2c;          // n_c
   double *gn_c, *gn_l;  // Gauss-Newton step

@@ -176,7 +176,10 @@ class Solver:
         out = np.zeros(10)
         self._chk(lib().d2ba_debug_kernel_times(self.h, C.c_int32(iters), abi.ptr(out)), "kernel_times")
         kt = {k: out[i] / max(out[7], 1) for i, k in enumerate(KERNEL_NAMES)}
-        self.chol_split = {"sb_elim": out[8] / max(out[7], 1), "sb_back": out[9] / max(out[7], 1)}   # shares of kt["chol"]
+        # the speed-bias elimination is timed inside the gather bucket, its back substitution inside the chol bucket
+        se, sbk = out[8] / max(out[7], 1), out[9] / max(out[7], 1)
+        kt["lm_gather"] -= se; kt["chol"] -= sbk; kt["sb_elim"] = se; kt["sb_back"] = sbk
+        self.chol_split = {"sb_elim": se, "sb_back": sbk}
         return kt
 
     def host_times(self):

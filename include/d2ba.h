@@ -280,8 +280,8 @@ int d2ba_debug_linearize(d2ba_handle *h);
 int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int64_t out_bytes,
                    int64_t *needed_bytes);
 /* Device time (ms, CUDA events on the solver stream) of each kernel of the iteration sequence, summed over
- * `iters` iterations: [lm_gather, schur, chol, step, misc_lin, proj_lin, control, iters, sb_elim, sb_back] (the last
- * two are included in chol). */
+ * `iters` iterations: [lm_gather, schur, chol, step, misc_lin, proj_lin, control, iters, sb_elim, sb_back] (sb_elim is
+ * included in lm_gather, sb_back in chol). */
 int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out /* [10] */);
 /* Host wall-clock (ms) of the phases of the last d2ba_finalize: [plan (pair-major order, groups, jobs), prefix sums +
  * staging resize, staging fill, upload enqueue, error check, read-back buffers, device ms of the uploads, device ms of tile build + prep kernels], followed by
