@@ -840,7 +840,7 @@ int d2ba_finalize(d2ba_handle *h) {
       d.sb_elim = ok ? 1 : 0; d.n_sbe = nb;
       // the dense Cholesky only sees the pose part then: decide its kernel with that size
       if (ok) d.chol_smem = (chol_smem_need(d.n_lc) <= (size_t)232448 - 16) ? 1 : 0;
-      d.wt_rows = d.nl_pad + (ok ? roundup(9 * nb, 32) : 0);
+      d.wt_rows = ok ? roundup(nl + 9 * nb, 32) : d.nl_pad;   // the eliminated rows start right after the last landmark row
     }
     if (!d.schur_small) {
       int ntw = (d.n_lc + 1 + 31) / 32;

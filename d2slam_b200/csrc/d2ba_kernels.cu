@@ -1745,7 +1745,7 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   double *us = invd + (size_t)nb * 9;               // n : u = g / D^2 of the accepted linearisation
   double *gs = us + n;                              // 9 nb : speed-bias part of the gradient
   const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
-  double *Yg = d.Wt + w.offW + (size_t)w.nl_pad * w.ldw;   // the eliminated rows follow the landmark rows of Wt
+  double *Yg = d.Wt + w.offW + (size_t)w.nl * w.ldw;   // the eliminated rows follow the landmark rows of Wt directly
   const double mu = ctl->mu;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int fail;
@@ -1898,7 +1898,7 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
   double *xp = sm;                       // nlc (padded to 32)
   double *rhs = sm + ((nlc + 31) & ~31); // 9 nb : z - Y x_p
   double *LE = rhs + 9 * nb;             // nb x 171
-  const double *Yg = d.Wt + w.offW + (size_t)w.nl_pad * w.ldw, *LEg = d.sbLE + w.offLE;
+  const double *Yg = d.Wt + w.offW + (size_t)w.nl * w.ldw, *LEg = d.sbLE + w.offLE;
   double *gn = d.gn_c + w.offc;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   for (int c = tid; c < nlc; c += nt) xp[c] = -gn[c];
@@ -2459,8 +2459,8 @@ void launch_chol_smem(const Dev &d, int max_n, cudaStream_t s) {
 __global__ void k_zero_sb_rows(Dev d) {
   const WinDesc &w = d.win[blockIdx.x];
   if (!w.sb_elim) return;
-  double *Yg = d.Wt + w.offW + (size_t)w.nl_pad * w.ldw;
-  const size_t tot = (size_t)(w.wt_rows - w.nl_pad) * w.ldw;
+  double *Yg = d.Wt + w.offW + (size_t)w.nl * w.ldw;
+  const size_t tot = (size_t)(w.wt_rows - w.nl) * w.ldw;
   for (size_t e = threadIdx.x; e < tot; e += blockDim.x) Yg[e] = 0.0;
 }
 void launch_zero_sb_rows(const Dev &d, cudaStream_t s) { k_zero_sb_rows<<<d.n_win, 256, 0, s>>>(d); }

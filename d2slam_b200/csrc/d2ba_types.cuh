@@ -74,7 +74,7 @@ struct WinDesc {
   int schur_small;             // landmark-coupled part <= 127 columns: one-CTA Schur kernel
   // speed-bias elimination (k_sb_elim): block-tridiagonal speed-bias part eliminated before the dense Cholesky
   int sb_elim, n_sbe;          // enabled, number of (non-constant) speed-bias blocks
-  int wt_rows;                 // rows of Wt the Schur kernels sum over: nl_pad landmark rows (+ the eliminated speed-bias rows, padded to 32)
+  int wt_rows;                 // rows of Wt the Schur kernels sum over: nl landmark rows + 9 n_sbe eliminated speed-bias rows, padded to 32
   int64_t offLE;               // offset (doubles) into Dev::sbLE
 };
 
