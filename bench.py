@@ -355,7 +355,9 @@ def run_ours(args, rank, world, local_rank):
     # CPU baseline on rank 0, bounded sample, one thread (ceres_options.num_threads = 1)
     cpu_v, cpu_n, cpu_dt = cpu_sample(probs, iters, 1, min(B, args.cpu_windows))
     n_variants = 1
-    launches = args.steps * (3 + n_variants + iters * (6 + n_variants))
+    # per solve: tr_reset, misc_lin, proj_lin, control; per iteration: lm_gather16, sb_elim, schur_small, chol_smem, sb_back, step,
+    # misc_lin, proj_lin (n_variants), control
+    launches = args.steps * (3 + n_variants + iters * (8 + n_variants))
     line = {
         "metric": "BA solver iterations/sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
