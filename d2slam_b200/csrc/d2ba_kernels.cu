@@ -853,9 +853,9 @@ __global__ void k_proj_debug(Dev d, double *out /*[tiles*32][81]*/, int n_tiles_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-landmark reduction (warp per landmark).  Observations of a landmark are visited serially, the
-// 16/32 record entries in parallel across lanes, so there are no write conflicts and the result is
-// deterministic.  Output: Wt[l][0..n_lc) = w_l / sqrt(h'), Wt[l][n_lc] = g_l / sqrt(h'),
+// Per-landmark reduction, wide records (warp per landmark; compact records: k_lm_gather16 below).  The landmark's
+// records are visited serially, the 32 record entries in parallel across lanes, so there are no write conflicts and
+// the result is deterministic.  Output: Wt[l][0..n_lc) = w_l / sqrt(h'), Wt[l][n_lc] = g_l / sqrt(h'),
 // h' = h_l + mu D_l^2.
 constexpr int kGatherWarps = 8;
 __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const int *lm_win, int n_lm_total, int max_ldw) {
@@ -875,60 +875,30 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   for (int c = lane; c <= nlc; c += 32) row[c] = 0.0;
   __syncwarp();
   const int *ptr = d.lm_ptr + w.off_lmptr;
-  const int stride = w.rec_stride;
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
   double h = 0, g = 0;
   const int kb = ptr[l], ke = ptr[l + 1];
-  if (stride == 16) {
-    // compact records (128 B): two per warp load (half-warp each), up to 8 loads = 16 records in flight
-    const int half = lane >> 4, sub = lane & 15;
-    for (int k0 = kb; k0 < ke; k0 += 16) {
-      const int cnt = min(16, ke - k0);
-      double v[8];
+  // wide records (256 B: extrinsics / td free): one warp load per record, two records in flight
+  for (int k0 = kb; k0 < ke; k0 += 32) {
+    const int cnt = min(32, ke - k0);
+    for (int q = 0; q < cnt; q += 2) {
+      const int p0 = k0 + q, p1 = k0 + min(q + 1, cnt - 1);
+      const bool two = q + 1 < cnt;
+      double v0 = recs[(size_t)p0 * 32 + lane];
+      double v1 = two ? recs[(size_t)p1 * 32 + lane] : 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int o = 2 * q + half;
-        v[q] = (o < cnt) ? recs[(size_t)(k0 + o) * 16 + sub] : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        if (2 * q >= cnt) break;
-        const double c01 = __shfl_sync(0xffffffffu, v[q], (lane & 16) | 3);   // columns word of this half's record
+      for (int u = 0; u < 2; u++) {
+        const double v = u == 0 ? v0 : v1;
+        if (u == 1 && !two) break;
+        if (lane == 0) h += v;
+        if (lane == 1) g += v;
+        const double c01 = __shfl_sync(0xffffffffu, v, 3), c23 = __shfl_sync(0xffffffffu, v, 28), ctd = __shfl_sync(0xffffffffu, v, 29);
         int col = -1;
-        if (sub >= 4) { int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
-        if (sub == 0) h += v[q];
-        if (sub == 1) g += v[q];
-        // the two halves may hit the same columns (anchor pose): apply them one after the other
-        if (half == 0 && col >= 0) row[col] += v[q];
+        if (lane >= 4 && lane < 16) { int sc = lane < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (lane - 4) % 6; }
+        if (lane >= 16 && lane < 28) { int sc = lane < 22 ? __double2hiint(c23) : __double2loint(c23); if (sc >= 0) col = sc + (lane - 4) % 6; }
+        if (lane == 2) col = __double2hiint(ctd);
+        if (col >= 0) row[col] += v;
         __syncwarp();
-        if (half == 1 && col >= 0 && 2 * q + 1 < cnt) row[col] += v[q];
-        __syncwarp();
-      }
-    }
-    h += __shfl_xor_sync(0xffffffffu, h, 16);
-    g += __shfl_xor_sync(0xffffffffu, g, 16);
-  } else {
-    for (int k0 = kb; k0 < ke; k0 += 32) {
-      const int cnt = min(32, ke - k0);
-      for (int q = 0; q < cnt; q += 2) {
-        const int p0 = k0 + q, p1 = k0 + min(q + 1, cnt - 1);
-        const bool two = q + 1 < cnt;
-        double v0 = recs[(size_t)p0 * 32 + lane];
-        double v1 = two ? recs[(size_t)p1 * 32 + lane] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const double v = u == 0 ? v0 : v1;
-          if (u == 1 && !two) break;
-          if (lane == 0) h += v;
-          if (lane == 1) g += v;
-          const double c01 = __shfl_sync(0xffffffffu, v, 3), c23 = __shfl_sync(0xffffffffu, v, 28), ctd = __shfl_sync(0xffffffffu, v, 29);
-          int col = -1;
-          if (lane >= 4 && lane < 16) { int sc = lane < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (lane - 4) % 6; }
-          if (lane >= 16 && lane < 28) { int sc = lane < 22 ? __double2hiint(c23) : __double2loint(c23); if (sc >= 0) col = sc + (lane - 4) % 6; }
-          if (lane == 2) col = __double2hiint(ctd);
-          if (col >= 0) row[col] += v;
-          __syncwarp();
-        }
       }
     }
   }
