@@ -29,6 +29,7 @@ void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s);
 void launch_prior_prep(const Dev &d, cudaStream_t s);
 void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s);
 int configure_kernels(int max_rows, int max_nc, int max_prior_m);
+int configure_gather(int max_ldw);
 void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int job_count, cudaStream_t s);
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s);
 void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, int any_compact, int any_wide, cudaStream_t s);
@@ -241,7 +242,7 @@ struct d2ba_handle {
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
   DBuf<SchurTileH> d_schur;
   DBuf<int> d_pr_m, d_pr_info, d_tile_src; DBuf<long long> d_pr_oJ, d_pr_ov, d_raw_off;
-  int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1;
+  int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1, cfg_max_ldw = -1;
   Dev dev;
   std::vector<WinDesc> h_win;
   HBuf<Ctl> h_ctl;   // pinned: D2H target of every solve
@@ -623,6 +624,9 @@ int d2ba_set_consensus(d2ba_handle *h, int32_t window, int32_t n, const d2ba_blo
                        int32_t n_slots_global) {
   HostWin *w = get_win(h, window);
   if (!w) return 1;
+  if (n_slots_global <= 0) return fail(h, 9, "set_consensus: n_slots_global must be positive");
+  for (int i = 0; i < n; i++)
+    if (slot[i] < 0 || slot[i] >= n_slots_global) return fail(h, 9, "set_consensus: slot index outside [0, n_slots_global)");
   w->used = true; h->finalized = false; w->admm = true; w->n_slots = n_slots_global;
   for (int i = 0; i < n; i++) {
     if (refs[i].kind == D2BA_POSE) { int k = find_in(w->pose_map, refs[i].id); if (k < 0) return fail(h, 9, "set_consensus: unknown frame"); w->pose_slot[k] = slot[i]; }
@@ -880,7 +884,10 @@ int d2ba_finalize(d2ba_handle *h) {
       h->sbe_smem = std::max(h->sbe_smem, sb_elim_smem(d.ldw, d.n_c, d.n_sbe)); h->sbb_smem = std::max(h->sbb_smem, sb_back_smem(d.n_lc, d.n_sbe));
     }
     if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.sb_elim ? d.n_lc : d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, (d.sb_elim ? d.n_lc : d.n_c) + 1); }
-    if (w.admm) { h->any_admm = true; h->n_slots = std::max(h->n_slots, w.n_slots); }
+    if (w.admm) {
+      if (h->any_admm && h->n_slots != w.n_slots) return fail(h, 26, "finalize: every window of a handle must name the same n_slots_global (the all-reduce count)");
+      h->any_admm = true; h->n_slots = w.n_slots;
+    }
     if (w.prior_m > 0 && w.prior_is_info) any_info = true;
   }
   int jbase[6]; { int r = 0; for (int v = 0; v < 6; v++) { jbase[v] = r; h->job_begin[v] = r; h->job_count[v] = njobs[v]; r += njobs[v]; } }
@@ -1048,6 +1055,10 @@ int d2ba_finalize(d2ba_handle *h) {
   if (h->cfg_max_rows != h->max_rows || h->cfg_max_nc != h->max_nc || h->cfg_max_prior != h->max_prior_m) {
     if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
     h->cfg_max_rows = h->max_rows; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
+  }
+  if (h->cfg_max_ldw < h->max_ldw) {
+    if (configure_gather(h->max_ldw)) return fail(h, 23, "cudaFuncSetAttribute(k_lm_gather) failed (landmark-coupled part too wide for the row buffers)");
+    h->cfg_max_ldw = h->max_ldw;
   }
   if (h->max_ldw_small > 0 && h->cfg_max_ldw_small != h->max_ldw_small) {
     if (configure_schur_small(h->max_ldw_small)) return fail(h, 23, "cudaFuncSetAttribute(k_schur_small) failed");
@@ -1344,8 +1355,8 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
     case D2BA_DBG_S: {
       if (h->d_dbg.n < (size_t)h->totH) return fail(h, 4, "debug_get(S): call d2ba_debug_linearize first");
       auto S = fetch(h->d_dbg.p + d.offH, (size_t)n * ld);
-      if (d.schur_small && d.chol_smem) {
-        // the speed-bias rows of such windows never pass through S (k_chol_smem reads them from Hcc): rebuild them
+      if (d.sb_elim || (d.schur_small && d.chol_smem)) {
+        // the speed-bias rows of such windows never pass through S (k_sb_elim / k_chol_smem read them from Hcc): rebuild them
         // for the debug view exactly as that kernel does (H + mu D^2 on the diagonal, mu = 1e-8 after tr_reset)
         auto H = fetch(h->d_H[cur].p + d.offH, (size_t)n * ld);
         for (int i = nlc; i < n; i++)

@@ -2324,17 +2324,20 @@ __global__ void __launch_bounds__(256) k_marg_reduce(const double *S, int ld, in
   if (tid == 0 && bad) *fail_flag = 1;
 }
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-process property of the kernel, while every handle asks for what
-// ITS windows need: only ever raise it, so a handle with small windows cannot pull the limit from under a live handle
-// with large ones.
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the kernel on ONE device (context), while every handle asks
+// for what ITS windows need: the cache is keyed by (device, kernel) and only ever raised, so a handle with small windows
+// cannot pull the limit from under a live handle with large ones and a second device gets its own attribute.
 template <typename K>
 cudaError_t raise_smem_limit(K kernel, size_t bytes) {
   static std::mutex mu;
-  static std::map<const void *, size_t> cur;
+  static std::map<std::pair<int, const void *>, size_t> cur;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lk(mu);
-  size_t &c = cur[(const void *)kernel];
+  size_t &c = cur[std::make_pair(dev, (const void *)kernel)];
   if (bytes <= c) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e == cudaSuccess) c = bytes;
   return e;
 }
@@ -2383,6 +2386,13 @@ int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   size_t st = (size_t)(40 + 3 * max_nc) * 8;
   e = raise_smem_limit(k_step, (size_t)(st)); if (e) return e;
   e = raise_smem_limit(k_misc_lin, (size_t)(misc_smem_bytes(max_prior_m))); if (e) return e;
+  return 0;
+}
+// the row buffers of the per-landmark gather grow with the landmark-coupled width (multi-agent windows: 6 x 88 poses)
+int configure_gather(int max_ldw) {
+  cudaError_t e;
+  e = raise_smem_limit(k_lm_gather, (size_t)kGatherWarps * max_ldw * 8); if (e) return e;
+  e = raise_smem_limit(k_lm_gather16, (size_t)kG16Lm * max_ldw * 8); if (e) return e;
   return 0;
 }
 

@@ -1,0 +1,36 @@
+// Stand-in for HKUST-Swarm swarm_msgs (branch D2SLAM, un-vendored) Swarm::Pose -- oracle/_ref build only.
+// Semantics ASSUMED from the upstream header: pose = (position, unit attitude quaternion); to_vector = [x y z qx qy qz qw];
+// a * b composes, DeltaPose(a, b) = a^-1 * b, tangentSpace = [translation ; rotation vector].
+#pragma once
+#include <Eigen/Dense>
+#include <cmath>
+#include <vector>
+using namespace Eigen;
+inline Eigen::Vector3d quat2eulers(const Eigen::Quaterniond &q) {
+  Eigen::Vector3d rpy;
+  rpy.x() = std::atan2(2 * (q.w() * q.x() + q.y() * q.z()), 1 - 2 * (q.x() * q.x() + q.y() * q.y()));
+  rpy.y() = std::asin(2 * (q.w() * q.y() - q.z() * q.x()));
+  rpy.z() = std::atan2(2 * (q.w() * q.z() + q.x() * q.y()), 1 - 2 * (q.y() * q.y() + q.z() * q.z()));
+  return rpy;
+}
+inline Eigen::Quaterniond eulers2quat(const Eigen::Vector3d &e) {
+  const double cr = std::cos(e.x() / 2), sr = std::sin(e.x() / 2), cp = std::cos(e.y() / 2), sp = std::sin(e.y() / 2), cy = std::cos(e.z() / 2), sy = std::sin(e.z() / 2);
+  return Eigen::Quaterniond(cy * cp * cr + sy * sp * sr, cy * cp * sr - sy * sp * cr, sy * cp * sr + cy * sp * cr, sy * cp * cr - cy * sp * sr);
+}
+namespace Swarm {
+class Pose {
+  Eigen::Vector3d position; Eigen::Quaterniond attitude;
+ public:
+  Pose() : position(0, 0, 0) {}
+  Pose(const Eigen::Vector3d &p, const Eigen::Quaterniond &q) : position(p), attitude(q.normalized()) {}
+  explicit Pose(const double *v, bool xyzyaw = false) : position(v[0], v[1], v[2]), attitude(v[6], v[3], v[4], v[5]) { (void)xyzyaw; attitude.normalize(); }
+  const Eigen::Vector3d &pos() const { return position; }
+  const Eigen::Quaterniond &att() const { return attitude; }
+  Eigen::Matrix3d R() const { return attitude.toRotationMatrix(); }
+  void to_vector(double *v) const { v[0] = position.x(); v[1] = position.y(); v[2] = position.z(); v[3] = attitude.x(); v[4] = attitude.y(); v[5] = attitude.z(); v[6] = attitude.w(); }
+  Pose inverse() const { Eigen::Quaterniond qi = attitude.inverse(); return Pose(-(qi * position), qi); }
+  Pose operator*(const Pose &b) const { return Pose(attitude * b.position + position, attitude * b.attitude); }
+  Eigen::Vector3d operator*(const Eigen::Vector3d &p) const { return attitude * p + position; }
+  static Pose DeltaPose(const Pose &a, const Pose &b, bool use_yaw_only = false) { (void)use_yaw_only; return a.inverse() * b; }
+};
+}  // namespace Swarm

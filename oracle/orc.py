@@ -19,7 +19,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "_build", "liborc_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("orc_factors.c", "orc_solver.c", "orc_margin.c", "orc_oracle.h", "orc_math.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("orc_factors.c", "orc_solver.c", "orc_oracle.h", "orc_math.h")]
     srcs.append(os.path.join(_HERE, "..", "include", "d2ba.h"))
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
     if force or stale:

@@ -1,0 +1,128 @@
+"""ctypes front-end of oracle/_ref/libd2ref.so: the REFERENCE's own factor classes (compiled unmodified from
+/root/reference by oracle/Makefile.ref against the stand-in headers of oracle/_shim).
+
+TEST INFRASTRUCTURE ONLY: used by tests/test_ref_pin.py (oracle restatement == reference, and the golden vectors under
+tests/golden/ref_factors.npz) and by tests/golden/make_ref_golden.py.  Nothing under d2slam_b200/ imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.environ.get("D2SLAM_REF", "/root/reference")
+_LIB = None
+
+
+def so_path():
+    return os.path.join(_HERE, "_ref", "libd2ref.so")
+
+
+def available():
+    return os.path.exists(so_path()) or os.path.isdir(os.path.join(REF_ROOT, "d2vins"))
+
+
+def build(force=False):
+    """Compile the reference sources where they lie (only possible where /root/reference exists)."""
+    so = so_path()
+    if os.path.isdir(os.path.join(REF_ROOT, "d2vins")):
+        subprocess.check_call(["make", "-C", _HERE, "-f", "Makefile.ref", "-s", f"REF={REF_ROOT}"] + (["-B"] if force else []))
+    if not os.path.exists(so):
+        raise RuntimeError("oracle/_ref/libd2ref.so missing and the reference tree is not present to build it")
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.ref_proj_eval.restype = C.c_int
+        _LIB.ref_imu_eval.restype = C.c_int
+        _LIB.ref_consensus_eval.restype = C.c_int
+        configure()
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def configure(focal_length=460.0, depth_sqrt_inf=20.0, g_norm=9.805, acc_n=0.1, gyr_n=0.05, acc_w=0.002, gyr_w=0.0004):
+    (_LIB or lib()).ref_configure(*[C.c_double(v) for v in (focal_length, depth_sqrt_inf, g_norm, acc_n, gyr_n, acc_w, gyr_w)])
+
+
+_BLOCKS = {0: (7, 7, 7, 1, 1), 1: (7, 7, 7, 7, 1, 1), 2: (7, 7, 1, 1), 3: (7, 7, 7, 1, 1)}
+
+
+def proj_eval(typ, pts_i, pts_j, vel_i, vel_j, td_i, td_j, depth_j, params):
+    """params: list of arrays in the factor's own block order.  -> (r, [J_k (rows x size_k)], tangent_base (2x3))."""
+    sizes = _BLOCKS[int(typ)]
+    rows = 3 if int(typ) == 3 else 2
+    ps = [np.ascontiguousarray(np.atleast_1d(p), dtype=np.float64) for p in params]
+    assert [len(p) for p in ps] == list(sizes), ([len(p) for p in ps], sizes)
+    parr = (C.c_void_p * len(ps))(*[_p(p) for p in ps])
+    r = np.zeros(rows)
+    Js = [np.zeros((rows, s)) for s in sizes]
+    jarr = (C.c_void_p * len(Js))(*[_p(j) for j in Js])
+    tb = np.zeros(6)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pts_i, pts_j, vel_i, vel_j)]
+    n = lib().ref_proj_eval(C.c_int(int(typ)), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), C.c_double(td_i), C.c_double(td_j), C.c_double(depth_j),
+                            parr, _p(r), jarr, _p(tb))
+    assert n == rows, n
+    return r, Js, tb.reshape(2, 3)
+
+
+def preintegrate(dt, acc, gyr, ba, bg):
+    dt = np.ascontiguousarray(dt, dtype=np.float64); acc = np.ascontiguousarray(acc, dtype=np.float64); gyr = np.ascontiguousarray(gyr, dtype=np.float64)
+    ba = np.ascontiguousarray(ba, dtype=np.float64); bg = np.ascontiguousarray(bg, dtype=np.float64)
+    out = np.zeros(11 + 450)
+    lib().ref_preintegrate(C.c_int(len(dt)), _p(dt), _p(acc), _p(gyr), _p(ba), _p(bg), _p(out))
+    return {"sum_dt": out[0], "delta_p": out[1:4].copy(), "delta_q": out[4:8].copy(), "delta_v": out[8:11].copy(),
+            "jacobian": out[11:236].copy(), "covariance": out[236:461].copy()}
+
+
+def imu_eval(pre, lin_ba, lin_bg, pose_i, sb_i, pose_j, sb_j):
+    ps = [np.ascontiguousarray(p, dtype=np.float64) for p in (pose_i, sb_i, pose_j, sb_j)]
+    parr = (C.c_void_p * 4)(*[_p(p) for p in ps])
+    r = np.zeros(15); Js = [np.zeros((15, s)) for s in (7, 9, 7, 9)]
+    jarr = (C.c_void_p * 4)(*[_p(j) for j in Js])
+    si = np.zeros(225)
+    f = [np.ascontiguousarray(pre[k], dtype=np.float64).ravel() for k in ("delta_p", "delta_q", "delta_v")]
+    ba = np.ascontiguousarray(lin_ba, dtype=np.float64); bg = np.ascontiguousarray(lin_bg, dtype=np.float64)
+    jac = np.ascontiguousarray(pre["jacobian"], dtype=np.float64).ravel(); cov = np.ascontiguousarray(pre["covariance"], dtype=np.float64).ravel()
+    n = lib().ref_imu_eval(C.c_double(float(pre["sum_dt"])), _p(f[0]), _p(f[1]), _p(f[2]), _p(ba), _p(bg), _p(jac), _p(cov), parr, _p(r), jarr, _p(si))
+    assert n == 15, n
+    return r, Js, si.reshape(15, 15)
+
+
+def consensus_eval(t_ref, q_ref, t_tilde, theta_tilde, rho_T, rho_theta, pose):
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (t_ref, q_ref, t_tilde, theta_tilde, pose)]
+    r = np.zeros(6); J = np.zeros((6, 7))
+    n = lib().ref_consensus_eval(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), C.c_double(rho_T), C.c_double(rho_theta), _p(a[4]), _p(r), _p(J))
+    assert n == 6, n
+    return r, J
+
+
+def pose_plus(x, delta):
+    x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
+    lib().ref_pose_plus(_p(x), _p(d), _p(o))
+    return o
+
+
+def pose_plus_jacobian(x):
+    x = np.ascontiguousarray(x, dtype=np.float64); J = np.zeros((7, 6))
+    lib().ref_pose_plus_jacobian(_p(x), _p(J))
+    return J
+
+
+def qleft_qright(q):
+    q = np.ascontiguousarray(q, dtype=np.float64); L = np.zeros((4, 4)); R = np.zeros((4, 4))
+    lib().ref_qleft_qright(_p(q), _p(L), _p(R))
+    return L, R
+
+
+def average_quats(qs):
+    qs = np.ascontiguousarray(qs, dtype=np.float64); o = np.zeros(4)
+    lib().ref_average_quats(C.c_int(len(qs)), _p(qs), _p(o))
+    return o

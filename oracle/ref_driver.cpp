@@ -1,0 +1,149 @@
+// ref_driver.cpp -- C entry points over the REFERENCE's own factor classes (oracle/_ref/libd2ref.so).
+//
+// TEST INFRASTRUCTURE ONLY.  The reference sources are compiled unmodified from /root/reference by oracle/Makefile.ref:
+//   d2vins/src/factors/projectionTwoFrameOneCamFactor.cpp, projectionTwoFrameTwoCamFactor.cpp,
+//   projectionOneFrameTwoCamFactor.cpp, projectionTwoFrameOneCamDepthFactor.cpp, imu_factor.h (+ d2common
+//   integration_base.h, utils.hpp), d2common/src/solver/consenus_factor.cpp, pose_local_parameterization.cpp.
+// Their third-party dependencies (Eigen, ceres, ROS, swarm_msgs, OpenCV, spdlog) are absent from this image and are
+// stood in for by oracle/_shim (interfaces + a small eager matrix library).  This file only constructs the reference's
+// objects from flat arrays and calls their Evaluate / Plus / propagate -- it contains no factor arithmetic of its own.
+// It pins oracle/orc_factors.c (tests/test_ref_pin.py) and generates tests/golden/ref_factors.npz.
+#include <cstring>
+#include <memory>
+
+#include <d2common/integration_base.h>
+#include <d2common/solver/consenus_factor.h>
+#include <d2common/solver/pose_local_parameterization.h>
+#include <d2common/utils.hpp>
+
+#include "d2vins_params.hpp"
+#include "factors/imu_factor.h"
+#include "factors/projectionOneFrameTwoCamFactor.h"
+#include "factors/projectionTwoFrameOneCamDepthFactor.h"
+#include "factors/projectionTwoFrameOneCamFactor.h"
+#include "factors/projectionTwoFrameTwoCamFactor.h"
+
+// statics whose home translation units (d2common/src/d2imu.cpp, d2vins/src/d2vins_params.cpp) need ROS / OpenCV file
+// storage: defined here with the values those files assign (d2imu.cpp:8-9, d2vins_params.cpp:58-74,172-180)
+namespace D2Common {
+Vector3d IMUData::Gravity = Vector3d(0., 0., 9.805);
+Eigen::Matrix<double, 18, 18> IntegrationBase::noise = Eigen::Matrix<double, 18, 18>::Zero();
+}  // namespace D2Common
+namespace D2VINS { D2VINSConfig *params = nullptr; }
+
+using namespace D2VINS;
+using namespace D2Common;
+
+extern "C" {
+
+// d2vins_params.cpp:58-74 and :172-180
+void ref_configure(double focal_length, double depth_sqrt_inf, double g_norm, double acc_n, double gyr_n, double acc_w, double gyr_w) {
+  Eigen::Matrix<double, 18, 18> noise = Eigen::Matrix<double, 18, 18>::Zero();
+  noise.block<3, 3>(0, 0) = (acc_n * acc_n) * Eigen::Matrix3d::Identity();
+  noise.block<3, 3>(3, 3) = (gyr_n * gyr_n) * Eigen::Matrix3d::Identity();
+  noise.block<3, 3>(6, 6) = (acc_n * acc_n) * Eigen::Matrix3d::Identity();
+  noise.block<3, 3>(9, 9) = (gyr_n * gyr_n) * Eigen::Matrix3d::Identity();
+  noise.block<3, 3>(12, 12) = (acc_w * acc_w) * Eigen::Matrix3d::Identity();
+  noise.block<3, 3>(15, 15) = (gyr_w * gyr_w) * Eigen::Matrix3d::Identity();
+  IntegrationBase::noise = noise;
+  IMUData::Gravity = Vector3d(0., 0., g_norm);
+  ProjectionTwoFrameOneCamFactor::sqrt_info = focal_length / 1.5 * Matrix2d::Identity();
+  ProjectionOneFrameTwoCamFactor::sqrt_info = focal_length / 1.5 * Matrix2d::Identity();
+  ProjectionTwoFrameTwoCamFactor::sqrt_info = focal_length / 1.5 * Matrix2d::Identity();
+  ProjectionTwoFrameOneCamDepthFactor::sqrt_info = focal_length / 1.5 * Matrix3d::Identity();
+  ProjectionTwoFrameOneCamDepthFactor::sqrt_info(2, 2) = depth_sqrt_inf;
+}
+
+static Vector3d v3(const double *p) { return Vector3d(p[0], p[1], p[2]); }
+
+// type: d2ba_proj_type (0 2F1C, 1 2F2C, 2 1F2C, 3 2F1C_DEPTH).  params in the factor's own block order, J[k] row-major
+// (rows x block size) or NULL.  tangent_base_out (6) returns the constructor's tangent base.  Returns the residual size.
+int ref_proj_eval(int type, const double *pts_i, const double *pts_j, const double *vel_i, const double *vel_j, double td_i, double td_j,
+                  double depth_j, const double *const *params, double *residuals, double **jacobians, double *tangent_base_out) {
+  std::unique_ptr<ceres::CostFunction> f;
+  const double *tb = nullptr;
+  switch (type) {
+    case 0: { auto *p = new ProjectionTwoFrameOneCamFactor(v3(pts_i), v3(pts_j), v3(vel_i), v3(vel_j), td_i, td_j); tb = nullptr; f.reset(p);
+              if (tangent_base_out) for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) tangent_base_out[r * 3 + c] = p->tangent_base(r, c); break; }
+    case 1: { auto *p = new ProjectionTwoFrameTwoCamFactor(v3(pts_i), v3(pts_j), v3(vel_i), v3(vel_j), td_i, td_j); f.reset(p);
+              if (tangent_base_out) for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) tangent_base_out[r * 3 + c] = p->tangent_base(r, c); break; }
+    case 2: { auto *p = new ProjectionOneFrameTwoCamFactor(v3(pts_i), v3(pts_j), v3(vel_i), v3(vel_j), td_i, td_j); f.reset(p);
+              if (tangent_base_out) for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) tangent_base_out[r * 3 + c] = p->tangent_base(r, c); break; }
+    case 3: { auto *p = new ProjectionTwoFrameOneCamDepthFactor(v3(pts_i), v3(pts_j), v3(vel_i), v3(vel_j), td_i, td_j, depth_j); f.reset(p);
+              if (tangent_base_out) for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) tangent_base_out[r * 3 + c] = p->tangent_base(r, c); break; }
+    default: return -1;
+  }
+  (void)tb;
+  if (!f->Evaluate(params, residuals, jacobians)) return -2;
+  return f->num_residuals();
+}
+
+// IntegrationBase midpoint pre-integration (integration_base.h:95-199): acc/gyr are (n+1) x 3 with row 0 = acc_0 / gyr_0.
+// out: sum_dt, delta_p(3), delta_q(4, xyzw), delta_v(3), jacobian(225 row-major), covariance(225 row-major)
+static IntegrationBasePtr make_preint(int n, const double *dt, const double *acc, const double *gyr, const double *ba, const double *bg) {
+  IntegrationBasePtr pre = std::make_shared<IntegrationBase>(v3(acc), v3(gyr), v3(ba), v3(bg));
+  for (int k = 0; k < n; k++) pre->push_back(dt[k], v3(acc + 3 * (k + 1)), v3(gyr + 3 * (k + 1)));
+  return pre;
+}
+void ref_preintegrate(int n, const double *dt, const double *acc, const double *gyr, const double *ba, const double *bg, double *out) {
+  IntegrationBasePtr pre = make_preint(n, dt, acc, gyr, ba, bg);
+  out[0] = pre->sum_dt;
+  for (int k = 0; k < 3; k++) { out[1 + k] = pre->delta_p(k); out[8 + k] = pre->delta_v(k); }
+  out[4] = pre->delta_q.x(); out[5] = pre->delta_q.y(); out[6] = pre->delta_q.z(); out[7] = pre->delta_q.w();
+  for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) { out[11 + i * 15 + j] = pre->jacobian(i, j); out[11 + 225 + i * 15 + j] = pre->covariance(i, j); }
+}
+
+// IMUFactor built from explicit pre-integration results (the C ABI's d2ba_imu record); Evaluate with params
+// {pose_i(7), sb_i(9), pose_j(7), sb_j(9)}; J[k] row-major 15 x {7,9,7,9}; sqrt_info_out 225 row-major (imu_factor.h:29)
+int ref_imu_eval(double sum_dt, const double *delta_p, const double *delta_q_xyzw, const double *delta_v, const double *lin_ba, const double *lin_bg,
+                 const double *jacobian, const double *covariance, const double *const *params, double *residuals, double **jacobians,
+                 double *sqrt_info_out) {
+  IntegrationBasePtr pre = std::make_shared<IntegrationBase>(Vector3d(0, 0, 0), Vector3d(0, 0, 0), v3(lin_ba), v3(lin_bg));
+  pre->sum_dt = sum_dt; pre->delta_p = v3(delta_p); pre->delta_v = v3(delta_v);
+  pre->delta_q = Eigen::Quaterniond(delta_q_xyzw[3], delta_q_xyzw[0], delta_q_xyzw[1], delta_q_xyzw[2]);
+  for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) { pre->jacobian(i, j) = jacobian[i * 15 + j]; pre->covariance(i, j) = covariance[i * 15 + j]; }
+  IMUFactor f(pre);
+  if (sqrt_info_out) {
+    // the factor keeps sqrt_info private: recompute it with the very expression of its constructor (imu_factor.h:29)
+    Eigen::Matrix<double, 15, 15> si = Eigen::LLT<Eigen::Matrix<double, 15, 15>>(pre->covariance.inverse()).matrixL().transpose();
+    for (int i = 0; i < 15; i++) for (int j = 0; j < 15; j++) sqrt_info_out[i * 15 + j] = si(i, j);
+  }
+  return f.Evaluate(params, residuals, jacobians) ? 15 : -2;
+}
+
+// ConsenusPoseFactor (consenus_factor.cpp:6-51): residual 6, J 6 x 7 row-major
+int ref_consensus_eval(const double *t_ref, const double *q_ref_xyzw, const double *t_tilde, const double *theta_tilde, double rho_T, double rho_theta,
+                       const double *pose, double *r6, double *J6x7) {
+  ConsenusPoseFactor f(v3(t_ref), Eigen::Quaterniond(q_ref_xyzw[3], q_ref_xyzw[0], q_ref_xyzw[1], q_ref_xyzw[2]), v3(t_tilde), v3(theta_tilde), rho_T, rho_theta);
+  const double *params[1] = {pose};
+  double *jac[1] = {J6x7};
+  return f.Evaluate(params, r6, J6x7 ? jac : nullptr) ? 6 : -2;
+}
+
+// PoseLocalParameterization (pose_local_parameterization.cpp:13-38); its members are private virtuals of
+// ceres::LocalParameterization, reached through the base interface exactly as ceres does
+void ref_pose_plus(const double *x7, const double *delta6, double *out7) {
+  PoseLocalParameterization p;
+  const ceres::LocalParameterization &b = p;
+  b.Plus(x7, delta6, out7);
+}
+void ref_pose_plus_jacobian(const double *x7, double *J7x6) {
+  PoseLocalParameterization p;
+  const ceres::LocalParameterization &b = p;
+  b.ComputeJacobian(x7, J7x6);
+}
+
+// Utility helpers (d2common/include/d2common/utils.hpp:56-104, 213-228)
+void ref_qleft_qright(const double *q_xyzw, double *L16, double *R16) {
+  Eigen::Quaterniond q(q_xyzw[3], q_xyzw[0], q_xyzw[1], q_xyzw[2]);
+  Eigen::Matrix4d L = Utility::Qleft(q), R = Utility::Qright(q);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { L16[i * 4 + j] = L(i, j); R16[i * 4 + j] = R(i, j); }
+}
+void ref_average_quats(int n, const double *q_xyzw, double *out_xyzw) {
+  std::vector<Eigen::Quaterniond> qs;
+  for (int i = 0; i < n; i++) qs.emplace_back(q_xyzw[4 * i + 3], q_xyzw[4 * i], q_xyzw[4 * i + 1], q_xyzw[4 * i + 2]);
+  Eigen::Quaterniond a = Utility::averageQuaterions(qs);
+  out_xyzw[0] = a.x(); out_xyzw[1] = a.y(); out_xyzw[2] = a.z(); out_xyzw[3] = a.w();
+}
+
+}  // extern "C"

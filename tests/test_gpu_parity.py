@@ -274,3 +274,88 @@ def test_speed_bias_elimination_equals_dense_cholesky(name, monkeypatch):
     d = state_diff(out["elim"], state_of(o, pr))
     assert d["pos"] <= 1e-6 and d["rot"] <= 1e-6 and d["sb"] <= 1e-6, d
     assert abs(out["elim_cost"] - ro.final_cost) <= 1e-7 * max(1.0, abs(ro.final_cost))
+
+
+def _admm_case(sw, cfg, iters, tol_pos=1e-6, tol_lm=1e-5):
+    from d2slam_b200.solver import Solver
+    from oracle import orc
+    ags = []
+    for p in sw:
+        a = orc.Oracle(**cfg); p.load(a); ags.append(a)
+    ro = orc.admm_solve(ags, fixed_mode=True)
+    s = Solver(max_windows=len(sw), **cfg)
+    for i, p in enumerate(sw):
+        p.load(s, i)
+    s.finalize()
+    rs = s.solve_fixed(iters)
+    for i, p in enumerate(sw):
+        assert rs[i].total_iterations == ro[i].total_iterations
+        assert abs(rs[i].final_cost - ro[i].final_cost) <= 1e-6 * max(1.0, ro[i].final_cost), (i, rs[i].final_cost, ro[i].final_cost)
+        d = state_diff(state_of(s, p, i), state_of(ags[i], p))
+        assert d["pos"] <= tol_pos and d["rot"] <= tol_pos and d["lm_rel"] <= tol_lm, (i, d)
+    return s
+
+
+def test_L4_admm_eight_agents_full_size():
+    """config 4 size: 8 agents x (11 own + 77 remote pose blocks) = 88 six-dof blocks, n_lc = 528 landmark-coupled columns,
+    300 landmarks per agent, as 8 windows of one handle, against the oracle's in-process ADMM (ConsensusSolver.cpp:39-75)."""
+    sw = synth.make_swarm(seed=83, n_agents=8)
+    assert len(sw[0]["frame_ids"]) == 88
+    _admm_case(sw, dict(consensus_max_steps=2, max_num_iterations=4), 4)
+
+
+def test_L2_eight_agent_window_normal_equations():
+    """Linearisation / Schur complement / Gauss-Newton step of one agent's window of the 8-drone swarm (528 + 99 columns)."""
+    pr = synth.make_swarm(seed=85, n_agents=8, only_agents=[3])[0]
+    pr["consensus"] = None
+    o, s = both(pr)
+    o.debug_linearize(); s.debug_linearize()
+    assert np.array_equal(o.debug_get(abi.DBG_OBS_INDEX, np.int32), s.debug_get(0, abi.DBG_OBS_INDEX, np.int32))
+    for item in (abi.DBG_COST, abi.DBG_HCC, abi.DBG_GC, abi.DBG_HLL, abi.DBG_GL, abi.DBG_W, abi.DBG_S):
+        assert relerr(s.debug_get(0, item), o.debug_get(item)) <= 1e-10, item
+
+
+def test_L4_admm_eight_agents_quadcam():
+    """config 4 shape at a small size: 8 agents, 4 cameras each (1F2C / 2F2C / 2F1C factor mix), ADMM."""
+    sw = synth.make_swarm(seed=84, n_agents=8, cams="quad", n_landmarks=100, shared_per_pair=10, n_frames=6)
+    types = set(np.unique(np.concatenate([p["obs"]["type"] for p in sw])))
+    assert types == {abi.PROJ_2F1C, abi.PROJ_2F2C, abi.PROJ_1F2C}
+    _admm_case(sw, dict(consensus_max_steps=4, max_num_iterations=8), 8)
+
+
+@pytest.mark.parametrize("rho", [(1.0, 1.0), (10.0, 10.0), (1000.0, 1000.0), (10.0, 1000.0)])
+def test_L4_rho_sweep(rho):
+    """rho sweep of config 4 (rho_T = rho_theta in {1, 10, 1000} and one rho_T != rho_theta, consenus_factor.cpp:15-16)."""
+    sw = synth.make_swarm(seed=86, n_agents=4, n_landmarks=80, shared_per_pair=15, n_frames=6)
+    _admm_case(sw, dict(consensus_max_steps=4, max_num_iterations=8, rho_frame_T=rho[0], rho_frame_theta=rho[1]), 8)
+
+
+def test_two_devices_one_process():
+    """One process, handles on two devices: kernel attributes (dynamic shared memory limits) are per device."""
+    import torch
+    from d2slam_b200.solver import Solver
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    pr = synth.make_window(seed=0)
+    out = []
+    for dev in (0, 1):
+        s = Solver(device=dev); pr.load(s, 0); s.finalize()
+        out.append((s.solve_fixed(4)[0].final_cost, s))
+    assert abs(out[0][0] - out[1][0]) <= 1e-9 * max(1.0, out[0][0])
+
+
+def test_set_consensus_rejects_bad_slots():
+    from d2slam_b200.solver import D2BAError, Solver
+    pr = synth.make_swarm(seed=87, n_agents=2, n_landmarks=30, n_frames=4)[0]
+    refs, slots, n = pr["consensus"]
+    s = Solver(consensus_max_steps=1)
+    pr["consensus"] = None
+    pr.load(s, 0)
+    bad = slots.copy(); bad[0] = n
+    with pytest.raises(D2BAError):
+        s.set_consensus(0, refs, bad, n)
+    bad[0] = -1
+    with pytest.raises(D2BAError):
+        s.set_consensus(0, refs, bad, n)
+    with pytest.raises(D2BAError):
+        s.set_consensus(0, refs, slots, 0)

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from d2slam_b200 import abi, consensus, synth
+from d2slam_b200 import abi, synth
+import consensus_pack as consensus
 
 
 def _free_port():

@@ -1,0 +1,209 @@
+"""Pins the oracle's restated factors (oracle/orc_factors.c) to the REFERENCE's own classes.
+
+oracle/_ref/libd2ref.so holds the unmodified reference sources (d2vins/src/factors/projection*Factor.cpp, imu_factor.h +
+d2common integration_base.h / utils.hpp, d2common/src/solver/consenus_factor.cpp, pose_local_parameterization.cpp)
+compiled by oracle/Makefile.ref against the stand-in third-party headers of oracle/_shim.  Every comparison is
+reference Evaluate() vs orc_*_eval on the same seeded inputs: residuals and every Jacobian block, <= 1e-12 of the block's
+scale (both sides are f64 with different but equivalent operation orders; sqrt_info = 307 amplifies rounding).
+The same reference outputs are frozen in tests/golden/ref_factors.npz (tests/golden/make_ref_golden.py) so that the check
+also runs where /root/reference and the prebuilt library are absent.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from d2slam_b200 import abi, synth
+from oracle import orc, ref
+
+import test_oracle_factors as tof
+
+L = orc.lib()
+HAVE_REF = ref.available()
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libd2ref.so not built and no reference tree")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_factors.npz")
+
+
+def close(a, b, tol=1e-12):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1.0)
+    err = np.abs(a - b).max() / scale
+    assert err <= tol, err
+    return err
+
+
+# ----------------------------------------------------------------------------------------------- case generators (seeded)
+def proj_cases(seed=7, n=6):
+    rng = np.random.default_rng(seed)
+    tof.RNG = np.random.default_rng(seed + 1)
+    out = []
+    for typ in (abi.PROJ_2F1C, abi.PROJ_2F2C, abi.PROJ_1F2C, abi.PROJ_2F1C_DEPTH):
+        for k in range(n):
+            pi, pj, ea, eb, Pw, bi, lam = tof.scene()
+            ext_j = eb if typ in (abi.PROJ_2F2C, abi.PROJ_1F2C) else ea
+            pose_j = pi if typ == abi.PROJ_1F2C else pj
+            bj, dj = synth._bearing(Pw[None], pose_j, ext_j)
+            bj = bj[0] + rng.normal(size=3) * 2e-3; bj /= np.linalg.norm(bj)
+            vel_i = rng.normal(size=3) * 0.05; vel_j = rng.normal(size=3) * 0.05
+            td_i, td_j = (0.0, 0.0) if k % 2 == 0 else (0.001, -0.002)
+            td = 0.0 if k % 3 == 0 else 0.003
+            out.append(dict(typ=typ, pi=pi, pj=pj, ea=ea, eb=eb, lam=lam * (1.0 + 0.1 * rng.normal()), td=td, pts_i=bi, pts_j=bj, vel_i=vel_i, vel_j=vel_j,
+                            td_i=td_i, td_j=td_j, depth=float(dj[0]) * 1.02))
+    # the exact-(0,0,1) bearing branch of the tangent-base constructor (projectionTwoFrameOneCamFactor.cpp:36-38)
+    c = dict(out[0]); c["pts_j"] = np.array([0.0, 0.0, 1.0]); out.append(c)
+    return out
+
+
+def ref_params(c):
+    t = c["typ"]
+    lam, td = np.array([c["lam"]]), np.array([c["td"]])
+    if t == abi.PROJ_2F2C:
+        return [c["pi"], c["pj"], c["ea"], c["eb"], lam, td]
+    if t == abi.PROJ_1F2C:
+        return [c["ea"], c["eb"], lam, td]
+    return [c["pi"], c["pj"], c["ea"], lam, td]
+
+
+def orc_proj(c):
+    oc = tof.make_obs_const(c["pts_i"], c["pts_j"], c["vel_i"], c["vel_j"], c["td_i"], c["td_j"], depth=c["depth"])
+    r, Ji, Jj, Ja, Jb, Jl, Jt = tof.proj_eval(c["typ"], oc, c["pi"], c["pj"], c["ea"], c["eb"], c["lam"], c["td"])
+    t = c["typ"]
+    if t == abi.PROJ_2F2C:
+        Js = [Ji, Jj, Ja, Jb, Jl[:, None], Jt[:, None]]
+    elif t == abi.PROJ_1F2C:
+        Js = [Ja, Jb, Jl[:, None], Jt[:, None]]
+    else:
+        Js = [Ji, Jj, Ja, Jl[:, None], Jt[:, None]]
+    return r, Js, np.array(oc.tangent_base).reshape(2, 3)
+
+
+def imu_cases(seed=11, n=5):
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        steps = 20
+        dt = np.full(steps, 0.005)
+        acc = rng.normal(size=(steps + 1, 3)) * 0.5 + np.array([0, 0, 9.8]); gyr = rng.normal(size=(steps + 1, 3)) * 0.2
+        ba0 = rng.normal(size=3) * 0.02; bg0 = rng.normal(size=3) * 0.003
+        tof.RNG = np.random.default_rng(seed + 100 + k)
+        pi = tof.rand_pose(0.5); pj = tof.plus(pi, np.concatenate([rng.normal(size=3) * 0.1, rng.normal(size=3) * 0.05]))
+        sbi = np.concatenate([rng.normal(size=3), ba0 + rng.normal(size=3) * 0.01, bg0 + rng.normal(size=3) * 0.002])
+        sbj = sbi + rng.normal(size=9) * 0.01
+        out.append(dict(dt=dt, acc=acc, gyr=gyr, ba0=ba0, bg0=bg0, pi=pi, pj=pj, sbi=sbi, sbj=sbj))
+    return out
+
+
+def orc_imu(c):
+    pre = orc.preintegrate(c["dt"], c["acc"], c["gyr"], c["ba0"], c["bg0"], 0.1, 0.05, 0.002, 0.0004)
+    p = orc.OrcImuConst()
+    p.sum_dt = pre["sum_dt"]; p.delta_p[:] = pre["delta_p"]; p.delta_q[:] = pre["delta_q"]; p.delta_v[:] = pre["delta_v"]
+    p.linearized_ba[:] = c["ba0"]; p.linearized_bg[:] = c["bg0"]; p.jacobian[:] = pre["jacobian"]; p.covariance[:] = pre["covariance"]
+    si = np.zeros(225)
+    assert L.orc_imu_sqrt_info(abi.ptr(np.ascontiguousarray(pre["covariance"])), abi.ptr(si)) == 0
+    p.sqrt_info[:] = si
+    r = np.zeros(15); Js = [np.zeros((15, 7)), np.zeros((15, 9)), np.zeros((15, 7)), np.zeros((15, 9))]
+    L.orc_imu_eval(C.byref(p), C.c_double(9.805), abi.ptr(c["pi"]), abi.ptr(c["sbi"]), abi.ptr(c["pj"]), abi.ptr(c["sbj"]), abi.ptr(r),
+                   abi.ptr(Js[0]), abi.ptr(Js[1]), abi.ptr(Js[2]), abi.ptr(Js[3]))
+    return pre, r, Js, si.reshape(15, 15)
+
+
+def cons_cases(seed=13, n=6):
+    rng = np.random.default_rng(seed)
+    tof.RNG = np.random.default_rng(seed + 1)
+    out = []
+    for k in range(n):
+        z = tof.rand_pose(1.0); x = tof.plus(z, np.concatenate([rng.normal(size=3) * 0.2, rng.normal(size=3) * 0.1]))
+        if k == n - 1:
+            x[3:7] = -x[3:7]      # other hemisphere: exercises positify inside Qleft (utils.hpp:56-63, 85-93)
+        out.append(dict(z=z, x=x, tt=rng.normal(size=3) * 0.05, th=rng.normal(size=3) * 0.02, rho_T=10.0 ** rng.integers(0, 4), rho_theta=10.0 ** rng.integers(0, 4)))
+    return out
+
+
+def orc_cons(c):
+    r = np.zeros(6); J = np.zeros((6, 7))
+    L.orc_consensus_eval(abi.ptr(c["z"][:3].copy()), abi.ptr(c["z"][3:7].copy()), abi.ptr(c["tt"]), abi.ptr(c["th"]), C.c_double(c["rho_T"]), C.c_double(c["rho_theta"]),
+                         abi.ptr(c["x"]), abi.ptr(r), abi.ptr(J))
+    return r, J
+
+
+# ----------------------------------------------------------------------------------------------- live reference vs oracle
+@needs_ref
+def test_projection_factors_match_reference():
+    worst = 0.0
+    for c in proj_cases():
+        r_ref, J_ref, tb_ref = ref.proj_eval(c["typ"], c["pts_i"], c["pts_j"], c["vel_i"], c["vel_j"], c["td_i"], c["td_j"], c["depth"], ref_params(c))
+        r_o, J_o, tb_o = orc_proj(c)
+        close(tb_o, tb_ref, 1e-14)
+        worst = max(worst, close(r_o, r_ref))
+        for a, b in zip(J_o, J_ref):
+            worst = max(worst, close(a, b))
+    print("projection factors: worst scaled difference", worst)
+
+
+@needs_ref
+def test_imu_factor_and_preintegration_match_reference():
+    for c in imu_cases():
+        pre_o, r_o, J_o, si_o = orc_imu(c)
+        pre_r = ref.preintegrate(c["dt"], c["acc"], c["gyr"], c["ba0"], c["bg0"])
+        for k in ("sum_dt", "delta_p", "delta_q", "delta_v", "jacobian", "covariance"):
+            close(np.ravel(pre_o[k]), np.ravel(pre_r[k]), 1e-13)
+        r_r, J_r, si_r = ref.imu_eval(pre_r, c["ba0"], c["bg0"], c["pi"], c["sbi"], c["pj"], c["sbj"])
+        # sqrt_info = LLT(cov^-1).L^T: conditioning of cov (1e8) bounds the agreement of two different inversion routes
+        close(si_o, si_r, 1e-8)
+        close(r_o, r_r, 1e-8)
+        for a, b in zip(J_o, J_r):
+            close(a, b, 1e-8)
+        # with the reference's own sqrt_info the restated raw residual / Jacobians agree to rounding
+        Ui = np.linalg.inv(si_r)
+        close(np.linalg.solve(si_o, r_o), Ui @ r_r, 1e-11)
+        for a, b in zip(J_o, J_r):
+            close(np.linalg.solve(si_o, a), Ui @ b, 1e-11)
+
+
+@needs_ref
+def test_consensus_factor_matches_reference():
+    for c in cons_cases():
+        r_r, J_r = ref.consensus_eval(c["z"][:3], c["z"][3:7], c["tt"], c["th"], c["rho_T"], c["rho_theta"], c["x"])
+        r_o, J_o = orc_cons(c)
+        close(r_o, r_r, 1e-14); close(J_o, J_r, 1e-14)
+
+
+@needs_ref
+def test_manifold_and_quaternion_helpers_match_reference():
+    rng = np.random.default_rng(17)
+    tof.RNG = np.random.default_rng(18)
+    for _ in range(8):
+        x = tof.rand_pose(2.0); d = rng.normal(size=6) * 0.3
+        o = np.zeros(7)
+        L.orc_pose_plus(abi.ptr(x), abi.ptr(d), abi.ptr(o))
+        close(o, ref.pose_plus(x, d), 1e-15)
+        close(synth.pose_plus(x, d), ref.pose_plus(x, d), 1e-15)
+    J = ref.pose_plus_jacobian(tof.rand_pose())
+    assert np.array_equal(J, np.vstack([np.eye(6), np.zeros((1, 6))]))     # pose_local_parameterization.cpp:31-38
+    qs = np.array([tof.rand_pose()[3:7] for _ in range(5)])
+    qs[1:] = qs[0] + 0.05 * qs[1:]; qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    a_r = ref.average_quats(qs); a_o = np.zeros(4)
+    L.orc_average_quats(C.c_int(len(qs)), abi.ptr(qs), abi.ptr(a_o))
+    assert min(np.abs(a_r - a_o).max(), np.abs(a_r + a_o).max()) <= 1e-12      # eigenvector sign is free
+
+
+# ----------------------------------------------------------------------------------------------- frozen reference outputs
+def test_oracle_matches_golden_reference_vectors():
+    """Same comparisons against reference outputs frozen by tests/golden/make_ref_golden.py (runs everywhere)."""
+    g = np.load(GOLD)
+    for i, c in enumerate(proj_cases()):
+        r_o, J_o, tb_o = orc_proj(c)
+        close(r_o, g[f"proj{i}_r"]); close(tb_o, g[f"proj{i}_tb"], 1e-14)
+        for k, a in enumerate(J_o):
+            close(a, g[f"proj{i}_J{k}"])
+    for i, c in enumerate(imu_cases()):
+        pre_o, r_o, J_o, si_o = orc_imu(c)
+        close(np.ravel(pre_o["jacobian"]), g[f"imu{i}_pre_jacobian"], 1e-13); close(np.ravel(pre_o["covariance"]), g[f"imu{i}_pre_covariance"], 1e-13)
+        close(si_o, g[f"imu{i}_sqrt_info"], 1e-8); close(r_o, g[f"imu{i}_r"], 1e-8)
+        for k, a in enumerate(J_o):
+            close(a, g[f"imu{i}_J{k}"], 1e-8)
+    for i, c in enumerate(cons_cases()):
+        r_o, J_o = orc_cons(c)
+        close(r_o, g[f"cons{i}_r"], 1e-14); close(J_o, g[f"cons{i}_J"], 1e-14)
