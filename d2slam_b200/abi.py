@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("relaxation_alpha", C.c_double),
         ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
         ("min_relative_decrease", C.c_double), ("function_tolerance", C.c_double),
-        ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("max_solver_time_in_seconds", C.c_double),
     ]
 
 

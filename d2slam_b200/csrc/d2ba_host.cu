@@ -34,6 +34,12 @@ void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s);
 void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, int any_compact, int any_wide, cudaStream_t s);
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s);
+int configure_leaf_elim(size_t smem);
+void launch_leaf_elim(const Dev &d, size_t smem, cudaStream_t s);
+void launch_leaf_back(const Dev &d, size_t smem, cudaStream_t s);
+size_t leaf_back_smem(int n, int n_hub);
+int configure_leaf_back(size_t smem);
+void launch_zero_leaf_rows(const Dev &d, cudaStream_t s);
 void launch_schur_small(const Dev &d, int max_ldw, cudaStream_t s);
 int configure_schur_small(int max_ldw);
 void launch_chol(const Dev &d, int max_rows, cudaStream_t s);
@@ -55,7 +61,9 @@ void launch_cons_init(const Dev &d, int n6_total, cudaStream_t s);
 void launch_cons_pack(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
 void launch_cons_apply(const Dev &d, int n6_total, const int *blk_win, cudaStream_t s);
 void launch_cons_refs(const Dev &d, int nsb_total, int nl_total, const int *sb_win, const int *lm_win, cudaStream_t s);
-struct SchurTileH { int win, kind, tm, tn; };
+typedef SchurTile SchurTileH;
+size_t leaf_elim_smem(int n, int n_hub);
+int leaf_max_cols();
 int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr, double *A, double *b, int *fail_flag,
                        cudaStream_t s);
 void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s);
@@ -144,6 +152,7 @@ struct HostWin {
   std::vector<int> pose_col, ext_col, sb_col; int td_col = -1, n_lc = 0, n_c = 0;
   std::vector<int> order;            // pair-major order: sorted index -> observation index
   std::vector<int> sorted_pos;       // tile slot (window-local) of the k-th sorted observation
+  std::vector<int> canon_of_dev;     // device reduced column -> canonical (insertion-order) column, for the debug views
   void clear() {   // keeps every allocation (the estimator re-adds a similar problem for the next solve)
     used = false;
     pose_id.clear(); ext_id.clear(); sb_id.clear(); lm_id.clear();
@@ -230,6 +239,7 @@ struct d2ba_handle {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_it[2] = {nullptr, nullptr};   // solver time budget: iteration k-2 complete
   cudaEvent_t evf0 = nullptr, evf1 = nullptr, evf2 = nullptr;   // device span of the last finalize: uploads | tile build + prep kernels
   bool finalized = false, state_dirty = false;
   // device arena
@@ -240,7 +250,8 @@ struct d2ba_handle {
   DBuf<Group> d_grp; DBuf<Job> d_job; DBuf<ImuDesc> d_imu; DBuf<PriorBlk> d_prior_blk;
   DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
-  DBuf<SchurTileH> d_schur;
+  DBuf<SchurTileH> d_schur; DBuf<int> d_schur_chunks; DBuf<Leaf> d_leaf; DBuf<HSeg> d_hseg; DBuf<unsigned long long> d_lm_mask; DBuf<double> d_leafL; DBuf<int> d_leaf_lm;
+  int n_schur0 = 0, n_leaf_total = 0, max_hub = 0; size_t leaf_smem = 0, cfg_leaf_smem = 0, leafb_smem = 0, cfg_leafb_smem = 0;
   DBuf<int> d_pr_m, d_pr_info, d_tile_src; DBuf<long long> d_pr_oJ, d_pr_ov, d_raw_off;
   int cfg_max_rows = -1, cfg_max_nc = -1, cfg_max_prior = -1, cfg_max_ldw = -1;
   Dev dev;
@@ -253,6 +264,7 @@ struct d2ba_handle {
   int max_rows = 1, max_nc = 1, max_prior_m = 0, max_ldw = 8, n_slots = 0;
   int max_n_smem = 0, max_rows_glob = 1; bool any_chol_glob = false; int cfg_max_n_smem = -1;
   int max_ldw_small = 0, cfg_max_ldw_small = -1;
+  int max_row_tiles = 1;
   int any_compact = 0, any_wide = 0;   // record widths present (which gather kernels to launch)
   size_t sbb_smem = 0, cfg_sbb_smem = 0;   // k_sb_back dynamic shared memory
   size_t sbe_smem = 0, cfg_sbe_smem = 0;   // speed-bias elimination: dynamic shared memory of k_sb_elim (0 = no window uses it)
@@ -268,6 +280,7 @@ struct d2ba_handle {
   d2ba_handle *marg = nullptr;   // scratch handle of d2ba_marginalize
   double mu0 = 1e-8;
   bool force_full_S = false;     // the Schur kernels must write the complete reduced system (marginalization reads it)
+  bool no_leaf = false;          // D2BA_NO_LEAF=1: keep remote-frame blocks in the dense part (A/B switch)
   bool no_sb_elim = false;       // D2BA_NO_SB_ELIM=1: keep the dense Cholesky of the whole reduced system (A/B switch for tests / profiling)
   double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wall-clock phases of the last d2ba_finalize (d2ba_debug_host_times)
   double solve_ms[4] = {0, 0, 0, 0};             // host wall-clock of the last solve: enqueue, wait for the device, write-back
@@ -339,6 +352,7 @@ int d2ba_create(const d2ba_config *cfg, d2ba_handle **out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) return 5;
   d2ba_handle *h = new d2ba_handle();
   { const char *e = getenv("D2BA_NO_SB_ELIM"); h->no_sb_elim = e && e[0] == '1'; }
+  { const char *e = getenv("D2BA_NO_LEAF"); h->no_leaf = e && e[0] == '1'; }
   h->cfg = *cfg;
   if (h->cfg.max_windows < 1) h->cfg.max_windows = 1;
   if (h->cfg.initial_trust_region_radius <= 0) h->cfg.initial_trust_region_radius = 1e4;
@@ -350,6 +364,7 @@ int d2ba_create(const d2ba_config *cfg, d2ba_handle **out) {
   h->win.resize(h->cfg.max_windows);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return 6; }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evf0); cudaEventCreate(&h->evf1); cudaEventCreate(&h->evf2);
+  cudaEventCreateWithFlags(&h->ev_it[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_it[1], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
   memset(&h->dev, 0, sizeof(h->dev));
   *out = h;
@@ -372,12 +387,13 @@ int d2ba_destroy(d2ba_handle *h) {
   h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release();
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
-  h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release();
+  h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release(); h->d_schur_chunks.release(); h->d_leaf.release(); h->d_hseg.release(); h->d_lm_mask.release(); h->d_leafL.release(); h->d_leaf_lm.release();
   h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release(); h->d_tile_src.release(); h->d_raw_off.release();
   cudaStreamSynchronize(h->copy_stream);
   for (auto &w : h->win) { w.rawj.release(); w.anch.release(); w.d_rawj.release(); w.d_anch.release(); }
   cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_copy);
   d2ba_release_staging(h);
+  cudaEventDestroy(h->ev_it[0]); cudaEventDestroy(h->ev_it[1]);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evf0); cudaEventDestroy(h->evf1); cudaEventDestroy(h->evf2);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -646,10 +662,12 @@ struct WinPlan {
   std::vector<Group> groups;
   std::vector<int> grp_begin, grp_cnt, grp_tile0;   // sorted-obs range and first (window-local) tile of each group
   std::vector<Job> jobs[6];                         // tile_begin window-local, grp window-local
-  std::vector<SchurTileH> schur;
+  std::vector<SchurTileH> schur[2];                  // stage 0 (tiles with leaf columns), stage 1 (hub x hub)
+  std::vector<int> schur_chunks;                     // chunk lists, window-local offsets in SchurTile::cb
+  std::vector<Leaf> leaves; std::vector<HSeg> hseg; std::vector<unsigned long long> lm_mask; std::vector<int> leaf_lm; int leaf_lm_off = 0;
   int n_tiles = 0, n_lmobs = 0;
   int job_off[6] = {0, 0, 0, 0, 0, 0};
-  int schur_off = 0;
+  int schur_off[2] = {0, 0}, chunk_off = 0;
 };
 
 template <typename F>
@@ -676,6 +694,7 @@ struct Staging {   // every array finalize uploads lives in ONE pinned arena -> 
   HView<long long> raw_off;
   HView<long long> pr_offJ, pr_offv;
   HView<Group> grp; HView<Job> job; HView<ImuDesc> imu; HView<PriorBlk> pblk; HView<SchurTileH> schur;
+  HView<int> schur_chunks, leaf_lm; HView<Leaf> leaf; HView<HSeg> hseg; HView<unsigned long long> lm_mask;
   template <typename T> void reserve(HView<T> &v, size_t count) { v.n = count; v.off = cursor; cursor += (count * sizeof(T) + 255) & ~(size_t)255; }
   template <typename T> void place(HView<T> &v) { v.p = (T *)(arena.p + v.off); }
 };
@@ -738,15 +757,101 @@ int d2ba_finalize(d2ba_handle *h) {
     WinDesc &d = pl.d; memset(&d, 0, sizeof d);
     const int np = (int)w.pose_id.size(), ne = (int)w.ext_id.size(), nsb = (int)w.sb_id.size(), nl = (int)w.lm_id.size();
     d.np = np; d.ne = ne; d.n6 = np + ne; d.nsb = nsb; d.nl = nl; d.has_td = w.has_td ? 1 : 0;
+    // ---- leaves: connected components (through co-observation) of the free pose blocks that no IMU factor / prior
+    //      touches -- the remote frames of another drone in a multi-agent window (d2vinsstate.cpp:476-485: no speed-bias).
+    //      They couple only to themselves and to the hub (own frames, extrinsics, td), so they are eliminated from the
+    //      reduced system before the dense Cholesky.  Reduced columns: [leaf 0 | leaf 1 | ... | hub poses | ext | td | sb].
+    std::vector<int> leaf_of(np, -1);
+    std::vector<std::vector<int>> leaves;
+    int nsb_free = 0, n6_free = 0;
+    for (int i = 0; i < nsb; i++) if (!w.sb_c[i]) nsb_free++;
+    for (int i = 0; i < np; i++) if (!w.pose_c[i]) n6_free++;
+    for (int i = 0; i < ne; i++) if (!w.ext_c[i]) n6_free++;
+    const bool td_free = w.has_td && !w.td_c;
+    const int nlc_cnt = 6 * n6_free + (td_free ? 1 : 0), nc_cnt = nlc_cnt + 9 * nsb_free;
+    bool sb_ok;
+    {   // speed-bias elimination: needs a block-tridiagonal speed-bias part (IMU factors / prior blocks only between
+        // neighbouring speed-bias blocks); the test does not depend on the column order
+      std::vector<int> pos(nsb, -1);
+      int nb = 0;
+      for (int i = 0; i < nsb; i++) if (!w.sb_c[i]) pos[i] = nb++;
+      sb_ok = !h->force_full_S && !h->no_sb_elim && nb >= 1 && nlc_cnt >= 1;
+      for (size_t a = 0; a < w.imu.size() && sb_ok; a++) {
+        const int pa = pos[w.imu[a].si], pb = pos[w.imu[a].sj];
+        if (pa >= 0 && pb >= 0 && std::abs(pa - pb) > 1) sb_ok = false;
+      }
+      int pmin = 1 << 30, pmax = -1;
+      for (const HPriorBlk &b : w.prior_blk) if (b.kind == D2BA_SPEED_BIAS && pos[b.index] >= 0) { pmin = std::min(pmin, pos[b.index]); pmax = std::max(pmax, pos[b.index]); }
+      if (pmax - pmin > 1) sb_ok = false;
+      if (sb_ok && nb > sb_max_blocks()) sb_ok = false;
+      d.n_sbe = nb;
+    }
+    if (!h->force_full_S && !h->no_leaf && (sb_ok || nsb_free == 0) && nlc_cnt + 1 > 96) {   // small systems keep the one-CTA dense path (k_schur_small)
+      std::vector<char> hub(np, 0);
+      for (const HImu &m : w.imu) { hub[m.pi] = 1; hub[m.pj] = 1; }
+      for (const HPriorBlk &b : w.prior_blk) if (b.kind == D2BA_POSE) hub[b.index] = 1;
+      std::vector<int> uf(np);
+      for (int i = 0; i < np; i++) uf[i] = i;
+      auto find = [&](int x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+      // two poses belong to one component when some landmark is observed from both (the landmark's elimination couples them)
+      std::vector<int> first_pose(nl, -1);
+      for (const HObs &o : w.obs) {
+        const int ps[2] = {o.pi, o.pj};
+        for (int q = 0; q < 2; q++) {
+          const int pz = ps[q];
+          if (pz < 0 || hub[pz] || w.pose_c[pz]) continue;
+          if (first_pose[o.lm] < 0) { first_pose[o.lm] = pz; continue; }
+          const int a = find(pz), b = find(first_pose[o.lm]);
+          if (a != b) uf[std::max(a, b)] = std::min(a, b);
+        }
+      }
+      std::vector<int> comp_id(np, -1);
+      for (int i = 0; i < np; i++) {
+        if (hub[i] || w.pose_c[i]) continue;
+        const int r = find(i);
+        if (comp_id[r] < 0) { comp_id[r] = (int)leaves.size(); leaves.emplace_back(); }
+        leaves[comp_id[r]].push_back(i);
+      }
+      // a leaf must fit the elimination kernel's shared memory together with its hub coupling; otherwise it stays in the hub
+      int n_hub_cols = nlc_cnt;
+      for (auto &lf : leaves) n_hub_cols -= 6 * (int)lf.size();
+      std::vector<std::vector<int>> kept;
+      for (auto &lf : leaves) {
+        const int nl6 = 6 * (int)lf.size();
+        if (nl6 <= leaf_max_cols() && n_hub_cols >= 1 && leaf_elim_smem(nl6, n_hub_cols) <= (size_t)200 * 1024) kept.push_back(lf);
+        else n_hub_cols += nl6;
+      }
+      // worthwhile only when the hub is a real reduction of the dense part
+      if (kept.empty() || n_hub_cols > 3 * nlc_cnt / 4) kept.clear();
+      leaves.swap(kept);
+      for (size_t li = 0; li < leaves.size(); li++) for (int i : leaves[li]) leaf_of[i] = (int)li;
+    }
     int c = 0;
     w.pose_col.assign(np, -1); w.ext_col.assign(ne, -1); w.sb_col.assign(nsb, -1);
-    for (int i = 0; i < np; i++) if (!w.pose_c[i]) { w.pose_col[i] = c; c += 6; }
+    pl.leaves.clear();
+    for (size_t li = 0; li < leaves.size(); li++) {
+      Leaf lf; memset(&lf, 0, sizeof lf);
+      lf.win = wi; lf.col0 = c; lf.n = 6 * (int)leaves[li].size();
+      for (int i : leaves[li]) { w.pose_col[i] = c; c += 6; }
+      pl.leaves.push_back(lf);
+    }
+    d.hub0 = c;
+    for (int i = 0; i < np; i++) if (!w.pose_c[i] && leaf_of[i] < 0) { w.pose_col[i] = c; c += 6; }
     for (int i = 0; i < ne; i++) if (!w.ext_c[i]) { w.ext_col[i] = c; c += 6; }
-    w.td_col = (w.has_td && !w.td_c) ? c : -1;
+    w.td_col = td_free ? c : -1;
     if (w.td_col >= 0) c += 1;
     w.n_lc = c;
     for (int i = 0; i < nsb; i++) if (!w.sb_c[i]) { w.sb_col[i] = c; c += 9; }
     w.n_c = c;
+    d.n_hub = w.n_lc - d.hub0; d.n_leaf = (int)leaves.size();
+    {   // canonical (insertion-order) columns for the debug views: canon_of_dev[device column] = column the oracle uses
+      w.canon_of_dev.assign(w.n_c, -1);
+      int cc = 0;
+      for (int i = 0; i < np; i++) if (!w.pose_c[i]) { for (int q = 0; q < 6; q++) w.canon_of_dev[w.pose_col[i] + q] = cc + q; cc += 6; }
+      for (int i = 0; i < ne; i++) if (!w.ext_c[i]) { for (int q = 0; q < 6; q++) w.canon_of_dev[w.ext_col[i] + q] = cc + q; cc += 6; }
+      if (w.td_col >= 0) w.canon_of_dev[w.td_col] = cc++;
+      for (int i = 0; i < nsb; i++) if (!w.sb_c[i]) { for (int q = 0; q < 9; q++) w.canon_of_dev[w.sb_col[i] + q] = cc + q; cc += 9; }
+    }
     d.td_col = w.td_col; d.n_lc = w.n_lc; d.n_c = w.n_c; d.ldh = std::max(4, roundup(w.n_c, 4));
     d.ldw = roundup(w.n_lc + 1, 8); d.nl_pad = roundup(nl, 32);
     d.admm_on = w.admm ? 1 : 0; d.n_imu = (int)w.imu.size();
@@ -784,6 +889,16 @@ int d2ba_finalize(d2ba_handle *h) {
     }
     w.order.resize(M); w.sorted_pos.assign(M, -1);
     for (size_t k = 0; k < M; k++) w.order[k] = (int)keys[k].second;
+    // Hcc pattern (lower triangle, block rows): rows[r] collects the [c0, c1) runs some factor writes
+    std::vector<std::vector<std::pair<int, int>>> hrows(w.n_c);
+    auto hblock = [&](int ra, int rs, int ca, int cs) {
+      if (ra < 0 || ca < 0) return;
+      if (ra < ca) { std::swap(ra, ca); std::swap(rs, cs); }
+      for (int r = 0; r < rs; r++) hrows[ra + r].push_back({ca, ca + cs});
+    };
+    // landmark masks: W-space column tiles (32 columns) a landmark's coupling row touches; the rhs column n_lc always
+    pl.lm_mask.assign(nl, 1ull << (w.n_lc / 32));
+    auto mark = [&](int lm, int col, int width) { if (col >= 0) pl.lm_mask[lm] |= (1ull << (col / 32)) | (1ull << ((col + width - 1) / 32)); };
     bool any_wide = false;
     size_t k = 0; int tile_run = 0;
     while (k < M) {
@@ -813,6 +928,17 @@ int d2ba_finalize(d2ba_handle *h) {
       const int cnt = (int)(e - k), ntile = (cnt + kTile - 1) / kTile;
       const int gi = (int)pl.groups.size();
       pl.groups.push_back(g); pl.grp_begin.push_back((int)k); pl.grp_cnt.push_back(cnt); pl.grp_tile0.push_back(tile_run);
+      // pattern of the group's J^T J blocks and of its landmarks' coupling rows
+      for (int a = 0; a < ns; a++) {
+        for (int b = 0; b <= a; b++) hblock(g.slot_col[a], 6, g.slot_col[b], 6);
+        if (g.td_col >= 0) hblock(g.td_col, 1, g.slot_col[a], 6);
+      }
+      if (g.td_col >= 0) hblock(g.td_col, 1, g.td_col, 1);
+      for (size_t q = k; q < e; q++) {
+        const int lm = w.obs[w.order[q]].lm;
+        for (int a = 0; a < ns; a++) mark(lm, g.slot_col[a], 6);
+        mark(lm, g.td_col, 1);
+      }
       // balanced split of the group's tiles into jobs
       const int njob = (ntile + tpj_target - 1) / tpj_target;
       for (int j = 0; j < njob; j++) {
@@ -824,41 +950,121 @@ int d2ba_finalize(d2ba_handle *h) {
       k = e;
     }
     pl.n_tiles = tile_run; d.n_tile = tile_run; d.n_grp = (int)pl.groups.size();
+    {   // landmarks of every leaf (ascending, each once) and the widest coupling row in 32-column tiles
+      pl.leaf_lm.clear();
+      std::vector<std::vector<int>> per_leaf(pl.leaves.size());
+      if (!pl.leaves.empty()) {
+        std::vector<int> last_leaf_of_lm(nl, -1);   // landmark-major obs order is not given: dedupe per (landmark, leaf) with a stamp matrix
+        std::vector<char> seen((size_t)nl * pl.leaves.size(), 0);
+        for (const HObs &o : w.obs) {
+          const int ps[2] = {o.pi, o.pj};
+          for (int q = 0; q < 2; q++) if (ps[q] >= 0 && leaf_of[ps[q]] >= 0) {
+            char &sn = seen[(size_t)o.lm * pl.leaves.size() + leaf_of[ps[q]]];
+            if (!sn) { sn = 1; per_leaf[leaf_of[ps[q]]].push_back(o.lm); }
+          }
+        }
+        (void)last_leaf_of_lm;
+      }
+      for (size_t li = 0; li < pl.leaves.size(); li++) {
+        std::sort(per_leaf[li].begin(), per_leaf[li].end());
+        pl.leaves[li].lm_begin = (int)pl.leaf_lm.size(); pl.leaves[li].lm_count = (int)per_leaf[li].size();
+        pl.leaf_lm.insert(pl.leaf_lm.end(), per_leaf[li].begin(), per_leaf[li].end());
+      }
+      int rt = 1;
+      if (pl.leaves.empty()) rt = w.n_lc / 32 + 1;
+      else for (int l = 0; l < nl; l++) rt = std::max(rt, __builtin_popcountll(pl.lm_mask[l]));
+      d.row_tiles = rt;
+    }
     d.rec_stride = any_wide ? 32 : 16;
     pl.n_lmobs = (int)M;
     d.schur_small = (d.n_lc + 1 <= 96) ? 1 : 0;
-    {   // speed-bias elimination: needs a block-tridiagonal speed-bias part (IMU factors / prior blocks only between
-        // neighbouring speed-bias blocks)
-      std::vector<int> pos(nsb, -1);
-      int nb = 0;
-      for (int i = 0; i < nsb; i++) if (w.sb_col[i] >= 0) pos[i] = nb++;
-      bool ok = !h->force_full_S && !h->no_sb_elim && nb >= 1 && d.n_lc >= 1 && w.n_c == w.n_lc + 9 * nb;
-      for (size_t a = 0; a < w.imu.size() && ok; a++) {
-        const int pa = pos[w.imu[a].si], pb = pos[w.imu[a].sj];
-        if (pa >= 0 && pb >= 0 && std::abs(pa - pb) > 1) ok = false;
-      }
-      int pmin = 1 << 30, pmax = -1;
-      for (const HPriorBlk &b : w.prior_blk) if (b.kind == D2BA_SPEED_BIAS && pos[b.index] >= 0) { pmin = std::min(pmin, pos[b.index]); pmax = std::max(pmax, pos[b.index]); }
-      if (pmax - pmin > 1) ok = false;
-      if (ok && (sb_elim_smem(d.ldw, d.n_c, nb) > (size_t)200 * 1024 || nb > sb_max_blocks() || sb_back_smem(d.n_lc, nb) > (size_t)200 * 1024)) ok = false;
-      d.sb_elim = ok ? 1 : 0; d.n_sbe = nb;
-      // the dense Cholesky only sees the pose part then: decide its kernel with that size
-      if (ok) d.chol_smem = (chol_smem_need(d.n_lc) <= (size_t)232448 - 16) ? 1 : 0;
-      d.wt_rows = ok ? roundup(nl + 9 * nb, 32) : d.nl_pad;   // the eliminated rows start right after the last landmark row
+    d.hub_small = (d.n_leaf > 0 && d.n_hub + 1 <= 96) ? 1 : 0;
+    {
+      const int nb = d.n_sbe;
+      const int hubw = roundup(d.n_hub + 1, 8);
+      bool ok = sb_ok && w.n_c == w.n_lc + 9 * nb;
+      if (ok && (sb_elim_smem(hubw, d.n_c, nb) > (size_t)200 * 1024 || sb_back_smem(d.n_hub, nb) > (size_t)200 * 1024)) ok = false;
+      if (!ok && d.n_leaf > 0 && nb > 0) { h->err = "internal: leaves without speed-bias elimination"; }
+      d.sb_elim = ok ? 1 : 0;
+      // the dense Cholesky only sees the hub of the pose part then: decide its kernel with that size
+      if (ok || d.n_leaf > 0) d.chol_smem = (chol_smem_need(d.n_hub) <= (size_t)232448 - 16) ? 1 : 0;
+      // rows of Wt the Schur kernels sum over: landmark rows, then the eliminated speed-bias rows, then the leaves' rows
+      int rows = nl + (ok ? 9 * nb : 0);
+      for (Leaf &lf : pl.leaves) { lf.row0 = rows; rows += lf.n; }
+      d.wt_rows = roundup(std::max(rows, 1), 32);
     }
+    // other Hcc blocks: IMU factors, prior, ADMM terms
+    for (const HImu &m : w.imu) {
+      const int bc[4] = {w.pose_col[m.pi], w.sb_col[m.si], w.pose_col[m.pj], w.sb_col[m.sj]}, bs[4] = {6, 9, 6, 9};
+      for (int a = 0; a < 4; a++) for (int b = 0; b <= a; b++) hblock(bc[a], bs[a], bc[b], bs[b]);
+    }
+    {
+      std::vector<std::pair<int, int>> pb;
+      for (const HPriorBlk &b : w.prior_blk) {
+        int col = b.kind == D2BA_POSE ? w.pose_col[b.index] : b.kind == D2BA_EXTRINSIC ? w.ext_col[b.index] : b.kind == D2BA_SPEED_BIAS ? w.sb_col[b.index] : b.kind == D2BA_TD ? w.td_col : -1;
+        if (col >= 0) pb.push_back({col, b.eff});
+      }
+      for (size_t a = 0; a < pb.size(); a++) for (size_t b = 0; b <= a; b++) hblock(pb[a].first, pb[a].second, pb[b].first, pb[b].second);
+    }
+    if (w.admm) {
+      for (int i = 0; i < np; i++) if (w.pose_slot[i] >= 0) hblock(w.pose_col[i], 6, w.pose_col[i], 6);
+      for (int i = 0; i < ne; i++) if (w.ext_slot[i] >= 0) hblock(w.ext_col[i], 6, w.ext_col[i], 6);
+      for (int i = 0; i < nsb; i++) hblock(w.sb_col[i], 9, w.sb_col[i], 9);
+      if (w.td_col >= 0) hblock(w.td_col, 1, w.td_col, 1);
+    }
+    pl.hseg.clear();
+    for (int r = 0; r < w.n_c; r++) {
+      auto &v = hrows[r];
+      if (v.empty()) continue;
+      std::sort(v.begin(), v.end());
+      int a = v[0].first, bnd = v[0].second;
+      for (size_t q = 1; q <= v.size(); q++) {
+        if (q < v.size() && v[q].first <= bnd) { bnd = std::max(bnd, v[q].second); continue; }
+        pl.hseg.push_back(HSeg{r, a, std::min(bnd, r + 1) - a});   // lower triangle only
+        if (q < v.size()) { a = v[q].first; bnd = v[q].second; }
+      }
+    }
+    d.n_hseg = (int)pl.hseg.size();
     if (!d.schur_small) {
-      int ntw = (d.n_lc + 1 + 31) / 32;
-      if (d.n_lc > 0) for (int tm = 0; tm < ntw; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 0, tm, tn});
+      // ---- Schur tiles with their 32-row chunk lists.  A chunk of Wt rows takes part in tile (tm, tn) iff some row of it
+      //      has entries in both column tiles.  Stage 0 = tiles with leaf columns (computed before the leaf elimination,
+      //      landmark rows only), stage 1 = tiles of the hub x hub part (after it: landmark rows + all eliminated rows).
+      const int ntw = (d.n_lc + 1 + 31) / 32, nchunk = d.wt_rows / 32;
+      std::vector<unsigned long long> cmask(nchunk, 0ull);
+      for (int l = 0; l < nl; l++) cmask[l / 32] |= pl.lm_mask[l];
+      unsigned long long hubmask = 0ull;
+      for (int t = d.hub0 / 32; t <= d.n_lc / 32; t++) hubmask |= 1ull << t;
+      const int first_elim_row = nl;
+      for (int r = nl; r < d.wt_rows; r++) cmask[r / 32] |= hubmask;   // eliminated rows (and the zero padding): hub columns + rhs
+      const int lm_chunks = (nl + 31) / 32;
+      (void)first_elim_row;
+      // tile pattern of Hcc (a tile without chunks still copies Hcc into S)
+      std::vector<char> hpat((size_t)ntw * ntw, 0);
+      for (const HSeg &sg : pl.hseg) if (sg.row < d.n_lc) for (int cidx = sg.c0; cidx < sg.c0 + sg.len; cidx += 1) { hpat[(size_t)(sg.row / 32) * ntw + cidx / 32] = 1; }
+      for (int stage = 0; stage < 2; stage++)
+        for (int tm = 0; tm < ntw && d.n_lc > 0; tm++)
+          for (int tn = 0; tn <= tm; tn++) {
+            const bool in_hub = (tm * 32 + 31 >= d.hub0) && (tn * 32 + 31 >= d.hub0);
+            const bool has_leaf = tn * 32 < d.hub0;
+            if (stage == 0 ? !has_leaf : (!in_hub || d.hub_small)) continue;   // hub_small: k_schur_small forms the hub x hub part
+            SchurTileH t{wi, stage == 0 ? 2 : 0, tm, tn, (int)pl.schur_chunks.size(), 0};   // kind 2: only entries in leaf columns are stored
+            const int kend = stage == 0 ? lm_chunks : nchunk;
+            for (int kc = 0; kc < kend; kc++) if (((cmask[kc] >> tm) & 1ull) && ((cmask[kc] >> tn) & 1ull)) pl.schur_chunks.push_back(kc);
+            t.cn = (int)pl.schur_chunks.size() - t.cb;
+            if (t.cn == 0 && !hpat[(size_t)tm * ntw + tn] && tm != ntw - 1) continue;   // structurally zero tile: never read
+            pl.schur[stage].push_back(t);
+          }
       int t_lo = d.n_lc / 32, t_hi = d.n_c / 32;
-      for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur.push_back({wi, 1, tm, tn});
+      if (!d.sb_elim) for (int tm = t_lo; tm <= t_hi; tm++) for (int tn = 0; tn <= tm; tn++) pl.schur[1].push_back(SchurTileH{wi, 1, tm, tn, 0, 0});
     }
   });
   lap(0);
   // ---- serial prefix sums
   h->n_used = nw; h->max_rows = 1; h->max_nc = 1; h->max_prior_m = 0; h->max_ldw = 8; h->n_slots = 0; h->any_admm = false;
-  h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0; h->any_compact = h->any_wide = 0; h->sbe_smem = 0; h->sbb_smem = 0;
+  h->max_row_tiles = 1; h->max_n_smem = 0; h->max_rows_glob = 1; h->any_chol_glob = false; h->max_ldw_small = 0; h->any_compact = h->any_wide = 0; h->sbe_smem = 0; h->sbb_smem = 0;
   int64_t offLE = 0;
-  int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0;
+  int off6 = 0, offsb = 0, offlm = 0, off_tile = 0, off_grp = 0, off_imu = 0, off_lmptr = 0, off_pblk = 0, n_schur = 0, n_sch[2] = {0, 0}, n_chunks = 0, off_leaf = 0, off_hseg = 0, n_leaf_lm = 0;
+  int64_t offLL = 0; size_t leaf_smem = 0, leafb_smem = 0; int max_hub = 0;
   int64_t offH = 0, offW = 0, offc = 0, off_lmobs = 0, off_pJ = 0, off_pv = 0, off_rec = 0; long long off_raw = 0;
   int njobs[6] = {0, 0, 0, 0, 0, 0};
   bool any_info = false;
@@ -874,16 +1080,24 @@ int d2ba_finalize(d2ba_handle *h) {
     d.offW = offW; offW += (int64_t)std::max(d.wt_rows, 32) * d.ldw;
     d.offc = offc; offc += roundup(d.n_c + 1, 4);
     for (int v = 0; v < 6; v++) { pl.job_off[v] = njobs[v]; njobs[v] += (int)pl.jobs[v].size(); }
-    pl.schur_off = n_schur; n_schur += (int)pl.schur.size();
+    for (int sg = 0; sg < 2; sg++) { pl.schur_off[sg] = n_sch[sg]; n_sch[sg] += (int)pl.schur[sg].size(); }
+    pl.chunk_off = n_chunks; n_chunks += (int)pl.schur_chunks.size();
+    pl.leaf_lm_off = n_leaf_lm; n_leaf_lm += (int)pl.leaf_lm.size();
+    h->max_row_tiles = std::max(h->max_row_tiles, d.row_tiles);
+    d.off_leaf = off_leaf; off_leaf += d.n_leaf; d.off_hseg = off_hseg; off_hseg += d.n_hseg;
+    for (Leaf &lf : pl.leaves) { lf.offL = offLL; offLL += (int64_t)lf.n * lf.n + lf.n; leaf_smem = std::max(leaf_smem, leaf_elim_smem(lf.n, d.n_hub)); leafb_smem = std::max(leafb_smem, leaf_back_smem(lf.n, d.n_hub)); }
+    max_hub = std::max(max_hub, d.n_hub);
     h->max_rows = std::max(h->max_rows, d.n_c + 1); h->max_nc = std::max(h->max_nc, d.n_c); h->max_ldw = std::max(h->max_ldw, d.ldw);
     h->max_prior_m = std::max(h->max_prior_m, d.prior_m);
     if (d.schur_small) h->max_ldw_small = std::max(h->max_ldw_small, d.ldw);
+    if (d.hub_small) h->max_ldw_small = std::max(h->max_ldw_small, roundup(d.n_hub + 1, 8));
     if (d.rec_stride == 16) h->any_compact = 1; else h->any_wide = 1;
     if (d.sb_elim) {
       d.offLE = offLE; offLE += (int64_t)d.n_sbe * 171;
-      h->sbe_smem = std::max(h->sbe_smem, sb_elim_smem(d.ldw, d.n_c, d.n_sbe)); h->sbb_smem = std::max(h->sbb_smem, sb_back_smem(d.n_lc, d.n_sbe));
+      h->sbe_smem = std::max(h->sbe_smem, sb_elim_smem(roundup(d.n_hub + 1, 8), d.n_c, d.n_sbe)); h->sbb_smem = std::max(h->sbb_smem, sb_back_smem(d.n_hub, d.n_sbe));
     }
-    if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, d.sb_elim ? d.n_lc : d.n_c); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, (d.sb_elim ? d.n_lc : d.n_c) + 1); }
+    { const int ndense = (d.sb_elim || d.n_leaf > 0) ? d.n_hub : d.n_c;
+      if (d.chol_smem) h->max_n_smem = std::max(h->max_n_smem, ndense); else { h->any_chol_glob = true; h->max_rows_glob = std::max(h->max_rows_glob, ndense + 1); } }
     if (w.admm) {
       if (h->any_admm && h->n_slots != w.n_slots) return fail(h, 26, "finalize: every window of a handle must name the same n_slots_global (the all-reduce count)");
       h->any_admm = true; h->n_slots = w.n_slots;
@@ -892,7 +1106,8 @@ int d2ba_finalize(d2ba_handle *h) {
   }
   int jbase[6]; { int r = 0; for (int v = 0; v < 6; v++) { jbase[v] = r; h->job_begin[v] = r; h->job_count[v] = njobs[v]; r += njobs[v]; } }
   const int n_jobs = jbase[5] + njobs[5];
-  h->n6_total = off6; h->nsb_total = offsb; h->nl_total = offlm; h->n_tiles = off_tile; h->n_imu_total = off_imu; h->n_schur = n_schur;
+  h->n6_total = off6; h->nsb_total = offsb; h->nl_total = offlm; h->n_tiles = off_tile; h->n_imu_total = off_imu; n_schur = n_sch[0] + n_sch[1]; h->n_schur = n_schur; h->n_schur0 = n_sch[0];
+  h->n_leaf_total = off_leaf; h->leaf_smem = leaf_smem; h->leafb_smem = leafb_smem; h->max_hub = max_hub;
   h->totH = offH; h->totW = offW; h->totc = offc; h->totLE = offLE;
   // ---- staging sizes
   st.cursor = 0;
@@ -901,14 +1116,14 @@ int d2ba_finalize(d2ba_handle *h) {
   st.reserve(st.lm_win, offlm); st.reserve(st.tile_grp, off_tile); st.reserve(st.tile_win, off_tile); st.reserve(st.obs_lm, (size_t)off_tile * kTile);
   st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, 2 * (size_t)nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.obs_slot, (size_t)off_tile * kTile);
   st.reserve(st.grp, off_grp); st.reserve(st.job, n_jobs); st.reserve(st.imu, off_imu); st.reserve(st.imu_c, (size_t)off_imu * kImuStride);
-  st.reserve(st.pblk, off_pblk); st.reserve(st.prior_J, (size_t)off_pJ); st.reserve(st.prior_e0, (size_t)off_pv); st.reserve(st.schur, n_schur);
+  st.reserve(st.pblk, off_pblk); st.reserve(st.prior_J, (size_t)off_pJ); st.reserve(st.prior_e0, (size_t)off_pv); st.reserve(st.schur, n_schur); st.reserve(st.schur_chunks, n_chunks); st.reserve(st.leaf, off_leaf); st.reserve(st.hseg, off_hseg); st.reserve(st.lm_mask, offlm); st.reserve(st.leaf_lm, n_leaf_lm);
   st.reserve(st.pr_m, nw); st.reserve(st.pr_info, nw); st.reserve(st.pr_offJ, nw); st.reserve(st.pr_offv, nw);
   bool ok = st.arena.resize(st.cursor + 256);
   if (ok) {
     st.place(st.win); st.place(st.x6); st.place(st.xsb); st.place(st.xlm); st.place(st.xtd); st.place(st.col6); st.place(st.colsb); st.place(st.slot6);
     st.place(st.blk_win); st.place(st.sb_win); st.place(st.lm_win); st.place(st.tile_grp); st.place(st.tile_win); st.place(st.obs_lm); st.place(st.tile_src);
     st.place(st.raw_off); st.place(st.lm_ptr); st.place(st.obs_slot); st.place(st.grp); st.place(st.job); st.place(st.imu); st.place(st.imu_c); st.place(st.pblk);
-    st.place(st.prior_J); st.place(st.prior_e0); st.place(st.schur); st.place(st.pr_m); st.place(st.pr_info); st.place(st.pr_offJ); st.place(st.pr_offv);
+    st.place(st.prior_J); st.place(st.prior_e0); st.place(st.schur); st.place(st.schur_chunks); st.place(st.leaf); st.place(st.hseg); st.place(st.lm_mask); st.place(st.leaf_lm); st.place(st.pr_m); st.place(st.pr_info); st.place(st.pr_offJ); st.place(st.pr_offv);
   }
   if (!ok) return fail(h, 24, "pinned staging allocation failed");
   lap(1);
@@ -963,7 +1178,13 @@ int d2ba_finalize(d2ba_handle *h) {
         Job jb = pl.jobs[v][j]; jb.grp += d.off_grp; jb.tile_begin += d.off_tile;
         st.job.p[jbase[v] + pl.job_off[v] + j] = jb;
       }
-    for (size_t t = 0; t < pl.schur.size(); t++) st.schur.p[pl.schur_off + t] = pl.schur[t];
+    for (int sg = 0; sg < 2; sg++)
+      for (size_t t = 0; t < pl.schur[sg].size(); t++) { SchurTileH q = pl.schur[sg][t]; q.cb += pl.chunk_off; st.schur.p[(sg ? n_sch[0] : 0) + pl.schur_off[sg] + t] = q; }
+    for (size_t t = 0; t < pl.schur_chunks.size(); t++) st.schur_chunks.p[pl.chunk_off + t] = pl.schur_chunks[t];
+    for (size_t t = 0; t < pl.leaves.size(); t++) { Leaf lf = pl.leaves[t]; lf.lm_begin += pl.leaf_lm_off; st.leaf.p[d.off_leaf + t] = lf; }
+    for (size_t t = 0; t < pl.leaf_lm.size(); t++) st.leaf_lm.p[pl.leaf_lm_off + t] = pl.leaf_lm[t];
+    for (size_t t = 0; t < pl.hseg.size(); t++) st.hseg.p[d.off_hseg + t] = pl.hseg[t];
+    for (int l = 0; l < d.nl; l++) st.lm_mask.p[d.offlm + l] = pl.lm_mask[l];
     for (int i = 0; i < d.n_imu; i++) {
       const HImu &m = w.imu[i];
       st.imu.p[d.off_imu + i] = ImuDesc{m.pi, m.si, m.pj, m.sj};
@@ -1008,6 +1229,7 @@ int d2ba_finalize(d2ba_handle *h) {
   for (int b = 0; b < 2; b++) {
     CK(h->d_R6[b].alloc((size_t)off6 * 12)); CK(h->d_rec[b].alloc(rec_doubles));
     CK(h->d_H[b].alloc((size_t)offH)); CK(h->d_gc[b].alloc((size_t)offc));
+    CK(cudaMemsetAsync(h->d_H[b].p, 0, std::max<size_t>((size_t)offH, 1) * 8, h->stream));   // entries no factor writes stay zero
   }
   if ((rc = up(h, h->d_col6, st.col6)) || (rc = up(h, h->d_colsb, st.colsb)) || (rc = up(h, h->d_tile_grp, st.tile_grp)) ||
       (rc = up(h, h->d_tile_win, st.tile_win)) || (rc = up(h, h->d_obs_lm, st.obs_lm)) || (rc = up(h, h->d_tile_src, st.tile_src)) ||
@@ -1015,7 +1237,8 @@ int d2ba_finalize(d2ba_handle *h) {
       (rc = up(h, h->d_lm_win, st.lm_win)) || (rc = up(h, h->d_blk_win, st.blk_win)) || (rc = up(h, h->d_sb_win, st.sb_win)) ||
       (rc = up(h, h->d_grp, st.grp)) || (rc = up(h, h->d_job, st.job)) || (rc = up(h, h->d_imu, st.imu)) || (rc = up(h, h->d_imu_c, st.imu_c)) ||
       (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
-      (rc = up(h, h->d_schur, st.schur)))
+      (rc = up(h, h->d_schur, st.schur)) || (rc = up(h, h->d_schur_chunks, st.schur_chunks)) || (rc = up(h, h->d_leaf, st.leaf)) || (rc = up(h, h->d_leaf_lm, st.leaf_lm)) ||
+      (rc = up(h, h->d_hseg, st.hseg)) || (rc = up(h, h->d_lm_mask, st.lm_mask)))
     return rc;
   // the device builds the tiles from the raw records
   CK(h->d_obs.alloc((size_t)off_tile * kTile * kObsFields));
@@ -1029,7 +1252,9 @@ int d2ba_finalize(d2ba_handle *h) {
   CK(h->d_td_ref.alloc(nw));
   if ((rc = alloc_zero(h, h->d_cons, (size_t)std::max(h->n_slots, 1) * 14))) return rc;
   if ((rc = alloc_zero(h, h->d_Wt, (size_t)offW))) return rc;   // padding rows / columns must be zero
-  CK(h->d_dinv.alloc(offlm)); CK(h->d_hl.alloc(offlm)); CK(h->d_gl.alloc(offlm)); CK(h->d_S.alloc((size_t)offH));
+  CK(h->d_dinv.alloc(offlm)); CK(h->d_hl.alloc(offlm)); CK(h->d_gl.alloc(offlm));
+  if ((rc = alloc_zero(h, h->d_S, (size_t)offH))) return rc;   // tiles outside the structural pattern are never written
+  CK(h->d_leafL.alloc((size_t)std::max<int64_t>(offLL, 1)));
   CK(h->d_gred.alloc((size_t)offc)); CK(h->d_D2c.alloc((size_t)offc)); CK(h->d_gn_c.alloc((size_t)offc)); CK(h->d_gn_l.alloc(offlm));
   CK(h->d_sbLE.alloc((size_t)std::max<int64_t>(offLE, 1)));
   CK(h->d_step_c.alloc((size_t)offc)); CK(h->d_step_l.alloc(offlm)); CK(h->d_wu.alloc(offlm)); CK(h->d_uc.alloc((size_t)offc)); CK(h->d_D2l.alloc(offlm));
@@ -1039,6 +1264,7 @@ int d2ba_finalize(d2ba_handle *h) {
   D.win = h->d_win.p; D.ctl = h->d_ctl.p; D.n_win = nw;
   for (int b = 0; b < 2; b++) { D.x6[b] = h->d_x6[b].p; D.R6[b] = h->d_R6[b].p; D.xsb[b] = h->d_xsb[b].p; D.xlm[b] = h->d_xlm[b].p; D.xtd[b] = h->d_xtd[b].p; D.rec[b] = h->d_rec[b].p; D.Hcc[b] = h->d_H[b].p; D.gc[b] = h->d_gc[b].p; }
   D.col6 = h->d_col6.p; D.colsb = h->d_colsb.p; D.grp = h->d_grp.p; D.job = h->d_job.p; D.n_job = n_jobs;
+  D.lm_mask = h->d_lm_mask.p; D.hseg = h->d_hseg.p; D.leaf = h->d_leaf.p; D.n_leaf_total = h->n_leaf_total; D.leafL = h->d_leafL.p; D.schur_chunks = h->d_schur_chunks.p; D.leaf_lm = h->d_leaf_lm.p;
   D.tile_grp = h->d_tile_grp.p; D.obs = h->d_obs.p; D.obs_lm = h->d_obs_lm.p; D.lm_ptr = h->d_lm_ptr.p; D.obs_slot = h->d_obs_slot.p;
   D.imu = h->d_imu.p; D.imu_c = h->d_imu_c.p; D.imu_U = h->d_imu_U.p; D.prior_blk = h->d_prior_blk.p; D.prior_J = h->d_prior_J.p;
   D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
@@ -1052,13 +1278,13 @@ int d2ba_finalize(d2ba_handle *h) {
   P.initial_radius = h->cfg.initial_trust_region_radius; P.max_radius = h->cfg.max_trust_region_radius; P.min_rel_decrease = h->cfg.min_relative_decrease;
   P.ftol = h->cfg.function_tolerance; P.gtol = h->cfg.gradient_tolerance; P.ptol = h->cfg.parameter_tolerance;
   P.max_iter = h->cfg.max_num_iterations; P.fixed_mode = 0; P.mu0 = h->mu0;
-  if (h->cfg_max_rows != h->max_rows || h->cfg_max_nc != h->max_nc || h->cfg_max_prior != h->max_prior_m) {
-    if (configure_kernels(h->max_rows, h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
-    h->cfg_max_rows = h->max_rows; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
+  if (h->cfg_max_rows != h->max_rows_glob || h->cfg_max_nc != h->max_nc || h->cfg_max_prior != h->max_prior_m) {
+    if (configure_kernels(std::max(h->max_rows_glob, 2), h->max_nc, h->max_prior_m)) return fail(h, 23, "cudaFuncSetAttribute failed (shared memory request too large?)");
+    h->cfg_max_rows = h->max_rows_glob; h->cfg_max_nc = h->max_nc; h->cfg_max_prior = h->max_prior_m;
   }
-  if (h->cfg_max_ldw < h->max_ldw) {
-    if (configure_gather(h->max_ldw)) return fail(h, 23, "cudaFuncSetAttribute(k_lm_gather) failed (landmark-coupled part too wide for the row buffers)");
-    h->cfg_max_ldw = h->max_ldw;
+  if (h->cfg_max_ldw < h->max_row_tiles * 32) {
+    if (configure_gather(h->max_row_tiles * 32)) return fail(h, 23, "cudaFuncSetAttribute(k_lm_gather) failed (landmark-coupled part too wide for the row buffers)");
+    h->cfg_max_ldw = h->max_row_tiles * 32;
   }
   if (h->max_ldw_small > 0 && h->cfg_max_ldw_small != h->max_ldw_small) {
     if (configure_schur_small(h->max_ldw_small)) return fail(h, 23, "cudaFuncSetAttribute(k_schur_small) failed");
@@ -1071,6 +1297,14 @@ int d2ba_finalize(d2ba_handle *h) {
   if (h->sbb_smem > 0 && h->cfg_sbb_smem < h->sbb_smem) {
     if (configure_sb_back(h->sbb_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_sb_back) failed");
     h->cfg_sbb_smem = h->sbb_smem;
+  }
+  if (h->leaf_smem > 0 && h->cfg_leaf_smem < h->leaf_smem) {
+    if (configure_leaf_elim(h->leaf_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_leaf_elim) failed");
+    h->cfg_leaf_smem = h->leaf_smem;
+  }
+  if (h->leafb_smem > 0 && h->cfg_leafb_smem < h->leafb_smem) {
+    if (configure_leaf_back(h->leafb_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_leaf_back) failed");
+    h->cfg_leafb_smem = h->leafb_smem;
   }
   if (h->max_n_smem > 0 && h->cfg_max_n_smem != h->max_n_smem) {
     if (configure_chol_smem(h->max_n_smem)) return fail(h, 23, "cudaFuncSetAttribute(k_chol_smem) failed");
@@ -1141,14 +1375,27 @@ static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
   for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, eval_cur, h->job_begin[v], h->job_count[v], h->stream);
 }
 
-static void enqueue_iteration(d2ba_handle *h) {
-  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
-  if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);   // Y rows into Wt: the Schur kernels subtract them too
+// reduced camera system: tiles with leaf columns -> leaf elimination (rows Y behind the landmark rows of Wt) -> hub tiles
+static void enqueue_schur(d2ba_handle *h) {
+  // (the leaf kernel forms its own part of the reduced system from Hcc and its landmarks' rows: the stage-0 tiles are
+  //  only launched for the debug view of S)
+  if (h->n_leaf_total > 0) launch_leaf_elim(h->dev, h->leaf_smem, h->stream);
   if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
-  launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+  if (h->n_schur > h->n_schur0) launch_schur(h->dev, h->d_schur.p + h->n_schur0, h->n_schur - h->n_schur0, h->stream);
+}
+// dense Cholesky of the hub, then the eliminated parts' back substitutions
+static void enqueue_solve_reduced(d2ba_handle *h) {
   if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
-  if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
+  if (h->any_chol_glob) launch_chol(h->dev, h->max_rows_glob, h->stream);
   if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
+  if (h->n_leaf_total > 0) launch_leaf_back(h->dev, h->leafb_smem, h->stream);
+}
+
+static void enqueue_iteration(d2ba_handle *h) {
+  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_row_tiles * 32, h->any_compact, h->any_wide, h->stream);
+  if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);   // Y rows into Wt: the Schur kernels subtract them too
+  enqueue_schur(h);
+  enqueue_solve_reduced(h);
   launch_step(h->dev, h->max_nc, h->stream);
   enqueue_linearize(h, 0);
   launch_control(h->dev, 0, h->stream);
@@ -1183,7 +1430,19 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
   CK(cudaEventRecord(h->ev0, h->stream));
   launch_tr_reset(h->dev, 1, h->stream);
   if (h->any_admm) launch_cons_init(h->dev, h->n6_total, h->stream);
+  // ceres max_solver_time_in_seconds: an iteration is only started while the budget of this (sub-)step lasts.  The
+  // iterations are enqueued asynchronously, so the host trails the device by at most two of them: before enqueuing
+  // iteration k it waits for iteration k-2 and compares the wall clock.
+  const double budget_s = (!fixed && h->cfg.max_solver_time_in_seconds > 0) ? h->cfg.max_solver_time_in_seconds / steps : 0.0;
+  std::chrono::steady_clock::time_point t_step0;
+  auto over_budget = [&](int it) {
+    if (budget_s <= 0.0 || it < 2) return false;
+    cudaEventSynchronize(h->ev_it[it & 1]);   // recorded after iteration it-2
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_step0).count() > budget_s;
+  };
+  auto mark = [&](int it) { if (budget_s > 0.0) cudaEventRecord(h->ev_it[it & 1], h->stream); };
   for (int st = 0; st < steps; st++) {
+    t_step0 = std::chrono::steady_clock::now();
     if (st > 0) launch_tr_reset(h->dev, 0, h->stream);
     if (h->any_admm) { int rc = consensus_exchange(h); if (rc) return rc; }
     enqueue_linearize(h, 1);
@@ -1200,9 +1459,9 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
         cudaGraphDestroy(g);
         h->graph_key = key;
       }
-      for (int it = 0; it < iters; it++) CK(cudaGraphLaunch(h->iter_graph, h->stream));
+      for (int it = 0; it < iters; it++) { if (over_budget(it)) break; CK(cudaGraphLaunch(h->iter_graph, h->stream)); mark(it); }
     } else {
-      for (int it = 0; it < iters; it++) enqueue_iteration(h);
+      for (int it = 0; it < iters; it++) { if (over_budget(it)) break; enqueue_iteration(h); mark(it); }
     }
   }
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -1224,7 +1483,12 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
   for (auto &w : h->win) {
     if (!w.used) continue;
     const WinDesc &d = h->h_win[wi]; const int cur = h->h_ctl.p[wi].cur;
-    for (int i = 0; i < d.np; i++) memcpy(&w.pose[7 * i], &h->h_x6[cur].p[(size_t)(d.off6 + i) * 8], 56);
+    double chg2 = 0.0;
+    for (int i = 0; i < d.np; i++) {
+      const double *xn = &h->h_x6[cur].p[(size_t)(d.off6 + i) * 8];
+      for (int q = 0; q < 3; q++) { const double dq = xn[q] - w.pose[7 * i + q]; chg2 += dq * dq; }
+      memcpy(&w.pose[7 * i], xn, 56);
+    }
     for (int i = 0; i < d.ne; i++) memcpy(&w.ext[7 * i], &h->h_x6[cur].p[(size_t)(d.off6 + d.np + i) * 8], 56);
     if (d.nsb) memcpy(w.sb.data(), &h->h_xsb[cur].p[(size_t)d.offsb * 9], (size_t)d.nsb * 72);
     if (d.nl) memcpy(w.lm.data(), &h->h_xlm[cur].p[d.offlm], (size_t)d.nl * 8);
@@ -1232,7 +1496,7 @@ static int run_solve(d2ba_handle *h, int fixed_iters, d2ba_report *reports) {
     if (reports) {
       const Ctl &c = h->h_ctl.p[wi]; d2ba_report &r = reports[wi];
       r.total_iterations = c.lin_count; r.successful_steps = c.succ; r.termination = c.term; r.succ = c.term != 4;
-      r.total_time = ms * 1e-3; r.initial_cost = c.initial_cost; r.final_cost = c.cost; r.state_changes = 0;
+      r.total_time = ms * 1e-3; r.initial_cost = c.initial_cost; r.final_cost = c.cost; r.state_changes = sqrt(chg2);
       r.final_gradient_max_norm = c.gmax_c; r.final_radius = c.radius;
     }
     wi++;
@@ -1299,21 +1563,19 @@ int d2ba_debug_linearize(d2ba_handle *h) {
   launch_tr_reset(h->dev, 1, h->stream);
   enqueue_linearize(h, 1);
   launch_control(h->dev, 1, h->stream);
-  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
+  launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_row_tiles * 32, h->any_compact, h->any_wide, h->stream);
   // debug view: the landmark-only Schur complement (eliminated speed-bias rows zeroed), kept un-factored in d_dbg
   if (h->sbe_smem > 0) launch_zero_sb_rows(h->dev, h->stream);
+  if (h->n_leaf_total > 0) launch_zero_leaf_rows(h->dev, h->stream);
   if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
-  launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+  launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);   // both stages back to back: no eliminated rows in this view
   CK(h->d_dbg.alloc((size_t)h->totH));
   CK(cudaMemcpyAsync(h->d_dbg.p, h->d_S.p, (size_t)h->totH * 8, cudaMemcpyDeviceToDevice, h->stream));
-  if (h->sbe_smem > 0) {   // now the system the solver factors: Y rows in place, Schur again
-    launch_sb_elim(h->dev, h->sbe_smem, h->stream);
-    if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
-    launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
+  if (h->sbe_smem > 0 || h->n_leaf_total > 0) {   // now the system the solver factors: Y rows in place, Schur again
+    if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);
+    enqueue_schur(h);
   }
-  if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream);
-  if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream);
-  if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
+  enqueue_solve_reduced(h);
   launch_step(h->dev, h->max_nc, h->stream);
   CK(cudaMemcpyAsync(h->h_ctl.p, h->d_ctl.p, sizeof(Ctl) * h->n_used, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1332,23 +1594,25 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
   auto put_d = [&](const std::vector<double> &v) { buf.resize(v.size() * 8); memcpy(buf.data(), v.data(), buf.size()); };
   auto fetch = [&](const double *src, size_t cnt) { std::vector<double> v(cnt); if (cnt) cudaMemcpy(v.data(), src, cnt * 8, cudaMemcpyDeviceToHost); return v; };
   const int cur = h->h_ctl.p[window].cur;
+  const std::vector<int> &cn = w->canon_of_dev;   // device column -> canonical (insertion-order) column
+  auto canon_blk = [&](int c) { return c < 0 ? -1 : cn[c]; };
   switch (item) {
     case D2BA_DBG_N_CAM: { int64_t v = n; buf.resize(8); memcpy(buf.data(), &v, 8); break; }
     case D2BA_DBG_N_LC: { int64_t v = nlc; buf.resize(8); memcpy(buf.data(), &v, 8); break; }
-    case D2BA_DBG_HCC: {
+    case D2BA_DBG_HCC: {   // Hcc is stored lower-triangular in device column order: symmetric, canonical order out
       auto H = fetch(h->d_H[cur].p + d.offH, (size_t)n * ld);
       std::vector<double> o((size_t)n * n);
-      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) o[(size_t)i * n + j] = H[(size_t)i * ld + j];
+      for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { const int a = cn[i], b = cn[j]; o[(size_t)a * n + b] = H[(size_t)i * ld + j]; o[(size_t)b * n + a] = H[(size_t)i * ld + j]; }
       put_d(o); break;
     }
-    case D2BA_DBG_GC: put_d(fetch(h->d_gc[cur].p + d.offc, n)); break;
+    case D2BA_DBG_GC: { auto g = fetch(h->d_gc[cur].p + d.offc, n); std::vector<double> o(n); for (int i = 0; i < n; i++) o[cn[i]] = g[i]; put_d(o); break; }
     case D2BA_DBG_HLL: put_d(fetch(h->d_hl.p + d.offlm, nl)); break;
     case D2BA_DBG_GL: put_d(fetch(h->d_gl.p + d.offlm, nl)); break;
     case D2BA_DBG_W: {
       auto Wt = fetch(h->d_Wt.p + d.offW, (size_t)nl * d.ldw);
       auto di = fetch(h->d_dinv.p + d.offlm, nl);
       std::vector<double> o((size_t)nl * nlc);
-      for (int l = 0; l < nl; l++) for (int c = 0; c < nlc; c++) o[(size_t)l * nlc + c] = Wt[(size_t)l * d.ldw + c] / di[l];
+      for (int l = 0; l < nl; l++) for (int c = 0; c < nlc; c++) o[(size_t)l * nlc + cn[c]] = Wt[(size_t)l * d.ldw + c] / di[l];
       put_d(o); break;
     }
     case D2BA_DBG_COST: { std::vector<double> v(1, h->h_ctl.p[window].cost); put_d(v); break; }
@@ -1367,11 +1631,13 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
           }
       }
       std::vector<double> o((size_t)n * n);
-      for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { o[(size_t)i * n + j] = S[(size_t)i * ld + j]; o[(size_t)j * n + i] = S[(size_t)i * ld + j]; }
+      for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) { const int a = cn[i], b = cn[j]; o[(size_t)a * n + b] = S[(size_t)i * ld + j]; o[(size_t)b * n + a] = S[(size_t)i * ld + j]; }
       put_d(o); break;
     }
     case D2BA_DBG_GN_STEP: case D2BA_DBG_STEP: {
-      auto a = fetch((item == D2BA_DBG_GN_STEP ? h->d_gn_c.p : h->d_step_c.p) + d.offc, n);
+      auto a0 = fetch((item == D2BA_DBG_GN_STEP ? h->d_gn_c.p : h->d_step_c.p) + d.offc, n);
+      std::vector<double> a(n);
+      for (int i = 0; i < n; i++) a[cn[i]] = a0[i];
       auto b = fetch((item == D2BA_DBG_GN_STEP ? h->d_gn_l.p : h->d_step_l.p) + d.offlm, nl);
       a.insert(a.end(), b.begin(), b.end()); put_d(a); break;
     }
@@ -1382,10 +1648,10 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
     }
     case D2BA_DBG_COL_OF_BLOCK: {
       std::vector<int32_t> v;
-      for (int c : w->pose_col) v.push_back(c);
-      for (int c : w->ext_col) v.push_back(c);
-      for (int c : w->sb_col) v.push_back(c);
-      v.push_back(w->td_col);
+      for (int c : w->pose_col) v.push_back(canon_blk(c));
+      for (int c : w->ext_col) v.push_back(canon_blk(c));
+      for (int c : w->sb_col) v.push_back(canon_blk(c));
+      v.push_back(canon_blk(w->td_col));
       buf.resize(v.size() * 4); memcpy(buf.data(), v.data(), buf.size()); break;
     }
     case D2BA_DBG_PROJ_RESJAC: {
@@ -1532,7 +1798,7 @@ int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove, const int
   launch_tr_reset(t->dev, 1, t->stream);
   enqueue_linearize(t, 1);
   launch_control(t->dev, 1, t->stream);
-  launch_lm_gather(t->dev, t->d_lm_win.p, t->nl_total, t->max_ldw, t->any_compact, t->any_wide, t->stream);
+  launch_lm_gather(t->dev, t->d_lm_win.p, t->nl_total, t->max_row_tiles * 32, t->any_compact, t->any_wide, t->stream);
   if (t->max_ldw_small > 0) launch_schur_small(t->dev, t->max_ldw_small, t->stream);
   launch_schur(t->dev, t->d_schur.p, t->n_schur, t->stream);
   // eliminate the removed camera columns
@@ -1573,15 +1839,22 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
   if (h->any_admm) { launch_cons_init(h->dev, h->n6_total, h->stream); int rc = consensus_exchange(h); if (rc) return rc; }
   enqueue_linearize(h, 1);
   launch_control(h->dev, 1, h->stream);
-  cudaEvent_t ev[8], evs[2];
+  cudaEvent_t ev[8], evs[2], evl[3];
+  for (int i = 0; i < 3; i++) cudaEventCreate(&evl[i]);
   for (int i = 0; i < 8; i++) cudaEventCreate(&ev[i]);
   cudaEventCreate(&evs[0]); cudaEventCreate(&evs[1]);
-  for (int i = 0; i < 10; i++) ms_out[i] = 0;
+  for (int i = 0; i < 12; i++) ms_out[i] = 0;
   for (int it = 0; it < iters; it++) {
-    cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_ldw, h->any_compact, h->any_wide, h->stream);
+    cudaEventRecord(ev[0], h->stream); launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_row_tiles * 32, h->any_compact, h->any_wide, h->stream);
     cudaEventRecord(evs[0], h->stream); if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);
-    cudaEventRecord(ev[1], h->stream); if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream); launch_schur(h->dev, h->d_schur.p, h->n_schur, h->stream);
-    cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows, h->stream); cudaEventRecord(evs[1], h->stream); if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
+    cudaEventRecord(ev[1], h->stream);
+    cudaEventRecord(evl[0], h->stream);
+    if (h->n_leaf_total > 0) launch_leaf_elim(h->dev, h->leaf_smem, h->stream);
+    cudaEventRecord(evl[1], h->stream);
+    if (h->max_ldw_small > 0) launch_schur_small(h->dev, h->max_ldw_small, h->stream);
+    if (h->n_schur > h->n_schur0) launch_schur(h->dev, h->d_schur.p + h->n_schur0, h->n_schur - h->n_schur0, h->stream);
+    cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows_glob, h->stream); cudaEventRecord(evs[1], h->stream); if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
+    cudaEventRecord(evl[2], h->stream); if (h->n_leaf_total > 0) launch_leaf_back(h->dev, h->leafb_smem, h->stream);
     cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);
     cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream);
     cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);
@@ -1589,11 +1862,13 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
     cudaEventRecord(ev[7], h->stream);
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < 7; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); ms_out[i] += ms; }
-    { float ms = 0; cudaEventElapsedTime(&ms, evs[0], ev[1]); ms_out[8] += ms; cudaEventElapsedTime(&ms, evs[1], ev[3]); ms_out[9] += ms; }
+    { float ms = 0; cudaEventElapsedTime(&ms, evs[0], ev[1]); ms_out[8] += ms; cudaEventElapsedTime(&ms, evs[1], evl[2]); ms_out[9] += ms;
+      cudaEventElapsedTime(&ms, evl[0], evl[1]); ms_out[10] += ms; cudaEventElapsedTime(&ms, evl[2], ev[3]); ms_out[11] += ms; }
   }
   ms_out[7] = iters;
   for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
   cudaEventDestroy(evs[0]); cudaEventDestroy(evs[1]);
+  for (int i = 0; i < 3; i++) cudaEventDestroy(evl[i]);
   CK(cudaGetLastError());
   h->state_dirty = true;
   return 0;

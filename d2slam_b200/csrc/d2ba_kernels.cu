@@ -233,10 +233,14 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
   const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
   double cost = 0.0;
   bool zeroed = false;
+  // zero only the runs of Hcc some factor writes (lower triangle; the rest stays at the zero of the finalize-time memset)
   auto zero_H = [&](int t0, int tn) {
-    double2 *H2 = reinterpret_cast<double2 *>(H);
-    const size_t tot2 = ((size_t)(n + 1) * ld) / 2;  // ld is a multiple of 4
-    for (size_t e = t0; e < tot2; e += tn) H2[e] = make_double2(0.0, 0.0);
+    const HSeg *sg = d.hseg + w.off_hseg;
+    for (int e = t0; e < w.n_hseg; e += tn) {
+      const HSeg q = sg[e];
+      double *p = H + (size_t)q.row * ld + q.c0;
+      for (int k = 0; k < q.len; k++) p[k] = 0.0;
+    }
     for (int e = t0; e < n; e += tn) g[e] = 0.0;
   };
   for (int f0 = 0; f0 < w.n_imu; f0 += kImuChunk) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
             for (int u = 0; u < 2; u++) {
               const int bo = 8 * tb + 2 * q4 + u;
               const double v = u == 0 ? c0 : c1;
-              if (bo < 30) { const int gb = gcol(bo); if (gb >= 0 && v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }
+              if (bo < 30) { const int gb = gcol(bo); if (gb >= 0 && gb <= ga && v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }   // lower triangle
               else if (bo == 30) atomicAdd(&g[ga], v);
             }
           }
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
     for (int e = tid; e < m * m; e += nt) {
       int i = e / m, j = e % m;
       int gi = cmap[i], gj = cmap[j];
-      if (gi < 0 || gj < 0) continue;
+      if (gi < 0 || gj < 0 || gj > gi) continue;   // lower triangle
       double v = A[e];
       if (v != 0.0) atomicAdd(&H[(size_t)gi * ld + gj], v);
     }
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
         double gi = 0, gq = 0;
         for (int k = 0; k < 3; k++) { gi += wT * Rz[i * 3 + k] * r[k]; gq += wq * L3[k * 3 + i] * r[3 + k]; }
         atomicAdd(&g[c + i], gi); atomicAdd(&g[c + 3 + i], gq);
-        for (int j = 0; j < 3; j++) {
+        for (int j = 0; j <= i; j++) {   // lower triangle
           double hT = 0, hq = 0;
           for (int k = 0; k < 3; k++) { hT += Rz[i * 3 + k] * Rz[j * 3 + k]; hq += L3[k * 3 + i] * L3[k * 3 + j]; }
           atomicAdd(&H[(size_t)(c + i) * ld + c + j], wT * wT * hT);
@@ -630,9 +634,11 @@ __global__ void __launch_bounds__(128) k_proj_lin(Dev d, int eval_cur, int job_b
           if (n == RCOL) atomicAdd(&gv[gm], v);
           else {
             const int gn = l2g(n);
+            // Hcc is stored lower-triangular: an off-diagonal tile pair lands once at (max, min); a diagonal tile holds
+            // both triangles of its symmetric block, of which the lower one is kept
             if (gn >= 0) {
-              atomicAdd(&H[(size_t)gm * ld + gn], v);
-              if (cm != cn) atomicAdd(&H[(size_t)gn * ld + gm], v);
+              if (cm != cn) atomicAdd(&H[(size_t)max(gm, gn) * ld + min(gm, gn)], v);
+              else if (gn <= gm) atomicAdd(&H[(size_t)gm * ld + gn], v);
             }
           }
         }
@@ -793,7 +799,10 @@ __global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int
         if (n == RCOL) atomicAdd(&gv[gm], v);
         else {
           const int gn = l2g(n);
-          if (gn >= 0) { atomicAdd(&H[(size_t)gm * ld + gn], v); if (cm != cn) atomicAdd(&H[(size_t)gn * ld + gm], v); }
+          if (gn >= 0) {   // lower-triangular storage (see k_proj_lin)
+            if (cm != cn) atomicAdd(&H[(size_t)max(gm, gn) * ld + min(gm, gn)], v);
+            else if (gn <= gm) atomicAdd(&H[(size_t)gm * ld + gn], v);
+          }
         }
       }
     }
@@ -857,6 +866,8 @@ __global__ void k_proj_debug(Dev d, double *out /*[tiles*32][81]*/, int n_tiles_
 // records are visited serially, the 32 record entries in parallel across lanes, so there are no write conflicts and
 // the result is deterministic.  Output: Wt[l][0..n_lc) = w_l / sqrt(h'), Wt[l][n_lc] = g_l / sqrt(h'),
 // h' = h_l + mu D_l^2.
+// position of W-space column `col` in a row buffer that holds only the 32-column tiles named by `mask` (ascending)
+D2BA_DEV int row_slot(unsigned long long mask, int col) { return __popcll(mask & ((1ull << (col >> 5)) - 1ull)) * 32 + (col & 31); }
 constexpr int kGatherWarps = 8;
 __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const int *lm_win, int n_lm_total, int max_ldw) {
   extern __shared__ double sm[];
@@ -872,7 +883,10 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   const int l = gl_idx - w.offlm;
   double *row = sm + warp * max_ldw;
   const int nlc = w.n_lc;
-  for (int c = lane; c <= nlc; c += 32) row[c] = 0.0;
+  // column tiles (32 wide) this landmark's coupling row touches; windows without leaves (single drone) treat the row as dense
+  const unsigned long long mask = w.n_leaf ? d.lm_mask[gl_idx] : ((2ull << (w.n_lc / 32)) - 1ull);
+  const int nrt = __popcll(mask);   // the row buffer holds just these tiles, packed
+  for (int k = 0; k < nrt; k++) row[k * 32 + lane] = 0.0;
   __syncwarp();
   const int *ptr = d.lm_ptr + w.off_lmptr;
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
@@ -897,7 +911,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
         if (lane >= 4 && lane < 16) { int sc = lane < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (lane - 4) % 6; }
         if (lane >= 16 && lane < 28) { int sc = lane < 22 ? __double2hiint(c23) : __double2loint(c23); if (sc >= 0) col = sc + (lane - 4) % 6; }
         if (lane == 2) col = __double2hiint(ctd);
-        if (col >= 0) row[col] += v;
+        if (col >= 0) row[row_slot(mask, col)] += v;
         __syncwarp();
       }
     }
@@ -915,8 +929,11 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_lm_gather(Dev d, const in
   double *Wt = d.Wt + w.offW + (size_t)l * w.ldw;
   const double *uc = d.uc + w.offc;
   double wu = 0;
-  for (int c = lane; c < w.ldw; c += 32) {
-    double rv = (c < nlc) ? row[c] : 0.0;
+  int kk = 0;
+  for (unsigned long long m = mask; m; m &= m - 1, kk++) {   // the other tiles of the row stay zero (finalize-time memset)
+    const int c = (__ffsll((long long)m) - 1) * 32 + lane;
+    if (c >= w.ldw) continue;
+    double rv = (c < nlc) ? row[kk * 32 + lane] : 0.0;
     Wt[c] = (c < nlc) ? rv * di : (c == nlc ? g * di : 0.0);
     if (c < nlc) wu += rv * uc[c];
   }
@@ -946,7 +963,10 @@ __global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *l
   const int l = gl_idx - w.offlm;
   double *row = sm + hw * max_ldw;
   const int nlc = w.n_lc;
-  for (int c = sub; c <= nlc; c += 16) row[c] = 0.0;
+  // column tiles (32 wide) this landmark's coupling row touches; windows without leaves (single drone) treat the row as dense
+  const unsigned long long mask = w.n_leaf ? d.lm_mask[gl_idx] : ((2ull << (w.n_lc / 32)) - 1ull);
+  const int nrt = __popcll(mask);   // the row buffer holds just these tiles, packed
+  for (int k = sub; k < nrt * 32; k += 16) row[k] = 0.0;
   __syncwarp(hmask);
   const int *ptr = d.lm_ptr + w.off_lmptr;
   const double *recs = d.rec[buf] + (size_t)w.off_rec;
@@ -965,7 +985,7 @@ __global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *l
       if (sub >= 4) { const int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
       if (sub == 0) h += v[q];
       if (sub == 1) g += v[q];
-      if (col >= 0) row[col] += v[q];
+      if (col >= 0) row[row_slot(mask, col)] += v[q];
       __syncwarp(hmask);   // the two slots of different records may name the same column block
     }
   }
@@ -982,10 +1002,17 @@ __global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *l
   double *Wt = d.Wt + w.offW + (size_t)l * w.ldw;
   const double *uc = d.uc + w.offc;
   double wu = 0;
-  for (int c = sub; c < w.ldw; c += 16) {
-    const double rv = (c < nlc) ? row[c] : 0.0;
-    Wt[c] = (c < nlc) ? rv * di : (c == nlc ? g * di : 0.0);
-    if (c < nlc) wu += rv * uc[c];
+  int kk = 0;
+  for (unsigned long long m = mask; m; m &= m - 1, kk++) {   // the other tiles of the row stay zero (finalize-time memset)
+    const int c0 = (__ffsll((long long)m) - 1) * 32 + sub;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int c = c0 + 16 * u;
+      if (c >= w.ldw) continue;
+      const double rv = (c < nlc) ? row[kk * 32 + sub + 16 * u] : 0.0;
+      Wt[c] = (c < nlc) ? rv * di : (c == nlc ? g * di : 0.0);
+      if (c < nlc) wu += rv * uc[c];
+    }
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) wu += __shfl_xor_sync(hmask, wu, o);
@@ -999,7 +1026,9 @@ __global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *l
 // ------------------------------------------------------------------------------------------------
 // Reduced camera system.  Tile list entries: kind 0 = SYRK tile in W-space (32x32), kind 1 = copy tile
 // (rows/cols of the speed-bias part, which have no landmark coupling).
-struct SchurTile { int win, kind, tm, tn; };
+// (SchurTile: d2ba_types.cuh.)  Each tile sums over its own list of 32-row chunks of Wt -- the chunks in which some row has
+// entries in both column tiles (block sparsity of the landmark rows in multi-agent windows).  kind 2 tiles run before the
+// leaf elimination and store only entries in leaf columns (c < hub0), kind 0 tiles after it and store the hub x hub part.
 constexpr int kSyrkK = 32;
 constexpr int kSyrkLd = 36;  // == 4 (mod 16): conflict-free fragment loads
 __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
@@ -1044,7 +1073,9 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
   const double *Wt = d.Wt + w.offW;
   const int ldw = w.ldw;
   const int kq = lane & 3, cr = lane >> 2;
-  for (int k0 = 0; k0 < w.wt_rows; k0 += kSyrkK) {   // landmark rows, then the eliminated speed-bias rows Y
+  const int *chunks = d.schur_chunks + t.cb;
+  for (int ci = 0; ci < t.cn; ci++) {   // landmark rows, then (hub tiles) the eliminated speed-bias / leaf rows Y
+    const int k0 = chunks[ci] * kSyrkK;
     for (int e = tid; e < kSyrkK * 32; e += 128) {
       int k = e / 32, c = e % 32;
       const double *rowp = Wt + (size_t)(k0 + k) * ldw;
@@ -1064,6 +1095,8 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
     __syncthreads();
   }
   // epilogue: W-space (m, c) -> S-space; index nlc of W-space is the rhs row n of S
+  const int hub0 = w.hub0;
+  const bool leaf_stage = t.kind == 2;
 #pragma unroll
   for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -1072,6 +1105,7 @@ __global__ void __launch_bounds__(128) k_schur(Dev d, const SchurTile *tiles) {
       for (int e = 0; e < 2; e++) {
         int m = m0 + wm + a * 8 + cr, c = n0 + wn + b * 8 + kq * 2 + e;
         double v = acc[a][b][e];
+        if ((c < hub0) != leaf_stage) continue;   // a tile straddling the leaf / hub boundary is visited in both stages
         if (m < nlc && c <= m) {
           double hv = H[(size_t)m * ld + c];
           uhu += (m == c ? 1.0 : 2.0) * hv * ucv[m] * ucv[c];
@@ -1094,17 +1128,20 @@ constexpr int kSsMaxB = 10;   // 12*13/2 = 78 lower blocks over 8 warps
 __global__ void __launch_bounds__(kSsThreads, 2) k_schur_small(Dev d) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
-  if (!w.schur_small) return;
+  if (!w.schur_small && !w.hub_small) return;
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse) return;
   const int buf = ctl->cur;
-  const int n = w.n_c, nlc = w.n_lc, ld = w.ldh, ldw = w.ldw;
+  // window of W-space columns this kernel forms: everything (single-drone window) or the hub [hub0, n_lc] behind the leaves;
+  // below, nlc / ldw / the pointers are all relative to that window
+  const int c0 = w.hub_small ? w.hub0 : 0;
+  const int n = w.n_c - c0, nlc = w.n_lc - c0, ld = w.ldh, ldw = w.hub_small ? ((nlc + 1 + 7) & ~7) : w.ldw, ldwg = w.ldw;
   const double mu = ctl->mu;
-  const double *H = d.Hcc[buf] + w.offH;
-  const double *gcv = d.gc[buf] + w.offc;
-  const double *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
-  double *S = d.S + w.offH;
-  const double *Wt = d.Wt + w.offW;
+  const double *H = d.Hcc[buf] + w.offH + (size_t)c0 * ld + c0;
+  const double *gcv = d.gc[buf] + w.offc + c0;
+  const double *ucv = d.uc + w.offc + c0, *D2v = d.D2c + w.offc + c0;
+  double *S = d.S + w.offH + (size_t)c0 * ld + c0;
+  const double *Wt = d.Wt + w.offW + c0;
   extern __shared__ double sm[];
   const int ldws = ldw + 4;
   double *Ws = sm;                            // 2 buffers x 32 x ldws (TMA bulk staged)
@@ -1133,9 +1170,9 @@ __global__ void __launch_bounds__(kSsThreads, 2) k_schur_small(Dev d) {
     // producer: one thread issues 32 row copies per chunk (rows are padded in shared memory for conflict-free fragments)
     auto issue = [&](int c, int b) {
       mbar_expect_tx(&bar[b], 32u * row_bytes);
-      const double *src = Wt + (size_t)c * 32 * ldw;
+      const double *src = Wt + (size_t)c * 32 * ldwg;
       double *dst = Ws + b * 32 * ldws;
-      for (int k = 0; k < 32; k++) bulk_g2s(dst + k * ldws, src + (size_t)k * ldw, row_bytes, &bar[b]);
+      for (int k = 0; k < 32; k++) bulk_g2s(dst + k * ldws, src + (size_t)k * ldwg, row_bytes, &bar[b]);
     };
     if (tid == 0) { issue(0, 0); if (nchunk > 1) issue(1, 1); }
     for (int c = 0; c < nchunk; c++) {
@@ -1231,8 +1268,11 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
   double *Dg = redb + 16 * 32;      // kNB x (kNB+1) diagonal block (row-major, lower)
   double *invd = Dg + kNB * (kNB + 1);  // reciprocal diagonal of L, all n columns
   __shared__ int fail;
-  const int n = w.sb_elim ? w.n_lc : w.n_c, n1 = n + 1, ld = w.ldh;   // speed-bias blocks eliminated beforehand: pose part only
-  double *S = d.S + w.offH;
+  // speed-bias blocks / leaves eliminated beforehand: the dense part is the hub [hub0, n_lc) with the rhs in row n_lc
+  const bool reduced = w.sb_elim || w.n_leaf > 0;
+  const int c0 = reduced ? w.hub0 : 0;
+  const int n = reduced ? w.n_hub : w.n_c, n1 = n + 1, ld = w.ldh;
+  double *S = d.S + w.offH + (size_t)c0 * ld + c0;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) fail = 0;
   __syncthreads();
@@ -1368,7 +1408,7 @@ __global__ void __launch_bounds__(kCholThreads) k_chol(Dev d, int max_rows) {
     }
     __syncthreads();
   }
-  double *gn = d.gn_c + w.offc;
+  double *gn = d.gn_c + w.offc + c0;
   for (int i = tid; i < n; i += nt) gn[i] = -xs[i];
 }
 
@@ -1474,12 +1514,14 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ __align__(16) double sm[];
   // after the speed-bias elimination (k_sb_elim + Schur) only the landmark-coupled part is left: S rows 0..n_lc (rhs)
-  const bool reduced = w.sb_elim != 0;
-  const int n = reduced ? w.n_lc : w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;
+  // ... and after the leaf elimination only the hub [hub0, n_lc) of it
+  const bool reduced = w.sb_elim != 0 || w.n_leaf > 0;
+  const int c0 = reduced ? w.hub0 : 0;
+  const int n = reduced ? w.n_hub : w.n_c, n1 = n + 1, ld = chol_smem_ld(n), ldg = w.ldh, ldp = (n + 2) & ~1;
   double *A = sm;                         // n1 x ld
   double *invd = A + (size_t)n1 * ld;     // n (padded to even)
   double *P = invd + ((n + 1) & ~1);      // kCsNB x ldp transposed panel; later xs / partial sums
-  const double *S = d.S + w.offH;
+  const double *S = d.S + w.offH + (size_t)c0 * ldg + c0;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   __shared__ int fail;
   // row-scaled diagonal block for the TRSM: parked in the (never touched) upper-right corner of A, or behind the panel
@@ -1632,7 +1674,7 @@ __global__ void __launch_bounds__(kCsThreads) k_chol_smem(Dev d) {
     TLAP(8);
     __syncthreads();
   }
-  double *gn = d.gn_c + w.offc;
+  double *gn = d.gn_c + w.offc + c0;
   for (int i = tid; i < n; i += nt) gn[i] = -xs[i];
 #ifdef D2BA_CHOL_TIMING
   TLAP(9);
@@ -1707,7 +1749,9 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ __align__(16) double sm[];
   const int nlc = w.n_lc, nb = w.n_sbe, n = w.n_c, ld = w.ldh, cur = ctl->cur;
-  const int ldys = w.ldw, ncol = nlc + 1, slot_sz = kSeSlotRows * ldys;   // ldw: multiple of 8, >= n_lc + 1
+  // the speed-bias blocks couple (IMU factors, prior) only to hub columns [hub0, n_lc): the B rows are that wide
+  const int c0 = w.hub0, nh = nlc - c0, ldgw = w.ldw;
+  const int ldys = (nh + 1 + 7) & ~7, ncol = nh + 1, slot_sz = kSeSlotRows * ldys;   // ring rows: multiple of 8, >= n_hub + 1
   double *Yr = sm;                                  // ring of 3 slots x 9 rows x ldw: [B_k | g_k] -> Y_k
   double *Dk = Yr + (size_t)3 * slot_sz;            // nb x 81 : D_k -> L_kk
   double *Ek = Dk + (size_t)nb * 81;                // nb x 81 : E_k (rows: block k+1, cols: block k) -> E'_k
@@ -1727,11 +1771,11 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
   }
   __syncthreads();
   // B rows of a block: one TMA bulk copy per row into ring slot k % 3 (issued by one follower lane, two blocks ahead)
-  const unsigned row_bytes = (unsigned)(((nlc + 1) & ~1) * 8);
+  const unsigned row_bytes = (unsigned)(((nh + 1) & ~1) * 8);   // hub0 is a multiple of 6 (even): 16-byte aligned source
   auto issue_rows = [&](int k) {
     mbar_expect_tx(&bar_B[k], 9u * row_bytes);
     double *dst = Yr + (size_t)(k % 3) * slot_sz;
-    for (int i = 0; i < 9; i++) bulk_g2s(dst + (size_t)i * ldys, H + (size_t)(nlc + 9 * k + i) * ld, row_bytes, &bar_B[k]);
+    for (int i = 0; i < 9; i++) bulk_g2s(dst + (size_t)i * ldys, H + (size_t)(nlc + 9 * k + i) * ld + c0, row_bytes, &bar_B[k]);
   };
   if (tid == 32) { issue_rows(0); if (nb > 1) issue_rows(1); }
   // ---- the 9x9 blocks, u, g_s (8-byte cp.async: everything in flight at once); the blocks' share of u^T H u; mu D^2
@@ -1809,14 +1853,14 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
       const double *Lk = Dk + (size_t)k * 81, *iv = invd + k * 9, *Ep = Ek + (size_t)(k > 0 ? k - 1 : 0) * 81;
       for (int c = t1; c < ldys; c += n1t) {
         double y[9];
-        if (c < nlc) {
+        if (c < nh) {
           double ub = 0.0;
 #pragma unroll
           for (int i = 0; i < 9; i++) { y[i] = Yk[(size_t)i * ldys + c]; ub += y[i] * us[nlc + 9 * k + i]; }
-          uhu += 2.0 * ub * us[c];
+          uhu += 2.0 * ub * us[c0 + c];
         } else {
 #pragma unroll
-          for (int i = 0; i < 9; i++) y[i] = c == nlc ? gs[9 * k + i] : 0.0;
+          for (int i = 0; i < 9; i++) y[i] = c == nh ? gs[9 * k + i] : 0.0;
         }
         if (c < ncol) {
           if (k > 0) {
@@ -1837,7 +1881,7 @@ __global__ void __launch_bounds__(kSeThreads, 4) k_sb_elim(Dev d) {
           }
         }
 #pragma unroll
-        for (int i = 0; i < 9; i++) { Yk[(size_t)i * ldys + c] = y[i]; Yg[(size_t)(9 * k + i) * ldys + c] = y[i]; }
+        for (int i = 0; i < 9; i++) { Yk[(size_t)i * ldys + c] = y[i]; if (c < ncol) Yg[(size_t)(9 * k + i) * ldgw + c0 + c] = y[i]; }
       }
       asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");   // slot (k+2) % 3 == slot of block k-1 is dead now
       if (t1 == 0 && k + 2 < nb) { fence_proxy_async(); issue_rows(k + 2); }
@@ -1864,14 +1908,14 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
   Ctl *ctl = d.ctl + wi;
   if (ctl->done || ctl->reuse || ctl->chol_fail) return;
   extern __shared__ double sm[];
-  const int nlc = w.n_lc, nb = w.n_sbe, ldy = w.ldw;
-  double *xp = sm;                       // nlc (padded to 32)
-  double *rhs = sm + ((nlc + 31) & ~31); // 9 nb : z - Y x_p
+  const int c0 = w.hub0, nh = w.n_lc - c0, nlc = w.n_lc, nb = w.n_sbe, ldy = w.ldw;   // Y lives in the hub columns [hub0, n_lc] of its rows
+  double *xp = sm;                       // n_hub (padded to 32)
+  double *rhs = sm + ((nh + 31) & ~31);  // 9 nb : z - Y x_p
   double *LE = rhs + 9 * nb;             // nb x 171
   const double *Yg = d.Wt + w.offW + (size_t)w.nl * w.ldw, *LEg = d.sbLE + w.offLE;
   double *gn = d.gn_c + w.offc;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-  for (int c = tid; c < nlc; c += nt) xp[c] = -gn[c];
+  for (int c = tid; c < nh; c += nt) xp[c] = -gn[c0 + c];
   for (int e = tid; e < nb * 171; e += nt) cp_async8(LE + e, LEg + e);   // needed only by the recursion: lands during the products
   __syncthreads();
   for (int r0 = warp * 4; r0 < 9 * nb; r0 += nwarp * 4) {
@@ -1879,8 +1923,8 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       if (r0 + q >= 9 * nb) break;
-      const double *yr = Yg + (size_t)(r0 + q) * ldy;
-      for (int c = lane; c < nlc; c += 32) s_[q] += yr[c] * xp[c];
+      const double *yr = Yg + (size_t)(r0 + q) * ldy + c0;
+      for (int c = lane; c < nh; c += 32) s_[q] += yr[c] * xp[c];
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -1922,6 +1966,221 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Leaf elimination (multi-agent windows).  A leaf = the pose blocks of one remote drone: through the landmarks they couple
+// only to themselves and to the hub (own frames / extrinsics / td), never to another leaf, so the pose part of the reduced
+// system is an arrow:  [S_11 . . B_1^T; . S_22 . B_2^T; ...; B_1 B_2 ... S_hh].  One CTA per (window, leaf) factors
+// S_bb = L L^T in shared memory (8-column panels: chol_diag8 on the diagonal block, one-row-per-thread TRSM, fp64
+// tensor-core trailing update) with the hub rows [B_b ; g_b^T] riding along as extra rows, which turns them into
+// Y_b^T = [B_b ; g_b^T] L^-T.  The rows Y_b go behind the landmark / speed-bias rows of Wt, so the hub tiles of the Schur
+// kernel (which run next) subtract Y_b^T Y_b together with the landmark terms; k_leaf_back recovers the leaf step from
+// L^T x_b = z_b - Y_b x_hub.  The dense Cholesky shrinks from 6 x (all poses) to the hub (66 columns for an 11-frame window).
+constexpr int kLeafThreads = 256;
+constexpr int kLeafMaxCols = 96;
+constexpr int kLeafLmChunk = 16;   // landmarks whose coupling rows are staged at a time (a multiple of the MMA k = 4)
+__host__ __device__ inline int leaf_lda(int n) { return (n + 2) & ~1; }
+__host__ __device__ inline size_t leaf_elim_smem_bytes(int n, int nh) {
+  const int n1 = n + nh + 1;
+  return ((size_t)n1 * leaf_lda(n) + (size_t)((n + 1) & ~1) + (size_t)kCsNB * ((n1 + 1) & ~1) + 64 + (size_t)kLeafLmChunk * n1 + 8) * 8;
+}
+// C(8x8 at rows gi0.., cols gj0..) -= P^T P over the 8 panel columns; rows of the leaf block (gi < n) keep the lower
+// triangle only, the extra rows (gi >= n) all n columns
+D2BA_DEV void leaf_tile8(double *A, int ld, const double *P, int ldp, int gi0, int gj0, int ri, int rj, int pmax, int n1, int n, int lane) {
+  const int q = lane & 3, g = lane >> 2;
+  const int ia = min(ri + g, pmax), ib = min(rj + g, pmax);
+  const double a0 = -P[q * ldp + ia], a1 = -P[(q + 4) * ldp + ia];
+  const double b0 = P[q * ldp + ib], b1 = P[(q + 4) * ldp + ib];
+  const int gi = gi0 + g, gj = gj0 + 2 * q;
+  const bool rowok = gi < n1 && gj < n;
+  double2 c = make_double2(0.0, 0.0);
+  if (rowok) { c.x = A[(size_t)gi * ld + gj]; if (gj + 1 < n) c.y = A[(size_t)gi * ld + gj + 1]; }
+  dmma(c.x, c.y, a0, b0);
+  dmma(c.x, c.y, a1, b1);
+  if (rowok) {
+    const int lim = gi < n ? gi : n - 1;   // last column of this row that is stored
+    if (gj <= lim) A[(size_t)gi * ld + gj] = c.x;
+    if (gj + 1 <= lim) A[(size_t)gi * ld + gj + 1] = c.y;
+  }
+}
+
+// C(8x8 at rows gi0.., cols gj0..) -= W^T W over nq4 staged landmark rows (W: [landmark][n1 columns], zero padded to a
+// multiple of 4 rows); same storage rule as leaf_tile8
+D2BA_DEV void leaf_rank8(double *A, int ld, const double *W, int ldw, int gi0, int gj0, int nq4, int n1, int n, int lane) {
+  const int q = lane & 3, g = lane >> 2;
+  const int ia = min(gi0 + g, n1 - 1), ib = min(gj0 + g, n1 - 1);
+  const int gi = gi0 + g, gj = gj0 + 2 * q;
+  const bool rowok = gi < n1 && gj < n;
+  double2 c = make_double2(0.0, 0.0);
+  if (rowok) { c.x = A[(size_t)gi * ld + gj]; if (gj + 1 < n) c.y = A[(size_t)gi * ld + gj + 1]; }
+  for (int ks = 0; ks < nq4; ks += 4) dmma(c.x, c.y, -W[(size_t)(ks + q) * ldw + ia], W[(size_t)(ks + q) * ldw + ib]);
+  if (rowok) {
+    const int lim = gi < n ? gi : n - 1;
+    if (gj <= lim) A[(size_t)gi * ld + gj] = c.x;
+    if (gj + 1 <= lim) A[(size_t)gi * ld + gj + 1] = c.y;
+  }
+}
+
+__global__ void __launch_bounds__(kLeafThreads) k_leaf_elim(Dev d) {
+  const Leaf lf = d.leaf[blockIdx.x];
+  const WinDesc &w = d.win[lf.win];
+  Ctl *ctl = d.ctl + lf.win;
+  if (ctl->done || ctl->reuse || ctl->chol_fail) return;
+  extern __shared__ __align__(16) double sm[];
+  const int n = lf.n, nh = w.n_hub, n1 = n + nh + 1, lda = leaf_lda(n), ldp = (n1 + 1) & ~1, ldg = w.ldh, cur = ctl->cur;
+  double *A = sm;                                   // n1 x lda: leaf block (lower), then the hub rows and the rhs row
+  double *invd = A + (size_t)n1 * lda;              // n (padded to even)
+  double *P = invd + ((n + 1) & ~1);                // kCsNB x ldp: transposed panel
+  double *Ms = P + (size_t)kCsNB * ldp;             // 8 x 8 row-scaled diagonal block
+  double *Wl = Ms + 64;                             // kLeafLmChunk x n1: coupling rows of a chunk of this leaf's landmarks
+  const double *H = d.Hcc[cur] + w.offH, *gcv = d.gc[cur] + w.offc, *ucv = d.uc + w.offc, *D2v = d.D2c + w.offc;
+  const double mu = ctl->mu;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  __shared__ int fail;
+  if (tid == 0) fail = 0;
+  // ---- this leaf's part of the reduced system, formed here:  [H_bb ; H_hub,b ; g_b^T] - sum over its landmarks of
+  //      [w_l,b ; w_l,hub ; g~_l]^T w_l,b  (the leaf's landmarks touch no other leaf).  Asynchronous 8-byte copies keep the
+  //      whole block in flight at once; the upper triangle of the leaf block is never read.
+  for (int e = tid; e < n1 * n; e += nt) {
+    const int r = e / n, c = e - r * n;
+    double *dst = A + (size_t)r * lda + c;
+    if (r < n) { if (c <= r) cp_async8(dst, H + (size_t)(lf.col0 + r) * ldg + lf.col0 + c); }
+    else if (r < n + nh) cp_async8(dst, H + (size_t)(w.hub0 + r - n) * ldg + lf.col0 + c);
+    else cp_async8(dst, gcv + lf.col0 + c);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  {   // the block's share of u^T Hcc u (lower entries, off-diagonal twice), then mu D^2 on the diagonal
+    double *us = Wl;   // u of the leaf columns, then of the hub columns (the staging area is free until the rank updates)
+    for (int e = tid; e < n + nh; e += nt) us[e] = e < n ? ucv[lf.col0 + e] : ucv[w.hub0 + e - n];
+    __syncthreads();
+    double uhu = 0.0;
+    for (int e = tid; e < (n + nh) * n; e += nt) {
+      const int r = e / n, c = e - r * n;
+      if (r < n && c > r) continue;
+      uhu += ((r < n && c == r) ? 1.0 : 2.0) * A[(size_t)r * lda + c] * us[r] * us[c];
+    }
+    uhu = warp_sum(uhu);
+    if (lane == 0 && uhu != 0.0) atomicAdd(&ctl->uHu_cam, uhu);
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) A[(size_t)i * lda + i] += mu * D2v[lf.col0 + i];
+  }
+  const double *Wt = d.Wt + w.offW;
+  const int *lml = d.leaf_lm + lf.lm_begin;
+  for (int l0 = 0; l0 < lf.lm_count; l0 += kLeafLmChunk) {
+    const int nq = min(kLeafLmChunk, lf.lm_count - l0);
+    __syncthreads();
+    const int nq4 = (nq + 3) & ~3;
+    for (int e = tid; e < nq4 * n1; e += nt) {
+      const int q = e / n1, c = e - q * n1;
+      if (q < nq) {
+        const double *row = Wt + (size_t)lml[l0 + q] * w.ldw;
+        cp_async8(Wl + (size_t)q * n1 + c, c < n ? row + lf.col0 + c : row + w.hub0 + (c - n));
+      } else Wl[(size_t)q * n1 + c] = 0.0;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int Tr0 = (n1 + 7) >> 3, Tc0 = (n + 7) >> 3;   // fp64 tensor-core rank update, 8x8 tiles of the lower trapezoid
+    for (int job = warp; job < Tr0 * Tc0; job += nwarp) {
+      const int ti = job / Tc0, tj = job - ti * Tc0;
+      if (tj > ti) continue;
+      leaf_rank8(A, lda, Wl, n1, 8 * ti, 8 * tj, nq4, n1, n, lane);
+    }
+  }
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += kCsNB) {
+    const int nb = min(kCsNB, n - k0), nxt = k0 + nb;
+    if (warp == 0) { if (chol_diag8(A, lda, invd, Ms, kCsNB, k0, nb, lane)) fail = 1; }
+    __syncthreads();
+    // rows below the diagonal block (rest of the leaf block + every extra row): a L_d^T = x, one row per thread
+    for (int r = nxt + tid; r < n1; r += nt) {
+      double a[kCsNB];
+      double *ar = A + (size_t)r * lda + k0;
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) a[c] = (c < nb) ? ar[c] * invd[k0 + c] : 0.0;
+#pragma unroll
+      for (int c = 1; c < kCsNB; c++) {
+        double s_ = a[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) s_ = fma(-a[k], Ms[c * kCsNB + k], s_);
+        a[c] = s_;
+      }
+#pragma unroll
+      for (int c = 0; c < kCsNB; c++) { if (c < nb) ar[c] = a[c]; P[c * ldp + (r - k0)] = a[c]; }
+    }
+    __syncthreads();
+    if (nxt >= n) break;
+    const int pmax = n1 - 1 - k0;
+    const int Tr = (n1 - nxt + 7) >> 3, Tc = (n - nxt + 7) >> 3;
+    for (int job = warp; job < Tr * Tc; job += nwarp) {
+      const int ti = job / Tc, tj = job - ti * Tc;
+      if (tj > ti) continue;
+      leaf_tile8(A, lda, P, ldp, nxt + 8 * ti, nxt + 8 * tj, nb + 8 * ti, nb + 8 * tj, pmax, n1, n, lane);
+    }
+    __syncthreads();
+  }
+  if (fail) { if (tid == 0) ctl->chol_fail = 1; return; }
+  // L and 1/diag(L) for the back substitution; Y (transposed extra rows) into its rows of Wt, hub columns + rhs column
+  double *Lg = d.leafL + lf.offL;
+  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; Lg[e] = j <= i ? A[(size_t)i * lda + j] : 0.0; }
+  for (int e = tid; e < n; e += nt) Lg[(size_t)n * n + e] = invd[e];
+  double *Yg = d.Wt + w.offW + (size_t)lf.row0 * w.ldw + w.hub0;
+  for (int e = tid; e < n * (nh + 1); e += nt) {
+    const int k = e / (nh + 1), c = e - k * (nh + 1);
+    Yg[(size_t)k * w.ldw + c] = A[(size_t)(n + c) * lda + k];
+  }
+}
+
+// Leaf part of the Gauss-Newton step: L^T x_b = z_b - Y_b x_hub, one CTA per (window, leaf)
+constexpr int kLeafBackThreads = 128;
+__host__ __device__ inline size_t leaf_back_smem_bytes(int n, int nh) { return ((size_t)n * n + 2 * (size_t)n + (size_t)nh + 8) * 8; }
+__global__ void __launch_bounds__(kLeafBackThreads) k_leaf_back(Dev d) {
+  const Leaf lf = d.leaf[blockIdx.x];
+  const WinDesc &w = d.win[lf.win];
+  Ctl *ctl = d.ctl + lf.win;
+  if (ctl->done || ctl->reuse || ctl->chol_fail) return;
+  extern __shared__ double sm[];
+  const int n = lf.n, nh = w.n_hub;
+  double *L = sm, *iv = L + (size_t)n * n, *v = iv + n, *xh = v + n;
+  const double *Lg = d.leafL + lf.offL;
+  const double *Yg = d.Wt + w.offW + (size_t)lf.row0 * w.ldw + w.hub0;
+  double *gn = d.gn_c + w.offc;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  for (int e = tid; e < n * n + n; e += nt) cp_async8(L + e, Lg + e);   // iv follows L in both layouts; lands during the products below
+  for (int c = tid; c < nh; c += nt) xh[c] = -gn[w.hub0 + c];
+  __syncthreads();
+  for (int k0 = warp * 4; k0 < n; k0 += nwarp * 4) {   // four rows per pass: their loads are all in flight before the first reduction
+    double s_[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (k0 + q >= n) break;
+      const double *yr = Yg + (size_t)(k0 + q) * w.ldw;
+      for (int c = lane; c < nh; c += 32) s_[q] += yr[c] * xh[c];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const double t = warp_sum(s_[q]);
+      if (lane == 0 && k0 + q < n) v[k0 + q] = Yg[(size_t)(k0 + q) * w.ldw + nh] - t;
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (warp != 0) return;
+  for (int i = n - 1; i >= 0; i--) {
+    const double xi = v[i] * iv[i];
+    for (int j = lane; j < i; j += 32) v[j] -= L[(size_t)i * n + j] * xi;
+    if (lane == 0) gn[lf.col0 + i] = -xi;
+    __syncwarp();
+  }
+}
+
+__global__ void k_zero_leaf_rows(Dev d) {
+  const WinDesc &w = d.win[blockIdx.x];
+  if (!w.n_leaf) return;
+  double *Yg = d.Wt + w.offW + (size_t)w.nl * w.ldw;
+  const size_t tot = (size_t)(w.wt_rows - w.nl) * w.ldw;
+  for (size_t e = threadIdx.x; e < tot; e += blockDim.x) Yg[e] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Step kernel: one CTA per window.
 constexpr int kStepThreads = 256;
 __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
@@ -1960,7 +2219,12 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
         a[q] = 0.0;
         if (l0 + q < nl) {
           const double *row = Wt + (size_t)(l0 + q) * w.ldw;
-          for (int c = lane; c < nlc; c += 32) a[q] += row[c] * dcs[c];
+          if (!w.n_leaf) { for (int c = lane; c < nlc; c += 32) a[q] += row[c] * dcs[c]; }
+          else
+            for (unsigned long long m = d.lm_mask[w.offlm + l0 + q]; m; m &= m - 1) {   // only the column tiles the row has entries in
+              const int c = (__ffsll((long long)m) - 1) * 32 + lane;
+              if (c < nlc) a[q] += row[c] * dcs[c];
+            }
         }
       }
 #pragma unroll
@@ -2427,6 +2691,14 @@ int configure_schur_small(int max_ldw) {
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s) {
   if (n_tiles > 0) k_schur<<<n_tiles, 128, 0, s>>>(d, reinterpret_cast<const SchurTile *>(tiles));
 }
+size_t leaf_elim_smem(int n, int n_hub) { return leaf_elim_smem_bytes(n, n_hub); }
+size_t leaf_back_smem(int n, int n_hub) { return leaf_back_smem_bytes(n, n_hub); }
+int leaf_max_cols() { return kLeafMaxCols; }
+int configure_leaf_elim(size_t smem) { return (int)raise_smem_limit(k_leaf_elim, smem); }
+int configure_leaf_back(size_t smem) { return (int)raise_smem_limit(k_leaf_back, smem); }
+void launch_leaf_elim(const Dev &d, size_t smem, cudaStream_t s) { if (d.n_leaf_total > 0) k_leaf_elim<<<d.n_leaf_total, kLeafThreads, smem, s>>>(d); }
+void launch_leaf_back(const Dev &d, size_t smem, cudaStream_t s) { if (d.n_leaf_total > 0) k_leaf_back<<<d.n_leaf_total, kLeafBackThreads, smem, s>>>(d); }
+void launch_zero_leaf_rows(const Dev &d, cudaStream_t s) { k_zero_leaf_rows<<<d.n_win, 256, 0, s>>>(d); }
 size_t chol_smem_need(int n) { return chol_smem_bytes(n); }
 int configure_chol_smem(int max_n) {
   return (int)raise_smem_limit(k_chol_smem, (size_t)(chol_smem_bytes(max_n)));

@@ -45,6 +45,24 @@ struct ObsAnchor {   // the anchor half, stored once per run of residual blocks 
   double pts_i[3], vel_i[3], td_i, pad;
 };
 
+// One run of a row of Hcc that some factor writes (the per-linearisation zero-fill touches only these; everything else
+// of Hcc stays at the zero of the finalize-time memset).  Hcc is LOWER triangular storage: writers put (max, min).
+struct HSeg { int row, c0, len; };
+
+// A "leaf" = a set of pose blocks that couples (through landmarks) only to itself and to the hub (own frames, extrinsics,
+// td): the remote frames of one other drone in a multi-agent window.  Leaves are eliminated from the reduced system
+// before the dense Cholesky of the hub (k_leaf_elim), the way the speed-bias chain is (k_sb_elim).
+struct Leaf {
+  int win, col0, n;      // window, first reduced column, columns
+  int row0;              // first of its n rows Y = L^-1 [S_leaf,hub | g_leaf] behind the landmark / speed-bias rows of Wt (window-local row)
+  long long offL;        // offset (doubles) into Dev::leafL: L (n x n row-major) then 1/diag(L) (n)
+  int lm_begin, lm_count;  // its landmarks (the rows of Wt with entries in its columns): Dev::leaf_lm[lm_begin ..), window-local indices
+};
+
+// Reduced camera system tiles: kind 0 = SYRK tile in W-space (32x32) over the listed 32-row chunks of Wt,
+// kind 1 = copy tile (rows / cols of a not eliminated speed-bias part, which has no landmark coupling)
+struct SchurTile { int win, kind, tm, tn, cb, cn; };
+
 struct ImuDesc {
   int pi, si, pj, sj;  // window-local indices (six-dof table / speed-bias table)
 };
@@ -76,6 +94,12 @@ struct WinDesc {
   int sb_elim, n_sbe;          // enabled, number of (non-constant) speed-bias blocks
   int wt_rows;                 // rows of Wt the Schur kernels sum over: nl landmark rows + 9 n_sbe eliminated speed-bias rows, padded to 32
   int64_t offLE;               // offset (doubles) into Dev::sbLE
+  // leaves (multi-agent windows): columns are ordered [leaf 0 | leaf 1 | ... | hub | speed-bias]
+  int hub0, n_hub;             // first hub column, hub columns (n_lc - hub0); hub0 == 0 when the window has no leaves
+  int n_leaf, off_leaf;
+  int off_hseg, n_hseg;        // Hcc zero-fill segments
+  int hub_small;               // leaves present and n_hub + 1 <= 96: the hub x hub part of the reduced system comes from the one-CTA Schur kernel
+  int row_tiles;               // most 32-column tiles any landmark's coupling row touches (row buffers of the gather kernels)
 };
 
 struct PriorBlk {
@@ -135,6 +159,12 @@ struct Dev {
   double *rec[2];       // landmark-side per-observation records
   // landmark CSR
   const int *lm_ptr;
+  const unsigned long long *lm_mask;  // [NL] bit t set: the landmark's coupling row has entries in W-space columns [32 t, 32 t + 32)
+  const HSeg *hseg;
+  const Leaf *leaf; int n_leaf_total;
+  double *leafL;        // per leaf: L, 1/diag(L)
+  const int *schur_chunks;
+  const int *leaf_lm;
   const int *obs_slot;  // [T][32] position of the observation's record in its landmark's run (window-local), -1 = padding
   // imu
   const ImuDesc *imu;

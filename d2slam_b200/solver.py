@@ -173,12 +173,15 @@ class Solver:
         return Aflat[: mm * mm].reshape(mm, mm).copy(), b[:mm].copy(), refs, x0[:nx].copy()
 
     def kernel_times(self, iters):
-        out = np.zeros(10)
+        out = np.zeros(12)
         self._chk(lib().d2ba_debug_kernel_times(self.h, C.c_int32(iters), abi.ptr(out)), "kernel_times")
         kt = {k: out[i] / max(out[7], 1) for i, k in enumerate(KERNEL_NAMES)}
         # the speed-bias elimination is timed inside the gather bucket, its back substitution inside the chol bucket
         se, sbk = out[8] / max(out[7], 1), out[9] / max(out[7], 1)
-        kt["lm_gather"] -= se; kt["chol"] -= sbk; kt["sb_elim"] = se; kt["sb_back"] = sbk
+        le, lb = out[10] / max(out[7], 1), out[11] / max(out[7], 1)
+        kt["lm_gather"] -= se; kt["chol"] -= sbk + lb; kt["sb_elim"] = se; kt["sb_back"] = sbk
+        if le > 0 or lb > 0:
+            kt["schur"] -= le; kt["leaf_elim"] = le; kt["leaf_back"] = lb
         self.chol_split = {"sb_elim": se, "sb_back": sbk}
         return kt
 

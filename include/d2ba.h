@@ -121,6 +121,10 @@ typedef struct d2ba_config {
   double function_tolerance;          /* 1e-6 */
   double gradient_tolerance;          /* 1e-10 */
   double parameter_tolerance;         /* 1e-8 */
+  /* ceres max_solver_time_in_seconds (d2vins_params.cpp:143; divided by consensus_max_steps per ADMM sub-step, :156-160):
+   * no further trust-region iteration is started once the budget is used up (termination = NO_CONVERGENCE like ceres).
+   * 0 = no budget.  d2ba_solve_fixed ignores it. */
+  double max_solver_time_in_seconds;
 } d2ba_config;
 
 /* One reprojection residual block in reference terms: ids, not indices.
@@ -183,7 +187,7 @@ typedef struct d2ba_report {     /* SolverReport, SolverWrapper.hpp:14-37 */
   double total_time;             /* seconds, device time of the solve */
   double initial_cost;
   double final_cost;
-  double state_changes;
+  double state_changes;          /* |x_final - x_initial| over the free pose positions of the window (SolverReport.state_changes) */
   double final_gradient_max_norm;
   double final_radius;
 } d2ba_report;
@@ -279,10 +283,11 @@ enum d2ba_debug_item {
 int d2ba_debug_linearize(d2ba_handle *h);
 int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int64_t out_bytes,
                    int64_t *needed_bytes);
-/* Device time (ms, CUDA events on the solver stream) of each kernel of the iteration sequence, summed over
- * `iters` iterations: [lm_gather, schur, chol, step, misc_lin, proj_lin, control, iters, sb_elim, sb_back] (sb_elim is
- * included in lm_gather, sb_back in chol). */
-int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out /* [10] */);
+/* Device time (ms, CUDA events on the solver stream) of each kernel of the iteration sequence, summed over `iters`
+ * iterations: [0] lm_gather (+ sb_elim), [1] reduced system (Schur tiles + leaf elimination), [2] dense Cholesky (+ sb / leaf back
+ * substitution), [3] step, [4] misc_lin, [5] proj_lin, [6] control, [7] = iters, and the shares [8] sb_elim (of [0]),
+ * [9] sb_back (of [2]), [10] leaf_elim (of [1]), [11] leaf_back (of [2]). */
+int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out /* [12] */);
 /* Host wall-clock (ms) of the phases of the last d2ba_finalize: [plan (pair-major order, groups, jobs), prefix sums +
  * staging resize, staging fill, upload enqueue, error check, read-back buffers, device ms of the uploads, device ms of tile build + prep kernels], followed by
  * the thread-summed ms spent inside d2ba_add_proj since the last d2ba_reset: [id lookup, stamp scan, staging copy,

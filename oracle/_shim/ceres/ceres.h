@@ -4,6 +4,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <limits>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -57,7 +59,34 @@ class HuberLoss : public LossFunction {
 enum LinearSolverType { DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR, SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR };
 enum TrustRegionStrategyType { LEVENBERG_MARQUARDT, DOGLEG };
 enum Ownership { DO_NOT_TAKE_OWNERSHIP, TAKE_OWNERSHIP };
-class Problem;
+typedef LocalParameterization Manifold;
+// Parameter-block bookkeeping of ceres::Problem (no residual storage, no solve): what D2Estimator::setStateProperties
+// pokes through SolverWrapper::getProblem() -- HasParameterBlock / SetParameterBlockConstant / SetParameterization -- and
+// what an adapter reads back with IsParameterBlockConstant.  Same member signatures as ceres 2.1.
+class Problem {
+ public:
+  struct Options {
+    Ownership cost_function_ownership = TAKE_OWNERSHIP, loss_function_ownership = TAKE_OWNERSHIP,
+              local_parameterization_ownership = TAKE_OWNERSHIP, manifold_ownership = TAKE_OWNERSHIP;
+  };
+  Problem() {}
+  explicit Problem(const Options &) {}
+  void AddParameterBlock(double *values, int size) { blocks_[values].size = size; }
+  void AddParameterBlock(double *values, int size, LocalParameterization *lp) { blocks_[values].size = size; blocks_[values].lp = lp; }
+  bool HasParameterBlock(const double *values) const { return blocks_.count(const_cast<double *>(values)) != 0; }
+  void SetParameterBlockConstant(const double *values) { blocks_.at(const_cast<double *>(values)).constant = true; }
+  void SetParameterBlockVariable(double *values) { blocks_.at(values).constant = false; }
+  bool IsParameterBlockConstant(const double *values) const { return blocks_.at(const_cast<double *>(values)).constant; }
+  void SetParameterization(double *values, LocalParameterization *lp) { blocks_.at(values).lp = lp; }
+  void SetManifold(double *values, Manifold *m) { blocks_.at(values).lp = m; }
+  const LocalParameterization *GetParameterization(const double *values) const { return blocks_.at(const_cast<double *>(values)).lp; }
+  int ParameterBlockSize(const double *values) const { return blocks_.at(const_cast<double *>(values)).size; }
+  int NumParameterBlocks() const { return (int)blocks_.size(); }
+  void *AddResidualBlock(CostFunction *, LossFunction *, const std::vector<double *> &ps) { for (double *p : ps) blocks_[p]; return nullptr; }
+ private:
+  struct Blk { int size = 0; bool constant = false; LocalParameterization *lp = nullptr; };
+  std::map<double *, Blk> blocks_;
+};
 struct Solver {
   struct Options {
     LinearSolverType linear_solver_type = DENSE_SCHUR;
@@ -65,7 +94,7 @@ struct Solver {
     int num_threads = 1; int max_num_iterations = 50; double max_solver_time_in_seconds = 1e9;
     bool minimizer_progress_to_stdout = false;
   };
-  struct Summary { int num_successful_steps = 0, num_unsuccessful_steps = 0; double initial_cost = 0, final_cost = 0; std::string BriefReport() const { return ""; } std::string FullReport() const { return ""; } };
+  struct Summary { int num_successful_steps = 0, num_unsuccessful_steps = 0; double initial_cost = 0, final_cost = 0, total_time_in_seconds = 0; std::string BriefReport() const { return ""; } std::string FullReport() const { return ""; } };
 };
 using std::cos; using std::sin; using std::floor; using std::sqrt; using std::atan2; using std::abs;
 }  // namespace ceres

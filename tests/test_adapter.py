@@ -1,0 +1,150 @@
+"""D2GpuSolver (adapter/): the SolverWrapper that puts libd2ba.so under D2Estimator, driven like the estimator drives its
+solver -- the REFERENCE's own factor objects + residual descriptors through addResidual(), a properties callback that
+pokes the bookkeeping ceres::Problem, solve(), results through the raw state pointers (adapter/test_adapter.cpp).
+
+CPU: the flat C-ABI records the adapter marshals equal the generator's arrays bit for bit (ids, constants, constness).
+GPU: the solve through the adapter equals the solve of the same window fed directly through the C ABI."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from d2slam_b200 import abi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "adapter", "_build", "test_adapter")
+REF = os.environ.get("D2SLAM_REF", "/root/reference")
+
+
+def build_exe():
+    if os.path.isdir(os.path.join(REF, "d2vins")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "adapter"), "-s", f"REF={REF}"])
+    return os.path.exists(EXE)
+
+
+needs_exe = pytest.mark.skipif(not build_exe(), reason="adapter/_build/test_adapter not built and no reference tree")
+
+
+def to_jac_res(A, b):
+    """PriorFactor's toJacRes (prior_factor.cpp:132-177)."""
+    A = 0.5 * (A + A.T)
+    lam, V = np.linalg.eigh(A)
+    lam = np.where(lam > 1e-8, lam, 0.0)
+    s = np.sqrt(lam); si = np.where(s > 0, 1.0 / np.where(s > 0, s, 1.0), 0.0)
+    return (s[:, None] * V.T).copy(), si * (V.T @ b)
+
+
+def write_input(path, pr, iters):
+    J, e0 = (np.zeros((0, 0)), np.zeros(0))
+    refs = np.zeros(0, dtype=abi.blockref_dtype); x0 = np.zeros(0)
+    if pr.get("prior") is not None:
+        A, b, refs, x0 = pr["prior"]
+        J, e0 = to_jac_res(np.asarray(A, float), np.asarray(b, float))
+    with open(path, "wb") as f:
+        f.write(struct.pack("<9q", len(pr["frame_ids"]), len(pr["cam_ids"]), len(pr["sb_ids"]), len(pr["lm_ids"]), len(pr["obs"]), len(pr["imu"]),
+                            len(e0), len(refs), iters))
+        for a, dt in ((pr["frame_ids"], np.int64), (pr["poses"], np.float64), (pr["pose_const"], np.uint8), (pr["cam_ids"], np.int64), (pr["ext"], np.float64),
+                      (pr["ext_const"], np.uint8), (pr["sb_ids"], np.int64), (pr["sb"], np.float64)):
+            f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
+        f.write(struct.pack("<dq", float(pr["td"]), int(pr["td_const"])))
+        f.write(np.ascontiguousarray(pr["lm_ids"], np.int64).tobytes()); f.write(np.ascontiguousarray(pr["inv_dep"], np.float64).tobytes())
+        f.write(np.ascontiguousarray(pr["obs"], abi.proj_obs_dtype).tobytes()); f.write(np.ascontiguousarray(pr["imu"], abi.imu_dtype).tobytes())
+        f.write(np.ascontiguousarray(J, np.float64).tobytes()); f.write(np.ascontiguousarray(e0, np.float64).tobytes())
+        f.write(np.ascontiguousarray(refs, abi.blockref_dtype).tobytes())
+        x0 = np.ascontiguousarray(x0, np.float64)
+        f.write(struct.pack("<q", x0.size)); f.write(x0.tobytes())
+    return J, e0, refs, x0
+
+
+class Rd:
+    def __init__(self, path):
+        self.b = open(path, "rb").read(); self.o = 0
+
+    def arr(self, dt, n):
+        dt = np.dtype(dt); a = np.frombuffer(self.b, dtype=dt, count=n, offset=self.o); self.o += dt.itemsize * n; return a
+
+    def i64(self):
+        return int(self.arr(np.int64, 1)[0])
+
+    def f64(self):
+        return float(self.arr(np.float64, 1)[0])
+
+
+CASES = {"mono": dict(seed=3, n_landmarks=60, n_frames=6), "stereo_free": dict(seed=4, n_landmarks=50, n_frames=5, cams="stereo", estimate_extrinsic=True, estimate_td=True, td_offset=0.002),
+         "no_prior": dict(seed=5, n_landmarks=40, n_frames=4, with_prior=False)}
+
+
+@needs_exe
+@pytest.mark.parametrize("name", list(CASES))
+def test_adapter_marshals_the_generators_records(name, tmp_path):
+    pr = synth.make_window(**CASES[name])
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    J, e0, refs, x0 = write_input(fin, pr, 6)
+    subprocess.check_call([EXE, fin, fout, "marshal"])
+    r = Rd(fout)
+    # blocks come in first-use order of the residual list: compare by id
+    def blocks(n_per, ids_ref, vals_ref, const_ref):
+        n = r.i64(); ids = r.arr(np.int64, n); vals = r.arr(np.float64, n * n_per).reshape(n, n_per)
+        const = r.arr(np.uint8, n) if const_ref is not None else None
+        assert sorted(ids.tolist()) == sorted(np.asarray(ids_ref).tolist())
+        order = {int(i): k for k, i in enumerate(np.asarray(ids_ref))}
+        for k, i in enumerate(ids):
+            assert np.array_equal(vals[k], np.asarray(vals_ref, float).reshape(len(ids_ref), n_per)[order[int(i)]])
+            if const is not None:
+                assert int(const[k]) == int(const_ref[order[int(i)]]), (name, int(i))
+    blocks(7, pr["frame_ids"], pr["poses"], pr["pose_const"])
+    blocks(7, pr["cam_ids"], pr["ext"], pr["ext_const"])
+    n = r.i64(); ids = r.arr(np.int64, n); vals = r.arr(np.float64, n * 9)
+    assert sorted(ids.tolist()) == sorted(pr["sb_ids"].tolist())
+    n = r.i64(); ids = r.arr(np.int64, n); vals = r.arr(np.float64, n)
+    assert sorted(ids.tolist()) == sorted(pr["lm_ids"].tolist())
+    assert r.f64() == float(pr["td"]) and r.i64() == int(pr["td_const"])
+    n = r.i64(); obs = r.arr(abi.proj_obs_dtype, n)
+    assert n == len(pr["obs"])
+    for fld in ("type", "frame_a", "landmark_id", "cam_a", "pts_i", "pts_j", "vel_i", "vel_j", "td_i", "td_j"):
+        assert np.array_equal(obs[fld], pr["obs"][fld]), fld        # bit-exact: read back from the reference factor objects
+    two = pr["obs"]["type"] != abi.PROJ_1F2C
+    assert np.array_equal(obs["frame_b"][two], pr["obs"]["frame_b"][two])
+    n = r.i64(); imu = r.arr(abi.imu_dtype, n)
+    assert n == len(pr["imu"])
+    for fld in abi.imu_dtype.names:
+        assert np.array_equal(imu[fld], pr["imu"][fld]), fld
+    m = r.i64()
+    assert m == len(e0)
+    if m:
+        Jm = r.arr(np.float64, m * m).reshape(m, m); em = r.arr(np.float64, m)
+        # recovered through PriorFactor's public Evaluate at the linearisation point
+        assert np.allclose(Jm, J, rtol=0, atol=1e-12 * max(1.0, np.abs(J).max())) and np.allclose(em, e0, rtol=0, atol=1e-12)
+
+
+@needs_exe
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_adapter_solve_equals_direct_c_abi_solve(name, tmp_path):
+    from d2slam_b200.solver import Solver
+    pr = synth.make_window(**CASES[name])
+    iters = 6
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    J, e0, refs, x0 = write_input(fin, pr, iters)
+    subprocess.check_call([EXE, fin, fout, "solve"])
+    r = Rd(fout)
+    n_it = r.i64(); c0 = r.f64(); c1 = r.f64(); chg = r.f64()
+    poses = r.arr(np.float64, 7 * len(pr["frame_ids"])).reshape(-1, 7)
+    sb = r.arr(np.float64, 9 * len(pr["sb_ids"])).reshape(-1, 9)
+    lm = r.arr(np.float64, len(pr["lm_ids"]))
+    # the same window fed directly (prior in the same (J, e0) form)
+    q = synth.Problem(pr); q["prior"] = None
+    s = Solver(max_num_iterations=iters); q.load(s, 0)
+    if len(e0):
+        s.set_prior(0, J, e0, refs, x0)
+    s.finalize()
+    rep = s.solve()[0]
+    assert rep.total_iterations == n_it
+    assert abs(rep.final_cost - c1) <= 1e-9 * max(1.0, abs(c1)) and abs(rep.initial_cost - c0) <= 1e-9 * max(1.0, abs(c0))
+    dp, dr = synth.pose_errors(poses, s.get_blocks(0, abi.POSE, pr["frame_ids"]))
+    assert dp <= 1e-9 and dr <= 1e-8
+    assert np.abs(sb - s.get_blocks(0, abi.SPEED_BIAS, pr["sb_ids"])).max() <= 1e-8
+    assert np.abs(lm / s.get_blocks(0, abi.LANDMARK, pr["lm_ids"])[:, 0] - 1).max() <= 1e-8
+    assert chg > 0 and abs(chg - rep.state_changes) <= 1e-9

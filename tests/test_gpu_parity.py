@@ -306,7 +306,7 @@ def test_L4_admm_eight_agents_full_size():
 
 def test_L2_eight_agent_window_normal_equations():
     """Linearisation / Schur complement / Gauss-Newton step of one agent's window of the 8-drone swarm (528 + 99 columns)."""
-    pr = synth.make_swarm(seed=85, n_agents=8, only_agents=[3])[0]
+    pr = synth.make_swarm(seed=85, n_agents=8, only_agents=[3], shared_per_pair=40)[0]   # every remote frame set observes something
     pr["consensus"] = None
     o, s = both(pr)
     o.debug_linearize(); s.debug_linearize()
@@ -359,3 +359,39 @@ def test_set_consensus_rejects_bad_slots():
         s.set_consensus(0, refs, bad, n)
     with pytest.raises(D2BAError):
         s.set_consensus(0, refs, slots, 0)
+
+
+@pytest.mark.parametrize("n_agents", [2, 4])
+def test_L2_multi_agent_window_normal_equations(n_agents):
+    """One agent's window of a swarm (own frames + remote pose blocks = leaves of the arrow-shaped pose part): linearisation,
+    landmark Schur complement and Gauss-Newton step against the oracle, in the oracle's column order."""
+    pr = synth.make_swarm(seed=88, n_agents=n_agents, only_agents=[1], n_landmarks=150, shared_per_pair=40)[0]
+    pr["consensus"] = None
+    o, s = both(pr)
+    o.debug_linearize(); s.debug_linearize()
+    assert np.array_equal(o.debug_get(abi.DBG_COL_OF_BLOCK, np.int32), s.debug_get(0, abi.DBG_COL_OF_BLOCK, np.int32))
+    for item in (abi.DBG_COST, abi.DBG_HCC, abi.DBG_GC, abi.DBG_HLL, abi.DBG_GL, abi.DBG_W, abi.DBG_S):
+        assert relerr(s.debug_get(0, item), o.debug_get(item)) <= 1e-10, item
+    assert relerr(s.debug_get(0, abi.DBG_GN_STEP), o.debug_get(abi.DBG_GN_STEP)) <= 1e-6
+
+
+def test_leaf_elimination_equals_dense_cholesky(monkeypatch):
+    """Remote-frame blocks eliminated as leaves (k_leaf_elim -> hub Cholesky -> k_leaf_back) vs the dense Cholesky of the
+    whole pose part: two elimination orders of the same normal equations."""
+    from d2slam_b200.solver import Solver
+    from oracle import orc
+    sw = synth.make_swarm(seed=89, n_agents=3, n_landmarks=120, shared_per_pair=30)
+    pr = sw[0]
+    out = {}
+    for tag, env in (("leaf", "0"), ("dense", "1")):
+        monkeypatch.setenv("D2BA_NO_LEAF", env)     # read by d2ba_create
+        s = Solver(consensus_max_steps=1); pr.load(s, 0); s.finalize()
+        s.debug_linearize()
+        out[tag + "_gn"] = s.debug_get(0, abi.DBG_GN_STEP).copy()
+        s2 = Solver(consensus_max_steps=1, max_num_iterations=6); pr.load(s2, 0); s2.finalize()
+        rep = s2.solve_fixed(6)[0]
+        out[tag] = state_of(s2, pr, 0); out[tag + "_cost"] = rep.final_cost
+    assert relerr(out["leaf_gn"], out["dense_gn"]) <= 1e-6
+    d = state_diff(out["leaf"], out["dense"])
+    assert d["pos"] <= 1e-6 and d["rot"] <= 1e-6 and d["sb"] <= 1e-6 and d["lm_rel"] <= 1e-5, d
+    assert abs(out["leaf_cost"] - out["dense_cost"]) <= 1e-7 * max(1.0, abs(out["dense_cost"]))
