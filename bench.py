@@ -380,7 +380,7 @@ def swarm_one_gpu(args, local_rank, n_agents, n_swarms, iters, steps, warmup, cp
     # end to end from host buffers (sequential: feed -> finalize -> solve -> read back)
     from d2slam_b200.harness import Replay
     rp = Replay(probs)
-    nth = max(1, min(host_threads_available(), 16))
+    nth = max(1, min(host_threads_available(), 32))
     rp.run(s, 2, iters, nth)
     n = max(2, min(steps, 8))
     wall, _ = rp.run(s, n, iters, nth)
@@ -481,7 +481,7 @@ def run_ours(args, rank, world, local_rank):
     from d2slam_b200.harness import Replay
     rp = Replay(probs)
     ncpu = host_threads_available()
-    host_threads = max(1, min(ncpu // max(1, min(world, 4)), 16))
+    host_threads = max(1, min(ncpu // max(1, min(world, 8)), 32))
     e2e_steps = max(1, min(args.steps, 40))
     n_seq = min(e2e_steps, 10)
     rp.run(solver, 2, iters, host_threads)

@@ -4,6 +4,7 @@
 // fallback (d2ba_create fails without a CUDA device).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,10 +29,13 @@ void launch_state_prep(const Dev &d, int n6_total, int buf, cudaStream_t s);
 void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s);
 void launch_prior_prep(const Dev &d, cudaStream_t s);
 void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s);
+void launch_imu_lin(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s);
 int configure_kernels(int max_rows, int max_nc, int max_prior_m);
 int configure_gather(int max_ldw);
 void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int job_count, cudaStream_t s);
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s);
+void launch_imu_debug(const Dev &d, double *out, const int *imu_win, int n, cudaStream_t s);
+void launch_cons_debug(const Dev &d, double *out, const int *blk_win, int n, cudaStream_t s);
 void launch_lm_gather(const Dev &d, const int *lm_win, int n_lm_total, int max_ldw, int any_compact, int any_wide, cudaStream_t s);
 void launch_schur(const Dev &d, const void *tiles, int n_tiles, cudaStream_t s);
 int configure_leaf_elim(size_t smem);
@@ -248,7 +252,7 @@ struct d2ba_handle {
   DBuf<double> d_x6[2], d_R6[2], d_xsb[2], d_xlm[2], d_xtd[2];
   DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_obs_slot, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
   DBuf<Group> d_grp; DBuf<Job> d_job; DBuf<ImuDesc> d_imu; DBuf<PriorBlk> d_prior_blk;
-  DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
+  DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_imu_raw, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
   DBuf<SchurTileH> d_schur; DBuf<int> d_schur_chunks; DBuf<Leaf> d_leaf; DBuf<HSeg> d_hseg; DBuf<unsigned long long> d_lm_mask; DBuf<double> d_leafL; DBuf<int> d_leaf_lm;
   int n_schur0 = 0, n_leaf_total = 0, max_hub = 0; size_t leaf_smem = 0, cfg_leaf_smem = 0, leafb_smem = 0, cfg_leafb_smem = 0;
@@ -384,7 +388,7 @@ int d2ba_destroy(d2ba_handle *h) {
   for (int b = 0; b < 2; b++) { h->d_x6[b].release(); h->d_R6[b].release(); h->d_xsb[b].release(); h->d_xlm[b].release(); h->d_xtd[b].release(); h->d_rec[b].release(); h->d_H[b].release(); h->d_gc[b].release(); }
   h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_obs_slot.release();
   h->d_slot6.release(); h->d_lm_win.release(); h->d_blk_win.release(); h->d_sb_win.release(); h->d_tile_win.release();
-  h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release();
+  h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release(); h->d_imu_raw.release();
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
   h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release(); h->d_schur_chunks.release(); h->d_leaf.release(); h->d_hseg.release(); h->d_lm_mask.release(); h->d_leafL.release(); h->d_leaf_lm.release();
@@ -673,8 +677,9 @@ struct WinPlan {
 template <typename F>
 void parallel_for(int n, F f) {
   int nt = (int)std::thread::hardware_concurrency();
+  { cpu_set_t cs; CPU_ZERO(&cs); if (sched_getaffinity(0, sizeof cs, &cs) == 0 && CPU_COUNT(&cs) > 0) nt = CPU_COUNT(&cs); }   // the cores this process may run on
   if (nt < 1) nt = 1;
-  if (nt > 16) nt = 16;
+  if (nt > 32) nt = 32;
   if (nt > n) nt = n;
   if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
   std::atomic<int> next(0);
@@ -950,6 +955,26 @@ int d2ba_finalize(d2ba_handle *h) {
       k = e;
     }
     pl.n_tiles = tile_run; d.n_tile = tile_run; d.n_grp = (int)pl.groups.size();
+    {   // may k_lm_gather16 skip the barrier between records?  Only if, per landmark, no column block shows up at slot 0 of one
+        // record and at slot 1 of another (then every row entry is owned by one lane).  True for the reference's graphs:
+        // slot 0 is the anchor pose of the landmark, the other slot an observing frame.
+      std::vector<int> s0(nl, -1);   // the landmark's slot-0 column (-2: more than one -> keep the barrier)
+      bool clash = false;
+      for (int gi = 0; gi < (int)pl.groups.size() && !clash; gi++) {
+        const int c0g = pl.groups[gi].slot_col[0];
+        if (c0g < 0) continue;
+        for (int q = pl.grp_begin[gi]; q < pl.grp_begin[gi] + pl.grp_cnt[gi]; q++) {
+          int &s = s0[w.obs[w.order[q]].lm];
+          if (s == -1) s = c0g; else if (s != c0g) { clash = true; break; }
+        }
+      }
+      for (int gi = 0; gi < (int)pl.groups.size() && !clash; gi++) {
+        const int c1g = pl.groups[gi].slot_col[1];
+        if (c1g < 0) continue;
+        for (int q = pl.grp_begin[gi]; q < pl.grp_begin[gi] + pl.grp_cnt[gi]; q++) if (s0[w.obs[w.order[q]].lm] == c1g) { clash = true; break; }
+      }
+      d.gather_nosync = clash ? 0 : 1;
+    }
     {   // landmarks of every leaf (ascending, each once) and the widest coupling row in 32-column tiles
       pl.leaf_lm.clear();
       std::vector<std::vector<int>> per_leaf(pl.leaves.size());
@@ -1187,7 +1212,7 @@ int d2ba_finalize(d2ba_handle *h) {
     for (int l = 0; l < d.nl; l++) st.lm_mask.p[d.offlm + l] = pl.lm_mask[l];
     for (int i = 0; i < d.n_imu; i++) {
       const HImu &m = w.imu[i];
-      st.imu.p[d.off_imu + i] = ImuDesc{m.pi, m.si, m.pj, m.sj};
+      st.imu.p[d.off_imu + i] = ImuDesc{m.pi, m.si, m.pj, m.sj, wi};
       memcpy(st.imu_c.p + (size_t)(d.off_imu + i) * kImuStride, m.c, sizeof(double) * kImuStride);
     }
     st.pr_m.p[wi] = d.prior_m; st.pr_info.p[wi] = (d.prior_m > 0 && w.prior_is_info) ? 1 : 0; st.pr_offJ.p[wi] = d.off_prior_J; st.pr_offv.p[wi] = d.off_prior_v;
@@ -1247,7 +1272,9 @@ int d2ba_finalize(d2ba_handle *h) {
   CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
   CK(cudaEventRecord(h->evf1, h->stream));
   launch_build_tiles(h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
-  CK(h->d_imu_U.alloc((size_t)off_imu * 225)); CK(h->d_prior_A.alloc((size_t)off_pJ));
+  CK(h->d_imu_U.alloc((size_t)off_imu * 225));
+  if ((rc = alloc_zero(h, h->d_imu_raw, (size_t)off_imu * 465))) return rc;   // structural zeros of the raw Jacobians are never rewritten
+  CK(h->d_prior_A.alloc((size_t)off_pJ));
   CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
   CK(h->d_td_ref.alloc(nw));
   if ((rc = alloc_zero(h, h->d_cons, (size_t)std::max(h->n_slots, 1) * 14))) return rc;
@@ -1264,9 +1291,9 @@ int d2ba_finalize(d2ba_handle *h) {
   D.win = h->d_win.p; D.ctl = h->d_ctl.p; D.n_win = nw;
   for (int b = 0; b < 2; b++) { D.x6[b] = h->d_x6[b].p; D.R6[b] = h->d_R6[b].p; D.xsb[b] = h->d_xsb[b].p; D.xlm[b] = h->d_xlm[b].p; D.xtd[b] = h->d_xtd[b].p; D.rec[b] = h->d_rec[b].p; D.Hcc[b] = h->d_H[b].p; D.gc[b] = h->d_gc[b].p; }
   D.col6 = h->d_col6.p; D.colsb = h->d_colsb.p; D.grp = h->d_grp.p; D.job = h->d_job.p; D.n_job = n_jobs;
-  D.lm_mask = h->d_lm_mask.p; D.hseg = h->d_hseg.p; D.leaf = h->d_leaf.p; D.n_leaf_total = h->n_leaf_total; D.leafL = h->d_leafL.p; D.schur_chunks = h->d_schur_chunks.p; D.leaf_lm = h->d_leaf_lm.p;
+  D.lm_mask = h->d_lm_mask.p; D.hseg = h->d_hseg.p; D.leaf = h->d_leaf.p; D.n_leaf_total = h->n_leaf_total; { int np_ = 0; for (int q = 0; q < nw; q++) if (plan[q].d.n_leaf == 0) np_++; D.n_plain_win = np_; } D.leafL = h->d_leafL.p; D.schur_chunks = h->d_schur_chunks.p; D.leaf_lm = h->d_leaf_lm.p;
   D.tile_grp = h->d_tile_grp.p; D.obs = h->d_obs.p; D.obs_lm = h->d_obs_lm.p; D.lm_ptr = h->d_lm_ptr.p; D.obs_slot = h->d_obs_slot.p;
-  D.imu = h->d_imu.p; D.imu_c = h->d_imu_c.p; D.imu_U = h->d_imu_U.p; D.prior_blk = h->d_prior_blk.p; D.prior_J = h->d_prior_J.p;
+  D.imu = h->d_imu.p; D.imu_c = h->d_imu_c.p; D.imu_U = h->d_imu_U.p; D.imu_raw = h->d_imu_raw.p; D.prior_blk = h->d_prior_blk.p; D.prior_J = h->d_prior_J.p;
   D.prior_e0 = h->d_prior_e0.p; D.prior_A = h->d_prior_A.p; D.slot6 = h->d_slot6.p; D.z6 = h->d_z6.p; D.tilde6 = h->d_tilde6.p;
   D.lm_ref = h->d_lm_ref.p; D.sb_ref = h->d_sb_ref.p; D.td_ref = h->d_td_ref.p; D.cons_buf = h->d_cons.p; D.n_slots = h->n_slots;
   D.Wt = h->d_Wt.p; D.dinv = h->d_dinv.p; D.hl = h->d_hl.p; D.gl = h->d_gl.p; D.S = h->d_S.p; D.gred = h->d_gred.p; D.D2c = h->d_D2c.p;
@@ -1372,6 +1399,7 @@ static int upload_state(d2ba_handle *h) {
 
 static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
   launch_misc_lin(h->dev, eval_cur, h->max_prior_m, h->stream);
+  launch_imu_lin(h->dev, eval_cur, h->n_imu_total, h->stream);
   for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, eval_cur, h->job_begin[v], h->job_count[v], h->stream);
 }
 
@@ -1666,6 +1694,26 @@ int d2ba_debug_get(d2ba_handle *h, int32_t window, int32_t item, void *out, int6
       for (size_t k = 0; k < w->order.size(); k++) memcpy(&o[(size_t)w->order[k] * 81], &all[(size_t)w->sorted_pos[k] * 81], 81 * 8);
       put_d(o); break;
     }
+    case D2BA_DBG_IMU_RESJAC: {
+      // imu -> window map built here (debug only)
+      std::vector<int> iw;
+      for (int wi2 = 0; wi2 < h->n_used; wi2++) iw.insert(iw.end(), h->h_win[wi2].n_imu, wi2);
+      DBuf<double> tmp; DBuf<int> dw;
+      if (tmp.alloc((size_t)std::max<size_t>(iw.size(), 1) * 465) != cudaSuccess || dw.alloc(std::max<size_t>(iw.size(), 1)) != cudaSuccess) return fail(h, 5, "debug alloc");
+      if (!iw.empty()) cudaMemcpy(dw.p, iw.data(), iw.size() * sizeof(int), cudaMemcpyHostToDevice);
+      launch_imu_debug(h->dev, tmp.p, dw.p, (int)iw.size(), h->stream);
+      cudaStreamSynchronize(h->stream);
+      put_d(fetch(tmp.p + (size_t)d.off_imu * 465, (size_t)d.n_imu * 465));
+      tmp.release(); dw.release(); break;
+    }
+    case D2BA_DBG_CONS_RESJAC: {
+      DBuf<double> tmp;
+      if (tmp.alloc((size_t)std::max(h->n6_total, 1) * 62) != cudaSuccess) return fail(h, 5, "debug alloc");
+      launch_cons_debug(h->dev, tmp.p, h->d_blk_win.p, h->n6_total, h->stream);
+      cudaStreamSynchronize(h->stream);
+      put_d(fetch(tmp.p + (size_t)d.off6 * 62, (size_t)d.n6 * 62));
+      tmp.release(); break;
+    }
     default: return fail(h, 6, "debug_get: unknown item");
   }
   if (needed) *needed = (int64_t)buf.size();
@@ -1856,7 +1904,7 @@ int d2ba_debug_kernel_times(d2ba_handle *h, int32_t iters, double *ms_out) {
     cudaEventRecord(ev[2], h->stream); if (h->max_n_smem > 0) launch_chol_smem(h->dev, h->max_n_smem, h->stream); if (h->any_chol_glob) launch_chol(h->dev, h->max_rows_glob, h->stream); cudaEventRecord(evs[1], h->stream); if (h->sbe_smem > 0) launch_sb_back(h->dev, h->sbb_smem, h->stream);
     cudaEventRecord(evl[2], h->stream); if (h->n_leaf_total > 0) launch_leaf_back(h->dev, h->leafb_smem, h->stream);
     cudaEventRecord(ev[3], h->stream); launch_step(h->dev, h->max_nc, h->stream);
-    cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream);
+    cudaEventRecord(ev[4], h->stream); launch_misc_lin(h->dev, 0, h->max_prior_m, h->stream); launch_imu_lin(h->dev, 0, h->n_imu_total, h->stream);
     cudaEventRecord(ev[5], h->stream); for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, 0, h->job_begin[v], h->job_count[v], h->stream);
     cudaEventRecord(ev[6], h->stream); launch_control(h->dev, 0, h->stream);
     cudaEventRecord(ev[7], h->stream);

@@ -197,6 +197,20 @@ D2BA_DEV void prior_dx_pose(const double *x, const double *x0, double *dx) {  //
   else { dx[3] = 2.0 * p.x; dx[4] = 2.0 * p.y; dx[5] = 2.0 * p.z; }
 }
 
+// ConsenusPoseFactor::Evaluate (consenus_factor.cpp:19-51): r = [wT (Rz^T (t - t_z) + t~) ; wq (2 vec(q_z^-1 q) + th~)],
+// dT/dp = wT Rz^T, dth/dtheta = wq Qleft(q_z^-1 q)_3 (after positify).  NB the constructor's swap: wq = rho_T, wT = rho_theta.
+D2BA_DEV void cons_eval(const double *x, const double *z, const double *tl, double wq, double wT, double *r, double *Rz, double *L3) {
+  double dd[3] = {x[0] - z[0], x[1] - z[1], x[2] - z[2]}, t[3];
+  Q4 qz = qload(z + 3);
+  q2R(qz, Rz);
+  mtv3(Rz, dd, t);
+  Q4 qe = qmul(qinv(qz), qload(x + 3));
+  r[0] = wT * (t[0] + tl[0]); r[1] = wT * (t[1] + tl[1]); r[2] = wT * (t[2] + tl[2]);
+  r[3] = wq * (2 * qe.x + tl[3]); r[4] = wq * (2 * qe.y + tl[4]); r[5] = wq * (2 * qe.z + tl[5]);
+  Q4 p = qpos(qe);
+  L3[0] = p.w; L3[1] = -p.z; L3[2] = p.y; L3[3] = p.z; L3[4] = p.w; L3[5] = -p.x; L3[6] = -p.y; L3[7] = p.x; L3[8] = p.w;
+}
+
 // One CTA per window: zero Hcc/gc of the evaluated buffer, then add IMU, prior and ADMM terms.
 // Runs before k_proj_lin (which adds the reprojection blocks with atomics).
 constexpr int kMiscThreads = 256;
@@ -210,7 +224,7 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
   const int tid = threadIdx.x, nt = blockDim.x;
   extern __shared__ double sm[];
   double *red = sm;             // 40
-  double *Jr = sm + 40;         // chunk of IMU factors: raw J (15x30) + r(15) + J (15x30) + r(15)
+  double *Jr = sm + 40;         // prior scratch: dx, r, column map
   const int n = w.n_c, ld = w.ldh;
   double *H = d.Hcc[buf] + w.offH;
   double *g = d.gc[buf] + w.offc;
@@ -228,11 +242,7 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
   // ---- zero + IMU factors.  The raw residual / Jacobian of a factor is one long dependent chain (one lane per
   //      factor, all in warp 0); the other warps zero H / g and stage the sqrt-information meanwhile.  U J and
   //      [J r]^T [J r] then run on the fp64 tensor cores (m8n8k4), 8x8 output tiles spread over the warps.
-  constexpr int kImuChunk = kMiscImuChunk;
-  constexpr int kF = 15 * 30 + 15;  // doubles per factor for (J, r)
-  const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
   double cost = 0.0;
-  bool zeroed = false;
   // zero only the runs of Hcc some factor writes (lower triangle; the rest stays at the zero of the finalize-time memset)
   auto zero_H = [&](int t0, int tn) {
     const HSeg *sg = d.hseg + w.off_hseg;
@@ -243,107 +253,8 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
     }
     for (int e = t0; e < n; e += tn) g[e] = 0.0;
   };
-  for (int f0 = 0; f0 < w.n_imu; f0 += kImuChunk) {
-    const int nf = min(kImuChunk, w.n_imu - f0);
-    double *raw = Jr, *fin = Jr + kImuChunk * kF;
-    double *Us = fin + kImuChunk * kF;
-    int *fcols = reinterpret_cast<int *>(Us + kImuChunk * 225);
-    for (int e = tid; e < nf * kF; e += nt) raw[e] = 0.0;
-    __syncthreads();
-    if (warp == 0) {
-      if (lane < nf) {
-        const ImuDesc &im = d.imu[w.off_imu + f0 + lane];
-        imu_raw(d.imu_c + (size_t)(w.off_imu + f0 + lane) * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8,
-                xsb + im.sj * 9, d.prm.gravity, raw + lane * kF + 450, raw + lane * kF);
-      }
-    } else {
-      const int t0 = tid - 32, tn = nt - 32;
-      for (int e = t0; e < nf * 225; e += tn) Us[e] = d.imu_U[(size_t)(w.off_imu + f0) * 225 + e];
-      if (t0 < nf * 4) {
-        const ImuDesc &im = d.imu[w.off_imu + f0 + t0 / 4];
-        const int q = t0 & 3;
-        fcols[t0] = q == 0 ? col6[im.pi] : (q == 1 ? colsb[im.si] : (q == 2 ? col6[im.pj] : colsb[im.sj]));
-      }
-      if (!zeroed) zero_H(t0, tn);
-    }
-    zeroed = true;
-    __syncthreads();
-    MLAP(2);
-    // fin = U [Jraw | rraw]: per factor 2 x 4 output tiles, K = 15 (4 k-steps, the 16th masked)
-    {
-      const int g4 = lane >> 2, q4 = lane & 3;
-      for (int job = warp; job < nf * 8; job += nwarp) {
-        const int f = job >> 3, ti = (job >> 2) & 1, tj = job & 3;
-        const double *U = Us + f * 225, *src = raw + f * kF;
-        const int i = 8 * ti + g4, bc = 8 * tj + g4;
-        double c0 = 0.0, c1 = 0.0, av[4], bv[4];   // operands first: the (volatile) MMAs then issue back to back
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const int kq = 4 * kk + q4;
-          const bool kok = kq < 15;
-          av[kk] = (kok && i < 15) ? U[i * 15 + kq] : 0.0;
-          bv[kk] = !kok ? 0.0 : (bc < 30 ? src[kq * 30 + bc] : (bc == 30 ? src[450 + kq] : 0.0));
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
-        if (i < 15) {
-          double *dst = fin + f * kF;
-          const int j0 = 8 * tj + 2 * q4;
-          if (j0 < 30) { dst[i * 30 + j0] = c0; dst[i * 30 + j0 + 1] = c1; }
-          else if (j0 == 30) dst[450 + i] = c0;
-        }
-      }
-    }
-    __syncthreads();
-    MLAP(3);
-    // accumulate [J r]^T [J r]: per factor 4 x 4 output tiles (rows a < 30; column 30 is the gradient), flushed with
-    // L2 reductions (measured: faster than single-writer plain stores or read-modify-write passes here)
-    {
-      const int g4 = lane >> 2, q4 = lane & 3;
-      for (int job = warp; job < nf * 16; job += nwarp) {
-        const int f = job >> 4, ta = (job >> 2) & 3, tb = job & 3;
-        const double *Jf = fin + f * kF;
-        const int *cols = fcols + f * 4;
-        auto gcol = [&](int a) -> int {  // local 0..29 -> reduced column
-          const int b = a < 6 ? 0 : (a < 15 ? 1 : (a < 21 ? 2 : 3));
-          const int o = a < 6 ? a : (a < 15 ? a - 6 : (a < 21 ? a - 15 : a - 21));
-          return cols[b] < 0 ? -1 : cols[b] + o;
-        };
-        const int ar = 8 * ta + g4, bc = 8 * tb + g4;
-        double c0 = 0.0, c1 = 0.0, av[4], bv[4];   // operands first: the (volatile) MMAs then issue back to back
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const int kq = 4 * kk + q4;
-          const bool kok = kq < 15;
-          av[kk] = (kok && ar < 30) ? Jf[kq * 30 + ar] : 0.0;
-          bv[kk] = !kok ? 0.0 : (bc < 30 ? Jf[kq * 30 + bc] : (bc == 30 ? Jf[450 + kq] : 0.0));
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
-        if (ar < 30) {
-          const int ga = gcol(ar);
-          if (ga >= 0) {
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-              const int bo = 8 * tb + 2 * q4 + u;
-              const double v = u == 0 ? c0 : c1;
-              if (bo < 30) { const int gb = gcol(bo); if (gb >= 0 && gb <= ga && v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }   // lower triangle
-              else if (bo == 30) atomicAdd(&g[ga], v);
-            }
-          }
-        }
-      }
-    }
-    if (tid < nf) {
-      const double *rf = fin + tid * kF + 450;
-      double s = 0;
-      for (int q = 0; q < 15; q++) s += rf[q] * rf[q];
-      cost += 0.5 * s;
-    }
-    __syncthreads();
-    MLAP(4);
-  }
-  if (!zeroed) { zero_H(tid, nt); __syncthreads(); }
+  zero_H(tid, nt);
+  __syncthreads();
   // ---- prior: r = e0 + J dx ; H += J^T J ; g += J^T r
   if (w.prior_m > 0) {
     const int m = w.prior_m;
@@ -397,19 +308,12 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
       // ConsenusPoseFactor::Evaluate (consenus_factor.cpp:19-51); NB q weight = rho_T, T weight = rho_theta
       const double *z = d.z6 + (size_t)(w.off6 + b) * 8, *tl = d.tilde6 + (size_t)(w.off6 + b) * 6;
       const double *x = x6 + b * 8;
-      double Rz[9], dd[3] = {x[0] - z[0], x[1] - z[1], x[2] - z[2]}, t[3];
-      Q4 qz = qload(z + 3);
-      q2R(qz, Rz);
-      mtv3(Rz, dd, t);
-      Q4 qe = qmul(qinv(qz), qload(x + 3));
       const double wq = d.prm.rho_T, wT = d.prm.rho_theta;
-      double r[6] = {wT * (t[0] + tl[0]), wT * (t[1] + tl[1]), wT * (t[2] + tl[2]),
-                     wq * (2 * qe.x + tl[3]), wq * (2 * qe.y + tl[4]), wq * (2 * qe.z + tl[5])};
+      double Rz[9], L3[9], r[6];
+      cons_eval(x, z, tl, wq, wT, r, Rz, L3);
       for (int q = 0; q < 6; q++) cost += 0.5 * r[q] * r[q];
       int c = col6[b];
       if (c < 0) continue;
-      Q4 p = qpos(qe);
-      double L3[9] = {p.w, -p.z, p.y, p.z, p.w, -p.x, -p.y, p.x, p.w};
       // J_T = wT Rz^T (3x3), J_q = wq L3
       for (int i = 0; i < 3; i++) {
         double gi = 0, gq = 0;
@@ -448,6 +352,113 @@ __global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cu
   MLAP(6);
   if (wi == 0 && tid == 0) printf("misc timing: zero %lld uload %lld imu_raw %lld UJ %lld JtJ %lld prior %lld tail %lld\n", mk[0], mk[1], mk[2], mk[3], mk[4], mk[5], mk[6]);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMU factors: one WARP per factor over the whole batch (a window has only ~10 of them, so one CTA per window left the
+// SMs mostly idle during the long dependent chain of the raw residual / Jacobian).  Lane 0 evaluates the raw terms
+// (imu_raw), the warp then forms U [J r] and [J r]^T [J r] on the fp64 tensor cores (m8n8k4) and adds the lower triangle
+// into Hcc / gc with L2 reductions.  Runs after k_misc_lin (which zeroed the written runs of Hcc) and adds its cost to it.
+// k_imu_raw: one THREAD per factor -- the raw residual / Jacobian is one long dependent instruction stream, identical for every
+// factor, so 32 factors run it in lockstep per warp (one warp per factor would issue the same stream 32 times).  Output to
+// a global scratch [factor][465] whose never-written entries stay at the zero of the finalize-time memset.
+__global__ void __launch_bounds__(32) k_imu_raw(Dev d, int eval_cur, int n_imu_total) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_imu_total) return;
+  const ImuDesc im = d.imu[f];
+  const WinDesc &w = d.win[im.win];
+  const Ctl *ctl = d.ctl + im.win;
+  if (ctl->done || (!eval_cur && !ctl->step_valid)) return;
+  const int buf = eval_cur ? ctl->cur : 1 - ctl->cur;
+  const double *x6 = d.x6[buf] + (size_t)w.off6 * 8, *xsb = d.xsb[buf] + (size_t)w.offsb * 9;
+  double *raw = d.imu_raw + (size_t)f * (15 * 30 + 15);
+  imu_raw(d.imu_c + (size_t)f * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8, xsb + im.sj * 9, d.prm.gravity, raw + 450, raw);
+}
+constexpr int kImuWarps = 4;
+constexpr int kImuF = 15 * 30 + 15;   // doubles per factor for (J, r)
+constexpr int kImuWarpDoubles = 2 * kImuF + 225 + 1;   // raw, U [J r], sqrt-information
+__global__ void __launch_bounds__(kImuWarps * 32) k_imu_lin(Dev d, int eval_cur, int n_imu_total) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kImuWarps + warp;
+  if (f >= n_imu_total) return;
+  const ImuDesc im = d.imu[f];
+  const int wi = im.win;
+  const WinDesc &w = d.win[wi];
+  Ctl *ctl = d.ctl + wi;
+  if (ctl->done || (!eval_cur && !ctl->step_valid)) return;
+  const int buf = eval_cur ? ctl->cur : 1 - ctl->cur;
+  double *raw = sm + (size_t)warp * kImuWarpDoubles, *fin = raw + kImuF, *Us = fin + kImuF;
+  const int ld = w.ldh;
+  double *H = d.Hcc[buf] + w.offH, *g = d.gc[buf] + w.offc;
+  const int *col6 = d.col6 + w.off6, *colsb = d.colsb + w.offsb;
+  // raw (J, r) of k_imu_raw and the sqrt-information: coalesced, all in flight
+  {
+    const double *Ug = d.imu_U + (size_t)f * 225, *rg = d.imu_raw + (size_t)f * kImuF;
+    for (int e = lane; e < 225; e += 32) cp_async8(Us + e, Ug + e);
+    for (int e = lane; e < kImuF; e += 32) cp_async8(raw + e, rg + e);
+    cp_async_wait_all();
+  }
+  const int cols[4] = {col6[im.pi], colsb[im.si], col6[im.pj], colsb[im.sj]};
+  const double *U = Us;
+  __syncwarp();
+  const int g4 = lane >> 2, q4 = lane & 3;
+  // fin = U [Jraw | rraw]: 2 x 4 output tiles, K = 15 (4 k-steps, the 16th masked)
+  for (int job = 0; job < 8; job++) {
+    const int ti = job >> 2, tj = job & 3;
+    const int i = 8 * ti + g4, bc = 8 * tj + g4;
+    double c0 = 0.0, c1 = 0.0, av[4], bv[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const int kq = 4 * kk + q4;
+      const bool kok = kq < 15;
+      av[kk] = (kok && i < 15) ? U[i * 15 + kq] : 0.0;
+      bv[kk] = !kok ? 0.0 : (bc < 30 ? raw[kq * 30 + bc] : (bc == 30 ? raw[450 + kq] : 0.0));
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
+    if (i < 15) {
+      const int j0 = 8 * tj + 2 * q4;
+      if (j0 < 30) { fin[i * 30 + j0] = c0; fin[i * 30 + j0 + 1] = c1; }
+      else if (j0 == 30) fin[450 + i] = c0;
+    }
+  }
+  __syncwarp();
+  auto gcol = [&](int a) -> int {  // local 0..29 -> reduced column
+    const int b = a < 6 ? 0 : (a < 15 ? 1 : (a < 21 ? 2 : 3));
+    const int o = a < 6 ? a : (a < 15 ? a - 6 : (a < 21 ? a - 15 : a - 21));
+    return cols[b] < 0 ? -1 : cols[b] + o;
+  };
+  // [J r]^T [J r]: 4 x 4 output tiles (rows a < 30; column 30 is the gradient), lower triangle kept
+  for (int job = 0; job < 16; job++) {
+    const int ta = job >> 2, tb = job & 3;
+    const int ar = 8 * ta + g4, bc = 8 * tb + g4;
+    double c0 = 0.0, c1 = 0.0, av[4], bv[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const int kq = 4 * kk + q4;
+      const bool kok = kq < 15;
+      av[kk] = (kok && ar < 30) ? fin[kq * 30 + ar] : 0.0;
+      bv[kk] = !kok ? 0.0 : (bc < 30 ? fin[kq * 30 + bc] : (bc == 30 ? fin[450 + kq] : 0.0));
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) dmma(c0, c1, av[kk], bv[kk]);
+    if (ar < 30) {
+      const int ga = gcol(ar);
+      if (ga >= 0) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int bo = 8 * tb + 2 * q4 + u;
+          const double v = u == 0 ? c0 : c1;
+          if (bo < 30) { const int gb = gcol(bo); if (gb >= 0 && gb <= ga && v != 0.0) atomicAdd(&H[(size_t)ga * ld + gb], v); }
+          else if (bo == 30) atomicAdd(&g[ga], v);
+        }
+      }
+    }
+  }
+  double s_ = lane < 15 ? fin[450 + lane] * fin[450 + lane] : 0.0;
+  s_ = warp_sum(s_);
+  if (lane == 0) atomicAdd(&ctl->cand_cost_misc, 0.5 * s_);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -861,6 +872,44 @@ __global__ void k_proj_debug(Dev d, double *out /*[tiles*32][81]*/, int n_tiles_
   }
 }
 
+// debug: whitened residual + Jacobian of every IMU factor (one thread per factor), same imu_raw as k_misc_lin
+__global__ void k_imu_debug(Dev d, double *out /*[n_imu_total][465]*/, const int *imu_win, int n_imu_total) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_imu_total) return;
+  const int wi = imu_win[f];
+  const WinDesc &w = d.win[wi];
+  const int buf = d.ctl[wi].cur;
+  const double *x6 = d.x6[buf] + (size_t)w.off6 * 8, *xsb = d.xsb[buf] + (size_t)w.offsb * 9;
+  const ImuDesc &im = d.imu[f];
+  double raw[465];
+  for (int i = 0; i < 465; i++) raw[i] = 0.0;
+  imu_raw(d.imu_c + (size_t)f * kImuStride, x6 + im.pi * 8, xsb + im.si * 9, x6 + im.pj * 8, xsb + im.sj * 9, d.prm.gravity, raw + 450, raw);
+  const double *U = d.imu_U + (size_t)f * 225;
+  double *o = out + (size_t)f * 465;
+  for (int i = 0; i < 15; i++) {
+    double s = 0; for (int k = 0; k < 15; k++) s += U[i * 15 + k] * raw[450 + k];
+    o[i] = s;
+    for (int j = 0; j < 30; j++) { double a = 0; for (int k = 0; k < 15; k++) a += U[i * 15 + k] * raw[k * 30 + j]; o[15 + i * 30 + j] = a; }
+  }
+}
+__global__ void k_cons_debug(Dev d, double *out /*[n6_total][62]*/, const int *blk_win, int n6_total) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n6_total) return;
+  double *o = out + (size_t)b * 62;
+  for (int i = 0; i < 62; i++) o[i] = 0.0;
+  if (d.slot6[b] < 0) return;
+  const int wi = blk_win[b];
+  const double *x = d.x6[d.ctl[wi].cur] + (size_t)b * 8, *z = d.z6 + (size_t)b * 8, *tl = d.tilde6 + (size_t)b * 6;
+  double r[6], Rz[9], L3[9];
+  const double wq = d.prm.rho_T, wT = d.prm.rho_theta;
+  cons_eval(x, z, tl, wq, wT, r, Rz, L3);
+  for (int i = 0; i < 7; i++) { o[i] = x[i]; o[7 + i] = z[i]; }
+  for (int i = 0; i < 6; i++) { o[14 + i] = tl[i]; o[20 + i] = r[i]; }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { o[26 + i * 6 + j] = wT * Rz[j * 3 + i]; o[26 + (3 + i) * 6 + 3 + j] = wq * L3[i * 3 + j]; }
+}
+void launch_imu_debug(const Dev &d, double *out, const int *imu_win, int n, cudaStream_t s) { if (n > 0) k_imu_debug<<<(n + 31) / 32, 32, 0, s>>>(d, out, imu_win, n); }
+void launch_cons_debug(const Dev &d, double *out, const int *blk_win, int n, cudaStream_t s) { if (n > 0) k_cons_debug<<<(n + 63) / 64, 64, 0, s>>>(d, out, blk_win, n); }
+
 // ------------------------------------------------------------------------------------------------
 // Per-landmark reduction, wide records (warp per landmark; compact records: k_lm_gather16 below).  The landmark's
 // records are visited serially, the 32 record entries in parallel across lanes, so there are no write conflicts and
@@ -977,18 +1026,34 @@ __global__ void __launch_bounds__(kG16Lm * 16) k_lm_gather16(Dev d, const int *l
     double v[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = (q < cnt) ? recs[(size_t)(k0 + q) * 16 + sub] : 0.0;
+    if (w.gather_nosync) {
+      // a column block is only ever named by ONE slot position within this landmark's records (host-checked): a row entry
+      // is always updated by the same lane, in program order -- no barrier between records, the updates pipeline
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      if (q >= cnt) break;
-      const double c01 = __shfl_sync(hmask, v[q], hbase | 3);   // packed column word of the record
-      int col = -1;
-      if (sub >= 4) { const int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
-      if (sub == 0) h += v[q];
-      if (sub == 1) g += v[q];
-      if (col >= 0) row[row_slot(mask, col)] += v[q];
-      __syncwarp(hmask);   // the two slots of different records may name the same column block
+      for (int q = 0; q < 8; q++) {
+        if (q >= cnt) break;
+        const double c01 = __shfl_sync(hmask, v[q], hbase | 3);   // packed column word of the record
+        int col = -1;
+        if (sub >= 4) { const int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
+        if (sub == 0) h += v[q];
+        if (sub == 1) g += v[q];
+        if (col >= 0) row[w.n_leaf ? row_slot(mask, col) : col] += v[q];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (q >= cnt) break;
+        const double c01 = __shfl_sync(hmask, v[q], hbase | 3);   // packed column word of the record
+        int col = -1;
+        if (sub >= 4) { const int sc = sub < 10 ? __double2hiint(c01) : __double2loint(c01); if (sc >= 0) col = sc + (sub - 4) % 6; }
+        if (sub == 0) h += v[q];
+        if (sub == 1) g += v[q];
+        if (col >= 0) row[row_slot(mask, col)] += v[q];
+        __syncwarp(hmask);   // the two slots of different records may name the same column block
+      }
     }
   }
+  __syncwarp(hmask);
   h = __shfl_sync(hmask, h, hbase);
   g = __shfl_sync(hmask, g, hbase | 1);
   if (w.admm_on) {
@@ -1977,7 +2042,7 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
 constexpr int kLeafThreads = 256;
 constexpr int kLeafMaxCols = 96;
 constexpr int kLeafLmChunk = 16;   // landmarks whose coupling rows are staged at a time (a multiple of the MMA k = 4)
-__host__ __device__ inline int leaf_lda(int n) { return (n + 2) & ~1; }
+__host__ __device__ inline int leaf_lda(int n) { return n | 1; }   // odd: the one-row-per-thread TRSM walks the rows without bank conflicts (all accesses are scalar)
 __host__ __device__ inline size_t leaf_elim_smem_bytes(int n, int nh) {
   const int n1 = n + nh + 1;
   return ((size_t)n1 * leaf_lda(n) + (size_t)((n + 1) & ~1) + (size_t)kCsNB * ((n1 + 1) & ~1) + 64 + (size_t)kLeafLmChunk * n1 + 8) * 8;
@@ -2078,19 +2143,22 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_elim(Dev d) {
     }
     cp_async_wait_all();
     __syncthreads();
-    const int Tr0 = (n1 + 7) >> 3, Tc0 = (n + 7) >> 3;   // fp64 tensor-core rank update, 8x8 tiles of the lower trapezoid
-    for (int job = warp; job < Tr0 * Tc0; job += nwarp) {
-      const int ti = job / Tc0, tj = job - ti * Tc0;
-      if (tj > ti) continue;
+    // fp64 tensor-core rank update over the 8x8 tiles of the lower trapezoid: row tile ti has min(ti + 1, Tc0) column tiles;
+    // the warps walk the tile list with stride nwarp (no division)
+    const int Tr0 = (n1 + 7) >> 3, Tc0 = (n + 7) >> 3;
+    for (int ti = 0, tj = warp;; ) {
+      while (ti < Tr0 && tj >= min(ti + 1, Tc0)) { tj -= min(ti + 1, Tc0); ti++; }
+      if (ti >= Tr0) break;
       leaf_rank8(A, lda, Wl, n1, 8 * ti, 8 * tj, nq4, n1, n, lane);
+      tj += nwarp;
     }
   }
   __syncthreads();
+  if (warp == 0) { if (chol_diag8(A, lda, invd, Ms, kCsNB, 0, min(kCsNB, n), lane)) fail = 1; }
+  __syncthreads();
   for (int k0 = 0; k0 < n; k0 += kCsNB) {
     const int nb = min(kCsNB, n - k0), nxt = k0 + nb;
-    if (warp == 0) { if (chol_diag8(A, lda, invd, Ms, kCsNB, k0, nb, lane)) fail = 1; }
-    __syncthreads();
-    // rows below the diagonal block (rest of the leaf block + every extra row): a L_d^T = x, one row per thread
+    // rows below the (already factored) diagonal block -- rest of the leaf block + every extra row: a L_d^T = x, one row per thread
     for (int r = nxt + tid; r < n1; r += nt) {
       double a[kCsNB];
       double *ar = A + (size_t)r * lda + k0;
@@ -2108,12 +2176,20 @@ __global__ void __launch_bounds__(kLeafThreads) k_leaf_elim(Dev d) {
     }
     __syncthreads();
     if (nxt >= n) break;
-    const int pmax = n1 - 1 - k0;
+    const int pmax = n1 - 1 - k0, nb2 = min(kCsNB, n - nxt);
     const int Tr = (n1 - nxt + 7) >> 3, Tc = (n - nxt + 7) >> 3;
-    for (int job = warp; job < Tr * Tc; job += nwarp) {
-      const int ti = job / Tc, tj = job - ti * Tc;
-      if (tj > ti) continue;
-      leaf_tile8(A, lda, P, ldp, nxt + 8 * ti, nxt + 8 * tj, nb + 8 * ti, nb + 8 * tj, pmax, n1, n, lane);
+    // look-ahead: the tile column of the next panel first (all warps) ...
+    for (int ti = warp; ti < Tr; ti += nwarp) leaf_tile8(A, lda, P, ldp, nxt + 8 * ti, nxt, nb + 8 * ti, nb, pmax, n1, n, lane);
+    __syncthreads();
+    // ... then warp 0 factors the next diagonal block (a pure latency chain) while the other warps update the rest
+    if (warp == 0) { if (chol_diag8(A, lda, invd, Ms, kCsNB, nxt, nb2, lane)) fail = 1; }
+    else {
+      for (int ti = 1, tj = warp - 1;; ) {   // row tile ti >= 1 has column tiles 1 .. min(ti, Tc - 1)
+        while (ti < Tr && tj >= min(ti, Tc - 1)) { tj -= min(ti, Tc - 1); ti++; }
+        if (ti >= Tr) break;
+        leaf_tile8(A, lda, P, ldp, nxt + 8 * ti, nxt + 8 * (tj + 1), nb + 8 * ti, nb + 8 * (tj + 1), pmax, n1, n, lane);
+        tj += nwarp - 1;
+      }
     }
     __syncthreads();
   }
@@ -2149,16 +2225,27 @@ __global__ void __launch_bounds__(kLeafBackThreads) k_leaf_back(Dev d) {
   __syncthreads();
   for (int k0 = warp * 4; k0 < n; k0 += nwarp * 4) {   // four rows per pass: their loads are all in flight before the first reduction
     double s_[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *y0 = Yg + (size_t)k0 * w.ldw;
+    for (int c0 = lane; c0 < nh; c0 += 96) {   // 4 rows x 3 column chunks: 12 independent loads before the first use
+      double yv[3][4], xv[3];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      if (k0 + q >= n) break;
-      const double *yr = Yg + (size_t)(k0 + q) * w.ldw;
-      for (int c = lane; c < nh; c += 32) s_[q] += yr[c] * xh[c];
+      for (int u = 0; u < 3; u++) {
+        const int c = c0 + 32 * u;
+        xv[u] = c < nh ? xh[c] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) yv[u][q] = (c < nh && k0 + q < n) ? y0[(size_t)q * w.ldw + c] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) s_[q] = fma(yv[u][q], xv[u], s_[q]);
     }
+    const double zq = (lane < 4 && k0 + lane < n) ? y0[(size_t)lane * w.ldw + nh] : 0.0;   // z entries of the four rows
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const double t = warp_sum(s_[q]);
-      if (lane == 0 && k0 + q < n) v[k0 + q] = Yg[(size_t)(k0 + q) * w.ldw + nh] - t;
+      const double z = __shfl_sync(0xffffffffu, zq, q);
+      if (lane == 0 && k0 + q < n) v[k0 + q] = z - t;
     }
   }
   cp_async_wait_all();
@@ -2183,9 +2270,11 @@ __global__ void k_zero_leaf_rows(Dev d) {
 // ------------------------------------------------------------------------------------------------
 // Step kernel: one CTA per window.
 constexpr int kStepThreads = 256;
-__global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
+template <bool LEAF>   // LEAF: windows with leaves (block-sparse landmark rows); the other instantiation handles the dense rows
+__global__ void __launch_bounds__(kStepThreads, LEAF ? 4 : 3) k_step(Dev d, int max_nc) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
+  if ((w.n_leaf != 0) != LEAF) return;
   Ctl *ctl = d.ctl + wi;
   if (ctl->done) return;
   extern __shared__ double sm[];
@@ -2215,16 +2304,37 @@ __global__ void __launch_bounds__(kStepThreads) k_step(Dev d, int max_nc) {
     for (int l0 = warp * 8; l0 < nl; l0 += nw * 8) {
       double a[8];
 #pragma unroll
-      for (int q = 0; q < 8; q++) {
-        a[q] = 0.0;
-        if (l0 + q < nl) {
-          const double *row = Wt + (size_t)(l0 + q) * w.ldw;
-          if (!w.n_leaf) { for (int c = lane; c < nlc; c += 32) a[q] += row[c] * dcs[c]; }
-          else
+      for (int q = 0; q < 8; q++) a[q] = 0.0;
+      if (!LEAF) {
+        // dense rows (single-drone window): 4 rows x 3 column chunks = 12 independent loads in flight before the first use
+        for (int c0 = lane; c0 < nlc; c0 += 96) {
+          double dc[3];
+#pragma unroll
+          for (int u = 0; u < 3; u++) dc[u] = c0 + 32 * u < nlc ? dcs[c0 + 32 * u] : 0.0;
+#pragma unroll
+          for (int qh = 0; qh < 8; qh += 4) {
+            const double *r0 = Wt + (size_t)(l0 + qh) * w.ldw;
+            double v[3][4];
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+#pragma unroll
+              for (int q = 0; q < 4; q++) v[u][q] = (c0 + 32 * u < nlc && l0 + qh + q < nl) ? r0[(size_t)q * w.ldw + c0 + 32 * u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+#pragma unroll
+              for (int q = 0; q < 4; q++) a[qh + q] = fma(v[u][q], dc[u], a[qh + q]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          if (l0 + q < nl) {
+            const double *row = Wt + (size_t)(l0 + q) * w.ldw;
             for (unsigned long long m = d.lm_mask[w.offlm + l0 + q]; m; m &= m - 1) {   // only the column tiles the row has entries in
               const int c = (__ffsll((long long)m) - 1) * 32 + lane;
               if (c < nlc) a[q] += row[c] * dcs[c];
             }
+          }
         }
       }
 #pragma unroll
@@ -2625,10 +2735,11 @@ void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s) {
 }
 void launch_prior_prep(const Dev &d, cudaStream_t s) { k_prior_prep<<<d.n_win, 256, 0, s>>>(d); }
 
-size_t misc_smem_bytes(int max_prior_m) {
-  size_t imu = (size_t)(40 + 2 * kMiscImuChunk * (15 * 30 + 15) + kMiscImuChunk * 225 + 2 * kMiscImuChunk + 8) * 8;
-  size_t pri = (size_t)(40 + 3 * max_prior_m + 8) * 8;
-  return imu > pri ? imu : pri;
+size_t misc_smem_bytes(int max_prior_m) { return (size_t)(40 + 3 * max_prior_m + 8) * 8; }
+void launch_imu_lin(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s) {
+  if (n_imu_total <= 0) return;
+  k_imu_raw<<<(n_imu_total + 31) / 32, 32, 0, s>>>(d, eval_cur, n_imu_total);
+  k_imu_lin<<<(n_imu_total + kImuWarps - 1) / kImuWarps, kImuWarps * 32, (size_t)kImuWarps * kImuWarpDoubles * 8, s>>>(d, eval_cur, n_imu_total);
 }
 void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s) {
   k_misc_lin<<<d.n_win, kMiscThreads, misc_smem_bytes(max_prior_m), s>>>(d, eval_cur);
@@ -2645,11 +2756,14 @@ int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   e = raise_smem_limit(k_proj_lin<4, 4>, (size_t)(proj_smem<4, 4>())); if (e) return e;
   e = raise_smem_limit(k_proj_lin_pp<true>, (size_t)(proj_smem<2, 2>())); if (e) return e;
   e = raise_smem_limit(k_proj_lin_pp<false>, (size_t)(proj_smem<2, 2>())); if (e) return e;
+
   size_t chol = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   e = raise_smem_limit(k_chol, (size_t)(chol)); if (e) return e;
   size_t st = (size_t)(40 + 3 * max_nc) * 8;
-  e = raise_smem_limit(k_step, (size_t)(st)); if (e) return e;
+  e = raise_smem_limit(k_step<false>, (size_t)(st)); if (e) return e;
+  e = raise_smem_limit(k_step<true>, (size_t)(st)); if (e) return e;
   e = raise_smem_limit(k_misc_lin, (size_t)(misc_smem_bytes(max_prior_m))); if (e) return e;
+  e = raise_smem_limit(k_imu_lin, (size_t)kImuWarps * kImuWarpDoubles * 8); if (e) return e;
   return 0;
 }
 // the row buffers of the per-landmark gather grow with the landmark-coupled width (multi-agent windows: 6 x 88 poses)
@@ -2728,7 +2842,9 @@ void launch_chol(const Dev &d, int max_rows, cudaStream_t s) {
   k_chol<<<d.n_win, kCholThreads, sm, s>>>(d, max_rows);
 }
 void launch_step(const Dev &d, int max_nc, cudaStream_t s) {
-  k_step<<<d.n_win, kStepThreads, (size_t)(40 + 3 * max_nc) * 8, s>>>(d, max_nc);
+  // both kinds of windows may share a handle: each instantiation skips the other's windows
+  if (d.n_leaf_total < 0 || d.n_plain_win > 0) k_step<false><<<d.n_win, kStepThreads, (size_t)(40 + 3 * max_nc) * 8, s>>>(d, max_nc);
+  if (d.n_leaf_total > 0) k_step<true><<<d.n_win, kStepThreads, (size_t)(40 + 3 * max_nc) * 8, s>>>(d, max_nc);
 }
 void launch_control(const Dev &d, int init, cudaStream_t s) { k_control<<<d.n_win, kCtlThreads, 0, s>>>(d, init); }
 void launch_tr_reset(const Dev &d, int first, cudaStream_t s) { k_tr_reset<<<(d.n_win + 127) / 128, 128, 0, s>>>(d, first); }

@@ -65,6 +65,7 @@ struct SchurTile { int win, kind, tm, tn, cb, cn; };
 
 struct ImuDesc {
   int pi, si, pj, sj;  // window-local indices (six-dof table / speed-bias table)
+  int win;             // window of the factor (k_imu_lin runs one warp per factor over the whole batch)
 };
 
 struct WinDesc {
@@ -99,6 +100,7 @@ struct WinDesc {
   int n_leaf, off_leaf;
   int off_hseg, n_hseg;        // Hcc zero-fill segments
   int hub_small;               // leaves present and n_hub + 1 <= 96: the hub x hub part of the reduced system comes from the one-CTA Schur kernel
+  int gather_nosync;           // compact records: within a landmark no column block appears at both slot positions (k_lm_gather16 needs no barrier between records)
   int row_tiles;               // most 32-column tiles any landmark's coupling row touches (row buffers of the gather kernels)
 };
 
@@ -162,6 +164,7 @@ struct Dev {
   const unsigned long long *lm_mask;  // [NL] bit t set: the landmark's coupling row has entries in W-space columns [32 t, 32 t + 32)
   const HSeg *hseg;
   const Leaf *leaf; int n_leaf_total;
+  int n_plain_win;      // windows without leaves
   double *leafL;        // per leaf: L, 1/diag(L)
   const int *schur_chunks;
   const int *leaf_lm;
@@ -170,6 +173,7 @@ struct Dev {
   const ImuDesc *imu;
   const double *imu_c;  // [NIMU][kImuStride]
   double *imu_U;        // [NIMU][225] sqrt_info
+  double *imu_raw;      // [NIMU][465] raw Jacobian (15 x 30) + residual (15) of the current linearisation (k_imu_raw -> k_imu_lin)
   // prior
   const PriorBlk *prior_blk;
   const double *prior_J;  // m x m

@@ -277,7 +277,12 @@ enum d2ba_debug_item {
   D2BA_DBG_COL_OF_BLOCK = 10,/* int32 column offset of every block, kind-major                 */
   D2BA_DBG_PROJ_RESJAC = 11, /* per obs (input order): r[3], J (3 x 27) row-major tangent      */
   D2BA_DBG_STEP = 12,        /* last trust-region step, n_c + L                                */
-  D2BA_DBG_GN_STEP = 13
+  D2BA_DBG_GN_STEP = 13,
+  D2BA_DBG_IMU_RESJAC = 14,  /* per IMU factor (input order): r[15], J (15 x 30) row-major tangent columns
+                                [pose_i 6 | speed-bias_i 9 | pose_j 6 | speed-bias_j 9], both times sqrt_info        */
+  D2BA_DBG_CONS_RESJAC = 15  /* per six-dof block (poses then extrinsics, input order) 62 doubles: x[7], z[7], tilde[6],
+                                r[6], J (6 x 6) row-major tangent of ConsenusPoseFactor at the current state; zeros for
+                                blocks outside the consensus set                                                       */
 };
 /* Linearise at the current state (no step) so that the debug items are defined. */
 int d2ba_debug_linearize(d2ba_handle *h);

@@ -5,14 +5,15 @@
  * cpu_baseline / --impl reference legs may load liborc_oracle.so.  Nothing under
  * d2slam_b200/ links, imports or calls it; the product path fails loudly without CUDA.
  *
- * PARITY UNPINNED at the Ceres boundary: the reference cannot be compiled in this container
- * (Eigen, Ceres, ROS, OpenCV, LCM, swarm_msgs all absent) and ships no golden vectors or
- * asserting tests for this path.  The arithmetic of ceres::Solve
- * (ceres-solver, HKUST-Swarm fork, branch D2SLAM, nominal 2.1.0 -- docker/Dockerfile.x86:3,67)
- * and of swarm_msgs (Swarm::Pose) is restated from their published algorithms; every such
- * assumption is marked ASSUMED in the source.  What IS pinned: each factor's analytic
- * Jacobian against finite differences, the solver against the optimality conditions of the
- * same cost, and the ADMM loop against ConsensusSolver.cpp line by line.
+ * PARITY: the factor level is PINNED to the reference's own classes -- oracle/_ref/libd2ref.so holds the unmodified
+ * D2SLAM factor sources (projection*Factor.cpp, imu_factor.h + integration_base.h, consenus_factor.cpp,
+ * pose_local_parameterization.cpp) compiled by oracle/Makefile.ref against the stand-in third-party headers of
+ * oracle/_shim; tests/test_ref_pin.py compares every orc_*_eval with them and tests/golden/ref_factors.npz freezes their
+ * outputs.  UNPINNED (restated from published algorithms, every such assumption marked ASSUMED in the source): the
+ * arithmetic of ceres::Solve (ceres-solver, HKUST-Swarm fork, branch D2SLAM, nominal 2.1.0 -- docker/Dockerfile.x86:3,67),
+ * swarm_msgs (Swarm::Pose), and the two pieces whose translation units cannot be compiled against stubs (loss corrector
+ * BaseParamResInfo.cpp:71-92, PriorFactor prior_factor.cpp:45-177).  Those are checked against finite differences, the
+ * optimality conditions of the same cost, and ConsensusSolver.cpp line by line.
  *
  * The oracle mirrors the C ABI of include/d2ba.h (same input structs, one window per
  * oracle handle) so parity tests drive both sides with identical calls.
