@@ -285,7 +285,7 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ our arm: helpers
-def timed_solves(solver, probs, iters, steps, warmup, barrier=None):
+def timed_solves(solver, probs, iters, steps, warmup, barrier=None, step_barrier=None):
     """Device-resident throughput: problem already in HBM, only the (small) state is restored per step.
     -> (device seconds summed over steps [CUDA events on the solver stream], wall seconds)"""
     for _ in range(warmup):
@@ -296,6 +296,8 @@ def timed_solves(solver, probs, iters, steps, warmup, barrier=None):
     dev_ms = 0.0
     for _ in range(steps):
         reset_state(solver, probs)
+        if step_barrier:
+            step_barrier()   # ranks enter the solve together: the in-stream all-reduce otherwise waits out the peers' host-side jitter
         reps = solver.solve_fixed(iters)
         dev_ms += reps[0].total_time * 1e3
     if barrier:
@@ -468,7 +470,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_dev, wall = timed_solves(solver, probs, iters, args.steps, args.warmup, barrier)
+    t_dev, wall = timed_solves(solver, probs, iters, args.steps, args.warmup, barrier, barrier if swarm else None)
     clocks = sampler.stop() if rank == 0 else None
     tt = torch.tensor([wall, t_dev], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -504,6 +506,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_wall, _ = rp.run_pipelined(handles, e2e_steps, iters, host_threads)
         e2e_breakdown = {"stage_busy_" + k.replace("_s", "_ms"): round(v / e2e_steps * 1e3, 3) for k, v in rp.breakdown.items()}
         e2e_breakdown["sequential_single_handle"] = e2e_seq
+        e2e_breakdown["finalize_phases_ms"] = {k: v for k, v in solver.host_times().items() if k != "h2d_bytes"}
         barrier()
         h2d_step = solver.host_times()["h2d_bytes"]   # counted by the library: compact observation records + staging arena
         for hx in handles[1:]:
@@ -529,6 +532,8 @@ def run_ours(args, rank, world, local_rank):
             with stdout_to_stderr():
                 dist.broadcast(uid, 0)
                 sx.comm_init(bytes(uid.cpu().tolist()), rank, world)
+            sx.solve()          # warm-up: first collective on the new communicator, graph instantiation
+            reset_state(sx, probs)
             barrier()
             reps = sx.solve()   # convergence exits on: the iterations each window actually used
             its = torch.tensor([float(sum(r.total_iterations for r in reps)), reps[0].total_time], dtype=torch.float64, device="cuda")

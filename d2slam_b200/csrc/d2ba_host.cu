@@ -668,7 +668,7 @@ struct WinPlan {
   std::vector<Job> jobs[6];                         // tile_begin window-local, grp window-local
   std::vector<SchurTileH> schur[2];                  // stage 0 (tiles with leaf columns), stage 1 (hub x hub)
   std::vector<int> schur_chunks;                     // chunk lists, window-local offsets in SchurTile::cb
-  std::vector<Leaf> leaves; std::vector<HSeg> hseg; std::vector<unsigned long long> lm_mask; std::vector<int> leaf_lm; int leaf_lm_off = 0;
+  std::vector<uint64_t> hruns; std::vector<Leaf> leaves; std::vector<HSeg> hseg; std::vector<unsigned long long> lm_mask; std::vector<int> leaf_lm; int leaf_lm_off = 0;
   int n_tiles = 0, n_lmobs = 0;
   int job_off[6] = {0, 0, 0, 0, 0, 0};
   int schur_off[2] = {0, 0}, chunk_off = 0;
@@ -895,11 +895,13 @@ int d2ba_finalize(d2ba_handle *h) {
     w.order.resize(M); w.sorted_pos.assign(M, -1);
     for (size_t k = 0; k < M; k++) w.order[k] = (int)keys[k].second;
     // Hcc pattern (lower triangle, block rows): rows[r] collects the [c0, c1) runs some factor writes
-    std::vector<std::vector<std::pair<int, int>>> hrows(w.n_c);
+    // (one flat list of (row, c0, c1) runs, sorted and merged below: no per-row allocations on this per-solve path)
+    std::vector<uint64_t> &hruns = pl.hruns;
+    hruns.clear();
     auto hblock = [&](int ra, int rs, int ca, int cs) {
       if (ra < 0 || ca < 0) return;
       if (ra < ca) { std::swap(ra, ca); std::swap(rs, cs); }
-      for (int r = 0; r < rs; r++) hrows[ra + r].push_back({ca, ca + cs});
+      for (int r = 0; r < rs; r++) hruns.push_back(((uint64_t)(ra + r) << 40) | ((uint64_t)ca << 20) | (uint64_t)(ca + cs));
     };
     // landmark masks: W-space column tiles (32 columns) a landmark's coupling row touches; the rhs column n_lc always
     pl.lm_mask.assign(nl, 1ull << (w.n_lc / 32));
@@ -1038,16 +1040,19 @@ int d2ba_finalize(d2ba_handle *h) {
       if (w.td_col >= 0) hblock(w.td_col, 1, w.td_col, 1);
     }
     pl.hseg.clear();
-    for (int r = 0; r < w.n_c; r++) {
-      auto &v = hrows[r];
-      if (v.empty()) continue;
-      std::sort(v.begin(), v.end());
-      int a = v[0].first, bnd = v[0].second;
-      for (size_t q = 1; q <= v.size(); q++) {
-        if (q < v.size() && v[q].first <= bnd) { bnd = std::max(bnd, v[q].second); continue; }
+    std::sort(hruns.begin(), hruns.end());
+    for (size_t q = 0; q < hruns.size();) {
+      const int r = (int)(hruns[q] >> 40);
+      int a = (int)((hruns[q] >> 20) & 0xFFFFF), bnd = (int)(hruns[q] & 0xFFFFF);
+      size_t e2 = q + 1;
+      for (; e2 < hruns.size() && (int)(hruns[e2] >> 40) == r; e2++) {
+        const int c0 = (int)((hruns[e2] >> 20) & 0xFFFFF), c1 = (int)(hruns[e2] & 0xFFFFF);
+        if (c0 <= bnd) { bnd = std::max(bnd, c1); continue; }
         pl.hseg.push_back(HSeg{r, a, std::min(bnd, r + 1) - a});   // lower triangle only
-        if (q < v.size()) { a = v[q].first; bnd = v[q].second; }
+        a = c0; bnd = c1;
       }
+      pl.hseg.push_back(HSeg{r, a, std::min(bnd, r + 1) - a});
+      q = e2;
     }
     d.n_hseg = (int)pl.hseg.size();
     if (!d.schur_small) {
