@@ -402,6 +402,54 @@ def swarm_one_gpu(args, local_rank, n_agents, n_swarms, iters, steps, warmup, cp
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def pgo_leg(rank, world, local_rank, dist, cpu=True):
+    """BASELINE configs[4]: 10 000 poses on 8 trajectories, 40 000 relative-pose edges, Gauss-Newton with
+    matrix-free block-Jacobi PCG; with N ranks the edges are sharded e % N and J^T J p is all-reduced over NCCL per CG iteration."""
+    import torch
+    from d2slam_b200 import pgo, synth
+    g = pgo.make_pose_graph(seed=7, n_agents=8, poses_per_agent=1250, loops=30008)
+    sel = np.arange(rank, len(g["id_a"]), world)
+    s = pgo.PgoSolver(device=local_rank, max_iterations=12, pcg_max_iterations=300, pcg_tolerance=1e-8, lambda0=0.0, function_tolerance=1e-9)
+
+    def load():
+        s.set_poses(g["ids"], g["init"], g["fixed"]); s.add_edges(g["id_a"][sel], g["id_b"][sel], g["rel"][sel], g["sqrt_info"][sel])
+    load()
+    if world > 1:
+        from d2slam_b200.solver import comm_unique_id
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.tensor(list(comm_unique_id()), dtype=torch.uint8))
+        with stdout_to_stderr():
+            dist.broadcast(uid, 0)
+            s.comm_init(bytes(uid.cpu().tolist()), rank, world)
+    s.solve()                     # warm-up (module load, first collectives)
+    reps = []
+    for _ in range(3):
+        load()
+        if dist is not None:
+            torch.cuda.synchronize(); dist.barrier()
+        reps.append(s.solve())
+    r = min(reps, key=lambda q: q.device_ms)
+    ms = torch.tensor([r.device_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    x = s.get_poses(g["ids"])
+    e0, _ = synth.pose_errors(g["init"], g["gt"]); e1, _ = synth.pose_errors(x, g["gt"])
+    out = {"workload": f"{len(g['ids'])} poses / {len(g['id_a'])} edges (8 trajectories, odometry + loop closures), RelPoseFactorAD residual, Gauss-Newton + block-Jacobi PCG, edges sharded over {world} GPU(s)",
+           "lm_iterations": r.iterations, "pcg_iterations": r.pcg_iterations, "device_ms": float(ms.item()), "ms_per_lm_iteration": float(ms.item()) / max(1, r.iterations),
+           "lm_iterations_per_s": 1e3 * r.iterations / float(ms.item()), "initial_cost": r.initial_cost, "final_cost": r.final_cost, "converged": int(r.converged),
+           "max_position_error_vs_ground_truth_m": {"initial_guess": e0, "solved": e1}}
+    if cpu and rank == 0:
+        from oracle import pgo_oracle as po
+        t0 = time.perf_counter()
+        _, costs = po.solve(g["init"], g["fixed"], g["ea"], g["eb"], g["rel"], g["sqrt_info"], iters=3)
+        dt = time.perf_counter() - t0
+        out["cpu_oracle"] = {"kind": "port", "what": "numpy linearisation + scipy sparse direct Gauss-Newton (oracle/pgo_oracle.py), 1 thread", "iterations": len(costs) - 1 if len(costs) > 1 else 1,
+                             "s_per_iteration": dt / max(1, len(costs)), "cost_after": costs[-1]}
+    s.close()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from d2slam_b200.solver import Solver
@@ -589,6 +637,10 @@ def run_ours(args, rank, world, local_rank):
                                            for r in RHO_SWEEP]
     else:
         cpu_baseline = {"value": None, "unit": "iter/s", "cores": 0, "kind": "port", "sample": "timed at N=1 only (bench contract)"}
+    if not args.no_extras:
+        pg = pgo_leg(rank, world, local_rank, dist, cpu=(world == 1))
+        if rank == 0:
+            extra["pgo"] = pg
     n_variants = len(set(int(t) for t in np.unique(probs[0]["obs"]["type"]))) if args.cams != "mono" else 1
     # per solve: tr_reset, misc_lin, proj_lin, control (+ per ADMM sub-step: memset, cons_pack, cons_apply, cons_refs, tr_reset);
     # per iteration: lm_gather, sb_elim, schur (1-2 launches), leaf_elim, chol, sb_back, leaf_back, step, misc_lin, proj_lin (n_variants), control

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("D2BA_OUT") or os.path.join(HERE, "libd2ba.so")
-SOURCES = ["d2ba_kernels.cu", "d2ba_host.cu", "d2ba_margin.cu"]
+SOURCES = ["d2ba_kernels.cu", "d2ba_host.cu", "d2ba_margin.cu", "d2pgo.cu"]
 EXTRA_DEPS = ["d2ba_harness.cpp"]
-HEADERS = ["d2ba_types.cuh", "d2ba_math.cuh", "d2ba_proj.cuh", os.path.join("..", "..", "include", "d2ba.h")]
+HEADERS = ["d2ba_types.cuh", "d2ba_math.cuh", "d2ba_proj.cuh", os.path.join("..", "..", "include", "d2ba.h"), os.path.join("..", "..", "include", "d2pgo.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -1561,6 +1561,23 @@ int d2ba_get_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, con
 }
 
 // ------------------------------------------------------------------------------------------------ comm
+}  // extern "C"
+namespace d2ba {   // the dlopen'ed NCCL entry points for the other translation units of the library (d2pgo.cu)
+int nccl_comm_init(void **comm, const uint8_t *unique_id, int rank, int nranks, std::string &err) {
+  if (!g_nccl.load(err)) return 2;
+  ncclUniqueId_t id; memcpy(id.internal, unique_id, 128);
+  ncclComm_t c = nullptr;
+  const int r = g_nccl.CommInitRank(&c, nranks, id, rank);
+  if (r) { err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 3; }
+  *comm = c;
+  return 0;
+}
+int nccl_allreduce_f64(void *comm, double *buf, size_t n, cudaStream_t s) {
+  return g_nccl.AllReduce(buf, buf, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, (ncclComm_t)comm, s);
+}
+void nccl_comm_destroy(void *comm) { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)comm); }
+}  // namespace d2ba
+extern "C" {
 int d2ba_comm_unique_id(uint8_t out[128]) {
   std::string err;
   if (!g_nccl.load(err)) { fprintf(stderr, "d2ba: %s\n", err.c_str()); return 1; }

@@ -669,8 +669,11 @@ template __global__ void k_proj_lin<4, 4>(Dev, int, int, int);
 // whose two poses are free and whose extrinsics / td are constant (NCT = 2, KR = 2, slots = {pose_i, pose_j}).
 // Same arithmetic as proj_eval<2,false,false>, but the Jacobian rows are emitted straight into the staging tile
 // and the landmark record, which keeps the live state small enough for 3 CTAs / SM.
+#ifndef D2BA_PP_BLOCKS
+#define D2BA_PP_BLOCKS 4
+#endif
 template <bool SHIFT0>
-__global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int job_begin, int job_count) {
+__global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int eval_cur, int job_begin, int job_count) {
   constexpr int NCOL = 16, LDJ = kTile * 2 + 4, RCOL = 12;
   constexpr int kWarpDoubles = GC_SIZE + NCOL * LDJ;
   extern __shared__ double sm[];
@@ -739,40 +742,36 @@ __global__ void __launch_bounds__(128, 4) k_proj_lin_pp(Dev d, int eval_cur, int
 #pragma unroll
       for (int k = 0; k < 3; k++) { red[0][k] = sn * (B[k] - b0 * ph[k]); red[1][k] = sn * (B[3 + k] - b1 * ph[k]); }
     }
-    double jl[2], Ji[2][6], Jj[2][6];
+    // Jacobian rows go straight into the staging tile (K index = q * 32 + lane: conflict-free scalar stores, and the J^T J
+    // sums do not care about the order of the K rows) and into the coupling vector; pose_j's position block is minus
+    // pose_i's, so only nine of the twelve coupling entries are accumulated.  Keeps the live state small.
+    double jl[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) { double Dc[3]; rm3(red[q], gc + GC_JC, Dc); jl[q] = -il * dot3(Dc, Pci); }
+    if (!valid) { r0 = 0; r1 = 0; jl[0] = 0; jl[1] = 0; red[0][0] = red[0][1] = red[0][2] = red[1][0] = red[1][1] = red[1][2] = 0.0; } else cost += oc;
+    double wi[6] = {0, 0, 0, 0, 0, 0}, wjr[3] = {0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-      double A[3], Bm[3], Cr[3], Dc[3], c[3];
-      rm3(red[q], gc + GC_JC, Dc);
-      jl[q] = -il * dot3(Dc, Pci);
+      double A[3], Bm[3], Cr[3], c1[3], c2[3];
       rm3(red[q], gc + GC_JW, A);
       rm3(red[q], gc + GC_JM, Bm);
       Cr[0] = red[q][0] * gc[GC_RB + 0] + red[q][1] * gc[GC_RB + 1] + red[q][2] * gc[GC_RB + 2];
       Cr[1] = red[q][0] * gc[GC_RB + 3] + red[q][1] * gc[GC_RB + 4] + red[q][2] * gc[GC_RB + 5];
       Cr[2] = red[q][0] * gc[GC_RB + 6] + red[q][1] * gc[GC_RB + 7] + red[q][2] * gc[GC_RB + 8];
-      cross3(Bm, Pmi, c);
-      Ji[q][0] = A[0]; Ji[q][1] = A[1]; Ji[q][2] = A[2]; Ji[q][3] = -c[0]; Ji[q][4] = -c[1]; Ji[q][5] = -c[2];
-      cross3(Cr, Pmj, c);
-      Jj[q][0] = -A[0]; Jj[q][1] = -A[1]; Jj[q][2] = -A[2]; Jj[q][3] = c[0]; Jj[q][4] = c[1]; Jj[q][5] = c[2];
-    }
-    if (!valid) {
-      r0 = 0; r1 = 0; jl[0] = 0; jl[1] = 0;
+      cross3(Bm, Pmi, c1);
+      cross3(Cr, Pmj, c2);
+      double *jq = Js + q * kTile + lane;
 #pragma unroll
-      for (int k = 0; k < 6; k++) { Ji[0][k] = 0; Ji[1][k] = 0; Jj[0][k] = 0; Jj[1][k] = 0; }
-    } else cost += oc;
-    // staging tile + landmark record
+      for (int k = 0; k < 3; k++) {
+        jq[k * LDJ] = A[k]; jq[(3 + k) * LDJ] = -c1[k]; jq[(6 + k) * LDJ] = -A[k]; jq[(9 + k) * LDJ] = c2[k];
+        wi[k] = fma(A[k], jl[q], wi[k]); wi[3 + k] = fma(-c1[k], jl[q], wi[3 + k]); wjr[k] = fma(c2[k], jl[q], wjr[k]);
+      }
+    }
+    Js[RCOL * LDJ + lane] = r0; Js[RCOL * LDJ + kTile + lane] = r1;
     // records are stored landmark-major (obs_slot: tile slot -> position in the landmark's run), so the per-landmark
     // reduction streams them; padding lanes (slot -1) never write
     double *rec = d.rec[buf] + (size_t)w.off_rec + (size_t)(rslot < 0 ? 0 : rslot) * w.rec_stride;
-    double wi[6], wj[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-      *reinterpret_cast<double2 *>(Js + k * LDJ + lane * 2) = make_double2(Ji[0][k], Ji[1][k]);
-      *reinterpret_cast<double2 *>(Js + (6 + k) * LDJ + lane * 2) = make_double2(Jj[0][k], Jj[1][k]);
-      wi[k] = Ji[0][k] * jl[0] + Ji[1][k] * jl[1];
-      wj[k] = Jj[0][k] * jl[0] + Jj[1][k] * jl[1];
-    }
-    *reinterpret_cast<double2 *>(Js + RCOL * LDJ + lane * 2) = make_double2(r0, r1);
+    const double wj[6] = {-wi[0], -wi[1], -wi[2], wjr[0], wjr[1], wjr[2]};
     if (valid) {
       double2 *r2 = reinterpret_cast<double2 *>(rec);
       r2[0] = make_double2(jl[0] * jl[0] + jl[1] * jl[1], jl[0] * r0 + jl[1] * r1);
@@ -2756,6 +2755,11 @@ int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   e = raise_smem_limit(k_proj_lin<4, 4>, (size_t)(proj_smem<4, 4>())); if (e) return e;
   e = raise_smem_limit(k_proj_lin_pp<true>, (size_t)(proj_smem<2, 2>())); if (e) return e;
   e = raise_smem_limit(k_proj_lin_pp<false>, (size_t)(proj_smem<2, 2>())); if (e) return e;
+#if D2BA_PP_BLOCKS > 4
+  // 37 KB per CTA: the large shared-memory carveout lets the register file, not the L1 split, set the occupancy
+  cudaFuncSetAttribute(k_proj_lin_pp<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_proj_lin_pp<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
 
   size_t chol = (size_t)(kNB * (max_rows + 4) + 2 * max_rows + 16 + 16 * 32 + kNB * (kNB + 1)) * 8;
   e = raise_smem_limit(k_chol, (size_t)(chol)); if (e) return e;

@@ -13,10 +13,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "d2ba.h")).read()
+def declared_functions(header="d2ba.h", prefix="d2ba_"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(d2ba_[a-z_0-9]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z_0-9]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -28,6 +28,18 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert set(solver.EXPORTED) <= set(names)
+    from d2slam_b200 import pgo
+    pnames = declared_functions("d2pgo.h", "d2pgo_")
+    assert sorted(pnames) == sorted(pgo.PGO_EXPORTED) and not [n for n in pnames if not hasattr(lib, n)]
+
+
+def test_pgo_refuses_without_a_device():
+    import torch
+    from d2slam_b200 import pgo
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        pgo.PgoSolver()
 
 
 def test_struct_layouts_match_c():
@@ -86,3 +98,14 @@ def test_sass_has_fp64_tensor_mma():
         pytest.skip("cuobjdump unavailable")
     assert "DMMA" in sass
     assert "sm_100a" in sass or "EF_CUDA_SM100" in sass or "arch = sm_100" in sass
+
+
+def test_pgo_struct_layouts_match_c():
+    from d2slam_b200 import pgo
+    code = '#include <stdio.h>\n#include <stddef.h>\n#include "d2pgo.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(d2pgo_config), sizeof(d2pgo_report), offsetof(d2pgo_config, lambda0), offsetof(d2pgo_report, device_ms));return 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c"); exe = os.path.join(td, "t")
+        open(c, "w").write(code)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = list(map(int, subprocess.check_output([exe]).decode().split()))
+    assert out == [C.sizeof(pgo.PgoConfig), C.sizeof(pgo.PgoReport), pgo.PgoConfig.lambda0.offset, pgo.PgoReport.device_ms.offset]

@@ -1,0 +1,91 @@
+"""Pose-graph path (include/d2pgo.h, BASELINE config 5 / SURVEY 8f rank 3): factor restatement vs finite differences,
+g2o round trip in the reference's multi-agent id convention, edge sharding == full product (gloo-free numpy check),
+and on the GPU: per-edge residual / Jacobians and the converged solution against the scipy oracle."""
+import numpy as np
+import pytest
+
+from d2slam_b200 import pgo, synth
+from oracle import pgo_oracle as po
+
+
+def small_graph(seed=1, n_agents=3, n=40, loops=120):
+    return pgo.make_pose_graph(seed=seed, n_agents=n_agents, poses_per_agent=n, loops=loops)
+
+
+def test_rel_pose_factor_restatement_matches_finite_differences():
+    rng = np.random.default_rng(3)
+    g = small_graph()
+    S = g["sqrt_info"].reshape(-1, 6, 6)
+    for e in rng.integers(0, len(g["ea"]), 10):
+        a, b = g["ea"][e], g["eb"][e]
+        p0, p1 = g["init"][a], g["init"][b]
+        r, J0, J1 = po.edge_eval(p0, p1, g["rel"][e], S[e])
+        eps = 1e-6
+        for J, which in ((J0, 0), (J1, 1)):
+            num = np.zeros((6, 6))
+            for k in range(6):
+                d = np.zeros(6); d[k] = eps
+                pp = [p0, p1]; pm = [p0, p1]
+                pp[which] = synth.pose_plus(pp[which], d); pm[which] = synth.pose_plus(pm[which], -d)
+                num[:, k] = (po.edge_eval(pp[0], pp[1], g["rel"][e], S[e])[0] - po.edge_eval(pm[0], pm[1], g["rel"][e], S[e])[0]) / (2 * eps)
+            assert np.abs(num - J).max() <= 1e-6 * max(1.0, np.abs(J).max()), (which, np.abs(num - J).max())
+
+
+def test_g2o_round_trip_multi_agent_ids(tmp_path):
+    g = small_graph(seed=2, n_agents=3, n=12, loops=20)
+    path = str(tmp_path / "graph.g2o")
+    pgo.write_g2o(path, g["ids"], g["init"], g["id_a"], g["id_b"], g["rel"], g["sqrt_info"])
+    assert pgo.g2o_split_id(pgo.g2o_vertex_id(2, 77)) == (2, 77) and pgo.g2o_split_id(123) == (0, 123)
+    h = pgo.read_g2o(path)
+    assert np.array_equal(h["ids"], g["ids"]) and np.array_equal(h["id_a"], g["id_a"]) and np.array_equal(h["id_b"], g["id_b"])
+    assert np.allclose(h["poses"], g["init"], atol=1e-15) and np.allclose(h["rel"], g["rel"], atol=1e-15)
+    S0 = g["sqrt_info"].reshape(-1, 6, 6); S1 = h["sqrt_info"].reshape(-1, 6, 6)
+    assert np.allclose(np.einsum("eij,eik->ejk", S1, S1), np.einsum("eij,eik->ejk", S0, S0), rtol=1e-12)
+    only0 = pgo.read_g2o(path, max_agent_id=0)
+    assert set(only0["ids"] // 1_000_000) == {0} and len(only0["id_a"]) < len(h["id_a"])
+
+
+def test_edge_sharding_sums_to_the_full_normal_equations():
+    """What the multi-GPU path relies on: J^T J p summed over edge shards (e % nranks) == the full product."""
+    g = small_graph(seed=4)
+    S = g["sqrt_info"].reshape(-1, 6, 6); N = len(g["ids"])
+    rng = np.random.default_rng(0); p = rng.normal(size=(N, 6))
+
+    def product(sel):
+        y = np.zeros((N, 6))
+        for e in sel:
+            a, b = g["ea"][e], g["eb"][e]
+            _, J0, J1 = po.edge_eval(g["init"][a], g["init"][b], g["rel"][e], S[e])
+            t = J0 @ p[a] + J1 @ p[b]; y[a] += J0.T @ t; y[b] += J1.T @ t
+        return y
+    E = len(g["ea"]); full = product(range(E))
+    parts = sum(product(range(r, E, 3)) for r in range(3))
+    assert np.abs(full - parts).max() <= 1e-9 * np.abs(full).max()
+
+
+@pytest.mark.gpu
+def test_pgo_edges_on_device_match_oracle():
+    g = small_graph(seed=5)
+    s = pgo.PgoSolver()
+    s.set_poses(g["ids"], g["init"], g["fixed"]); s.add_edges(g["id_a"], g["id_b"], g["rel"], g["sqrt_info"])
+    dev = s.debug_edges()
+    S = g["sqrt_info"].reshape(-1, 6, 6)
+    for e in range(0, len(dev), 7):
+        r, J0, J1 = po.edge_eval(g["init"][g["ea"][e]], g["init"][g["eb"][e]], g["rel"][e], S[e])
+        ref = np.concatenate([r, J0.ravel(), J1.ravel()])
+        assert np.abs(dev[e] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+def test_pgo_converged_solution_matches_sparse_direct_oracle():
+    g = small_graph(seed=6, n_agents=4, n=60, loops=300)
+    s = pgo.PgoSolver(max_iterations=40, pcg_max_iterations=400, pcg_tolerance=1e-12, lambda0=0.0, function_tolerance=1e-14)
+    s.set_poses(g["ids"], g["init"], g["fixed"]); s.add_edges(g["id_a"], g["id_b"], g["rel"], g["sqrt_info"])
+    rep = s.solve()
+    x_ref, costs = po.solve(g["init"], g["fixed"], g["ea"], g["eb"], g["rel"], g["sqrt_info"], iters=40)
+    assert rep.final_cost < rep.initial_cost and abs(rep.final_cost - costs[-1]) <= 1e-8 * costs[-1], (rep.final_cost, costs[-1])
+    dp, dr = synth.pose_errors(s.get_poses(g["ids"]), x_ref)
+    assert dp <= 1e-6 and dr <= 1e-6, (dp, dr)
+    # and it actually removed the drift: far closer to the ground truth than the initial guess
+    e0, _ = synth.pose_errors(g["init"], g["gt"]); e1, _ = synth.pose_errors(s.get_poses(g["ids"]), g["gt"])
+    assert e1 < 0.5 * e0
