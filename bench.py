@@ -407,9 +407,9 @@ def pgo_leg(rank, world, local_rank, dist, cpu=True):
     matrix-free block-Jacobi PCG; with N ranks the edges are sharded e % N and J^T J p is all-reduced over NCCL per CG iteration."""
     import torch
     from d2slam_b200 import pgo, synth
-    g = pgo.make_pose_graph(seed=7, n_agents=8, poses_per_agent=1250, loops=30008)
+    g = pgo.make_pose_graph(seed=7, n_agents=8, poses_per_agent=1250, loops=30001)   # + 7 connecting closures = 40 000 edges
     sel = np.arange(rank, len(g["id_a"]), world)
-    s = pgo.PgoSolver(device=local_rank, max_iterations=12, pcg_max_iterations=300, pcg_tolerance=1e-8, lambda0=0.0, function_tolerance=1e-9)
+    s = pgo.PgoSolver(device=local_rank, max_iterations=30, pcg_max_iterations=2000, pcg_tolerance=1e-3, lambda0=1e-4, function_tolerance=1e-6)
 
     def load():
         s.set_poses(g["ids"], g["init"], g["fixed"]); s.add_edges(g["id_a"][sel], g["id_b"][sel], g["rel"][sel], g["sqrt_info"][sel])

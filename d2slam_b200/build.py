@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
-    link = [nvcc, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(link)
     # host-side harness (C++ stand-in for the D2Estimator call sequence), links against libd2ba.so
     harness = os.path.join(HERE, "libd2ba_harness.so")

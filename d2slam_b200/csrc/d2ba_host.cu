@@ -30,6 +30,8 @@ void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s);
 void launch_prior_prep(const Dev &d, cudaStream_t s);
 void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s);
 void launch_imu_lin(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s);
+void launch_imu_raw(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s);   // the two halves of launch_imu_lin
+void launch_imu_acc(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s);
 int configure_kernels(int max_rows, int max_nc, int max_prior_m);
 int configure_gather(int max_ldw);
 void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int job_count, cudaStream_t s);
@@ -147,7 +149,9 @@ struct HostWin {
   double td = 0; bool has_td = false; uint8_t td_c = 1;
   std::vector<HObs> obs;
   PinArr<ObsJ> rawj; PinArr<ObsAnchor> anch;              // compact observation constants (pinned)
-  DevArr<ObsJ> d_rawj; DevArr<ObsAnchor> d_anch;          // device copies (uploaded as they are appended)
+  DevArr<ObsJ> d_rawj; DevArr<ObsAnchor> d_anch;          // device copies (uploaded in batches as they are appended)
+  size_t pushed_j = 0, pushed_a = 0;                       // records already on the copy stream
+  int feed_lock = 0; bool push_pending = false;            // feeder / uploader hand-over (see flush_pending)
   double td_min = 1e300, td_max = -1e300;
   std::vector<HImu> imu;
   int prior_m = 0; std::vector<double> prior_J, prior_e0; std::vector<HPriorBlk> prior_blk; bool prior_is_info = false;
@@ -163,7 +167,7 @@ struct HostWin {
     pose_map.clear(); ext_map.clear(); sb_map.clear(); lm_map.clear();
     pose.clear(); ext.clear(); sb.clear(); lm.clear(); pose_c.clear(); ext_c.clear(); sb_c.clear();
     td = 0; has_td = false; td_c = 1;
-    obs.clear(); rawj.n = 0; anch.n = 0; imu.clear(); td_min = 1e300; td_max = -1e300;
+    obs.clear(); rawj.n = 0; anch.n = 0; pushed_j = pushed_a = 0; push_pending = false; imu.clear(); td_min = 1e300; td_max = -1e300;
     prior_m = 0; prior_J.clear(); prior_e0.clear(); prior_blk.clear(); prior_is_info = false;
     pose_slot.clear(); ext_slot.clear(); admm = false; n_slots = 0;
     pose_col.clear(); ext_col.clear(); sb_col.clear(); td_col = -1; n_lc = 0; n_c = 0;
@@ -241,6 +245,9 @@ struct d2ba_handle {
   std::string err;
   std::vector<HostWin> win;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t side = nullptr;                 // second lane of the iteration: IMU chain beside the reprojection kernels, sb elimination beside the landmark gather
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_misc = nullptr;
+  bool two_lanes = true;                       // D2BA_ONE_LANE=1: everything on `stream` (A/B)
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_it[2] = {nullptr, nullptr};   // solver time budget: iteration k-2 complete
@@ -289,6 +296,9 @@ struct d2ba_handle {
   double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wall-clock phases of the last d2ba_finalize (d2ba_debug_host_times)
   double solve_ms[4] = {0, 0, 0, 0};             // host wall-clock of the last solve: enqueue, wait for the device, write-back
   std::atomic<long long> h2d_bytes_add;          // bytes d2ba_add_proj put on the copy stream since the last reset
+  std::mutex push_mu, pend_mu;                   // one uploader at a time; guards pending_win / HostWin::push_pending
+  std::vector<int> pending_win;                  // windows with records not yet on the copy stream
+  std::atomic<long long> pending_bytes{0};
   long long h2d_bytes_fin = 0;                   // bytes of the last finalize's arena upload
   std::atomic<long long> add_ns[4];              // thread-summed ns inside d2ba_add_proj since the last reset: index, stamps, staging copy, CUDA calls
   // comm
@@ -370,6 +380,9 @@ int d2ba_create(const d2ba_config *cfg, d2ba_handle **out) {
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evf0); cudaEventCreate(&h->evf1); cudaEventCreate(&h->evf2);
   cudaEventCreateWithFlags(&h->ev_it[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_it[1], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking); cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_misc, cudaEventDisableTiming);
+  { const char *e = getenv("D2BA_ONE_LANE"); h->two_lanes = !(e && e[0] == '1'); }
   memset(&h->dev, 0, sizeof(h->dev));
   *out = h;
   return 0;
@@ -396,6 +409,7 @@ int d2ba_destroy(d2ba_handle *h) {
   cudaStreamSynchronize(h->copy_stream);
   for (auto &w : h->win) { w.rawj.release(); w.anch.release(); w.d_rawj.release(); w.d_anch.release(); }
   cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_copy);
+  cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_misc);
   d2ba_release_staging(h);
   cudaEventDestroy(h->ev_it[0]); cudaEventDestroy(h->ev_it[1]);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evf0); cudaEventDestroy(h->evf1); cudaEventDestroy(h->evf2);
@@ -410,6 +424,7 @@ int d2ba_reset(d2ba_handle *h) {
   h->finalized = false;
   for (auto &a : h->add_ns) a = 0;
   h->h2d_bytes_add = 0;
+  h->pending_win.clear(); h->pending_bytes = 0;
   return 0;
 }
 
@@ -477,6 +492,37 @@ int push_range(d2ba_handle *h, PinArr<T> &host, DevArr<T> &dev, size_t first_new
   h->h2d_bytes_add += (long long)((host.n - first_new) * sizeof(T));
   return 0;
 }
+
+// Uploads of the compact records are issued in batches by ONE thread at a time: 32 feeding threads calling
+// cudaMemcpyAsync once per window serialise on the driver's stream lock (that lock, not the copy loop, was the feed stage's
+// wall time).  A feeder that finds >= kPushBatch bytes pending and the uploader role free takes it; d2ba_finalize flushes
+// the rest.  A window still being appended to (feed_lock held) stays on the list.
+constexpr long long kPushBatch = 4 << 20;
+inline void win_lock(HostWin *w) { while (__atomic_exchange_n(&w->feed_lock, 1, __ATOMIC_ACQUIRE)) { } }
+inline bool win_try_lock(HostWin *w) { return !__atomic_exchange_n(&w->feed_lock, 1, __ATOMIC_ACQUIRE); }
+inline void win_unlock(HostWin *w) { __atomic_store_n(&w->feed_lock, 0, __ATOMIC_RELEASE); }
+int flush_pending(d2ba_handle *h, bool all) {   // caller holds h->push_mu
+  std::vector<int> list;
+  {
+    std::lock_guard<std::mutex> lk(h->pend_mu);
+    list.swap(h->pending_win);
+    for (int wi : list) h->win[wi].push_pending = false;
+    h->pending_bytes = 0;
+  }
+  int rc = 0;
+  for (int wi : list) {
+    HostWin *w = &h->win[wi];
+    if (all) win_lock(w);
+    else if (!win_try_lock(w)) {
+      std::lock_guard<std::mutex> lk(h->pend_mu);
+      if (!w->push_pending) { w->push_pending = true; h->pending_win.push_back(wi); }
+      continue;
+    }
+    if (!rc && !(rc = push_range(h, w->rawj, w->d_rawj, w->pushed_j)) && !(rc = push_range(h, w->anch, w->d_anch, w->pushed_a))) { w->pushed_j = w->rawj.n; w->pushed_a = w->anch.n; }
+    win_unlock(w);
+  }
+  return rc;
+}
 }  // namespace
 
 extern "C" {
@@ -490,7 +536,12 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   auto tq = std::chrono::steady_clock::now();
   auto lap = [&](int k) { auto t = std::chrono::steady_clock::now(); h->add_ns[k] += std::chrono::duration_cast<std::chrono::nanoseconds>(t - tq).count(); tq = t; };
   cudaSetDevice(h->cfg.device);   // callers may feed windows from their own threads
-  if (!w->rawj.reserve((size_t)n) || !w->anch.reserve((size_t)n)) return fail(h, 11, "add_proj: pinned allocation failed");
+  win_lock(w);                    // against the batch uploader (flush_pending), which reads the arrays this call may move
+  struct Unlock { HostWin *w; ~Unlock() { if (w) win_unlock(w); } } unlock_at_exit{w};
+  if (!w->rawj.reserve((size_t)n)) return fail(h, 11, "add_proj: pinned allocation failed");
+  if (w->rawj.moved) w->pushed_j = 0;
+  if (!w->anch.reserve((size_t)n)) return fail(h, 11, "add_proj: pinned allocation failed");
+  if (w->anch.moved) w->pushed_a = 0;
   w->obs.resize(base + n);
   lap(3);
   // one pass over the caller's records: ids -> block indices (one-entry caches: consecutive residuals of a track share
@@ -548,11 +599,19 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   w->td_min = tmin; w->td_max = tmax;
   w->rawj.n += (size_t)n; w->anch.n = na;
   lap(0);
-  // start the uploads right away (they overlap with the caller preparing the other blocks / windows)
-  int rc;
-  if ((rc = push_range(h, w->rawj, w->d_rawj, base)) || (rc = push_range(h, w->anch, w->d_anch, base_a))) return rc;
+  // the uploads overlap with the caller preparing the other blocks / windows; issued in batches (flush_pending)
+  win_unlock(w); unlock_at_exit.w = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(h->pend_mu);
+    if (!w->push_pending) { w->push_pending = true; h->pending_win.push_back(window); }
+  }
+  int rc = 0;
+  if ((h->pending_bytes += (long long)n * (long long)sizeof(ObsJ)) >= kPushBatch && h->push_mu.try_lock()) {
+    rc = flush_pending(h, false);
+    h->push_mu.unlock();
+  }
   lap(2);
-  return 0;
+  return rc;
 }
 
 int d2ba_add_landmark_tracks(d2ba_handle *h, int32_t window, int32_t n_landmarks, const int64_t *landmark_ids,
@@ -748,6 +807,7 @@ int d2ba_finalize(d2ba_handle *h) {
   // the pinned staging buffers are rewritten below: wait for the uploads of the previous finalize of this handle
   // (normally long complete -- a solve synchronises the stream); the uploads enqueued by THIS call are not waited for
   CK(cudaStreamSynchronize(h->stream));
+  { std::lock_guard<std::mutex> lk(h->push_mu); int rcp = flush_pending(h, true); if (rcp) return rcp; }   // the rest of the record uploads run beside the planning below
   auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](int slot) { auto t = std::chrono::steady_clock::now(); h->host_ms[slot] = std::chrono::duration<double, std::milli>(t - tp0).count(); tp0 = t; };
   std::vector<WinPlan> plan(nw);
@@ -1403,9 +1463,22 @@ static int upload_state(d2ba_handle *h) {
 }
 
 static void enqueue_linearize(d2ba_handle *h, int eval_cur) {
+  // two lanes: the IMU chain (latency bound, ~10 factors per window) runs beside k_misc_lin / the reprojection kernels
+  // (bandwidth bound).  Order kept: k_misc_lin zero-fills the written runs of Hcc and stores cand_cost_misc before
+  // k_imu_lin and k_proj_lin add to them.
+  const bool fork = h->two_lanes && h->n_imu_total > 0;
+  if (fork) {
+    cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    launch_imu_raw(h->dev, eval_cur, h->n_imu_total, h->side);
+  }
   launch_misc_lin(h->dev, eval_cur, h->max_prior_m, h->stream);
-  launch_imu_lin(h->dev, eval_cur, h->n_imu_total, h->stream);
+  if (fork) {
+    cudaEventRecord(h->ev_misc, h->stream); cudaStreamWaitEvent(h->side, h->ev_misc, 0);
+    launch_imu_acc(h->dev, eval_cur, h->n_imu_total, h->side);
+    cudaEventRecord(h->ev_join, h->side);
+  } else launch_imu_lin(h->dev, eval_cur, h->n_imu_total, h->stream);
   for (int v = 0; v < 6; v++) launch_proj_lin(h->dev, v, eval_cur, h->job_begin[v], h->job_count[v], h->stream);
+  if (fork) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
 }
 
 // reduced camera system: tiles with leaf columns -> leaf elimination (rows Y behind the landmark rows of Wt) -> hub tiles
@@ -1425,8 +1498,13 @@ static void enqueue_solve_reduced(d2ba_handle *h) {
 }
 
 static void enqueue_iteration(d2ba_handle *h) {
+  // the speed-bias elimination (Hcc -> its Y rows behind the landmark rows of Wt) does not touch what the landmark gather
+  // reads or writes: second lane
+  const bool fork = h->two_lanes && h->sbe_smem > 0;
+  if (fork) { cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->side, h->ev_fork, 0); launch_sb_elim(h->dev, h->sbe_smem, h->side); cudaEventRecord(h->ev_join, h->side); }
   launch_lm_gather(h->dev, h->d_lm_win.p, h->nl_total, h->max_row_tiles * 32, h->any_compact, h->any_wide, h->stream);
-  if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);   // Y rows into Wt: the Schur kernels subtract them too
+  if (fork) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  else if (h->sbe_smem > 0) launch_sb_elim(h->dev, h->sbe_smem, h->stream);   // Y rows into Wt: the Schur kernels subtract them too
   enqueue_schur(h);
   enqueue_solve_reduced(h);
   launch_step(h->dev, h->max_nc, h->stream);

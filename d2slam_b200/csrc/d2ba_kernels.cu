@@ -672,11 +672,18 @@ template __global__ void k_proj_lin<4, 4>(Dev, int, int, int);
 #ifndef D2BA_PP_BLOCKS
 #define D2BA_PP_BLOCKS 4
 #endif
+// The observation constants of a tile ([field][32] doubles, contiguous) are staged by ONE TMA bulk copy per tile into a
+// per-warp buffer (UBLKCP + mbarrier); the copy of tile t+1 is issued as soon as the lanes hold tile t in registers, so it
+// -- and the landmark index / inverse depth of the next tile -- are in flight during the arithmetic and the DMMA pass.
+constexpr int kPpRows = 13;                          // staged Jacobian rows: 12 + residual (rows 13..15 of the MMA tile read as zero)
+constexpr int kPpFields = 20;                        // fields 0..19 (inv_depth_j is not used by this path)
+constexpr int kPpWarpDoubles = GC_SIZE + kPpRows * (kTile * 2 + 4) + kPpFields * kTile;
+static size_t proj_pp_smem() { return (size_t)4 * kPpWarpDoubles * 8; }
 template <bool SHIFT0>
 __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int eval_cur, int job_begin, int job_count) {
-  constexpr int NCOL = 16, LDJ = kTile * 2 + 4, RCOL = 12;
-  constexpr int kWarpDoubles = GC_SIZE + NCOL * LDJ;
-  extern __shared__ double sm[];
+  constexpr int LDJ = kTile * 2 + 4, RCOL = 12;
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) unsigned long long bars[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ji = blockIdx.x * 4 + warp;
   if (ji >= job_count) return;
@@ -686,8 +693,26 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
   if (ctl->done || (!eval_cur && !ctl->step_valid)) return;
   const int buf = eval_cur ? ctl->cur : 1 - ctl->cur;
   const Group &g = d.grp[jb.grp];
-  double *gc = sm + warp * kWarpDoubles;
+  double *gc = sm + warp * kPpWarpDoubles;
   double *Js = gc + GC_SIZE;
+  double *tb = Js + kPpRows * LDJ;                    // [kPpFields][32]
+  unsigned long long *bar = &bars[warp];
+  auto issue = [&](int tile) {                        // lane 0
+    const double *src = d.obs + (size_t)tile * kObsFields * kTile;
+    if (SHIFT0) {                                     // velocities / stamps not needed: fields 0..5 and 14..19
+      mbar_expect_tx(bar, 2 * 6 * kTile * 8);
+      bulk_g2s(tb, src, 6 * kTile * 8, bar);
+      bulk_g2s(tb + 14 * kTile, src + 14 * kTile, 6 * kTile * 8, bar);
+    } else {
+      mbar_expect_tx(bar, kPpFields * kTile * 8);
+      bulk_g2s(tb, src, kPpFields * kTile * 8, bar);
+    }
+  };
+  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); issue(jb.tile_begin); }
+  const double *xlm = d.xlm[buf] + w.offlm;
+  int lm = d.obs_lm[(size_t)jb.tile_begin * kTile + lane];
+  int rslot = d.obs_slot[(size_t)jb.tile_begin * kTile + lane];   // needed only for the record store
+  double lam = lm >= 0 ? xlm[lm] : 1.0;
   {
     const double *x6 = d.x6[buf] + (size_t)w.off6 * 8;
     const double *R6 = d.R6[buf] + (size_t)w.off6 * 12;
@@ -696,19 +721,16 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
                        bb >= 0 ? R6 + bb * 12 : nullptr, bb >= 0 ? x6 + bb * 8 : nullptr, gc);
   }
   const double td = d.xtd[buf][jb.win];
-  const double *xlm = d.xlm[buf] + w.offlm;
   const double s_px = d.prm.sqrt_info_px, huber = d.prm.huber;
   double acc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   double cost = 0.0;
-  for (int c = RCOL + 1; c < NCOL; c++) *reinterpret_cast<double2 *>(Js + c * LDJ + lane * 2) = make_double2(0.0, 0.0);
   const int kq = lane & 3, cr = lane >> 2;
+  __syncwarp();
   for (int t = 0; t < jb.ntiles; t++) {
     const int tile = jb.tile_begin + t;
-    const double *ob = d.obs + (size_t)tile * kObsFields * kTile + lane;
-    const int lm = d.obs_lm[(size_t)tile * kTile + lane];
-    const int rslot = d.obs_slot[(size_t)tile * kTile + lane];   // needed only for the record store: in flight with the rest
     const bool valid = lm >= 0;
-    const double lam = valid ? xlm[lm] : 1.0;
+    mbar_wait(bar, t & 1);
+    const double *ob = tb + lane;
     double pi[3] = {ob[0 * kTile], ob[1 * kTile], ob[2 * kTile]};
     double pj[3] = {ob[3 * kTile], ob[4 * kTile], ob[5 * kTile]};
     if (!SHIFT0) {
@@ -719,6 +741,13 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
     double B[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) B[k] = ob[(14 + k) * kTile];
+    __syncwarp();                                     // every lane holds the tile: the buffer is free again
+    int lm_n = -1, rslot_n = -1;
+    if (t + 1 < jb.ntiles) {
+      if (lane == 0) { fence_proxy_async(); issue(tile + 1); }
+      lm_n = d.obs_lm[(size_t)(tile + 1) * kTile + lane];
+      rslot_n = d.obs_slot[(size_t)(tile + 1) * kTile + lane];
+    }
     const double il = 1.0 / lam;
     const double Pci[3] = {pi[0] * il, pi[1] * il, pi[2] * il};
     double Pmi[3], Pmj[3], Pcj[3], tt[3];
@@ -780,10 +809,12 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
       r2[5] = make_double2(wj[0], wj[1]); r2[6] = make_double2(wj[2], wj[3]); r2[7] = make_double2(wj[4], wj[5]);
       if (w.rec_stride == 32) r2[14] = make_double2(__hiloint2double(-1, -1), __hiloint2double(-1, -1));
     }
+    lm = lm_n; rslot = rslot_n;
+    lam = lm >= 0 ? xlm[lm] : 1.0;                    // next tile's inverse depth: in flight during the MMA pass
     __syncwarp();
 #pragma unroll 4
     for (int st = 0; st < kTile * 2 / 4; st++) {
-      const double v0 = Js[cr * LDJ + st * 4 + kq], v1 = Js[(8 + cr) * LDJ + st * 4 + kq];
+      const double v0 = Js[cr * LDJ + st * 4 + kq], v1 = cr < kPpRows - 8 ? Js[(8 + cr) * LDJ + st * 4 + kq] : 0.0;
       dmma(acc[0][0], acc[0][1], v0, v0);
       dmma(acc[1][0], acc[1][1], v0, v1);
       dmma(acc[2][0], acc[2][1], v1, v1);
@@ -2735,10 +2766,15 @@ void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s) {
 void launch_prior_prep(const Dev &d, cudaStream_t s) { k_prior_prep<<<d.n_win, 256, 0, s>>>(d); }
 
 size_t misc_smem_bytes(int max_prior_m) { return (size_t)(40 + 3 * max_prior_m + 8) * 8; }
+void launch_imu_raw(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s) {
+  if (n_imu_total > 0) k_imu_raw<<<(n_imu_total + 31) / 32, 32, 0, s>>>(d, eval_cur, n_imu_total);
+}
+void launch_imu_acc(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s) {
+  if (n_imu_total > 0) k_imu_lin<<<(n_imu_total + kImuWarps - 1) / kImuWarps, kImuWarps * 32, (size_t)kImuWarps * kImuWarpDoubles * 8, s>>>(d, eval_cur, n_imu_total);
+}
 void launch_imu_lin(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s) {
-  if (n_imu_total <= 0) return;
-  k_imu_raw<<<(n_imu_total + 31) / 32, 32, 0, s>>>(d, eval_cur, n_imu_total);
-  k_imu_lin<<<(n_imu_total + kImuWarps - 1) / kImuWarps, kImuWarps * 32, (size_t)kImuWarps * kImuWarpDoubles * 8, s>>>(d, eval_cur, n_imu_total);
+  launch_imu_raw(d, eval_cur, n_imu_total, s);
+  launch_imu_acc(d, eval_cur, n_imu_total, s);
 }
 void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s) {
   k_misc_lin<<<d.n_win, kMiscThreads, misc_smem_bytes(max_prior_m), s>>>(d, eval_cur);
@@ -2753,8 +2789,11 @@ int configure_kernels(int max_rows, int max_nc, int max_prior_m) {
   e = raise_smem_limit(k_proj_lin<4, 2>, (size_t)(proj_smem<4, 2>())); if (e) return e;
   e = raise_smem_limit(k_proj_lin<2, 4>, (size_t)(proj_smem<2, 4>())); if (e) return e;
   e = raise_smem_limit(k_proj_lin<4, 4>, (size_t)(proj_smem<4, 4>())); if (e) return e;
-  e = raise_smem_limit(k_proj_lin_pp<true>, (size_t)(proj_smem<2, 2>())); if (e) return e;
-  e = raise_smem_limit(k_proj_lin_pp<false>, (size_t)(proj_smem<2, 2>())); if (e) return e;
+  e = raise_smem_limit(k_proj_lin_pp<true>, proj_pp_smem()); if (e) return e;
+  e = raise_smem_limit(k_proj_lin_pp<false>, proj_pp_smem()); if (e) return e;
+  // 4 x 51 KB per SM needs the large shared-memory carveout
+  cudaFuncSetAttribute(k_proj_lin_pp<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_proj_lin_pp<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #if D2BA_PP_BLOCKS > 4
   // 37 KB per CTA: the large shared-memory carveout lets the register file, not the L1 split, set the occupancy
   cudaFuncSetAttribute(k_proj_lin_pp<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -2786,8 +2825,8 @@ void launch_proj_lin(const Dev &d, int variant, int eval_cur, int job_begin, int
     case 1: k_proj_lin<4, 2><<<grid, 128, proj_smem<4, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
     case 2: k_proj_lin<2, 4><<<grid, 128, proj_smem<2, 4>(), s>>>(d, eval_cur, job_begin, job_count); break;
     case 3: k_proj_lin<4, 4><<<grid, 128, proj_smem<4, 4>(), s>>>(d, eval_cur, job_begin, job_count); break;
-    case 4: k_proj_lin_pp<true><<<grid, 128, proj_smem<2, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
-    case 5: k_proj_lin_pp<false><<<grid, 128, proj_smem<2, 2>(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 4: k_proj_lin_pp<true><<<grid, 128, proj_pp_smem(), s>>>(d, eval_cur, job_begin, job_count); break;
+    case 5: k_proj_lin_pp<false><<<grid, 128, proj_pp_smem(), s>>>(d, eval_cur, job_begin, job_count); break;
   }
 }
 void launch_proj_debug(const Dev &d, double *out, int n_tiles, const int *tile_win, cudaStream_t s) {

@@ -27,8 +27,8 @@ using namespace d2ba;
 
 namespace {
 
-struct PgoScalars {      // device-resident CG / LM scalars
-  double rz, rz_new, pAp, rr, bb, cost, rr_last;
+struct PgoScalars {      // device-resident CG state that is not a per-block partial
+  double bb;             // |b|^2 of the current linear system
   int done, iters;
 };
 
@@ -39,10 +39,16 @@ struct PgoDev {
   const int *ea, *eb;     // [E] pose indices
   const double *rel;      // [E][8]
   const double *sinfo;    // [E][36] sqrt information, row-major
-  double *lin;            // [E][78]: r(6), J0 (6x6 row-major), J1 (6x6)
+  double *lin;            // [78][E] field-major: r(6), J0 (6x6 row-major), J1 (6x6)
   double *g, *D;          // [6N], [N][36]
   double *Minv;           // [N][36]
   double *dx, *r, *z, *p, *Ap;   // [6N]
+  double *damp;           // [6N] lambda diag(D) + 1e-12
+  double *t;              // [6][E] J p per edge
+  const int *inc_ptr, *inc;   // incidence lists: pose i -> (edge << 1 | side) of this rank's edges, ascending
+  double *rz_part, *rr_part;  // [2][nbp] per-block partials, ping-pong on the iteration parity
+  double *pAp_part;           // [nbp]
+  int nbp;                    // pose blocks of 128
   PgoScalars *s;
 };
 
@@ -84,8 +90,22 @@ D2BA_DEV void pgo_edge_eval(const double *p0, const double *p1, const double *re
   }
 }
 
-// linearise every local edge at d.x: lin records, cost, gradient g = J^T r and the block diagonal D = sum J^T J
-__global__ void __launch_bounds__(128) k_pgo_lin(PgoDev d, double *g, double *D, double *cost_out, int want_jac) {
+// Fixed-order sum of n per-block partials, the same value in every thread of every block (so that all blocks -- and all
+// ranks, which hold identical vectors -- take the same branch without a single-thread "decide" kernel in between).
+D2BA_DEV double total_of(const double *part, int n, double *red) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) v += part[i];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[39] = v;
+  }
+  __syncthreads();
+  return red[39];
+}
+
+// linearise every local edge at d.x: lin records [r | J0 | J1] and per-block cost partials (summed in fixed order by k_pgo_sum)
+__global__ void __launch_bounds__(128) k_pgo_lin(PgoDev d, double *cost_part, int want_jac) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ double red[40];
   double c = 0.0;
@@ -95,37 +115,54 @@ __global__ void __launch_bounds__(128) k_pgo_lin(PgoDev d, double *g, double *D,
     pgo_edge_eval(d.x + (size_t)a * 8, d.x + (size_t)b * 8, d.rel + (size_t)e * 8, d.sinfo + (size_t)e * 36, r, want_jac ? J0 : nullptr, J1);
     for (int k = 0; k < 6; k++) c += 0.5 * r[k] * r[k];
     if (want_jac) {
-      double *o = d.lin + (size_t)e * 78;
-      for (int k = 0; k < 6; k++) o[k] = r[k];
-      for (int k = 0; k < 36; k++) { o[6 + k] = J0[k]; o[42 + k] = J1[k]; }
-      const bool fa = d.fixed[a], fb = d.fixed[b];
-      for (int i = 0; i < 6; i++) {
-        double ga = 0, gb = 0;
-        for (int k = 0; k < 6; k++) { ga += J0[k * 6 + i] * r[k]; gb += J1[k * 6 + i] * r[k]; }
-        if (!fa) atomicAdd(&g[(size_t)a * 6 + i], ga);
-        if (!fb) atomicAdd(&g[(size_t)b * 6 + i], gb);
-        for (int j = 0; j < 6; j++) {
-          double ha = 0, hb = 0;
-          for (int k = 0; k < 6; k++) { ha += J0[k * 6 + i] * J0[k * 6 + j]; hb += J1[k * 6 + i] * J1[k * 6 + j]; }
-          if (!fa && ha != 0.0) atomicAdd(&D[(size_t)a * 36 + i * 6 + j], ha);
-          if (!fb && hb != 0.0) atomicAdd(&D[(size_t)b * 36 + i * 6 + j], hb);
-        }
-      }
+      double *o = d.lin + e;   // field-major [78][E]: consecutive edges (threads) touch consecutive addresses
+      const size_t E = (size_t)d.n_edge;
+      for (int k = 0; k < 6; k++) o[k * E] = r[k];
+      for (int k = 0; k < 36; k++) { o[(6 + k) * E] = J0[k]; o[(42 + k) * E] = J1[k]; }
     }
   }
   c = block_sum(c, red);
-  if (threadIdx.x == 0 && c != 0.0) atomicAdd(cost_out, c);
+  if (threadIdx.x == 0) cost_part[blockIdx.x] = c;
+}
+__global__ void k_pgo_sum(const double *part, int n, double *out) {
+  __shared__ double red[40];
+  const double v = total_of(part, n, red);
+  if (threadIdx.x == 0) out[0] = v;
 }
 
-// block-Jacobi preconditioner: Minv = (D + lambda diag(D))^-1 per free pose (6x6 Cholesky, one thread per pose)
+// gradient g_i = sum J^T r and block diagonal D_i = sum J^T J over the edges incident to pose i, in the fixed order of the
+// incidence list (no atomics: bitwise reproducible)
+__global__ void __launch_bounds__(128) k_pgo_gD(PgoDev d, double *g, double *D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n_pose) return;
+  double gi[6] = {0, 0, 0, 0, 0, 0}, Di[36];
+  for (int k = 0; k < 36; k++) Di[k] = 0.0;
+  if (!d.fixed[i])
+    for (int q = d.inc_ptr[i]; q < d.inc_ptr[i + 1]; q++) {
+      const int c = d.inc[q];
+      const size_t E = (size_t)d.n_edge;
+      const double *o = d.lin + (c >> 1), *J = o + (size_t)(6 + 36 * (c & 1)) * E;
+      for (int k = 0; k < 6; k++) {
+        const double rk = o[k * E];
+        double row[6];
+        for (int a = 0; a < 6; a++) { row[a] = J[(size_t)(k * 6 + a) * E]; gi[a] += row[a] * rk; }
+        for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) Di[a * 6 + b] += row[a] * row[b];
+      }
+    }
+  for (int k = 0; k < 6; k++) g[(size_t)i * 6 + k] = gi[k];
+  for (int k = 0; k < 36; k++) D[(size_t)i * 36 + k] = Di[k];
+}
+
+// block-Jacobi preconditioner: Minv = (D + lambda diag(D))^-1 per free pose (6x6 Cholesky, one thread per pose); also the
+// damping diagonal lambda diag(D) + 1e-12 the products add
 __global__ void k_pgo_precond(PgoDev d, const double *D, double lambda) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.n_pose) return;
   double *M = d.Minv + (size_t)i * 36;
-  if (d.fixed[i]) { for (int k = 0; k < 36; k++) M[k] = 0.0; return; }
+  if (d.fixed[i]) { for (int k = 0; k < 36; k++) M[k] = 0.0; for (int k = 0; k < 6; k++) d.damp[(size_t)i * 6 + k] = 0.0; return; }
   double A[36], Li[36];
   for (int k = 0; k < 36; k++) A[k] = D[(size_t)i * 36 + k];
-  for (int k = 0; k < 6; k++) A[k * 7] += lambda * A[k * 7] + 1e-12;
+  for (int k = 0; k < 6; k++) { const double dk = lambda * A[k * 7] + 1e-12; d.damp[(size_t)i * 6 + k] = dk; A[k * 7] += dk; }
   for (int j = 0; j < 6; j++) {   // Cholesky, lower
     double s = A[j * 6 + j];
     for (int k = 0; k < j; k++) s -= A[j * 6 + k] * A[j * 6 + k];
@@ -143,8 +180,118 @@ __global__ void k_pgo_precond(PgoDev d, const double *D, double lambda) {
   for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) { double t = 0; for (int k = 0; k < 6; k++) t += Li[k * 6 + r] * Li[k * 6 + c]; M[r * 6 + c] = t; }
 }
 
-// CG start: dx = 0, r = -g, z = Minv r, p = z, scalars
-__global__ void k_pgo_cg_init(PgoDev d, const double *g) {
+// ---- conjugate gradients.  One iteration = three kernels (the three grid-wide dependencies of CG):
+//   k_pgo_cg_edge : t_e = J0 p_a + J1 p_b with p = z + beta p_old formed on the fly            (needs rz of the last update)
+//   k_pgo_cg_pose : stores p, Ap_i = sum_inc J^T t (+ damping), partials of p.Ap               (needs every t)
+//   k_pgo_cg_step : alpha = rz / pAp; dx += alpha p; r -= alpha Ap; z = Minv r; partials of r.z, r.r   (needs p.Ap)
+// Scalars live as per-block partials summed in fixed order by every block (total_of); rz / rr ping-pong on the iteration
+// parity `par`.  Once converged the sticky flag s->done turns the remaining launches of a graph into no-ops.
+struct CgView { double rz_prev, rz_cur, rr_cur; bool done, first; };
+D2BA_DEV CgView cg_view(const PgoDev &d, int par, double tol2, double *red) {
+  CgView v;
+  const PgoScalars *s = d.s;
+  v.first = s->iters == 0;
+  v.rz_cur = total_of(d.rz_part + (size_t)(par ^ 1) * d.nbp, d.nbp, red);
+  v.rr_cur = total_of(d.rr_part + (size_t)(par ^ 1) * d.nbp, d.nbp, red);
+  v.rz_prev = v.first ? 1.0 : total_of(d.rz_part + (size_t)par * d.nbp, d.nbp, red);
+  v.done = s->done || !(v.rr_cur > tol2 * s->bb) || !(v.rz_cur > 0.0) || !isfinite(v.rz_cur);
+  return v;
+}
+D2BA_DEV void cg_p_new(const PgoDev &d, int i, double beta, double *p) {
+  for (int k = 0; k < 6; k++) p[k] = d.z[(size_t)i * 6 + k] + beta * d.p[(size_t)i * 6 + k];   // p holds 0 before the first iteration
+}
+
+__global__ void __launch_bounds__(128) k_pgo_cg_edge(PgoDev d, int par, double tol2) {
+  __shared__ double red[40];
+  const CgView v = cg_view(d, par, tol2, red);
+  if (v.done) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.n_edge) return;
+  const double beta = v.first ? 0.0 : v.rz_cur / v.rz_prev;
+  const int a = d.ea[e], b = d.eb[e];
+  const size_t E = (size_t)d.n_edge;
+  const double *J0 = d.lin + 6 * E + e, *J1 = J0 + 36 * E;
+  double pa[6], pb[6];
+  cg_p_new(d, a, beta, pa); cg_p_new(d, b, beta, pb);
+  for (int k = 0; k < 6; k++) {
+    double s = 0;
+    for (int q = 0; q < 6; q++) s += J0[(size_t)(k * 6 + q) * E] * pa[q] + J1[(size_t)(k * 6 + q) * E] * pb[q];
+    d.t[(size_t)k * E + e] = s;
+  }
+}
+
+// LOCAL: this rank's edges only, no damping / p.Ap yet (the all-reduce of Ap comes first; k_pgo_cg_pAp follows)
+template <bool LOCAL>
+__global__ void __launch_bounds__(128) k_pgo_cg_pose(PgoDev d, int par, double tol2) {
+  __shared__ double red[40];
+  const CgView v = cg_view(d, par, tol2, red);
+  if (v.done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < d.n_pose) {
+    const double beta = v.first ? 0.0 : v.rz_cur / v.rz_prev;
+    double p[6], y[6] = {0, 0, 0, 0, 0, 0};
+    cg_p_new(d, i, beta, p);
+    if (!d.fixed[i])
+      for (int q = d.inc_ptr[i]; q < d.inc_ptr[i + 1]; q++) {
+        const int c = d.inc[q];
+        const size_t E = (size_t)d.n_edge;
+        const double *J = d.lin + (size_t)(6 + 36 * (c & 1)) * E + (c >> 1), *t = d.t + (c >> 1);
+        for (int k = 0; k < 6; k++) { const double tk = t[k * E]; for (int a = 0; a < 6; a++) y[a] += J[(size_t)(k * 6 + a) * E] * tk; }
+      }
+    for (int k = 0; k < 6; k++) {
+      d.p[(size_t)i * 6 + k] = p[k];
+      if (!LOCAL) { y[k] += d.damp[(size_t)i * 6 + k] * p[k]; s += p[k] * y[k]; }
+      d.Ap[(size_t)i * 6 + k] = y[k];
+    }
+  }
+  if (!LOCAL) { s = block_sum(s, red); if (threadIdx.x == 0) d.pAp_part[blockIdx.x] = s; }
+}
+template __global__ void k_pgo_cg_pose<true>(PgoDev, int, double);
+template __global__ void k_pgo_cg_pose<false>(PgoDev, int, double);
+
+__global__ void __launch_bounds__(128) k_pgo_cg_pAp(PgoDev d, int par, double tol2) {   // multi-rank: after the all-reduce of Ap
+  __shared__ double red[40];
+  const CgView v = cg_view(d, par, tol2, red);
+  if (v.done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < d.n_pose)
+    for (int k = 0; k < 6; k++) {
+      const double pk = d.p[(size_t)i * 6 + k], y = d.Ap[(size_t)i * 6 + k] + d.damp[(size_t)i * 6 + k] * pk;
+      d.Ap[(size_t)i * 6 + k] = y; s += pk * y;
+    }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) d.pAp_part[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(128) k_pgo_cg_step(PgoDev d, int par, double tol2) {
+  __shared__ double red[40];
+  const CgView v = cg_view(d, par, tol2, red);
+  if (v.done) { if (blockIdx.x == 0 && threadIdx.x == 0) d.s->done = 1; return; }
+  const double pAp = total_of(d.pAp_part, d.nbp, red);
+  const double alpha = pAp > 0.0 ? v.rz_cur / pAp : 0.0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0, rr = 0;
+  if (i < d.n_pose && !d.fixed[i]) {
+    double r[6];
+    for (int k = 0; k < 6; k++) {
+      d.dx[(size_t)i * 6 + k] += alpha * d.p[(size_t)i * 6 + k];
+      r[k] = d.r[(size_t)i * 6 + k] - alpha * d.Ap[(size_t)i * 6 + k];
+      d.r[(size_t)i * 6 + k] = r[k];
+    }
+    const double *M = d.Minv + (size_t)i * 36;
+    for (int k = 0; k < 6; k++) { double t = 0; for (int q = 0; q < 6; q++) t += M[k * 6 + q] * r[q]; d.z[(size_t)i * 6 + k] = t; rz += r[k] * t; rr += r[k] * r[k]; }
+  }
+  rz = block_sum(rz, red); rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    d.rz_part[(size_t)par * d.nbp + blockIdx.x] = rz; d.rr_part[(size_t)par * d.nbp + blockIdx.x] = rr;
+    if (blockIdx.x == 0) d.s->iters = d.s->iters + 1;   // read by the next kernel, not by this one's other blocks (cg_view ran before)
+  }
+}
+
+// CG start: dx = 0, r = -g, z = Minv r, p = 0 (the first k_pgo_cg_edge forms p = z); partials into the parity-1 slots
+__global__ void __launch_bounds__(128) k_pgo_cg_init(PgoDev d, const double *g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ double red[40];
   double rz = 0, rr = 0;
@@ -154,84 +301,17 @@ __global__ void k_pgo_cg_init(PgoDev d, const double *g) {
     const double *M = d.Minv + (size_t)i * 36;
     for (int k = 0; k < 6; k++) { double t = 0; for (int q = 0; q < 6; q++) t += M[k * 6 + q] * r[q]; z[k] = t; }
     for (int k = 0; k < 6; k++) {
-      d.dx[(size_t)i * 6 + k] = 0.0; d.r[(size_t)i * 6 + k] = r[k]; d.z[(size_t)i * 6 + k] = z[k]; d.p[(size_t)i * 6 + k] = z[k]; d.Ap[(size_t)i * 6 + k] = 0.0;
+      d.dx[(size_t)i * 6 + k] = 0.0; d.r[(size_t)i * 6 + k] = r[k]; d.z[(size_t)i * 6 + k] = z[k]; d.p[(size_t)i * 6 + k] = 0.0;
       rz += r[k] * z[k]; rr += r[k] * r[k];
     }
   }
   rz = block_sum(rz, red); rr = block_sum(rr, red);
-  if (threadIdx.x == 0) { atomicAdd(&d.s->rz, rz); atomicAdd(&d.s->bb, rr); }
+  if (threadIdx.x == 0) { d.rz_part[(size_t)d.nbp + blockIdx.x] = rz; d.rr_part[(size_t)d.nbp + blockIdx.x] = rr; }
 }
-
-// Ap += J^T (J p) over the local edges (matrix-free)
-__global__ void __launch_bounds__(128) k_pgo_matvec(PgoDev d) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d.n_edge || d.s->done) return;
-  const int a = d.ea[e], b = d.eb[e];
-  const double *J0 = d.lin + (size_t)e * 78 + 6, *J1 = J0 + 36;
-  double pa[6], pb[6], t[6];
-  for (int k = 0; k < 6; k++) { pa[k] = d.p[(size_t)a * 6 + k]; pb[k] = d.p[(size_t)b * 6 + k]; }
-  for (int k = 0; k < 6; k++) { double s = 0; for (int q = 0; q < 6; q++) s += J0[k * 6 + q] * pa[q] + J1[k * 6 + q] * pb[q]; t[k] = s; }
-  const bool fa = d.fixed[a], fb = d.fixed[b];
-  for (int q = 0; q < 6; q++) {
-    double ya = 0, yb = 0;
-    for (int k = 0; k < 6; k++) { ya += J0[k * 6 + q] * t[k]; yb += J1[k * 6 + q] * t[k]; }
-    if (!fa) atomicAdd(&d.Ap[(size_t)a * 6 + q], ya);
-    if (!fb) atomicAdd(&d.Ap[(size_t)b * 6 + q], yb);
-  }
-}
-
-// damping + p.Ap
-__global__ void k_pgo_cg_damp(PgoDev d, const double *D, double lambda) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_pgo_cg_init2(PgoDev d) {   // |b|^2 and the counters
   __shared__ double red[40];
-  double s = 0;
-  if (i < d.n_pose && !d.s->done && !d.fixed[i])
-    for (int k = 0; k < 6; k++) {
-      const double pk = d.p[(size_t)i * 6 + k];
-      const double ap = d.Ap[(size_t)i * 6 + k] + (lambda * D[(size_t)i * 36 + k * 7] + 1e-12) * pk;
-      d.Ap[(size_t)i * 6 + k] = ap; s += pk * ap;
-    }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0 && s != 0.0) atomicAdd(&d.s->pAp, s);
-}
-
-// dx += alpha p; r -= alpha Ap; z = Minv r; r.z, r.r; Ap = 0 for the next product
-__global__ void k_pgo_cg_update(PgoDev d) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ double red[40];
-  double rz = 0, rr = 0;
-  if (i < d.n_pose && !d.s->done && !d.fixed[i]) {
-    const double alpha = d.s->rz / d.s->pAp;
-    double r[6];
-    for (int k = 0; k < 6; k++) {
-      d.dx[(size_t)i * 6 + k] += alpha * d.p[(size_t)i * 6 + k];
-      r[k] = d.r[(size_t)i * 6 + k] - alpha * d.Ap[(size_t)i * 6 + k];
-      d.r[(size_t)i * 6 + k] = r[k]; d.Ap[(size_t)i * 6 + k] = 0.0;
-    }
-    const double *M = d.Minv + (size_t)i * 36;
-    for (int k = 0; k < 6; k++) { double t = 0; for (int q = 0; q < 6; q++) t += M[k * 6 + q] * r[q]; d.z[(size_t)i * 6 + k] = t; rz += r[k] * t; rr += r[k] * r[k]; }
-  }
-  rz = block_sum(rz, red); rr = block_sum(rr, red);
-  if (threadIdx.x == 0) { if (rz != 0.0) atomicAdd(&d.s->rz_new, rz); if (rr != 0.0) atomicAdd(&d.s->rr, rr); }
-}
-
-// p = z + beta p
-__global__ void k_pgo_cg_dir(PgoDev d) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.n_pose * 6 || d.s->done) return;
-  const double beta = d.s->rz_new / d.s->rz;
-  d.p[i] = d.z[i] + beta * d.p[i];
-}
-
-// rotate the scalars, convergence test
-__global__ void k_pgo_cg_next(PgoDev d, double tol2) {
-  PgoScalars *s = d.s;
-  if (s->done) return;
-  s->iters++;
-  // tol2 < 0 (multi-rank): the ranks decide together on the host from all-reduced values, never from this rank's own flag
-  if ((tol2 >= 0.0 && !(s->rr > tol2 * s->bb)) || !(s->rz_new > 0.0) || !isfinite(s->rz_new)) s->done = 1;
-  s->rr_last = s->rr;
-  s->rz = s->rz_new; s->rz_new = 0.0; s->pAp = 0.0; s->rr = 0.0;
+  const double bb = total_of(d.rr_part + d.nbp, d.nbp, red);
+  if (threadIdx.x == 0) { d.s->bb = bb; d.s->done = 0; d.s->iters = 0; }
 }
 
 // candidate poses: x_out = x (+) dx   (PoseLocalParameterization::Plus)
@@ -261,8 +341,10 @@ struct d2pgo_handle {
   std::vector<int64_t> ids; std::unordered_map<int64_t, int> index;
   std::vector<double> poses; std::vector<unsigned char> fixed;
   std::vector<int> ea, eb; std::vector<double> rel, sinfo;
-  Buf<double> d_x[2], d_rel, d_sinfo, d_lin, d_g[2], d_D[2], d_Minv, d_dx, d_r, d_z, d_p, d_Ap, d_cost;
-  Buf<unsigned char> d_fixed; Buf<int> d_ea, d_eb; Buf<PgoScalars> d_s;
+  Buf<double> d_x[2], d_rel, d_sinfo, d_lin[2], d_g[2], d_D[2], d_Minv, d_dx, d_r, d_z, d_p, d_Ap, d_cost, d_damp, d_t, d_part, d_cost_part;
+  Buf<unsigned char> d_fixed; Buf<int> d_ea, d_eb, d_inc_ptr, d_inc; Buf<PgoScalars> d_s;
+  cudaGraphExec_t cg_graph[2] = {nullptr, nullptr};   // 16 CG iterations on the linearisation buffer 0 / 1 (single rank)
+  double graph_tol2 = -1.0;
   bool uploaded = false;
   void *comm = nullptr; int rank = 0, nranks = 1;
 };
@@ -296,8 +378,9 @@ int d2pgo_destroy(d2pgo_handle *h) {
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   if (h->comm) nccl_comm_destroy(h->comm);
-  for (int b = 0; b < 2; b++) { h->d_x[b].release(); h->d_g[b].release(); h->d_D[b].release(); }
-  h->d_rel.release(); h->d_sinfo.release(); h->d_lin.release(); h->d_Minv.release(); h->d_dx.release(); h->d_r.release(); h->d_z.release(); h->d_p.release();
+  for (int b = 0; b < 2; b++) { h->d_x[b].release(); h->d_g[b].release(); h->d_D[b].release(); h->d_lin[b].release(); if (h->cg_graph[b]) cudaGraphExecDestroy(h->cg_graph[b]); }
+  h->d_damp.release(); h->d_t.release(); h->d_part.release(); h->d_cost_part.release(); h->d_inc_ptr.release(); h->d_inc.release();
+  h->d_rel.release(); h->d_sinfo.release(); h->d_Minv.release(); h->d_dx.release(); h->d_r.release(); h->d_z.release(); h->d_p.release();
   h->d_Ap.release(); h->d_cost.release(); h->d_fixed.release(); h->d_ea.release(); h->d_eb.release(); h->d_s.release();
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaStreamDestroy(h->stream);
   delete h;
@@ -340,18 +423,33 @@ int d2pgo_comm_init(d2pgo_handle *h, const uint8_t unique_id[128], int32_t rank,
   return 0;
 }
 
+static void pgo_drop_graphs(d2pgo_handle *h) {
+  for (int b = 0; b < 2; b++) if (h->cg_graph[b]) { cudaGraphExecDestroy(h->cg_graph[b]); h->cg_graph[b] = nullptr; }
+}
+
 static int pgo_upload(d2pgo_handle *h) {
-  const size_t N = h->ids.size(), E = h->ea.size();
-  for (int b = 0; b < 2; b++) { PCK(h->d_x[b].alloc(N * 8)); PCK(h->d_g[b].alloc(N * 6)); PCK(h->d_D[b].alloc(N * 36)); }
-  PCK(h->d_rel.alloc(E * 8)); PCK(h->d_sinfo.alloc(E * 36)); PCK(h->d_lin.alloc(E * 78)); PCK(h->d_Minv.alloc(N * 36));
+  const size_t N = h->ids.size(), E = h->ea.size(), nbp = (N + 127) / 128, nbe = (E + 127) / 128;
+  pgo_drop_graphs(h);
+  for (int b = 0; b < 2; b++) { PCK(h->d_x[b].alloc(N * 8)); PCK(h->d_g[b].alloc(N * 6)); PCK(h->d_D[b].alloc(N * 36)); PCK(h->d_lin[b].alloc(E * 78)); }
+  PCK(h->d_rel.alloc(E * 8)); PCK(h->d_sinfo.alloc(E * 36)); PCK(h->d_Minv.alloc(N * 36));
   PCK(h->d_dx.alloc(N * 6)); PCK(h->d_r.alloc(N * 6)); PCK(h->d_z.alloc(N * 6)); PCK(h->d_p.alloc(N * 6)); PCK(h->d_Ap.alloc(N * 6)); PCK(h->d_cost.alloc(2));
-  PCK(h->d_fixed.alloc(N)); PCK(h->d_ea.alloc(E)); PCK(h->d_eb.alloc(E)); PCK(h->d_s.alloc(1));
+  PCK(h->d_damp.alloc(N * 6)); PCK(h->d_t.alloc(E * 6)); PCK(h->d_part.alloc(5 * nbp)); PCK(h->d_cost_part.alloc(nbe + 1));
+  PCK(h->d_fixed.alloc(N)); PCK(h->d_ea.alloc(E)); PCK(h->d_eb.alloc(E)); PCK(h->d_s.alloc(1)); PCK(h->d_inc_ptr.alloc(N + 1)); PCK(h->d_inc.alloc(2 * E));
+  // incidence lists (pose -> its edges, ascending edge order): the fixed summation order of every product
+  std::vector<int> ptr(N + 1, 0), inc(2 * E);
+  for (size_t e = 0; e < E; e++) { ptr[h->ea[e] + 1]++; ptr[h->eb[e] + 1]++; }
+  for (size_t i = 0; i < N; i++) ptr[i + 1] += ptr[i];
+  { std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (size_t e = 0; e < E; e++) { inc[fill[h->ea[e]]++] = (int)(e << 1); inc[fill[h->eb[e]]++] = (int)(e << 1 | 1); } }
   PCK(cudaMemcpyAsync(h->d_x[0].p, h->poses.data(), N * 64, cudaMemcpyHostToDevice, h->stream));
   PCK(cudaMemcpyAsync(h->d_fixed.p, h->fixed.data(), N, cudaMemcpyHostToDevice, h->stream));
+  PCK(cudaMemcpyAsync(h->d_inc_ptr.p, ptr.data(), (N + 1) * 4, cudaMemcpyHostToDevice, h->stream));
   if (E) {
+    PCK(cudaMemcpyAsync(h->d_inc.p, inc.data(), 2 * E * 4, cudaMemcpyHostToDevice, h->stream));
     PCK(cudaMemcpyAsync(h->d_ea.p, h->ea.data(), E * 4, cudaMemcpyHostToDevice, h->stream)); PCK(cudaMemcpyAsync(h->d_eb.p, h->eb.data(), E * 4, cudaMemcpyHostToDevice, h->stream));
     PCK(cudaMemcpyAsync(h->d_rel.p, h->rel.data(), E * 64, cudaMemcpyHostToDevice, h->stream)); PCK(cudaMemcpyAsync(h->d_sinfo.p, h->sinfo.data(), E * 288, cudaMemcpyHostToDevice, h->stream));
   }
+  PCK(cudaStreamSynchronize(h->stream));   // ptr / inc go out of scope
   h->uploaded = true;
   return 0;
 }
@@ -359,24 +457,45 @@ static int pgo_upload(d2pgo_handle *h) {
 static PgoDev pgo_view(d2pgo_handle *h, int cur) {
   PgoDev d; memset(&d, 0, sizeof d);
   d.n_pose = (int)h->ids.size(); d.n_edge = (int)h->ea.size(); d.x = h->d_x[cur].p; d.fixed = h->d_fixed.p; d.ea = h->d_ea.p; d.eb = h->d_eb.p;
-  d.rel = h->d_rel.p; d.sinfo = h->d_sinfo.p; d.lin = h->d_lin.p; d.Minv = h->d_Minv.p; d.dx = h->d_dx.p; d.r = h->d_r.p; d.z = h->d_z.p; d.p = h->d_p.p;
-  d.Ap = h->d_Ap.p; d.s = h->d_s.p;
+  d.rel = h->d_rel.p; d.sinfo = h->d_sinfo.p; d.lin = h->d_lin[cur].p; d.Minv = h->d_Minv.p; d.dx = h->d_dx.p; d.r = h->d_r.p; d.z = h->d_z.p; d.p = h->d_p.p;
+  d.Ap = h->d_Ap.p; d.s = h->d_s.p; d.damp = h->d_damp.p; d.t = h->d_t.p; d.inc_ptr = h->d_inc_ptr.p; d.inc = h->d_inc.p;
+  d.nbp = (d.n_pose + 127) / 128; d.rz_part = h->d_part.p; d.rr_part = h->d_part.p + 2 * (size_t)d.nbp; d.pAp_part = h->d_part.p + 4 * (size_t)d.nbp;
   return d;
 }
 
-// cost (+ gradient / block diagonal into buffer `gb`) at pose buffer `xb`; all-reduced across the ranks
-static int pgo_linearize(d2pgo_handle *h, int xb, int gb, int want_jac, double *cost) {
-  PgoDev d = pgo_view(h, xb);
+// cost (+ lin records, gradient, block diagonal of buffer `b`) at pose buffer `b`; all-reduced across the ranks
+static int pgo_linearize(d2pgo_handle *h, int b, int want_jac, double *cost) {
+  PgoDev d = pgo_view(h, b);
   const size_t N = h->ids.size();
-  PCK(cudaMemsetAsync(h->d_cost.p, 0, 16, h->stream));
-  if (want_jac) { PCK(cudaMemsetAsync(h->d_g[gb].p, 0, N * 48, h->stream)); PCK(cudaMemsetAsync(h->d_D[gb].p, 0, N * 288, h->stream)); }
-  if (d.n_edge > 0) k_pgo_lin<<<(d.n_edge + 127) / 128, 128, 0, h->stream>>>(d, h->d_g[gb].p, h->d_D[gb].p, h->d_cost.p, want_jac);
+  const int nbe = (d.n_edge + 127) / 128;
+  if (d.n_edge > 0) k_pgo_lin<<<nbe, 128, 0, h->stream>>>(d, h->d_cost_part.p, want_jac);
+  k_pgo_sum<<<1, 128, 0, h->stream>>>(h->d_cost_part.p, nbe, h->d_cost.p);
+  if (want_jac) k_pgo_gD<<<d.nbp, 128, 0, h->stream>>>(d, h->d_g[b].p, h->d_D[b].p);
   if (h->comm) {
     if (nccl_allreduce_f64(h->comm, h->d_cost.p, 1, h->stream)) { h->err = "ncclAllReduce(cost) failed"; return 40; }
-    if (want_jac && (nccl_allreduce_f64(h->comm, h->d_g[gb].p, N * 6, h->stream) || nccl_allreduce_f64(h->comm, h->d_D[gb].p, N * 36, h->stream))) { h->err = "ncclAllReduce(g, D) failed"; return 40; }
+    if (want_jac && (nccl_allreduce_f64(h->comm, h->d_g[b].p, N * 6, h->stream) || nccl_allreduce_f64(h->comm, h->d_D[b].p, N * 36, h->stream))) { h->err = "ncclAllReduce(g, D) failed"; return 40; }
   }
   PCK(cudaMemcpyAsync(cost, h->d_cost.p, 8, cudaMemcpyDeviceToHost, h->stream));
   PCK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+constexpr int kCgChunk = 16;   // CG iterations between two looks at the convergence flag (one graph launch on a single rank)
+
+static int pgo_cg_chunk(d2pgo_handle *h, const PgoDev &d, double tol2) {
+  const int ge = (d.n_edge + 127) / 128;
+  for (int k = 0; k < kCgChunk; k++) {
+    const int par = k & 1;
+    if (d.n_edge > 0) k_pgo_cg_edge<<<ge, 128, 0, h->stream>>>(d, par, tol2);
+    if (h->comm) {
+      k_pgo_cg_pose<true><<<d.nbp, 128, 0, h->stream>>>(d, par, tol2);
+      // every rank holds the same r, z, p (the all-reduced products are bitwise identical), so all of them reach the same
+      // `done` decision at the same iteration and the collective below is always matched
+      if (nccl_allreduce_f64(h->comm, d.Ap, (size_t)d.n_pose * 6, h->stream)) { h->err = "ncclAllReduce(Ap) failed"; return 40; }
+      k_pgo_cg_pAp<<<d.nbp, 128, 0, h->stream>>>(d, par, tol2);
+    } else k_pgo_cg_pose<false><<<d.nbp, 128, 0, h->stream>>>(d, par, tol2);
+    k_pgo_cg_step<<<d.nbp, 128, 0, h->stream>>>(d, par, tol2);
+  }
   return 0;
 }
 
@@ -385,53 +504,42 @@ int d2pgo_solve(d2pgo_handle *h, d2pgo_report *rep) {
   cudaSetDevice(h->cfg.device);
   int rc;
   if (!h->uploaded && (rc = pgo_upload(h))) return rc;
-  const int N = (int)h->ids.size(), E = (int)h->ea.size();
-  const int gp = (N + 127) / 128, ge = (E + 127) / 128, gv = (N * 6 + 255) / 256;
+  const int N = (int)h->ids.size();
+  const int gp = (N + 127) / 128;
   d2pgo_report R; memset(&R, 0, sizeof R);
   PCK(cudaEventRecord(h->ev0, h->stream));
-  int cur = 0;                    // pose buffer / (g, D) buffer of the accepted point
+  int cur = 0;                    // buffer (poses, lin records, g, D) of the accepted point
   double cost = 0, lambda = h->cfg.lambda0;
-  if ((rc = pgo_linearize(h, cur, cur, 1, &cost))) return rc;
+  if ((rc = pgo_linearize(h, cur, 1, &cost))) return rc;
   R.initial_cost = cost;
+  const double tol2 = h->cfg.pcg_tolerance * h->cfg.pcg_tolerance;
+  if (tol2 != h->graph_tol2) { pgo_drop_graphs(h); h->graph_tol2 = tol2; }
   for (int it = 0; it < h->cfg.max_iterations; it++) {
     PgoDev d = pgo_view(h, cur);
-    const double *g = h->d_g[cur].p, *D = h->d_D[cur].p;
     // (J^T J + lambda diag D) dx = -g by block-Jacobi preconditioned CG; J^T J is never formed
-    k_pgo_precond<<<gp, 128, 0, h->stream>>>(d, D, lambda);
-    PCK(cudaMemsetAsync(h->d_s.p, 0, sizeof(PgoScalars), h->stream));
-    k_pgo_cg_init<<<gp, 128, 0, h->stream>>>(d, g);
-    const double tol2 = h->cfg.pcg_tolerance * h->cfg.pcg_tolerance;
-    for (int k = 0; k < h->cfg.pcg_max_iterations; k++) {
-      if (E > 0) k_pgo_matvec<<<ge, 128, 0, h->stream>>>(d);
-      if (h->comm && nccl_allreduce_f64(h->comm, h->d_Ap.p, (size_t)N * 6, h->stream)) { h->err = "ncclAllReduce(Ap) failed"; return 40; }
-      k_pgo_cg_damp<<<gp, 128, 0, h->stream>>>(d, D, lambda);
-      k_pgo_cg_update<<<gp, 128, 0, h->stream>>>(d);
-      k_pgo_cg_dir<<<gv, 256, 0, h->stream>>>(d);
-      k_pgo_cg_next<<<1, 1, 0, h->stream>>>(d, h->comm ? -1.0 : tol2);
-      if ((k & 15) == 15) {   // every 16 iterations: converged?
-        PgoScalars s;
-        if (h->comm) {
-          // every rank must leave the loop at the same iteration (the all-reduce inside it is collective): decide from
-          // all-reduced residual norms, which are bitwise identical on all ranks
-          PCK(cudaMemcpyAsync(h->d_cost.p, &d.s->rr_last, 8, cudaMemcpyDeviceToDevice, h->stream));
-          PCK(cudaMemcpyAsync(h->d_cost.p + 1, &d.s->bb, 8, cudaMemcpyDeviceToDevice, h->stream));
-          if (nccl_allreduce_f64(h->comm, h->d_cost.p, 2, h->stream)) { h->err = "ncclAllReduce(residual) failed"; return 40; }
-          double v[2];
-          PCK(cudaMemcpyAsync(v, h->d_cost.p, 16, cudaMemcpyDeviceToHost, h->stream));
-          PCK(cudaStreamSynchronize(h->stream));
-          if (!(v[0] > tol2 * v[1])) break;
-        } else {
-          PCK(cudaMemcpyAsync(&s, h->d_s.p, sizeof s, cudaMemcpyDeviceToHost, h->stream));
-          PCK(cudaStreamSynchronize(h->stream));
-          if (s.done) break;
+    k_pgo_precond<<<gp, 128, 0, h->stream>>>(d, h->d_D[cur].p, lambda);
+    k_pgo_cg_init<<<gp, 128, 0, h->stream>>>(d, h->d_g[cur].p);
+    k_pgo_cg_init2<<<1, 128, 0, h->stream>>>(d);
+    PgoScalars s; memset(&s, 0, sizeof s);
+    for (int k = 0; k < h->cfg.pcg_max_iterations; k += kCgChunk) {
+      if (!h->comm) {
+        if (!h->cg_graph[cur]) {
+          cudaGraph_t g;
+          PCK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+          pgo_cg_chunk(h, d, tol2);
+          PCK(cudaStreamEndCapture(h->stream, &g));
+          PCK(cudaGraphInstantiate(&h->cg_graph[cur], g, 0));
+          cudaGraphDestroy(g);
         }
-      }
+        PCK(cudaGraphLaunch(h->cg_graph[cur], h->stream));
+      } else if ((rc = pgo_cg_chunk(h, d, tol2))) return rc;
+      PCK(cudaMemcpyAsync(&s, h->d_s.p, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+      PCK(cudaStreamSynchronize(h->stream));
+      if (s.done) break;   // identical on every rank (see pgo_cg_chunk)
     }
-    PgoScalars s;
-    PCK(cudaMemcpyAsync(&s, h->d_s.p, sizeof s, cudaMemcpyDeviceToHost, h->stream));
     k_pgo_retract<<<gp, 128, 0, h->stream>>>(d, h->d_x[1 - cur].p);
     double cand = 0;
-    if ((rc = pgo_linearize(h, 1 - cur, 1 - cur, 1, &cand))) return rc;
+    if ((rc = pgo_linearize(h, 1 - cur, 1, &cand))) return rc;
     R.pcg_iterations += s.iters; R.iterations++;
     if (cand < cost && isfinite(cand)) {
       const double rel_dec = (cost - cand) / (cost > 0 ? cost : 1.0);
@@ -471,8 +579,10 @@ int d2pgo_debug_edges(d2pgo_handle *h, double *out, int64_t out_doubles) {
   const size_t E = h->ea.size();
   if ((size_t)out_doubles < E * 78) { h->err = "debug_edges: buffer too small"; return 2; }
   double cost;
-  if ((rc = pgo_linearize(h, 0, 0, 1, &cost))) return rc;
-  PCK(cudaMemcpy(out, h->d_lin.p, E * 78 * 8, cudaMemcpyDeviceToHost));
+  if ((rc = pgo_linearize(h, 0, 1, &cost))) return rc;
+  std::vector<double> tmp(E * 78);
+  PCK(cudaMemcpy(tmp.data(), h->d_lin[0].p, E * 78 * 8, cudaMemcpyDeviceToHost));
+  for (size_t e = 0; e < E; e++) for (int k = 0; k < 78; k++) out[e * 78 + k] = tmp[(size_t)k * E + e];   // device layout is field-major
   return 0;
 }
 

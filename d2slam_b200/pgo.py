@@ -147,7 +147,16 @@ def make_pose_graph(seed=0, n_agents=8, poses_per_agent=1250, loops=30000, sigma
         j = order[(lo + (rng.random(loops) * (hi - lo)).astype(np.int64)).clip(0, N - 1)]
         ok = (np.abs(i - j) > 5) & (np.linalg.norm(gt[i, :3] - gt[j, :3], axis=1) < loop_radius)
         la += i[ok].tolist(); lb += j[ok].tolist(); tries += 1
-    la = np.array(la[:loops], np.int64); lb = np.array(lb[:loops], np.int64)
+    la = la[:loops]; lb = lb[:loops]
+    # one guaranteed inter-agent closure per agent (closest pair to any earlier agent) so that the graph is connected and the
+    # single fixed pose removes the whole gauge freedom
+    for a in range(1, n_agents):
+        mine = np.arange(a * poses_per_agent, (a + 1) * poses_per_agent); prev = np.arange(0, a * poses_per_agent)
+        sub = prev[:: max(1, len(prev) // 2000)]
+        d2 = ((gt[mine, None, :3] - gt[None, sub, :3]) ** 2).sum(-1)
+        i, j = np.unravel_index(np.argmin(d2), d2.shape)
+        la.append(int(mine[i])); lb.append(int(sub[j]))
+    la = np.array(la, np.int64); lb = np.array(lb, np.int64)
     ea = np.concatenate([ia, la]); eb = np.concatenate([ib, lb]); E = len(ea)
     rel = relative_pose(gt[ea], gt[eb])
     rel[:, :3] += rng.normal(0, sigma_t, (E, 3))

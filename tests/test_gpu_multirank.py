@@ -20,3 +20,14 @@ def test_two_rank_admm_matches_oracle():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(out.stdout[-2000:]); sys.stderr.write(out.stderr[-2000:])
     assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout
+
+
+def test_two_rank_pose_graph_matches_single_rank():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", os.path.join(ROOT, "tools", "pgo_multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(out.stdout[-2000:]); sys.stderr.write(out.stderr[-2000:])
+    assert out.returncode == 0 and "PGO_MULTI_GPU_CHECK PASS" in out.stdout
