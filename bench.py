@@ -531,7 +531,10 @@ def run_ours(args, rank, world, local_rank):
     from d2slam_b200.harness import Replay
     rp = Replay(probs)
     ncpu = host_threads_available()
-    host_threads = max(1, min(ncpu // max(1, min(world, 8)), 32))
+    # per pipeline stage: the feed and finalize stages of different handles run at the same time, so each gets a share of the cores
+    host_threads = max(1, min(ncpu // max(1, min(world, 8)), 32 if args.handles <= 2 else 12))
+    if args.host_threads > 0:
+        host_threads = args.host_threads
     e2e_steps = max(1, min(args.steps, 40))
     n_seq = min(e2e_steps, 10)
     rp.run(solver, 2, iters, host_threads)
@@ -694,7 +697,8 @@ def main():
     ap.add_argument("--rho-sweep", action="store_true")
     ap.add_argument("--swarm-agents", type=int, default=4)   # north-star leg at N=1: 4-agent swarms on one GPU
     ap.add_argument("--swarms", type=int, default=148)
-    ap.add_argument("--handles", type=int, default=2)
+    ap.add_argument("--handles", type=int, default=4)
+    ap.add_argument("--host-threads", type=int, default=0, help="feeding / planning threads per stage of the e2e leg (0 = min(cores, 32))")
     ap.add_argument("--no-extras", action="store_true", help="N=1: skip the latency_b1 / swarm_1gpu legs")
     ap.add_argument("--impl", default="ours")
     args = ap.parse_args()

@@ -26,7 +26,7 @@
 namespace d2ba {
 // launchers implemented in d2ba_kernels.cu
 void launch_state_prep(const Dev &d, int n6_total, int buf, cudaStream_t s);
-void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s);
+void launch_imu_prep(const Dev &d, const double *packed, double *full, int n_imu, cudaStream_t s);
 void launch_prior_prep(const Dev &d, cudaStream_t s);
 void launch_misc_lin(const Dev &d, int eval_cur, int max_prior_m, cudaStream_t s);
 void launch_imu_lin(const Dev &d, int eval_cur, int n_imu_total, cudaStream_t s);
@@ -72,7 +72,7 @@ size_t leaf_elim_smem(int n, int n_hub);
 int leaf_max_cols();
 int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int nk, const int *rem_idx, int nr, double *A, double *b, int *fail_flag,
                        cudaStream_t s);
-void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s);
+void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, const double *xtd, double *obs, int n_tiles, cudaStream_t s);
 void launch_prior_from_info(int n_win, int max_m, const int *m_of, const long long *offJ, const long long *offv, const int *is_info,
                             double *A, double *V, double *b, cudaStream_t s);
 }  // namespace d2ba
@@ -113,7 +113,7 @@ struct HObs { int type, pi, pj, ea, eb, lm, fa; };   // index form of one residu
 // landmark, so it is stored once per run of identical anchors -- less than half the bytes of the caller's 160-byte
 // records cross PCIe.  The tiled layout and the tangent bases are built on the device by k_build_tiles.
 // Capacity survives d2ba_reset.
-template <typename T>
+template <typename T, bool WC = true>
 struct PinArr {
   T *p = nullptr; size_t cap = 0, n = 0;
   bool moved = false;   // the last reserve() re-allocated (the whole array must be uploaded again)
@@ -124,7 +124,7 @@ struct PinArr {
     T *q = nullptr;
     // write-combined: the feeding threads only ever append (no read-for-ownership, no cache pollution) and the DMA engine
     // does not have to snoop the CPU caches; reading it back (marginalization, growth) is slow but rare
-    if (cudaHostAlloc((void **)&q, want * sizeof(T), cudaHostAllocWriteCombined) != cudaSuccess) return false;
+    if (cudaHostAlloc((void **)&q, want * sizeof(T), WC ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return false;
     if (n) memcpy(q, p, n * sizeof(T));
     if (p) cudaFreeHost(p);
     p = q; cap = want; moved = true;
@@ -148,9 +148,12 @@ struct HostWin {
   std::vector<uint8_t> pose_c, ext_c, sb_c;
   double td = 0; bool has_td = false; uint8_t td_c = 1;
   std::vector<HObs> obs;
-  PinArr<ObsJ> rawj; PinArr<ObsAnchor> anch;              // compact observation constants (pinned)
+  PinArr<ObsJ> rawj; PinArr<ObsAnchor> anch;              // compact observation constants (pinned): geometry ...
+  PinArr<ObsJm, false> rawjm; PinArr<ObsAnchorM, false> anchm;   // ... and motion (uploaded at finalize, only when the time shift can be non-zero;
+                                                                  //     cacheable: normally never read by the DMA engine, and two fewer write-combining streams per feeder)
   DevArr<ObsJ> d_rawj; DevArr<ObsAnchor> d_anch;          // device copies (uploaded in batches as they are appended)
-  size_t pushed_j = 0, pushed_a = 0;                       // records already on the copy stream
+  DevArr<ObsJm> d_rawjm; DevArr<ObsAnchorM> d_anchm;
+  size_t pushed_j = 0, pushed_a = 0, pushed_jm = 0, pushed_am = 0;   // records already on the copy stream
   int feed_lock = 0; bool push_pending = false;            // feeder / uploader hand-over (see flush_pending)
   double td_min = 1e300, td_max = -1e300;
   std::vector<HImu> imu;
@@ -167,7 +170,7 @@ struct HostWin {
     pose_map.clear(); ext_map.clear(); sb_map.clear(); lm_map.clear();
     pose.clear(); ext.clear(); sb.clear(); lm.clear(); pose_c.clear(); ext_c.clear(); sb_c.clear();
     td = 0; has_td = false; td_c = 1;
-    obs.clear(); rawj.n = 0; anch.n = 0; pushed_j = pushed_a = 0; push_pending = false; imu.clear(); td_min = 1e300; td_max = -1e300;
+    obs.clear(); rawj.n = 0; anch.n = 0; rawjm.n = 0; anchm.n = 0; pushed_j = pushed_a = pushed_jm = pushed_am = 0; push_pending = false; imu.clear(); td_min = 1e300; td_max = -1e300;
     prior_m = 0; prior_J.clear(); prior_e0.clear(); prior_blk.clear(); prior_is_info = false;
     pose_slot.clear(); ext_slot.clear(); admm = false; n_slots = 0;
     pose_col.clear(); ext_col.clear(); sb_col.clear(); td_col = -1; n_lc = 0; n_c = 0;
@@ -252,14 +255,16 @@ struct d2ba_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_it[2] = {nullptr, nullptr};   // solver time budget: iteration k-2 complete
   cudaEvent_t evf0 = nullptr, evf1 = nullptr, evf2 = nullptr;   // device span of the last finalize: uploads | tile build + prep kernels
-  bool finalized = false, state_dirty = false;
+  bool motion_skipped = false;                 // some window's motion halves stayed on the host (debug views fetch them: ensure_motion)
+  std::atomic<bool> finalized{false}, state_dirty{false};   // written by the per-window feeding calls of several threads
+  std::mutex err_mu;                                        // guards err (fail() may be reached from several feeding threads)
   // device arena
   DBuf<char> d_arena;   // device image of the pinned staging arena (one H2D copy per finalize); the DBufs it backs are views
   DBuf<WinDesc> d_win; DBuf<Ctl> d_ctl;
   DBuf<double> d_x6[2], d_R6[2], d_xsb[2], d_xlm[2], d_xtd[2];
   DBuf<int> d_col6, d_colsb, d_tile_grp, d_obs_lm, d_lm_ptr, d_obs_slot, d_slot6, d_lm_win, d_blk_win, d_sb_win, d_tile_win;
   DBuf<Group> d_grp; DBuf<Job> d_job; DBuf<ImuDesc> d_imu; DBuf<PriorBlk> d_prior_blk;
-  DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_U, d_imu_raw, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
+  DBuf<double> d_obs, d_rec[2], d_imu_c, d_imu_pk, d_imu_U, d_imu_raw, d_prior_J, d_prior_e0, d_prior_A, d_z6, d_tilde6, d_lm_ref, d_sb_ref, d_td_ref,
       d_cons, d_H[2], d_gc[2], d_Wt, d_dinv, d_hl, d_gl, d_S, d_gred, d_D2c, d_gn_c, d_gn_l, d_step_c, d_step_l, d_wu, d_uc, d_D2l, d_dbg;
   DBuf<SchurTileH> d_schur; DBuf<int> d_schur_chunks; DBuf<Leaf> d_leaf; DBuf<HSeg> d_hseg; DBuf<unsigned long long> d_lm_mask; DBuf<double> d_leafL; DBuf<int> d_leaf_lm;
   int n_schur0 = 0, n_leaf_total = 0, max_hub = 0; size_t leaf_smem = 0, cfg_leaf_smem = 0, leafb_smem = 0, cfg_leafb_smem = 0;
@@ -310,7 +315,7 @@ namespace {
 #define CK(call)                                                                                   \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 100 + (int)e_; } } while (0)
 
-int fail(d2ba_handle *h, int rc, const std::string &m) { h->err = m; return rc; }
+int fail(d2ba_handle *h, int rc, const std::string &m) { std::lock_guard<std::mutex> lk(h->err_mu); h->err = m; return rc; }
 
 HostWin *get_win(d2ba_handle *h, int w) {
   if (!h || w < 0 || w >= (int)h->win.size()) return nullptr;
@@ -401,13 +406,13 @@ int d2ba_destroy(d2ba_handle *h) {
   for (int b = 0; b < 2; b++) { h->d_x6[b].release(); h->d_R6[b].release(); h->d_xsb[b].release(); h->d_xlm[b].release(); h->d_xtd[b].release(); h->d_rec[b].release(); h->d_H[b].release(); h->d_gc[b].release(); }
   h->d_col6.release(); h->d_colsb.release(); h->d_tile_grp.release(); h->d_obs_lm.release(); h->d_lm_ptr.release(); h->d_obs_slot.release();
   h->d_slot6.release(); h->d_lm_win.release(); h->d_blk_win.release(); h->d_sb_win.release(); h->d_tile_win.release();
-  h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_U.release(); h->d_imu_raw.release();
+  h->d_grp.release(); h->d_job.release(); h->d_imu.release(); h->d_prior_blk.release(); h->d_obs.release(); h->d_imu_c.release(); h->d_imu_pk.release(); h->d_imu_U.release(); h->d_imu_raw.release();
   h->d_prior_J.release(); h->d_prior_e0.release(); h->d_prior_A.release(); h->d_z6.release(); h->d_tilde6.release(); h->d_lm_ref.release(); h->d_sb_ref.release();
   h->d_td_ref.release(); h->d_cons.release(); h->d_Wt.release(); h->d_dinv.release(); h->d_hl.release(); h->d_gl.release(); h->d_S.release(); h->d_gred.release();
   h->d_D2c.release(); h->d_gn_c.release(); h->d_gn_l.release(); h->d_step_c.release(); h->d_step_l.release(); h->d_wu.release(); h->d_uc.release(); h->d_D2l.release(); h->d_dbg.release(); h->d_schur.release(); h->d_schur_chunks.release(); h->d_leaf.release(); h->d_hseg.release(); h->d_lm_mask.release(); h->d_leafL.release(); h->d_leaf_lm.release();
   h->d_pr_m.release(); h->d_pr_info.release(); h->d_pr_oJ.release(); h->d_pr_ov.release(); h->d_tile_src.release(); h->d_raw_off.release();
   cudaStreamSynchronize(h->copy_stream);
-  for (auto &w : h->win) { w.rawj.release(); w.anch.release(); w.d_rawj.release(); w.d_anch.release(); }
+  for (auto &w : h->win) { w.rawj.release(); w.anch.release(); w.d_rawj.release(); w.d_anch.release(); w.rawjm.release(); w.anchm.release(); w.d_rawjm.release(); w.d_anchm.release(); }
   cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_copy);
   cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_misc);
   d2ba_release_staging(h);
@@ -477,8 +482,8 @@ int d2ba_set_blocks(d2ba_handle *h, int32_t window, int32_t kind, int32_t n, con
 
 namespace {
 // append-range upload of a pinned array into its device mirror (copy stream)
-template <typename T>
-int push_range(d2ba_handle *h, PinArr<T> &host, DevArr<T> &dev, size_t first_new) {
+template <typename T, bool WC>
+int push_range(d2ba_handle *h, PinArr<T, WC> &host, DevArr<T> &dev, size_t first_new) {
   if (host.n > dev.cap) {
     if (dev.p) { cudaStreamSynchronize(h->copy_stream); cudaFree(dev.p); }
     dev.p = nullptr; dev.cap = 0;
@@ -501,6 +506,12 @@ constexpr long long kPushBatch = 4 << 20;
 inline void win_lock(HostWin *w) { while (__atomic_exchange_n(&w->feed_lock, 1, __ATOMIC_ACQUIRE)) { } }
 inline bool win_try_lock(HostWin *w) { return !__atomic_exchange_n(&w->feed_lock, 1, __ATOMIC_ACQUIRE); }
 inline void win_unlock(HostWin *w) { __atomic_store_n(&w->feed_lock, 0, __ATOMIC_RELEASE); }
+// td constant (or absent) and equal to every stamp of the window: the shift td - td_i is exactly zero for the whole solve
+inline bool motion_needed(const HostWin &w) {
+  if (w.td_min > w.td_max) return false;   // no reprojection factor at all
+  const bool td_free = w.has_td && !w.td_c;
+  return td_free || w.td_min != w.td_max || w.td_min != w.td;
+}
 int flush_pending(d2ba_handle *h, bool all) {   // caller holds h->push_mu
   std::vector<int> list;
   {
@@ -542,6 +553,9 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
   if (w->rawj.moved) w->pushed_j = 0;
   if (!w->anch.reserve((size_t)n)) return fail(h, 11, "add_proj: pinned allocation failed");
   if (w->anch.moved) w->pushed_a = 0;
+  if (!w->rawjm.reserve((size_t)n) || !w->anchm.reserve((size_t)n)) return fail(h, 11, "add_proj: pinned allocation failed");
+  if (w->rawjm.moved) w->pushed_jm = 0;
+  if (w->anchm.moved) w->pushed_am = 0;
   w->obs.resize(base + n);
   lap(3);
   // one pass over the caller's records: ids -> block indices (one-entry caches: consecutive residuals of a track share
@@ -552,9 +566,11 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
     return c.idx;
   };
   ObsJ *oj = w->rawj.p + w->rawj.n;
+  ObsJm *ojm = w->rawjm.p + w->rawjm.n;
   ObsAnchor *an = w->anch.p;
+  ObsAnchorM *anm = w->anchm.p;
   size_t na = w->anch.n;
-  ObsAnchor last; memset(&last, 0, sizeof last);   // cached copy of an[na - 1]: the pinned arrays are write-only for this loop
+  struct { double pts_i[3], vel_i[3], td_i; } last; memset(&last, 0, sizeof last);   // cached copy of anchor na - 1: the pinned arrays are write-only for this loop
   double tmin = w->td_min, tmax = w->td_max;
   for (int i = 0; i < n; i++) {
     const d2ba_proj_obs &p = in[i];
@@ -575,29 +591,32 @@ int d2ba_add_proj(d2ba_handle *h, int32_t window, int32_t n, const d2ba_proj_obs
         if (o.pi < 0 || o.pj < 0) err = "add_proj: unknown frame id";
       }
     }
-    if (err) { w->obs.resize(base); w->anch.n = base_a; return fail(h, 3, err); }
+    if (err) { w->obs.resize(base); w->anch.n = base_a; w->anchm.n = base_a; return fail(h, 3, err); }
     w->obs[base + i] = o;
     ObsJ &r = oj[i];
     if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
       tmin = std::min(tmin, std::min(p.td_i, p.td_j)); tmax = std::max(tmax, std::max(p.td_i, p.td_j));
       // anchor half: bitwise identical to the previous anchor -> share it
       if (na == base_a || memcmp(last.pts_i, p.pts_i, 24) != 0 || memcmp(last.vel_i, p.vel_i, 24) != 0 || memcmp(&last.td_i, &p.td_i, 8) != 0) {
-        memcpy(last.pts_i, p.pts_i, 24); memcpy(last.vel_i, p.vel_i, 24); last.td_i = p.td_i; last.pad = 0.0;
-        an[na++] = last;
+        memcpy(last.pts_i, p.pts_i, 24); memcpy(last.vel_i, p.vel_i, 24); last.td_i = p.td_i;
+        ObsAnchor ta; ObsAnchorM tm;
+        memcpy(ta.pts_i, p.pts_i, 24); memcpy(tm.vel_i, p.vel_i, 24); tm.td_i = p.td_i;
+        an[na] = ta; anm[na] = tm; na++;
       }
-      ObsJ t;
-      memcpy(t.pts_j, p.pts_j, 24); memcpy(t.vel_j, p.vel_j, 24); t.td_j = p.td_j;
+      ObsJ t; ObsJm tm;
+      memcpy(t.pts_j, p.pts_j, 24); memcpy(tm.vel_j, p.vel_j, 24); tm.td_j = p.td_j;
       t.depth = p.type == D2BA_PROJ_2F1C_DEPTH ? p.depth : 0.0;
       t.anchor = (int32_t)(na - 1); t.type = p.type;
-      r = t;   // one sequential 72-byte store burst
+      r = t; ojm[i] = tm;   // sequential store bursts
     } else {
       ObsJ t; memset(&t, 0, sizeof t);
+      ObsJm tm; memset(&tm, 0, sizeof tm);
       t.depth = p.depth; t.anchor = 0; t.type = p.type;
-      r = t;
+      r = t; ojm[i] = tm;
     }
   }
   w->td_min = tmin; w->td_max = tmax;
-  w->rawj.n += (size_t)n; w->anch.n = na;
+  w->rawj.n += (size_t)n; w->rawjm.n += (size_t)n; w->anch.n = na; w->anchm.n = na;
   lap(0);
   // the uploads overlap with the caller preparing the other blocks / windows; issued in batches (flush_pending)
   win_unlock(w); unlock_at_exit.w = nullptr;
@@ -808,6 +827,13 @@ int d2ba_finalize(d2ba_handle *h) {
   // (normally long complete -- a solve synchronises the stream); the uploads enqueued by THIS call are not waited for
   CK(cudaStreamSynchronize(h->stream));
   { std::lock_guard<std::mutex> lk(h->push_mu); int rcp = flush_pending(h, true); if (rcp) return rcp; }   // the rest of the record uploads run beside the planning below
+  for (int wi = 0; wi < nw; wi++) {   // motion halves: only where td - td_i can be non-zero (td free, or a stamp that differs from td)
+    HostWin &w = h->win[wi];
+    if (!motion_needed(w)) continue;
+    int rcp;
+    if ((rcp = push_range(h, w.rawjm, w.d_rawjm, w.pushed_jm)) || (rcp = push_range(h, w.anchm, w.d_anchm, w.pushed_am))) return rcp;
+    w.pushed_jm = w.rawjm.n; w.pushed_am = w.anchm.n;
+  }
   auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](int slot) { auto t = std::chrono::steady_clock::now(); h->host_ms[slot] = std::chrono::duration<double, std::milli>(t - tp0).count(); tp0 = t; };
   std::vector<WinPlan> plan(nw);
@@ -1204,8 +1230,8 @@ int d2ba_finalize(d2ba_handle *h) {
   st.reserve(st.win, nw); st.reserve(st.x6, (size_t)off6 * 8); st.reserve(st.xsb, (size_t)offsb * 9); st.reserve(st.xlm, offlm); st.reserve(st.xtd, nw);
   st.reserve(st.col6, off6); st.reserve(st.colsb, offsb); st.reserve(st.slot6, off6); st.reserve(st.blk_win, off6); st.reserve(st.sb_win, offsb);
   st.reserve(st.lm_win, offlm); st.reserve(st.tile_grp, off_tile); st.reserve(st.tile_win, off_tile); st.reserve(st.obs_lm, (size_t)off_tile * kTile);
-  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, 2 * (size_t)nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.obs_slot, (size_t)off_tile * kTile);
-  st.reserve(st.grp, off_grp); st.reserve(st.job, n_jobs); st.reserve(st.imu, off_imu); st.reserve(st.imu_c, (size_t)off_imu * kImuStride);
+  st.reserve(st.tile_src, (size_t)off_tile * kTile); st.reserve(st.raw_off, 4 * (size_t)nw); st.reserve(st.lm_ptr, off_lmptr); st.reserve(st.obs_slot, (size_t)off_tile * kTile);
+  st.reserve(st.grp, off_grp); st.reserve(st.job, n_jobs); st.reserve(st.imu, off_imu); st.reserve(st.imu_c, (size_t)off_imu * kImuPack);
   st.reserve(st.pblk, off_pblk); st.reserve(st.prior_J, (size_t)off_pJ); st.reserve(st.prior_e0, (size_t)off_pv); st.reserve(st.schur, n_schur); st.reserve(st.schur_chunks, n_chunks); st.reserve(st.leaf, off_leaf); st.reserve(st.hseg, off_hseg); st.reserve(st.lm_mask, offlm); st.reserve(st.leaf_lm, n_leaf_lm);
   st.reserve(st.pr_m, nw); st.reserve(st.pr_info, nw); st.reserve(st.pr_offJ, nw); st.reserve(st.pr_offv, nw);
   bool ok = st.arena.resize(st.cursor + 256);
@@ -1218,6 +1244,7 @@ int d2ba_finalize(d2ba_handle *h) {
   if (!ok) return fail(h, 24, "pinned staging allocation failed");
   lap(1);
   // ---- pass B (parallel): fill the staging buffers
+  std::atomic<int> skipped_any{0};
   parallel_for(nw, [&](int wi) {
     HostWin &w = h->win[wi]; WinPlan &pl = plan[wi]; const WinDesc &d = pl.d;
     st.win.p[wi] = d;
@@ -1278,7 +1305,10 @@ int d2ba_finalize(d2ba_handle *h) {
     for (int i = 0; i < d.n_imu; i++) {
       const HImu &m = w.imu[i];
       st.imu.p[d.off_imu + i] = ImuDesc{m.pi, m.si, m.pj, m.sj, wi};
-      memcpy(st.imu_c.p + (size_t)(d.off_imu + i) * kImuStride, m.c, sizeof(double) * kImuStride);
+      double *pk = st.imu_c.p + (size_t)(d.off_imu + i) * kImuPack;   // packed upload record (d2ba_types.cuh kImuPack)
+      memcpy(pk, m.c, 17 * 8);
+      for (int r = 0; r < 9; r++) memcpy(pk + 17 + r * 6, m.c + 17 + r * 15 + 9, 6 * 8);
+      for (int r = 0, q = 0; r < 15; r++) for (int c = 0; c <= r; c++) pk[71 + q++] = m.c[17 + 225 + r * 15 + c];
     }
     st.pr_m.p[wi] = d.prior_m; st.pr_info.p[wi] = (d.prior_m > 0 && w.prior_is_info) ? 1 : 0; st.pr_offJ.p[wi] = d.off_prior_J; st.pr_offv.p[wi] = d.off_prior_v;
     if (d.prior_m > 0) {
@@ -1303,7 +1333,10 @@ int d2ba_finalize(d2ba_handle *h) {
   for (int wi = 0; wi < nw; wi++) {
     HostWin &w = h->win[wi];
     if (w.rawj.n != w.obs.size()) return fail(h, 25, "internal: raw / index record count mismatch");
-    st.raw_off.p[2 * wi] = (long long)(uintptr_t)w.d_rawj.p; st.raw_off.p[2 * wi + 1] = (long long)(uintptr_t)w.d_anch.p;
+    st.raw_off.p[4 * wi] = (long long)(uintptr_t)w.d_rawj.p; st.raw_off.p[4 * wi + 1] = (long long)(uintptr_t)w.d_anch.p;
+    const bool mot = motion_needed(w);   // else: k_build_tiles writes zero velocities and td_i = td_j = td
+    if (!mot && w.rawj.n) skipped_any = 1;
+    st.raw_off.p[4 * wi + 2] = mot ? (long long)(uintptr_t)w.d_rawjm.p : 0; st.raw_off.p[4 * wi + 3] = mot ? (long long)(uintptr_t)w.d_anchm.p : 0;
   }
   if (st.cursor > h->d_arena.n) {   // growing: views of the old arena die with it
     CK(cudaStreamSynchronize(h->stream));
@@ -1325,7 +1358,7 @@ int d2ba_finalize(d2ba_handle *h) {
       (rc = up(h, h->d_tile_win, st.tile_win)) || (rc = up(h, h->d_obs_lm, st.obs_lm)) || (rc = up(h, h->d_tile_src, st.tile_src)) ||
       (rc = up(h, h->d_lm_ptr, st.lm_ptr)) || (rc = up(h, h->d_obs_slot, st.obs_slot)) || (rc = up(h, h->d_slot6, st.slot6)) ||
       (rc = up(h, h->d_lm_win, st.lm_win)) || (rc = up(h, h->d_blk_win, st.blk_win)) || (rc = up(h, h->d_sb_win, st.sb_win)) ||
-      (rc = up(h, h->d_grp, st.grp)) || (rc = up(h, h->d_job, st.job)) || (rc = up(h, h->d_imu, st.imu)) || (rc = up(h, h->d_imu_c, st.imu_c)) ||
+      (rc = up(h, h->d_grp, st.grp)) || (rc = up(h, h->d_job, st.job)) || (rc = up(h, h->d_imu, st.imu)) || (rc = up(h, h->d_imu_pk, st.imu_c)) ||
       (rc = up(h, h->d_prior_blk, st.pblk)) || (rc = up(h, h->d_prior_J, st.prior_J)) || (rc = up(h, h->d_prior_e0, st.prior_e0)) ||
       (rc = up(h, h->d_schur, st.schur)) || (rc = up(h, h->d_schur_chunks, st.schur_chunks)) || (rc = up(h, h->d_leaf, st.leaf)) || (rc = up(h, h->d_leaf_lm, st.leaf_lm)) ||
       (rc = up(h, h->d_hseg, st.hseg)) || (rc = up(h, h->d_lm_mask, st.lm_mask)))
@@ -1336,8 +1369,10 @@ int d2ba_finalize(d2ba_handle *h) {
   CK(cudaEventRecord(h->ev_copy, h->copy_stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
   CK(cudaEventRecord(h->evf1, h->stream));
-  launch_build_tiles(h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_obs.p, off_tile, h->stream);
+  h->motion_skipped = skipped_any.load() != 0;
+  launch_build_tiles(h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_xtd[0].p, h->d_obs.p, off_tile, h->stream);
   CK(h->d_imu_U.alloc((size_t)off_imu * 225));
+  if ((rc = alloc_zero(h, h->d_imu_c, (size_t)off_imu * kImuStride))) return rc;   // expanded from the packed upload by k_imu_unpack (launch_imu_prep)
   if ((rc = alloc_zero(h, h->d_imu_raw, (size_t)off_imu * 465))) return rc;   // structural zeros of the raw Jacobians are never rewritten
   CK(h->d_prior_A.alloc((size_t)off_pJ));
   CK(h->d_z6.alloc((size_t)off6 * 8)); CK(h->d_tilde6.alloc((size_t)off6 * 6)); CK(h->d_lm_ref.alloc(offlm)); CK(h->d_sb_ref.alloc((size_t)offsb * 9));
@@ -1403,7 +1438,7 @@ int d2ba_finalize(d2ba_handle *h) {
     h->cfg_max_n_smem = h->max_n_smem;
   }
   launch_state_prep(D, h->n6_total, 0, h->stream);
-  launch_imu_prep(D, h->n_imu_total, h->stream);
+  launch_imu_prep(D, h->d_imu_pk.p, h->d_imu_c.p, h->n_imu_total, h->stream);
   if (any_info) {
     if ((rc = up(h, h->d_pr_m, st.pr_m)) || (rc = up(h, h->d_pr_info, st.pr_info)) || (rc = up(h, h->d_pr_oJ, st.pr_offJ)) || (rc = up(h, h->d_pr_ov, st.pr_offv))) return rc;
     launch_prior_from_info(nw, h->max_prior_m, h->d_pr_m.p, h->d_pr_oJ.p, h->d_pr_ov.p, h->d_pr_info.p, h->d_prior_J.p, h->d_prior_A.p, h->d_prior_e0.p, h->stream);
@@ -1682,10 +1717,31 @@ int d2ba_consensus_buffer(d2ba_handle *h, void **dev_ptr, int64_t *n_doubles) {
 }
 
 // ------------------------------------------------------------------------------------------------ debug
+// The debug views report the full per-factor Jacobian, whose td column holds the feature velocities even where the solve
+// never needs them (td constant): fetch the motion halves that d2ba_finalize left on the host and rebuild the tiles.
+static int ensure_motion(d2ba_handle *h) {
+  if (!h->motion_skipped) return 0;
+  std::vector<long long> off(4 * (size_t)h->n_used);
+  CK(cudaMemcpy(off.data(), h->d_raw_off.p, off.size() * 8, cudaMemcpyDeviceToHost));
+  for (int wi = 0; wi < h->n_used; wi++) {
+    HostWin &w = h->win[wi];
+    int rc;
+    if ((rc = push_range(h, w.rawjm, w.d_rawjm, w.pushed_jm)) || (rc = push_range(h, w.anchm, w.d_anchm, w.pushed_am))) return rc;
+    w.pushed_jm = w.rawjm.n; w.pushed_am = w.anchm.n;
+    off[4 * wi + 2] = (long long)(uintptr_t)w.d_rawjm.p; off[4 * wi + 3] = (long long)(uintptr_t)w.d_anchm.p;
+  }
+  CK(cudaStreamSynchronize(h->copy_stream));
+  CK(cudaMemcpy(h->d_raw_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+  launch_build_tiles(h->d_raw_off.p, h->d_tile_src.p, h->d_tile_win.p, h->d_xtd[0].p, h->d_obs.p, h->n_tiles, h->stream);
+  h->motion_skipped = false;
+  return 0;
+}
+
 int d2ba_debug_linearize(d2ba_handle *h) {
   if (!h) return 1;
   cudaSetDevice(h->cfg.device);
   if (!h->finalized) { int rc = d2ba_finalize(h); if (rc) return rc; }
+  { int rc = ensure_motion(h); if (rc) return rc; }
   if (h->state_dirty) { int rc = upload_state(h); if (rc) return rc; }
   h->dev.prm.fixed_mode = 1; h->dev.prm.max_iter = 1;
   launch_tr_reset(h->dev, 1, h->stream);
@@ -1852,9 +1908,9 @@ int d2ba_marginalize(d2ba_handle *h, int32_t window, int32_t n_remove, const int
       p.frame_a = o.fa >= 0 ? w->pose_id[o.fa] : 0; p.frame_b = o.pj >= 0 ? w->pose_id[o.pj] : p.frame_a;
       p.cam_a = o.ea >= 0 ? (int32_t)w->ext_id[o.ea] : 0; p.cam_b = o.eb >= 0 ? (int32_t)w->ext_id[o.eb] : 0;
       if (o.type != D2BA_PROJ_DEPTH_PRIOR) {
-        const ObsAnchor &a = w->anch.p[r.anchor];
-        memcpy(p.pts_i, a.pts_i, 24); memcpy(p.vel_i, a.vel_i, 24); p.td_i = a.td_i;
-        memcpy(p.pts_j, r.pts_j, 24); memcpy(p.vel_j, r.vel_j, 24); p.td_j = r.td_j;
+        const ObsAnchor &a = w->anch.p[r.anchor]; const ObsAnchorM &am = w->anchm.p[r.anchor]; const ObsJm &rm = w->rawjm.p[k];
+        memcpy(p.pts_i, a.pts_i, 24); memcpy(p.vel_i, am.vel_i, 24); p.td_i = am.td_i;
+        memcpy(p.pts_j, r.pts_j, 24); memcpy(p.vel_j, rm.vel_j, 24); p.td_j = rm.td_j;
       }
       p.depth = r.depth;
       robs.push_back(p);

@@ -672,18 +672,17 @@ template __global__ void k_proj_lin<4, 4>(Dev, int, int, int);
 #ifndef D2BA_PP_BLOCKS
 #define D2BA_PP_BLOCKS 4
 #endif
-// The observation constants of a tile ([field][32] doubles, contiguous) are staged by ONE TMA bulk copy per tile into a
-// per-warp buffer (UBLKCP + mbarrier); the copy of tile t+1 is issued as soon as the lanes hold tile t in registers, so it
-// -- and the landmark index / inverse depth of the next tile -- are in flight during the arithmetic and the DMMA pass.
+// The 128-byte landmark records of a tile are staged in shared memory (16-byte units, XOR-swizzled) and written out four
+// whole records per store instruction: a lane storing its own record touched 32 different lines per instruction, eight
+// times per tile -- that, not DRAM, kept L1/TEX at 70 %.  The landmark index / inverse depth of the next tile are
+// fetched during the arithmetic and the DMMA pass of the current one.
 constexpr int kPpRows = 13;                          // staged Jacobian rows: 12 + residual (rows 13..15 of the MMA tile read as zero)
-constexpr int kPpFields = 20;                        // fields 0..19 (inv_depth_j is not used by this path)
-constexpr int kPpWarpDoubles = GC_SIZE + kPpRows * (kTile * 2 + 4) + kPpFields * kTile;
+constexpr int kPpWarpDoubles = GC_SIZE + kPpRows * (kTile * 2 + 4) + kTile * 16;
 static size_t proj_pp_smem() { return (size_t)4 * kPpWarpDoubles * 8; }
 template <bool SHIFT0>
 __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int eval_cur, int job_begin, int job_count) {
   constexpr int LDJ = kTile * 2 + 4, RCOL = 12;
   extern __shared__ __align__(16) double sm[];
-  __shared__ __align__(8) unsigned long long bars[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ji = blockIdx.x * 4 + warp;
   if (ji >= job_count) return;
@@ -695,20 +694,7 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
   const Group &g = d.grp[jb.grp];
   double *gc = sm + warp * kPpWarpDoubles;
   double *Js = gc + GC_SIZE;
-  double *tb = Js + kPpRows * LDJ;                    // [kPpFields][32]
-  unsigned long long *bar = &bars[warp];
-  auto issue = [&](int tile) {                        // lane 0
-    const double *src = d.obs + (size_t)tile * kObsFields * kTile;
-    if (SHIFT0) {                                     // velocities / stamps not needed: fields 0..5 and 14..19
-      mbar_expect_tx(bar, 2 * 6 * kTile * 8);
-      bulk_g2s(tb, src, 6 * kTile * 8, bar);
-      bulk_g2s(tb + 14 * kTile, src + 14 * kTile, 6 * kTile * 8, bar);
-    } else {
-      mbar_expect_tx(bar, kPpFields * kTile * 8);
-      bulk_g2s(tb, src, kPpFields * kTile * 8, bar);
-    }
-  };
-  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); issue(jb.tile_begin); }
+  double2 *stg = reinterpret_cast<double2 *>(Js + kPpRows * LDJ);   // [32 records][8 x 16 B], unit (r, c) at r * 8 + (c ^ (r & 7))
   const double *xlm = d.xlm[buf] + w.offlm;
   int lm = d.obs_lm[(size_t)jb.tile_begin * kTile + lane];
   int rslot = d.obs_slot[(size_t)jb.tile_begin * kTile + lane];   // needed only for the record store
@@ -729,8 +715,7 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
   for (int t = 0; t < jb.ntiles; t++) {
     const int tile = jb.tile_begin + t;
     const bool valid = lm >= 0;
-    mbar_wait(bar, t & 1);
-    const double *ob = tb + lane;
+    const double *ob = d.obs + (size_t)tile * kObsFields * kTile + lane;
     double pi[3] = {ob[0 * kTile], ob[1 * kTile], ob[2 * kTile]};
     double pj[3] = {ob[3 * kTile], ob[4 * kTile], ob[5 * kTile]};
     if (!SHIFT0) {
@@ -741,10 +726,8 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
     double B[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) B[k] = ob[(14 + k) * kTile];
-    __syncwarp();                                     // every lane holds the tile: the buffer is free again
     int lm_n = -1, rslot_n = -1;
     if (t + 1 < jb.ntiles) {
-      if (lane == 0) { fence_proxy_async(); issue(tile + 1); }
       lm_n = d.obs_lm[(size_t)(tile + 1) * kTile + lane];
       rslot_n = d.obs_slot[(size_t)(tile + 1) * kTile + lane];
     }
@@ -799,19 +782,33 @@ __global__ void __launch_bounds__(128, D2BA_PP_BLOCKS) k_proj_lin_pp(Dev d, int 
     Js[RCOL * LDJ + lane] = r0; Js[RCOL * LDJ + kTile + lane] = r1;
     // records are stored landmark-major (obs_slot: tile slot -> position in the landmark's run), so the per-landmark
     // reduction streams them; padding lanes (slot -1) never write
-    double *rec = d.rec[buf] + (size_t)w.off_rec + (size_t)(rslot < 0 ? 0 : rslot) * w.rec_stride;
-    const double wj[6] = {-wi[0], -wi[1], -wi[2], wjr[0], wjr[1], wjr[2]};
-    if (valid) {
-      double2 *r2 = reinterpret_cast<double2 *>(rec);
-      r2[0] = make_double2(jl[0] * jl[0] + jl[1] * jl[1], jl[0] * r0 + jl[1] * r1);
-      r2[1] = make_double2(0.0, __hiloint2double(g.slot_col[0], g.slot_col[1]));
-      r2[2] = make_double2(wi[0], wi[1]); r2[3] = make_double2(wi[2], wi[3]); r2[4] = make_double2(wi[4], wi[5]);
-      r2[5] = make_double2(wj[0], wj[1]); r2[6] = make_double2(wj[2], wj[3]); r2[7] = make_double2(wj[4], wj[5]);
-      if (w.rec_stride == 32) r2[14] = make_double2(__hiloint2double(-1, -1), __hiloint2double(-1, -1));
+    {
+      double2 *sr = stg + lane * 8;
+      const int sw = lane & 7;
+      sr[0 ^ sw] = make_double2(jl[0] * jl[0] + jl[1] * jl[1], jl[0] * r0 + jl[1] * r1);
+      sr[1 ^ sw] = make_double2(0.0, __hiloint2double(g.slot_col[0], g.slot_col[1]));
+      sr[2 ^ sw] = make_double2(wi[0], wi[1]); sr[3 ^ sw] = make_double2(wi[2], wi[3]); sr[4 ^ sw] = make_double2(wi[4], wi[5]);
+      sr[5 ^ sw] = make_double2(-wi[0], -wi[1]); sr[6 ^ sw] = make_double2(-wi[2], wjr[0]); sr[7 ^ sw] = make_double2(wjr[1], wjr[2]);
     }
+    const int my_slot = valid ? rslot : -1;
     lm = lm_n; rslot = rslot_n;
     lam = lm >= 0 ? xlm[lm] : 1.0;                    // next tile's inverse depth: in flight during the MMA pass
     __syncwarp();
+    {
+      // four whole records per store instruction: lanes 8k .. 8k+7 write the 128 contiguous bytes of record 4 j + k
+      double *recs = d.rec[buf] + (size_t)w.off_rec;
+      const int c = lane & 7, stride = w.rec_stride;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int r = 4 * j + (lane >> 3);
+        const int slot = __shfl_sync(0xffffffffu, my_slot, r);
+        if (slot >= 0) {
+          double2 *dst = reinterpret_cast<double2 *>(recs + (size_t)slot * stride);
+          dst[c] = stg[r * 8 + (c ^ (r & 7))];
+          if (stride == 32 && c == 0) dst[14] = make_double2(__hiloint2double(-1, -1), __hiloint2double(-1, -1));
+        }
+      }
+    }
 #pragma unroll 4
     for (int st = 0; st < kTile * 2 / 4; st++) {
       const double v0 = Js[cr * LDJ + st * 4 + kq], v1 = cr < kPpRows - 8 ? Js[(8 + cr) * LDJ + st * 4 + kq] : 0.0;
@@ -2069,7 +2066,10 @@ __global__ void __launch_bounds__(kSbBackThreads) k_sb_back(Dev d) {
 // Y_b^T = [B_b ; g_b^T] L^-T.  The rows Y_b go behind the landmark / speed-bias rows of Wt, so the hub tiles of the Schur
 // kernel (which run next) subtract Y_b^T Y_b together with the landmark terms; k_leaf_back recovers the leaf step from
 // L^T x_b = z_b - Y_b x_hub.  The dense Cholesky shrinks from 6 x (all poses) to the hub (66 columns for an 11-frame window).
-constexpr int kLeafThreads = 256;
+#ifndef D2BA_LEAF_THREADS
+#define D2BA_LEAF_THREADS 256
+#endif
+constexpr int kLeafThreads = D2BA_LEAF_THREADS;
 constexpr int kLeafMaxCols = 96;
 constexpr int kLeafLmChunk = 16;   // landmarks whose coupling rows are staged at a time (a multiple of the MMA k = 4)
 __host__ __device__ inline int leaf_lda(int n) { return n | 1; }   // odd: the one-row-per-thread TRSM walks the rows without bank conflicts (all accesses are scalar)
@@ -2114,7 +2114,11 @@ D2BA_DEV void leaf_rank8(double *A, int ld, const double *W, int ldw, int gi0, i
   }
 }
 
+#if D2BA_LEAF_THREADS > 256
+__global__ void __launch_bounds__(kLeafThreads, 2) k_leaf_elim(Dev d) {
+#else
 __global__ void __launch_bounds__(kLeafThreads) k_leaf_elim(Dev d) {
+#endif
   const Leaf lf = d.leaf[blockIdx.x];
   const WinDesc &w = d.win[lf.win];
   Ctl *ctl = d.ctl + lf.win;
@@ -2642,7 +2646,7 @@ __global__ void k_cons_init(Dev d, int n6_total) {
 // Build the 32-observation AoSoA tiles from the compact upload records (ObsJ + shared ObsAnchor): gathers the
 // record of every tile slot (pair-major order), computes the unit-sphere tangent base of the factor
 // constructor (projectionTwoFrameOneCamFactor.cpp:34-45) and writes [field][lane] planes.
-__global__ void __launch_bounds__(128) k_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles) {
+__global__ void __launch_bounds__(128) k_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, const double *xtd, double *obs, int n_tiles) {
   const int tile = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   const int src = tile_src[(size_t)tile * kTile + lane];
@@ -2651,12 +2655,18 @@ __global__ void __launch_bounds__(128) k_build_tiles(const long long *raw_off, c
   for (int k = 0; k < kObsFields; k++) f[k] = 0.0;
   if (src >= 0) {
     const int wi = tile_win[tile];
-    const ObsJ &p = reinterpret_cast<const ObsJ *>((uintptr_t)raw_off[2 * wi])[src];   // per-window base pointers
+    const ObsJ &p = reinterpret_cast<const ObsJ *>((uintptr_t)raw_off[4 * wi])[src];   // per-window base pointers
     if (p.type != D2BA_PROJ_DEPTH_PRIOR) {
-      const ObsAnchor &a0 = reinterpret_cast<const ObsAnchor *>((uintptr_t)raw_off[2 * wi + 1])[p.anchor];
+      const ObsAnchor &a0 = reinterpret_cast<const ObsAnchor *>((uintptr_t)raw_off[4 * wi + 1])[p.anchor];
+      const ObsJm *pm = reinterpret_cast<const ObsJm *>((uintptr_t)raw_off[4 * wi + 2]);
+      const ObsAnchorM *am = reinterpret_cast<const ObsAnchorM *>((uintptr_t)raw_off[4 * wi + 3]);
 #pragma unroll
-      for (int k = 0; k < 3; k++) { f[k] = a0.pts_i[k]; f[3 + k] = p.pts_j[k]; f[6 + k] = a0.vel_i[k]; f[9 + k] = p.vel_j[k]; }
-      f[12] = a0.td_i; f[13] = p.td_j;
+      for (int k = 0; k < 3; k++) { f[k] = a0.pts_i[k]; f[3 + k] = p.pts_j[k]; }
+      if (pm) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { f[6 + k] = am[p.anchor].vel_i[k]; f[9 + k] = pm[src].vel_j[k]; }
+        f[12] = am[p.anchor].td_i; f[13] = pm[src].td_j;
+      } else { f[12] = xtd[wi]; f[13] = xtd[wi]; }   // motion not uploaded: every stamp equals the constant td (host-checked)
       const double n = sqrt(f[3] * f[3] + f[4] * f[4] + f[5] * f[5]);
       const double a[3] = {f[3] / n, f[4] / n, f[5] / n};
       double t[3] = {0, 0, 1};
@@ -2679,8 +2689,8 @@ __global__ void __launch_bounds__(128) k_build_tiles(const long long *raw_off, c
 #pragma unroll
   for (int k = 0; k < kObsFields; k++) ob[k * kTile + lane] = f[k];
 }
-void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, double *obs, int n_tiles, cudaStream_t s) {
-  if (n_tiles > 0) k_build_tiles<<<(n_tiles + 3) / 4, 128, 0, s>>>(raw_off, tile_src, tile_win, obs, n_tiles);
+void launch_build_tiles(const long long *raw_off, const int *tile_src, const int *tile_win, const double *xtd, double *obs, int n_tiles, cudaStream_t s) {
+  if (n_tiles > 0) k_build_tiles<<<(n_tiles + 3) / 4, 128, 0, s>>>(raw_off, tile_src, tile_win, xtd, obs, n_tiles);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2760,7 +2770,25 @@ int launch_marg_reduce(const double *S, int ld, int n, const int *keep_idx, int 
 void launch_state_prep(const Dev &d, int n6_total, int buf, cudaStream_t s) {
   if (n6_total > 0) k_state_prep<<<(n6_total + 127) / 128, 128, 0, s>>>(d, n6_total, buf);
 }
-void launch_imu_prep(const Dev &d, int n_imu, cudaStream_t s) {
+// packed upload record (kImuPack) -> the full constant record imu_raw / k_imu_prep index (kImuStride); entries the factor
+// never reads stay at the zero of the finalize-time memset
+__global__ void k_imu_unpack(const double *pk, double *full, int n_imu) {
+  const int f = blockIdx.x, t = threadIdx.x;
+  if (f >= n_imu || t >= kImuPack) return;
+  int dst;
+  if (t < 17) dst = t;
+  else if (t < 71) { const int q = t - 17; dst = 17 + (q / 6) * 15 + 9 + q % 6; }
+  else {
+    const int q = t - 71;
+    int i = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= q) i++;
+    while (i * (i + 1) / 2 > q) i--;
+    dst = 17 + 225 + i * 15 + (q - i * (i + 1) / 2);
+  }
+  full[(size_t)f * kImuStride + dst] = pk[(size_t)f * kImuPack + t];
+}
+void launch_imu_prep(const Dev &d, const double *packed, double *full, int n_imu, cudaStream_t s) {
+  if (n_imu > 0) k_imu_unpack<<<n_imu, 192, 0, s>>>(packed, full, n_imu);
   if (n_imu > 0) k_imu_prep<<<(n_imu + 31) / 32, 32, 0, s>>>(d, n_imu);
 }
 void launch_prior_prep(const Dev &d, cudaStream_t s) { k_prior_prep<<<d.n_win, 256, 0, s>>>(d); }

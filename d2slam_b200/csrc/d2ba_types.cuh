@@ -34,16 +34,19 @@ struct Job {       // one warp's work: a run of tiles of one group
   int win, grp, tile_begin, ntiles;
 };
 
-// Compact upload format of the observation constants (built by d2ba_add_proj, consumed by k_build_tiles).
-struct ObsJ {        // per residual block: the observing half of a reprojection record (72 bytes)
-  double pts_j[3], vel_j[3], td_j;
+// Compact upload format of the observation constants (built by d2ba_add_proj, consumed by k_build_tiles).  Geometry and
+// motion (feature velocity, stamp) are separate arrays: with a constant td equal to every stamp of the window -- the
+// reference's default, estimate_td: 0 -- the time shift td - td_i is exactly zero, the velocities multiply zero, and the
+// motion arrays never cross PCIe.
+struct ObsJ {        // per residual block: the observing half of a reprojection record (40 bytes)
+  double pts_j[3];
   double depth;      // measured depth (2F1C_DEPTH, DEPTH_PRIOR), else 0
   int32_t anchor;    // index into the window's ObsAnchor table
   int32_t type;      // d2ba_proj_type
 };
-struct ObsAnchor {   // the anchor half, stored once per run of residual blocks that share it (64 bytes)
-  double pts_i[3], vel_i[3], td_i, pad;
-};
+struct ObsJm { double vel_j[3], td_j; };          // motion half of ObsJ (32 bytes), same index
+struct ObsAnchor { double pts_i[3]; };            // the anchor half, stored once per run of residual blocks that share it (24 bytes)
+struct ObsAnchorM { double vel_i[3], td_i; };     // motion half of ObsAnchor (32 bytes), same index
 
 // One run of a row of Hcc that some factor writes (the per-linearisation zero-fill touches only these; everything else
 // of Hcc stays at the zero of the finalize-time memset).  Hcc is LOWER triangular storage: writers put (max, min).
@@ -206,5 +209,8 @@ struct Dev {
 };
 
 constexpr int kImuStride = 1 + 3 + 4 + 3 + 3 + 3 + 225 + 225;  // sum_dt dp dq dv ba bg jac cov = 467
+// upload format of the same constants: the 17 scalars, rows 0..8 x columns 9..14 of the pre-integration Jacobian (the only
+// bias blocks IMUFactor reads) and the lower triangle of the covariance (the only half its Cholesky reads) -- 191 doubles
+constexpr int kImuPack = 17 + 54 + 120;
 
 }  // namespace d2ba

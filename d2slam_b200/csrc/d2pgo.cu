@@ -44,7 +44,7 @@ struct PgoDev {
   double *Minv;           // [N][36]
   double *dx, *r, *z, *p, *Ap;   // [6N]
   double *damp;           // [6N] lambda diag(D) + 1e-12
-  double *t;              // [6][E] J p per edge
+  double *t;              // [12][E] per edge: J0^T (J p) (6), J1^T (J p) (6)
   const int *inc_ptr, *inc;   // incidence lists: pose i -> (edge << 1 | side) of this rank's edges, ascending
   double *rz_part, *rr_part;  // [2][nbp] per-block partials, ping-pong on the iteration parity
   double *pAp_part;           // [nbp]
@@ -181,8 +181,8 @@ __global__ void k_pgo_precond(PgoDev d, const double *D, double lambda) {
 }
 
 // ---- conjugate gradients.  One iteration = three kernels (the three grid-wide dependencies of CG):
-//   k_pgo_cg_edge : t_e = J0 p_a + J1 p_b with p = z + beta p_old formed on the fly            (needs rz of the last update)
-//   k_pgo_cg_pose : stores p, Ap_i = sum_inc J^T t (+ damping), partials of p.Ap               (needs every t)
+//   k_pgo_cg_edge : per edge J0^T t, J1^T t with t = J0 p_a + J1 p_b, p = z + beta p_old formed on the fly   (needs rz of the last update)
+//   k_pgo_cg_pose : stores p, Ap_i = sum over incident edges (+ damping), partials of p.Ap               (needs every edge)
 //   k_pgo_cg_step : alpha = rz / pAp; dx += alpha p; r -= alpha Ap; z = Minv r; partials of r.z, r.r   (needs p.Ap)
 // Scalars live as per-block partials summed in fixed order by every block (total_of); rz / rr ping-pong on the iteration
 // parity `par`.  Once converged the sticky flag s->done turns the remaining launches of a graph into no-ops.
@@ -211,13 +211,16 @@ __global__ void __launch_bounds__(128) k_pgo_cg_edge(PgoDev d, int par, double t
   const int a = d.ea[e], b = d.eb[e];
   const size_t E = (size_t)d.n_edge;
   const double *J0 = d.lin + 6 * E + e, *J1 = J0 + 36 * E;
-  double pa[6], pb[6];
+  double pa[6], pb[6], ya[6] = {0, 0, 0, 0, 0, 0}, yb[6] = {0, 0, 0, 0, 0, 0};
   cg_p_new(d, a, beta, pa); cg_p_new(d, b, beta, pb);
+  // t = J0 pa + J1 pb, then this edge's two contributions J0^T t, J1^T t (the Jacobians are read once, coalesced; the
+  // per-pose kernel only sums six numbers per incident edge)
   for (int k = 0; k < 6; k++) {
-    double s = 0;
-    for (int q = 0; q < 6; q++) s += J0[(size_t)(k * 6 + q) * E] * pa[q] + J1[(size_t)(k * 6 + q) * E] * pb[q];
-    d.t[(size_t)k * E + e] = s;
+    double j0[6], j1[6], tk = 0;
+    for (int q = 0; q < 6; q++) { j0[q] = J0[(size_t)(k * 6 + q) * E]; j1[q] = J1[(size_t)(k * 6 + q) * E]; tk += j0[q] * pa[q] + j1[q] * pb[q]; }
+    for (int q = 0; q < 6; q++) { ya[q] += j0[q] * tk; yb[q] += j1[q] * tk; }
   }
+  for (int q = 0; q < 6; q++) { d.t[(size_t)q * E + e] = ya[q]; d.t[(size_t)(6 + q) * E + e] = yb[q]; }
 }
 
 // LOCAL: this rank's edges only, no damping / p.Ap yet (the all-reduce of Ap comes first; k_pgo_cg_pAp follows)
@@ -236,8 +239,8 @@ __global__ void __launch_bounds__(128) k_pgo_cg_pose(PgoDev d, int par, double t
       for (int q = d.inc_ptr[i]; q < d.inc_ptr[i + 1]; q++) {
         const int c = d.inc[q];
         const size_t E = (size_t)d.n_edge;
-        const double *J = d.lin + (size_t)(6 + 36 * (c & 1)) * E + (c >> 1), *t = d.t + (c >> 1);
-        for (int k = 0; k < 6; k++) { const double tk = t[k * E]; for (int a = 0; a < 6; a++) y[a] += J[(size_t)(k * 6 + a) * E] * tk; }
+        const double *t = d.t + (size_t)(6 * (c & 1)) * E + (c >> 1);
+        for (int a = 0; a < 6; a++) y[a] += t[a * E];
       }
     for (int k = 0; k < 6; k++) {
       d.p[(size_t)i * 6 + k] = p[k];
@@ -433,7 +436,7 @@ static int pgo_upload(d2pgo_handle *h) {
   for (int b = 0; b < 2; b++) { PCK(h->d_x[b].alloc(N * 8)); PCK(h->d_g[b].alloc(N * 6)); PCK(h->d_D[b].alloc(N * 36)); PCK(h->d_lin[b].alloc(E * 78)); }
   PCK(h->d_rel.alloc(E * 8)); PCK(h->d_sinfo.alloc(E * 36)); PCK(h->d_Minv.alloc(N * 36));
   PCK(h->d_dx.alloc(N * 6)); PCK(h->d_r.alloc(N * 6)); PCK(h->d_z.alloc(N * 6)); PCK(h->d_p.alloc(N * 6)); PCK(h->d_Ap.alloc(N * 6)); PCK(h->d_cost.alloc(2));
-  PCK(h->d_damp.alloc(N * 6)); PCK(h->d_t.alloc(E * 6)); PCK(h->d_part.alloc(5 * nbp)); PCK(h->d_cost_part.alloc(nbe + 1));
+  PCK(h->d_damp.alloc(N * 6)); PCK(h->d_t.alloc(E * 12)); PCK(h->d_part.alloc(5 * nbp)); PCK(h->d_cost_part.alloc(nbe + 1));
   PCK(h->d_fixed.alloc(N)); PCK(h->d_ea.alloc(E)); PCK(h->d_eb.alloc(E)); PCK(h->d_s.alloc(1)); PCK(h->d_inc_ptr.alloc(N + 1)); PCK(h->d_inc.alloc(2 * E));
   // incidence lists (pose -> its edges, ascending edge order): the fixed summation order of every product
   std::vector<int> ptr(N + 1, 0), inc(2 * E);

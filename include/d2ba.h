@@ -54,8 +54,11 @@
  *   - Every function returns 0 on success, non-zero on error (d2ba_last_error gives text).
  *     No exceptions cross this boundary.  There is no CPU fallback: without a CUDA device
  *     d2ba_create fails.
- *   - A handle is not thread-safe (the reference calls solve() under frame_mutex from one
- *     thread, d2estimator.cpp:324,529).
+ *   - Threads: d2ba_set_blocks / d2ba_add_proj / d2ba_add_landmark_tracks / d2ba_add_imu / d2ba_set_prior* /
+ *     d2ba_set_consensus may be called concurrently for DIFFERENT windows of one handle (one feeding thread per
+ *     window at a time); everything else -- create, reset, finalize, solve*, get_blocks, marginalize, comm_*,
+ *     debug_* -- must be called from one thread at a time with no feeding call in flight (the reference calls
+ *     solve() under frame_mutex from one thread, d2estimator.cpp:324,529).  Different handles are independent.
  */
 #ifndef D2BA_H_
 #define D2BA_H_
@@ -234,10 +237,11 @@ int d2ba_set_consensus(d2ba_handle *h, int32_t window, int32_t n, const d2ba_blo
 /* 128-byte NCCL unique id made on rank 0 and distributed by the caller. */
 int d2ba_comm_unique_id(uint8_t out[128]);
 int d2ba_comm_init(d2ba_handle *h, const uint8_t unique_id[128], int32_t rank, int32_t nranks);
-/* Pointer + element count of the device consensus buffer (f64), for callers that prefer to
- * run the all-reduce themselves (torch.distributed): call d2ba_consensus_pack, all-reduce
- * the buffer in place, then d2ba_consensus_apply. d2ba_solve does all three itself when a
- * communicator is attached or the handle is single-rank. */
+/* Pointer + element count of the device consensus buffer (f64, [n_slots][14] = sum p (3), sum vech(q q^T) (10), count):
+ * a read-only view of what the last ADMM sub-step exchanged (tests, tracing).  The exchange itself always runs inside
+ * d2ba_solve -- pack -> ncclAllReduce when a communicator is attached (d2ba_comm_init), local sum otherwise -> apply;
+ * there is no step-wise entry point for an external transport.  A multi-process swarm WITHOUT d2ba_comm_init therefore
+ * averages only the agents held by this handle. */
 int d2ba_consensus_buffer(d2ba_handle *h, void **dev_ptr, int64_t *n_doubles);
 
 /* ---------------------------------------------------------------- solve + output */

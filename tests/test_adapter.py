@@ -144,7 +144,7 @@ def test_adapter_solve_equals_direct_c_abi_solve(name, tmp_path):
     assert rep.total_iterations == n_it
     assert abs(rep.final_cost - c1) <= 1e-9 * max(1.0, abs(c1)) and abs(rep.initial_cost - c0) <= 1e-9 * max(1.0, abs(c0))
     dp, dr = synth.pose_errors(poses, s.get_blocks(0, abi.POSE, pr["frame_ids"]))
-    assert dp <= 1e-9 and dr <= 1e-8
+    assert dp <= 1e-9 and dr <= 1e-7   # the angle metric's own floor is sqrt(eps) ~ 3e-8 for quaternions one ulp apart
     assert np.abs(sb - s.get_blocks(0, abi.SPEED_BIAS, pr["sb_ids"])).max() <= 1e-8
     assert np.abs(lm / s.get_blocks(0, abi.LANDMARK, pr["lm_ids"])[:, 0] - 1).max() <= 1e-8
     assert chg > 0 and abs(chg - rep.state_changes) <= 1e-9
