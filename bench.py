@@ -409,7 +409,7 @@ def pgo_leg(rank, world, local_rank, dist, cpu=True):
     from d2slam_b200 import pgo, synth
     g = pgo.make_pose_graph(seed=7, n_agents=8, poses_per_agent=1250, loops=30001)   # + 7 connecting closures = 40 000 edges
     sel = np.arange(rank, len(g["id_a"]), world)
-    s = pgo.PgoSolver(device=local_rank, max_iterations=30, pcg_max_iterations=2000, pcg_tolerance=1e-3, lambda0=1e-4, function_tolerance=1e-6)
+    s = pgo.PgoSolver(device=local_rank, max_iterations=60, pcg_max_iterations=200, pcg_tolerance=1e-1, lambda0=1e-4, function_tolerance=1e-5)   # inexact LM: tools/pgo_sweep.py
 
     def load():
         s.set_poses(g["ids"], g["init"], g["fixed"]); s.add_edges(g["id_a"][sel], g["id_b"][sel], g["rel"][sel], g["sqrt_info"][sel])
@@ -532,14 +532,15 @@ def run_ours(args, rank, world, local_rank):
     rp = Replay(probs)
     ncpu = host_threads_available()
     # per pipeline stage: the feed and finalize stages of different handles run at the same time, so each gets a share of the cores
-    host_threads = max(1, min(ncpu // max(1, min(world, 8)), 32 if args.handles <= 2 else 12))
+    seq_threads = max(1, min(ncpu // max(1, min(world, 8)), 32))           # one handle at a time: all the threads for its stage
+    host_threads = seq_threads if (swarm or args.handles <= 2) else max(1, min(seq_threads, 12))
     if args.host_threads > 0:
         host_threads = args.host_threads
     e2e_steps = max(1, min(args.steps, 40))
     n_seq = min(e2e_steps, 10)
-    rp.run(solver, 2, iters, host_threads)
+    rp.run(solver, 2, iters, seq_threads)
     barrier()
-    seq_wall, _ = rp.run(solver, n_seq, iters, host_threads)
+    seq_wall, _ = rp.run(solver, n_seq, iters, seq_threads)
     e2e_seq = {k: round(v / n_seq * 1e3, 3) for k, v in rp.breakdown.items()}
     e2e_seq["total_ms"] = round(seq_wall / n_seq * 1e3, 3)
     e2e_seq["iter_per_s"] = B * iters * n_seq / seq_wall
@@ -664,7 +665,7 @@ def run_ours(args, rank, world, local_rank):
                                          "value(N) / (N value(1)) mixes hardware scaling with a larger problem per GPU") if swarm else None},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "iter/s", "h2d_bytes_per_step": int(h2d_step), "host_input_bytes_per_step": h2d_bytes(probs), "d2h_bytes_per_step": d2h_bytes(probs),
-                "steps": e2e_steps, "host_threads": host_threads, "handles_in_flight": n_handles, "numa_bound_cpus": bound_cpus,
+                "steps": e2e_steps, "host_threads": host_threads, "host_threads_sequential_leg": seq_threads, "handles_in_flight": n_handles, "numa_bound_cpus": bound_cpus,
                 "ms_per_step_breakdown": e2e_breakdown,
                 "note": "every step runs the full C-ABI sequence from HOST buffers: d2ba_reset + set_blocks/add_proj/add_imu/set_prior_info + d2ba_finalize (order, tile plan, pinned H2D) + d2ba_solve_fixed + d2ba_get_blocks (D2H), driven by the C++ harness; with handles_in_flight > 1 consecutive steps overlap on independent handles"},
         "roofline": {"bound": "hbm", "kernel": "k_proj_lin_pp (reprojection linearisation + group J^T J)", "achieved": proj_gbs, "peak": peak, "unit": "GB/s", "frac": proj_gbs / peak,
@@ -703,6 +704,12 @@ def main():
     ap.add_argument("--impl", default="ours")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # watchdog: a rank stuck in a collective must not hang the launcher -- dump every thread's Python stack and exit
+    import faulthandler
+    faulthandler.enable()
+    wd = int(os.environ.get("D2BA_BENCH_WATCHDOG", "0")) or (1500 if world > 1 else 0)
+    if wd > 0:
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

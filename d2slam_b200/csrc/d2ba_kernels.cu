@@ -215,7 +215,7 @@ D2BA_DEV void cons_eval(const double *x, const double *z, const double *tl, doub
 // Runs before k_proj_lin (which adds the reprojection blocks with atomics).
 constexpr int kMiscThreads = 256;
 constexpr int kMiscImuChunk = 12;
-__global__ void __launch_bounds__(kMiscThreads, 2) k_misc_lin(Dev d, int eval_cur) {
+__global__ void __launch_bounds__(kMiscThreads, 4) k_misc_lin(Dev d, int eval_cur) {
   const int wi = blockIdx.x;
   const WinDesc &w = d.win[wi];
   Ctl *ctl = d.ctl + wi;

@@ -37,16 +37,17 @@ if os.path.exists(launch):
     import shutil; shutil.copy(launch, os.path.join(P, f"{tag}_launches_B{B}.csv"))
 traffic = {}
 for f in sorted(os.listdir(G)):
-    m = re.match(rf"prof_(\w+)_B{B}\.ncu-rep", f)
+    m = re.match(rf"prof_(\w+)_(B{B}|A8)\.ncu-rep", f)
     if not m or m.group(1) in ("multi", "chol2"):
         continue
-    kn = m.group(1)
+    kn = m.group(1); sfx = m.group(2)
     raw = subprocess.run(["ncu", "-i", os.path.join(G, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     if len(r) < 3:
         continue
     h, u, v = r[0], r[1], r[-1]
-    lines = [f"# ncu --set full --clock-control none --import-source on, kernel k_{kn}, batch {B} W1 windows ({f})\n"]
+    what = f"batch {B} W1 windows" if sfx.startswith("B") else "74 eight-agent swarms (592 windows) on one GPU"
+    lines = [f"# ncu --set full --clock-control none --import-source on, kernel k_{kn}, {what} ({f})\n"]
     vals = {}
     for i, n in enumerate(h):
         if n in KEYS:
@@ -57,11 +58,12 @@ for f in sorted(os.listdir(G)):
         return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
     rd, wr = tobytes("dram__bytes_read.sum"), tobytes("dram__bytes_write.sum")
     if rd is not None and wr is not None:
-        traffic[kn] = rd + wr
+        if sfx.startswith("B"):
+            traffic[kn] = rd + wr
         lines.append(f"dram traffic per launch (read+write): {(rd+wr)/1e6:.1f} MB\n")
     src = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), os.path.join(G, f), f"k_{kn}", "16"], capture_output=True, text=True).stdout
     lines.append("\n# warp-stall samples by CUDA source line (top 16)\n" + src)
-    open(os.path.join(P, f"{tag}_ncu_{kn}_B{B}.txt"), "w").writelines(lines)
+    open(os.path.join(P, f"{tag}_ncu_{kn}_{sfx}.txt"), "w").writelines(lines)
 if traffic:
     json.dump({f"{k}_bytes_per_launch": v for k, v in traffic.items()} | {"batch": int(B), "tag": tag}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print("wrote", sorted(os.listdir(P)))
