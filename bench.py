@@ -604,6 +604,8 @@ def run_ours(args, rank, world, local_rank):
                                   "consensus_gap_m": consensus_gap([p.cpu().numpy() for p in allp], [f.cpu().numpy() for f in allf]),
                                   "final_cost_mean": cost.item() / world})
             sx.close()
+    # pose-graph leg: collective (every rank holds a shard of the edges), so it runs before the non-zero ranks leave
+    pg = pgo_leg(rank, world, local_rank, dist, cpu=False) if (world > 1 and not args.no_extras) else None
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -642,9 +644,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         cpu_baseline = {"value": None, "unit": "iter/s", "cores": 0, "kind": "port", "sample": "timed at N=1 only (bench contract)"}
     if not args.no_extras:
-        pg = pgo_leg(rank, world, local_rank, dist, cpu=(world == 1))
-        if rank == 0:
-            extra["pgo"] = pg
+        extra["pgo"] = pg if world > 1 else pgo_leg(rank, world, local_rank, dist, cpu=True)
     n_variants = len(set(int(t) for t in np.unique(probs[0]["obs"]["type"]))) if args.cams != "mono" else 1
     # per solve: tr_reset, misc_lin, proj_lin, control (+ per ADMM sub-step: memset, cons_pack, cons_apply, cons_refs, tr_reset);
     # per iteration: lm_gather, sb_elim, schur (1-2 launches), leaf_elim, chol, sb_back, leaf_back, step, misc_lin, proj_lin (n_variants), control
@@ -707,7 +707,7 @@ def main():
     # watchdog: a rank stuck in a collective must not hang the launcher -- dump every thread's Python stack and exit
     import faulthandler
     faulthandler.enable()
-    wd = int(os.environ.get("D2BA_BENCH_WATCHDOG", "0")) or (1500 if world > 1 else 0)
+    wd = int(os.environ.get("D2BA_BENCH_WATCHDOG", "0")) or (600 if world > 1 else 0)
     if wd > 0:
         faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":

@@ -29,3 +29,16 @@ def test_reference_arm_other_ranks_exit_silently():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_collective_legs_run_before_the_non_zero_ranks_leave():
+    """The pose-graph leg all-reduces across every rank: it must sit before the early return of rank != 0 in run_ours
+    (a rank-0-only call hangs the launcher -- found the hard way at N = 2)."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    body = src[src.index("def run_ours("):src.index("def main(")]
+    leave = body.index("if rank != 0:")
+    multi = body.index("pgo_leg(rank, world, local_rank, dist, cpu=False)")
+    assert multi < leave
+    # after the return only rank 0 is left: nothing collective may follow for world > 1
+    tail = body[leave:]
+    assert "pg if world > 1 else pgo_leg" in tail and "dist.all_reduce" not in tail and "dist.barrier" not in tail and "dist.broadcast" not in tail
