@@ -89,6 +89,11 @@ class MatrixBase {
   Scalar &w() { return vref(3); }
 
   PlainObject eval() const { return PlainObject(*this); }
+  template <class T> Matrix<T, RowsAtCompileTime, ColsAtCompileTime> cast() const {
+    Matrix<T, RowsAtCompileTime, ColsAtCompileTime> r(rows(), cols());
+    for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) r.ref(i, j) = T(coeff(i, j));
+    return r;
+  }
   TransposeReturn transpose() const {
     TransposeReturn t(cols(), rows());
     for (int i = 0; i < rows(); i++) for (int j = 0; j < cols(); j++) t.ref(j, i) = coeff(i, j);
@@ -508,6 +513,7 @@ class QuaternionBase {
   Scalar &z() { return c()[2]; }
   Scalar &w() { return c()[3]; }
   Vector3 vec() const { return Vector3(x(), y(), z()); }
+  template <class T> Quaternion<T> cast() const { return Quaternion<T>(T(w()), T(x()), T(y()), T(z())); }
   Matrix<Scalar, 4, 1> coeffs() const { return Matrix<Scalar, 4, 1>(x(), y(), z(), w()); }
   Scalar squaredNorm() const { return x() * x() + y() * y() + z() * z() + w() * w(); }
   Scalar norm() const { using std::sqrt; return sqrt(squaredNorm()); }

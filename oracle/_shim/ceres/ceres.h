@@ -32,6 +32,83 @@ class SizedCostFunction : public CostFunction {
   SizedCostFunction() { set_num_residuals(kNumResiduals); *mutable_parameter_block_sizes() = std::vector<int32>{Ns...}; }
   virtual ~SizedCostFunction() {}
 };
+
+// ---- forward-mode dual numbers + AutoDiffCostFunction (interface of ceres/jet.h, ceres/autodiff_cost_function.h): lets the
+//      reference's templated functors (RelPoseFactorAD ...) run with T = Jet, i.e. their Jacobians are the exact derivatives
+//      of the reference's own residual code.  Written here; not ceres code.
+template <typename T, int N>
+struct Jet {
+  T a; T v[N];
+  Jet() : a(T(0)) { for (int i = 0; i < N; i++) v[i] = T(0); }
+  Jet(const T &x) : a(x) { for (int i = 0; i < N; i++) v[i] = T(0); }
+  Jet(int x) : a(T(x)) { for (int i = 0; i < N; i++) v[i] = T(0); }
+  Jet(const T &x, int k) : a(x) { for (int i = 0; i < N; i++) v[i] = T(i == k ? 1 : 0); }
+  Jet &operator+=(const Jet &o) { a += o.a; for (int i = 0; i < N; i++) v[i] += o.v[i]; return *this; }
+  Jet &operator-=(const Jet &o) { a -= o.a; for (int i = 0; i < N; i++) v[i] -= o.v[i]; return *this; }
+  Jet &operator*=(const Jet &o) { *this = *this * o; return *this; }
+  Jet &operator/=(const Jet &o) { *this = *this / o; return *this; }
+};
+template <typename T, int N> Jet<T, N> operator+(const Jet<T, N> &x) { return x; }
+template <typename T, int N> Jet<T, N> operator-(const Jet<T, N> &x) { Jet<T, N> r; r.a = -x.a; for (int i = 0; i < N; i++) r.v[i] = -x.v[i]; return r; }
+template <typename T, int N> Jet<T, N> operator+(const Jet<T, N> &x, const Jet<T, N> &y) { Jet<T, N> r; r.a = x.a + y.a; for (int i = 0; i < N; i++) r.v[i] = x.v[i] + y.v[i]; return r; }
+template <typename T, int N> Jet<T, N> operator-(const Jet<T, N> &x, const Jet<T, N> &y) { Jet<T, N> r; r.a = x.a - y.a; for (int i = 0; i < N; i++) r.v[i] = x.v[i] - y.v[i]; return r; }
+template <typename T, int N> Jet<T, N> operator*(const Jet<T, N> &x, const Jet<T, N> &y) { Jet<T, N> r; r.a = x.a * y.a; for (int i = 0; i < N; i++) r.v[i] = x.a * y.v[i] + x.v[i] * y.a; return r; }
+template <typename T, int N> Jet<T, N> operator/(const Jet<T, N> &x, const Jet<T, N> &y) { Jet<T, N> r; const T inv = T(1) / y.a; r.a = x.a * inv; for (int i = 0; i < N; i++) r.v[i] = (x.v[i] - r.a * y.v[i]) * inv; return r; }
+#define D2_JET_SCALAR_OPS(op) \
+  template <typename T, int N> Jet<T, N> operator op(const Jet<T, N> &x, const T &s) { return x op Jet<T, N>(s); } \
+  template <typename T, int N> Jet<T, N> operator op(const T &s, const Jet<T, N> &x) { return Jet<T, N>(s) op x; }
+D2_JET_SCALAR_OPS(+) D2_JET_SCALAR_OPS(-) D2_JET_SCALAR_OPS(*) D2_JET_SCALAR_OPS(/)
+#undef D2_JET_SCALAR_OPS
+#define D2_JET_CMP(op) \
+  template <typename T, int N> bool operator op(const Jet<T, N> &x, const Jet<T, N> &y) { return x.a op y.a; } \
+  template <typename T, int N> bool operator op(const Jet<T, N> &x, const T &y) { return x.a op y; } \
+  template <typename T, int N> bool operator op(const T &x, const Jet<T, N> &y) { return x op y.a; }
+D2_JET_CMP(<) D2_JET_CMP(<=) D2_JET_CMP(>) D2_JET_CMP(>=) D2_JET_CMP(==) D2_JET_CMP(!=)
+#undef D2_JET_CMP
+template <typename T, int N> Jet<T, N> jet_chain(const Jet<T, N> &x, T f, T df) { Jet<T, N> r; r.a = f; for (int i = 0; i < N; i++) r.v[i] = df * x.v[i]; return r; }
+template <typename T, int N> Jet<T, N> sqrt(const Jet<T, N> &x) { const T s = std::sqrt(x.a); return jet_chain(x, s, T(0.5) / s); }
+template <typename T, int N> Jet<T, N> sin(const Jet<T, N> &x) { return jet_chain(x, std::sin(x.a), std::cos(x.a)); }
+template <typename T, int N> Jet<T, N> cos(const Jet<T, N> &x) { return jet_chain(x, std::cos(x.a), -std::sin(x.a)); }
+template <typename T, int N> Jet<T, N> atan2(const Jet<T, N> &y, const Jet<T, N> &x) {
+  const T d = x.a * x.a + y.a * y.a; Jet<T, N> r; r.a = std::atan2(y.a, x.a);
+  for (int i = 0; i < N; i++) r.v[i] = (x.a * y.v[i] - y.a * x.v[i]) / d;
+  return r;
+}
+template <typename T, int N> Jet<T, N> asin(const Jet<T, N> &x) { return jet_chain(x, std::asin(x.a), T(1) / std::sqrt(T(1) - x.a * x.a)); }
+template <typename T, int N> Jet<T, N> acos(const Jet<T, N> &x) { return jet_chain(x, std::acos(x.a), -T(1) / std::sqrt(T(1) - x.a * x.a)); }
+template <typename T, int N> Jet<T, N> abs(const Jet<T, N> &x) { return x.a < T(0) ? -x : x; }
+template <typename T, int N> Jet<T, N> fabs(const Jet<T, N> &x) { return x.a < T(0) ? -x : x; }
+template <typename T, int N> bool isfinite(const Jet<T, N> &x) { return std::isfinite(x.a); }
+
+// Exact derivatives of a templated functor by dual numbers.  A free function on purpose: the class below does NOT
+// instantiate the functor (RelPoseFactor.hpp's Create() helpers name AutoDiffCostFunction for factors -- 4-DoF, perturbation,
+// 9-D rotation -- whose bodies need more of Eigen than oracle/_shim/Eigen provides); oracle/ref_driver.cpp calls this for the
+// factor it pins.
+template <int kNumResiduals, int... Ns, typename Functor>
+bool AutoDiffEvaluate(const Functor &f, double const *const *parameters, double *residuals, double **jacobians) {
+  constexpr int kBlocks = sizeof...(Ns);
+  constexpr int kTotal = (Ns + ...);
+  static_assert(kBlocks == 2, "stand-in: two parameter blocks");
+  if (!jacobians) return f(parameters[0], parameters[1], residuals);
+  typedef Jet<double, kTotal> J;
+  const int sizes[kBlocks] = {Ns...};
+  std::vector<J> x(kTotal); const J *ptr[kBlocks];
+  for (int b = 0, o = 0; b < kBlocks; o += sizes[b], b++) { ptr[b] = x.data() + o; for (int k = 0; k < sizes[b]; k++) x[o + k] = J(parameters[b][k], o + k); }
+  J r[kNumResiduals];
+  if (!f(ptr[0], ptr[1], r)) return false;
+  for (int i = 0; i < kNumResiduals; i++) residuals[i] = r[i].a;
+  for (int b = 0, o = 0; b < kBlocks; o += sizes[b], b++)
+    if (jacobians[b]) for (int i = 0; i < kNumResiduals; i++) for (int k = 0; k < sizes[b]; k++) jacobians[b][i * sizes[b] + k] = r[i].v[o + k];
+  return true;
+}
+template <typename Functor, int kNumResiduals, int... Ns>
+class AutoDiffCostFunction : public SizedCostFunction<kNumResiduals, Ns...> {   // interface only (see AutoDiffEvaluate)
+  std::unique_ptr<Functor> f_;
+ public:
+  explicit AutoDiffCostFunction(Functor *f) : f_(f) {}
+  const Functor &functor() const { return *f_; }
+  bool Evaluate(double const *const *, double *, double **) const override { return false; }
+};
 class LocalParameterization {
  public:
   virtual ~LocalParameterization() {}

@@ -4,6 +4,8 @@
 #pragma once
 #include <Eigen/Dense>
 #include <cmath>
+#include <memory>
+#include <cstdint>
 #include <vector>
 using namespace Eigen;
 inline Eigen::Vector3d quat2eulers(const Eigen::Quaterniond &q) {
@@ -27,10 +29,19 @@ class Pose {
   const Eigen::Vector3d &pos() const { return position; }
   const Eigen::Quaterniond &att() const { return attitude; }
   Eigen::Matrix3d R() const { return attitude.toRotationMatrix(); }
+  double yaw() const { return quat2eulers(attitude).z(); }
+  void to_vector(std::shared_ptr<double> v) const { to_vector(v.get()); }
   void to_vector(double *v) const { v[0] = position.x(); v[1] = position.y(); v[2] = position.z(); v[3] = attitude.x(); v[4] = attitude.y(); v[5] = attitude.z(); v[6] = attitude.w(); }
   Pose inverse() const { Eigen::Quaterniond qi = attitude.inverse(); return Pose(-(qi * position), qi); }
   Pose operator*(const Pose &b) const { return Pose(attitude * b.position + position, attitude * b.attitude); }
   Eigen::Vector3d operator*(const Eigen::Vector3d &p) const { return attitude * p + position; }
   static Pose DeltaPose(const Pose &a, const Pose &b, bool use_yaw_only = false) { (void)use_yaw_only; return a.inverse() * b; }
+};
+// Stand-in for Swarm::LoopEdge (swarm_msgs, un-vendored): the members RelPoseFactor.hpp's Create() helpers touch.  ASSUMED.
+struct LoopEdge {
+  int64_t keyframe_id_a = -1, keyframe_id_b = -1; int id_a = -1, id_b = -1;
+  Pose relative_pose; Eigen::Matrix<double, 6, 6> sqrt_info;
+  Eigen::Matrix<double, 6, 6> getSqrtInfoMat() const { return sqrt_info; }
+  Eigen::Matrix<double, 4, 4> getSqrtInfoMat4D() const { Eigen::Matrix<double, 4, 4> m; m.setZero(); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = sqrt_info(i, j); m(3, 3) = sqrt_info(5, 5); return m; }
 };
 }  // namespace Swarm

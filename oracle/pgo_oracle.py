@@ -2,9 +2,10 @@
 
 numpy restatement of D2Common::RelPoseFactorAD (d2common/include/d2common/solver/RelPoseFactor.hpp:68-135) and a
 Gauss-Newton / LM solve of the same least-squares problem with scipy's sparse direct solver (the reference hands the
-per-agent problems to ceres SPARSE_NORMAL_CHOLESKY + LM, d2pgo/test/d2pgo_test.cpp:95-99).  PARITY UNPINNED for this
-row: the factor header pulls ceres autodiff + the estimator's header tree and cannot be compiled against oracle/_shim;
-the restatement is checked against finite differences (tests/test_pgo.py)."""
+per-agent problems to ceres SPARSE_NORMAL_CHOLESKY + LM, d2pgo/test/d2pgo_test.cpp:95-99).  Factor level PINNED: edge_eval
+is compared with the reference's own RelPoseFactorAD functor compiled into oracle/_ref/libd2ref.so (doubles for the
+residual, dual numbers for its exact Jacobians; tests/test_ref_pin.py, tests/golden/ref_factors.npz); the minimiser is a
+restatement (same optimum, not ceres' iterates)."""
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla

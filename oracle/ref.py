@@ -104,6 +104,24 @@ def consensus_eval(t_ref, q_ref, t_tilde, theta_tilde, rho_T, rho_theta, pose):
     return r, J
 
 
+def relpose_ad_eval(pose_a, pose_b, rel7, sqrt_info):
+    """RelPoseFactorAD (RelPoseFactor.hpp:68-135): residual (6) and the ambient Jacobians (6 x 7 each) by dual numbers."""
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pose_a, pose_b, rel7, np.asarray(sqrt_info).reshape(36))]
+    r = np.zeros(6); Ja = np.zeros((6, 7)); Jb = np.zeros((6, 7))
+    n = lib().ref_relpose_ad_eval(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(r), _p(Ja), _p(Jb))
+    assert n == 6, n
+    return r, Ja, Jb
+
+
+def loss_correct(r, J, huber_a):
+    """ResidualInfo::Evaluate's loss section (BaseParamResInfo.cpp:71-92) on a given residual / Jacobian."""
+    r = np.ascontiguousarray(r, dtype=np.float64); J = np.ascontiguousarray(J, dtype=np.float64)
+    ro = np.zeros_like(r); Jo = np.zeros_like(J)
+    n = lib().ref_loss_correct(C.c_int(J.shape[0]), C.c_int(J.shape[1]), _p(r), _p(J), C.c_double(huber_a), _p(ro), _p(Jo))
+    assert n == len(r), n
+    return ro, Jo
+
+
 def pose_plus(x, delta):
     x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
     lib().ref_pose_plus(_p(x), _p(d), _p(o))

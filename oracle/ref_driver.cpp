@@ -14,6 +14,8 @@
 #include <d2common/integration_base.h>
 #include <d2common/solver/consenus_factor.h>
 #include <d2common/solver/pose_local_parameterization.h>
+#include <d2common/solver/RelPoseFactor.hpp>
+#include <d2common/solver/BaseParamResInfo.hpp>
 #include <d2common/utils.hpp>
 
 #include "d2vins_params.hpp"
@@ -118,6 +120,51 @@ int ref_consensus_eval(const double *t_ref, const double *q_ref_xyzw, const doub
   const double *params[1] = {pose};
   double *jac[1] = {J6x7};
   return f.Evaluate(params, r6, J6x7 ? jac : nullptr) ? 6 : -2;
+}
+
+// RelPoseFactorAD (d2common/include/d2common/solver/RelPoseFactor.hpp:68-135), the pose-graph factor of d2pgo: the
+// reference's own templated functor, evaluated with T = double (residual) and with T = Jet (oracle/_shim/ceres: dual
+// numbers) -- i.e. the Jacobians are the exact derivatives of the reference's residual code w.r.t. the 7 ambient pose
+// parameters [p, q(xyzw)], what ceres autodiff hands to the manifold.  J: 6 x 7 row-major per pose.
+int ref_relpose_ad_eval(const double *pose_a, const double *pose_b, const double *rel7, const double *sqrt_info36, double *r6, double *Ja6x7, double *Jb6x7) {
+  Eigen::Matrix6d S;
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) S(i, j) = sqrt_info36[i * 6 + j];
+  D2Common::RelPoseFactorAD f(Swarm::Pose(rel7), S);
+  const double *params[2] = {pose_a, pose_b};
+  double *jac[2] = {Ja6x7, Jb6x7};
+  return ceres::AutoDiffEvaluate<6, 7, 7>(f, params, r6, Ja6x7 ? jac : nullptr) ? 6 : -2;
+}
+
+// Loss corrector: ResidualInfo::Evaluate(param_infos) (d2common/src/solver/BaseParamResInfo.cpp:46-92, compiled from the
+// reference) applied to a cost function that returns the given residual / Jacobian, with ceres::HuberLoss(a) (the shim's
+// restatement of the un-vendored ceres class).  One parameter block of n_par doubles; J row-major n_res x n_par.
+namespace {
+struct FixedCost : ceres::CostFunction {
+  const double *r; const double *J; int nr, np;
+  FixedCost(const double *r_, const double *J_, int nr_, int np_) : r(r_), J(J_), nr(nr_), np(np_) { set_num_residuals(nr_); mutable_parameter_block_sizes()->push_back(np_); }
+  bool Evaluate(double const *const *, double *res, double **jac) const override {
+    for (int i = 0; i < nr; i++) res[i] = r[i];
+    if (jac && jac[0]) for (int i = 0; i < nr * np; i++) jac[0][i] = J[i];
+    return true;
+  }
+};
+struct PlainResidualInfo : D2Common::ResidualInfo {
+  PlainResidualInfo() : D2Common::ResidualInfo(D2Common::NONE) {}
+  bool relavant(const std::set<FrameIdType> &) const override { return false; }
+  std::vector<D2Common::ParamInfo> paramsList(D2Common::D2State *) const override { return {}; }
+};
+}  // namespace
+int ref_loss_correct(int n_res, int n_par, const double *r_in, const double *J_in, double huber_a, double *r_out, double *J_out) {
+  PlainResidualInfo ri;
+  ri.cost_function = std::make_shared<FixedCost>(r_in, J_in, n_res, n_par);
+  if (huber_a > 0) ri.loss_function = std::make_shared<ceres::HuberLoss>(huber_a);
+  D2Common::ParamInfo p;
+  p.pointer = std::shared_ptr<double>(new double[n_par](), std::default_delete<double[]>());
+  p.size = n_par; p.eff_size = n_par;
+  ri.Evaluate(std::vector<D2Common::ParamInfo>{p}, false);
+  for (int i = 0; i < n_res; i++) r_out[i] = ri.residuals(i);
+  for (int i = 0; i < n_res; i++) for (int j = 0; j < n_par; j++) J_out[i * n_par + j] = ri.jacobians[0](i, j);
+  return n_res;
 }
 
 // PoseLocalParameterization (pose_local_parameterization.cpp:13-38); its members are private virtuals of

@@ -27,5 +27,11 @@ for i, c in enumerate(t.imu_cases()):
 for i, c in enumerate(t.cons_cases()):
     r, J = ref.consensus_eval(c["z"][:3], c["z"][3:7], c["tt"], c["th"], c["rho_T"], c["rho_theta"], c["x"])
     out[f"cons{i}_r"] = r; out[f"cons{i}_J"] = J
+for i, c in enumerate(t.relpose_cases()):
+    r, Ja, Jb = ref.relpose_ad_eval(c["pa"], c["pb"], c["rel"], c["S"])
+    out[f"relpose{i}_r"] = r; out[f"relpose{i}_Ja"] = Ja; out[f"relpose{i}_Jb"] = Jb
+for i, c in enumerate(t.loss_cases()):
+    r, J = ref.loss_correct(c["r"], c["J"], c["a"])
+    out[f"loss{i}_r"] = r; out[f"loss{i}_J"] = J
 np.savez_compressed(os.path.join(HERE, "ref_factors.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -89,3 +89,24 @@ def test_pgo_converged_solution_matches_sparse_direct_oracle():
     # and it actually removed the drift: far closer to the ground truth than the initial guess
     e0, _ = synth.pose_errors(g["init"], g["gt"]); e1, _ = synth.pose_errors(s.get_poses(g["ids"]), g["gt"])
     assert e1 < 0.5 * e0
+
+
+@pytest.mark.gpu
+def test_pgo_edges_on_device_match_the_reference_functor():
+    """Device residual / tangent Jacobians of every sampled edge vs the reference's own RelPoseFactorAD functor (shipped
+    oracle/_ref/libd2ref.so: doubles for the residual, dual numbers for the exact ambient Jacobians)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libd2ref.so not shipped")
+    from test_ref_pin import plus_jacobian
+    g = small_graph(seed=8)
+    rng = np.random.default_rng(1)
+    S = g["sqrt_info"].reshape(-1, 6, 6) + 0.5 * rng.normal(size=(len(g["ea"]), 6, 6))      # full square-root information
+    s = pgo.PgoSolver()
+    s.set_poses(g["ids"], g["init"], g["fixed"]); s.add_edges(g["id_a"], g["id_b"], g["rel"], S.reshape(-1, 36))
+    dev = s.debug_edges()
+    for e in range(0, len(dev), 5):
+        a, b = g["ea"][e], g["eb"][e]
+        r, Ja, Jb = ref.relpose_ad_eval(g["init"][a], g["init"][b], g["rel"][e], S[e])
+        want = np.concatenate([r, (Ja @ plus_jacobian(g["init"][a])).ravel(), (Jb @ plus_jacobian(g["init"][b])).ravel()])
+        assert np.abs(dev[e] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), e

@@ -189,6 +189,75 @@ def test_manifold_and_quaternion_helpers_match_reference():
     assert min(np.abs(a_r - a_o).max(), np.abs(a_r + a_o).max()) <= 1e-12      # eigenvector sign is free
 
 
+# ----------------------------------------------------------------------------------------------- loss corrector
+def loss_cases(seed=31):
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(8):
+        n = 2 + (k % 2)                                  # reprojection (2) and depth-augmented (3) residual blocks
+        out.append(dict(r=rng.normal(size=n) * (0.3 if k < 3 else 4.0), J=rng.normal(size=(n, 7)), a=1.0 if k % 4 else 0.5))
+    out.append(dict(r=np.zeros(2), J=rng.normal(size=(2, 7)), a=1.0))   # sq_norm == 0 branch
+    return out
+
+
+def orc_loss(c):
+    r, J = c["r"], c["J"]
+    rho = np.zeros(3); s = float(r @ r)
+    L.orc_huber(C.c_double(c["a"]), C.c_double(s), abi.ptr(rho))
+    rs = C.c_double(); sr = C.c_double(); asn = C.c_double()
+    L.orc_corrector(abi.ptr(rho), C.c_double(s), C.byref(rs), C.byref(sr), C.byref(asn))
+    return rs.value * r, sr.value * (J - asn.value * np.outer(r, r @ J))     # orc_solver.c:435-452
+
+
+@needs_ref
+def test_loss_corrector_matches_reference():
+    """orc_huber + orc_corrector as the oracle's minimiser applies them vs the reference's ResidualInfo::Evaluate loss section
+    (d2common/src/solver/BaseParamResInfo.cpp:71-92, compiled unmodified) with ceres::HuberLoss(a)."""
+    for c in loss_cases():
+        r_r, J_r = ref.loss_correct(c["r"], c["J"], c["a"])
+        r_o, J_o = orc_loss(c)
+        close(r_o, r_r, 1e-15); close(J_o, J_r, 1e-15)
+
+
+# ----------------------------------------------------------------------------------------------- pose-graph factor (d2pgo)
+def relpose_cases(seed=23, n=8):
+    rng = np.random.default_rng(seed)
+    tof.RNG = np.random.default_rng(seed + 1)
+    out = []
+    for k in range(n):
+        pa, pb = tof.rand_pose(3.0), tof.rand_pose(3.0)
+        rel = tof.rand_pose(2.0)
+        S = np.diag([20.0, 20.0, 20.0, 57.0, 57.0, 57.0]) + (0.0 if k % 2 == 0 else 1.0) * rng.normal(size=(6, 6))   # diagonal and full
+        out.append(dict(pa=pa, pb=pb, rel=rel, S=S))
+    return out
+
+
+def plus_jacobian(x):
+    """d (x (+) delta) / d delta at 0 for PoseLocalParameterization::Plus (pose_local_parameterization.cpp:13-29): 7 x 6.
+    (The class's own ComputeJacobian is the VINS-style [I6; 0] placeholder, not this derivative.)"""
+    v, w = x[3:6], x[6]
+    P = np.zeros((7, 6)); P[:3, :3] = np.eye(3)
+    P[3:6, 3:] = 0.5 * (w * np.eye(3) + np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])); P[6, 3:] = -0.5 * v
+    return P
+
+
+def check_relpose(c, r_ref, Ja, Jb):
+    from oracle import pgo_oracle as po
+    r_o, J0, J1 = po.edge_eval(c["pa"], c["pb"], c["rel"], c["S"])
+    close(r_o, r_ref, 1e-13)
+    # the reference Jacobians are w.r.t. the 7 ambient parameters (what autodiff hands to the manifold); the oracle's and the
+    # device's are in the tangent of the right-multiplicative retraction: J_tangent = J_ambient d(x (+) delta)/d delta
+    close(J0, Ja @ plus_jacobian(c["pa"]), 1e-13); close(J1, Jb @ plus_jacobian(c["pb"]), 1e-13)
+
+
+@needs_ref
+def test_rel_pose_factor_matches_reference():
+    """oracle/pgo_oracle.py::edge_eval vs the reference's RelPoseFactorAD functor (RelPoseFactor.hpp:68-135) run with doubles
+    (residual) and with dual numbers (exact derivatives of the reference's own residual code)."""
+    for c in relpose_cases():
+        check_relpose(c, *ref.relpose_ad_eval(c["pa"], c["pb"], c["rel"], c["S"]))
+
+
 # ----------------------------------------------------------------------------------------------- frozen reference outputs
 def test_oracle_matches_golden_reference_vectors():
     """Same comparisons against reference outputs frozen by tests/golden/make_ref_golden.py (runs everywhere)."""
@@ -207,3 +276,8 @@ def test_oracle_matches_golden_reference_vectors():
     for i, c in enumerate(cons_cases()):
         r_o, J_o = orc_cons(c)
         close(r_o, g[f"cons{i}_r"], 1e-14); close(J_o, g[f"cons{i}_J"], 1e-14)
+    for i, c in enumerate(relpose_cases()):
+        check_relpose(c, g[f"relpose{i}_r"], g[f"relpose{i}_Ja"], g[f"relpose{i}_Jb"])
+    for i, c in enumerate(loss_cases()):
+        r_o, J_o = orc_loss(c)
+        close(r_o, g[f"loss{i}_r"], 1e-15); close(J_o, g[f"loss{i}_J"], 1e-15)
