@@ -4,6 +4,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 #include <memory>
@@ -159,10 +161,15 @@ class Problem {
   const LocalParameterization *GetParameterization(const double *values) const { return blocks_.at(const_cast<double *>(values)).lp; }
   int ParameterBlockSize(const double *values) const { return blocks_.at(const_cast<double *>(values)).size; }
   int NumParameterBlocks() const { return (int)blocks_.size(); }
-  void *AddResidualBlock(CostFunction *, LossFunction *, const std::vector<double *> &ps) { for (double *p : ps) blocks_[p]; return nullptr; }
+  struct ResBlk { CostFunction *cost; LossFunction *loss; std::vector<double *> params; };
+  void *AddResidualBlock(CostFunction *c, LossFunction *l, const std::vector<double *> &ps) { for (double *p : ps) blocks_[p]; residual_blocks_.push_back(ResBlk{c, l, ps}); return nullptr; }
+  void *AddResidualBlock(CostFunction *c, LossFunction *l, double *p0) { return AddResidualBlock(c, l, std::vector<double *>{p0}); }
+  void *AddResidualBlock(CostFunction *c, LossFunction *l, double *p0, double *p1) { return AddResidualBlock(c, l, std::vector<double *>{p0, p1}); }
+  const std::vector<ResBlk> &residual_blocks() const { return residual_blocks_; }   // stand-in only: what the caller assembled
  private:
   struct Blk { int size = 0; bool constant = false; LocalParameterization *lp = nullptr; };
   std::map<double *, Blk> blocks_;
+  std::vector<ResBlk> residual_blocks_;
 };
 struct Solver {
   struct Options {
@@ -174,4 +181,27 @@ struct Solver {
   struct Summary { int num_successful_steps = 0, num_unsuccessful_steps = 0; double initial_cost = 0, final_cost = 0, total_time_in_seconds = 0; std::string BriefReport() const { return ""; } std::string FullReport() const { return ""; } };
 };
 using std::cos; using std::sin; using std::floor; using std::sqrt; using std::atan2; using std::abs;
+
+// ceres::NormalPrior(A, b): r = A (x - b), J = A (interface + the two lines of arithmetic of ceres/normal_prior.cc; stand-in)
+class NormalPrior : public CostFunction {
+ public:
+  NormalPrior(const Eigen::MatrixXd &A, const Eigen::VectorXd &b) : A_(A), b_(b) { set_num_residuals(A_.rows()); mutable_parameter_block_sizes()->push_back(b_.rows()); }
+  bool Evaluate(double const *const *p, double *r, double **J) const override {
+    const int m = A_.rows(), n = A_.cols();
+    for (int i = 0; i < m; i++) { double s = 0; for (int k = 0; k < n; k++) s += A_(i, k) * (p[0][k] - b_(k)); r[i] = s; }
+    if (J && J[0]) for (int i = 0; i < m; i++) for (int k = 0; k < n; k++) J[0][i * n + k] = A_(i, k);
+    return true;
+  }
+  const Eigen::MatrixXd &A() const { return A_; }
+  const Eigen::VectorXd &b() const { return b_; }
+ private:
+  Eigen::MatrixXd A_; Eigen::VectorXd b_;
+};
+
+// ceres::Solve stand-in: there is no minimiser in this shim.  The call is forwarded to a hook the test driver installs
+// (oracle/ref_driver.cpp replays a prescribed state trajectory through the reference's ADMM bookkeeping); without a hook
+// it leaves the parameter blocks untouched.
+typedef std::function<void(const Solver::Options &, Problem *, Solver::Summary *)> SolveHook;
+inline SolveHook &solve_hook() { static thread_local SolveHook h; return h; }
+inline void Solve(const Solver::Options &o, Problem *p, Solver::Summary *s) { if (solve_hook()) solve_hook()(o, p, s); }
 }  // namespace ceres

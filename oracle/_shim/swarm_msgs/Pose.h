@@ -25,6 +25,8 @@ class Pose {
  public:
   Pose() : position(0, 0, 0) {}
   Pose(const Eigen::Vector3d &p, const Eigen::Quaterniond &q) : position(p), attitude(q.normalized()) {}
+  explicit Pose(const std::shared_ptr<double> &v) : Pose(v.get()) {}
+  explicit Pose(const Eigen::VectorXd &v) : position(v(0), v(1), v(2)), attitude(v(6), v(3), v(4), v(5)) { attitude.normalize(); }
   explicit Pose(const double *v, bool xyzyaw = false) : position(v[0], v[1], v[2]), attitude(v[6], v[3], v[4], v[5]) { (void)xyzyaw; attitude.normalize(); }
   const Eigen::Vector3d &pos() const { return position; }
   const Eigen::Quaterniond &att() const { return attitude; }
@@ -36,6 +38,17 @@ class Pose {
   Pose operator*(const Pose &b) const { return Pose(attitude * b.position + position, attitude * b.attitude); }
   Eigen::Vector3d operator*(const Eigen::Vector3d &p) const { return attitude * p + position; }
   static Pose DeltaPose(const Pose &a, const Pose &b, bool use_yaw_only = false) { (void)use_yaw_only; return a.inverse() * b; }
+  // ASSUMED (upstream swarm_msgs/Pose.h): [translation ; angle * axis] with Eigen::AngleAxisd(q) conventions
+  // (angle = 2 atan2(|v|, |w|), axis sign follows w) -- the same assumption oracle/orc_factors.c::orc_delta_pose_tangent states
+  Eigen::Matrix<double, 6, 1> tangentSpace() const {
+    Eigen::Matrix<double, 6, 1> t; t.setZero();
+    t(0) = position.x(); t(1) = position.y(); t(2) = position.z();
+    const double n = std::sqrt(attitude.x() * attitude.x() + attitude.y() * attitude.y() + attitude.z() * attitude.z());
+    if (n > 0) { const double ang = 2.0 * std::atan2(n, std::fabs(attitude.w())), sg = attitude.w() < 0 ? -1.0 : 1.0; t(3) = ang * sg * attitude.x() / n; t(4) = ang * sg * attitude.y() / n; t(5) = ang * sg * attitude.z() / n; }
+    return t;
+  }
+  // ASSUMED: mean position + D2Common::Utility::averageQuaterions (defined in oracle/ref_driver.cpp against the reference's utils.hpp)
+  static Pose averagePoses(const std::vector<Pose> &poses);
 };
 // Stand-in for Swarm::LoopEdge (swarm_msgs, un-vendored): the members RelPoseFactor.hpp's Create() helpers touch.  ASSUMED.
 struct LoopEdge {

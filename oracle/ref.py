@@ -122,6 +122,19 @@ def loss_correct(r, J, huber_a):
     return ro, Jo
 
 
+def admm_replay(present, traj, relaxation_alpha, rho_T, rho_theta):
+    """The reference's ConsensusSolver::solve loop (ConsensusSolver.cpp:39-235) replaying a prescribed trajectory of local
+    poses: present [A][B] (agent a holds block b), traj [K+1][A][B][7] -> z [K][A][B][7], tilde [K][A][B][6] and the residuals
+    [K][A][B][6] of the ConsenusPoseFactor objects it created at every step (evaluated at the step's local poses)."""
+    present = np.ascontiguousarray(present, dtype=np.uint8); traj = np.ascontiguousarray(traj, dtype=np.float64)
+    K = traj.shape[0] - 1; A, B = present.shape
+    z = np.zeros((K, A, B, 7)); tl = np.zeros((K, A, B, 6)); rs = np.zeros((K, A, B, 6))
+    rc = lib().ref_admm_replay(C.c_int(A), C.c_int(B), C.c_int(K), C.c_double(relaxation_alpha), C.c_double(rho_T), C.c_double(rho_theta),
+                               _p(present), _p(traj), _p(z), _p(tl), _p(rs))
+    assert rc == 0, rc
+    return z, tl, rs
+
+
 def pose_plus(x, delta):
     x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
     lib().ref_pose_plus(_p(x), _p(d), _p(o))

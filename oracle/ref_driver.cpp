@@ -16,6 +16,9 @@
 #include <d2common/solver/pose_local_parameterization.h>
 #include <d2common/solver/RelPoseFactor.hpp>
 #include <d2common/solver/BaseParamResInfo.hpp>
+#include <d2common/solver/ConsensusSolver.hpp>
+#include <pthread.h>
+#include <thread>
 #include <d2common/utils.hpp>
 
 #include "d2vins_params.hpp"
@@ -194,3 +197,126 @@ void ref_average_quats(int n, const double *q_xyzw, double *out_xyzw) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ ADMM bookkeeping replay
+// The reference's OWN ConsensusSolver::solve loop (d2common/src/solver/ConsensusSolver.cpp:39-235, compiled unmodified:
+// syncData -> updateGlobal, problem assembly, updateTilde, solveLocalStep) run for N agents on N threads, with
+//   * broadcastData / waitForSync implemented as an in-process table + barrier (the reference's are LCM messages,
+//     VINSConsenusSolver.cpp:11-120),
+//   * ceres::Solve replaced by a hook that (a) snapshots param_global / param_tilde and evaluates the ConsenusPoseFactor
+//     objects updateTilde just created, and (b) writes the NEXT prescribed local poses into the state -- i.e. a given
+//     state trajectory is replayed through the reference's dual / global updates.
+// Swarm::Pose::{averagePoses, DeltaPose, tangentSpace} are the ASSUMED stand-ins of oracle/_shim/swarm_msgs/Pose.h.
+namespace Swarm {
+Pose Pose::averagePoses(const std::vector<Pose> &poses) {
+  Eigen::Vector3d p(0, 0, 0);
+  std::vector<Eigen::Quaterniond> qs;
+  for (const Pose &x : poses) { p += x.pos(); qs.push_back(x.att()); }
+  p = p / (double)poses.size();
+  return Pose(p, D2Common::Utility::averageQuaterions(qs));   // utils.hpp:213-228 (reference code)
+}
+}  // namespace Swarm
+namespace {
+struct ZeroCost : ceres::CostFunction {
+  explicit ZeroCost(int nblk) { set_num_residuals(1); for (int i = 0; i < nblk; i++) mutable_parameter_block_sizes()->push_back(7); }
+  bool Evaluate(double const *const *, double *res, double **) const override { res[0] = 0.0; return true; }
+};
+struct ReplayResInfo : D2Common::ResidualInfo {
+  std::vector<D2Common::ParamInfo> infos;
+  ReplayResInfo() : D2Common::ResidualInfo(D2Common::NONE) {}
+  bool relavant(const std::set<FrameIdType> &) const override { return false; }
+  std::vector<D2Common::ParamInfo> paramsList(D2Common::D2State *) const override { return infos; }
+};
+struct ReplayState : D2Common::D2State {
+  ReplayState(int id, int n) : D2Common::D2State(id) { for (int a = 0; a < n; a++) all_drones.insert(a); }
+};
+struct ReplayShared {
+  int n_agents, n_blocks, steps;
+  const uint8_t *present; const double *traj;     // [a][b], [(steps+1)][a][b][7]
+  double *z_out, *tilde_out, *res_out;            // [steps][a][b][7|6|6]
+  std::vector<double> table;                      // [a][b][7] what every agent last broadcast
+  pthread_barrier_t bar;
+};
+class ReplayAgent : public D2Common::ConsensusSolver {
+  int me; ReplayShared *sh; std::vector<D2Common::StatePtr> ptr; int step = 0;
+  void broadcastData() override {
+    for (int b = 0; b < sh->n_blocks; b++) if (ptr[b]) memcpy(&sh->table[((size_t)me * sh->n_blocks + b) * 7], ptr[b].get(), 56);
+  }
+  void exchange() {
+    pthread_barrier_wait(&sh->bar);               // every agent has broadcast
+    for (int b = 0; b < sh->n_blocks; b++) {
+      if (!ptr[b]) continue;
+      for (int a = 0; a < sh->n_agents; a++) {
+        if (!sh->present[a * sh->n_blocks + b]) continue;
+        VectorXd v(7);
+        for (int k = 0; k < 7; k++) v(k) = sh->table[((size_t)a * sh->n_blocks + b) * 7 + k];
+        remote_params[ptr[b]][a] = v;
+      }
+    }
+    pthread_barrier_wait(&sh->bar);               // every agent has read: the table may be overwritten
+  }
+  void waitForSync() override { exchange(); }
+  void receiveAll() override { exchange(); }
+  void on_solve(ceres::Problem *problem) {
+    const int k = step++;
+    for (int b = 0; b < sh->n_blocks; b++) {
+      if (!ptr[b]) continue;
+      const size_t o = ((size_t)k * sh->n_agents + me) * sh->n_blocks + b;
+      const D2Common::ConsenusParamState &cs = consenus_params.at(ptr[b]);
+      for (int q = 0; q < 7; q++) sh->z_out[o * 7 + q] = cs.param_global(q);
+      for (int q = 0; q < 6; q++) sh->tilde_out[o * 6 + q] = cs.param_tilde(q);
+    }
+    for (const auto &rb : problem->residual_blocks()) {     // the factors updateTilde created for this step
+      auto *f = dynamic_cast<ConsenusPoseFactor *>(rb.cost);
+      if (!f) continue;
+      for (int b = 0; b < sh->n_blocks; b++) {
+        if (!ptr[b] || ptr[b].get() != rb.params[0]) continue;
+        double r[6]; const double *pp[1] = {rb.params[0]};
+        f->Evaluate(pp, r, nullptr);
+        for (int q = 0; q < 6; q++) sh->res_out[(((size_t)k * sh->n_agents + me) * sh->n_blocks + b) * 6 + q] = r[q];
+      }
+    }
+    for (int b = 0; b < sh->n_blocks; b++)        // "the local solve": the next prescribed poses
+      if (ptr[b]) memcpy(ptr[b].get(), sh->traj + ((((size_t)(k + 1)) * sh->n_agents + me) * sh->n_blocks + b) * 7, 56);
+  }
+ public:
+  ReplayAgent(D2Common::D2State *st, D2Common::ConsensusSolverConfig cfg, int me_, ReplayShared *sh_) : D2Common::ConsensusSolver(st, cfg, 0), me(me_), sh(sh_), ptr(sh_->n_blocks) {
+    auto ri = std::make_shared<ReplayResInfo>();
+    int nb = 0;
+    for (int b = 0; b < sh->n_blocks; b++) {
+      if (!sh->present[me * sh->n_blocks + b]) continue;
+      ptr[b] = std::shared_ptr<double>(new double[7], std::default_delete<double[]>());
+      memcpy(ptr[b].get(), sh->traj + (((size_t)me) * sh->n_blocks + b) * 7, 56);
+      D2Common::ParamInfo p; p.pointer = ptr[b]; p.index = -1; p.size = 7; p.eff_size = 6; p.type = D2Common::POSE; p.id = b;
+      p.data_copied = Map<VectorXd>(ptr[b].get(), 7);
+      ri->infos.push_back(p); nb++;
+    }
+    ri->cost_function = std::make_shared<ZeroCost>(nb);
+    addResidual(ri);
+  }
+  void run() {
+    ceres::solve_hook() = [this](const ceres::Solver::Options &, ceres::Problem *p, ceres::Solver::Summary *) { on_solve(p); };
+    solve();
+    ceres::solve_hook() = nullptr;
+  }
+};
+}  // namespace
+extern "C" int ref_admm_replay(int n_agents, int n_blocks, int steps, double relaxation_alpha, double rho_T, double rho_theta, const uint8_t *present,
+                               const double *traj, double *z_out, double *tilde_out, double *res_out) {
+  ReplayShared sh;
+  sh.n_agents = n_agents; sh.n_blocks = n_blocks; sh.steps = steps; sh.present = present; sh.traj = traj;
+  sh.z_out = z_out; sh.tilde_out = tilde_out; sh.res_out = res_out; sh.table.assign((size_t)n_agents * n_blocks * 7, 0.0);
+  pthread_barrier_init(&sh.bar, nullptr, n_agents);
+  std::vector<std::unique_ptr<ReplayState>> states; std::vector<std::unique_ptr<ReplayAgent>> agents;
+  for (int a = 0; a < n_agents; a++) {
+    D2Common::ConsensusSolverConfig cfg;
+    cfg.max_steps = steps; cfg.self_id = a; cfg.relaxation_alpha = relaxation_alpha; cfg.rho_frame_T = rho_T; cfg.rho_frame_theta = rho_theta; cfg.sync_for_averaging = true;
+    states.emplace_back(new ReplayState(a, n_agents));
+    agents.emplace_back(new ReplayAgent(states.back().get(), cfg, a, &sh));
+  }
+  std::vector<std::thread> th;
+  for (int a = 0; a < n_agents; a++) th.emplace_back([&, a]() { agents[a]->run(); });
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&sh.bar);
+  return 0;
+}

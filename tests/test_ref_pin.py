@@ -189,6 +189,62 @@ def test_manifold_and_quaternion_helpers_match_reference():
     assert min(np.abs(a_r - a_o).max(), np.abs(a_r + a_o).max()) <= 1e-12      # eigenvector sign is free
 
 
+# ----------------------------------------------------------------------------------------------- ADMM loop
+ADMM_KW = dict(rho_frame_T=30.0, rho_frame_theta=70.0, relaxation_alpha=0.6)
+ADMM_STEPS, ADMM_ITERS_PER_STEP = 4, 2
+
+
+def admm_trajectory():
+    """The oracle's ADMM (orc_admm_solve) run for 0, 1, .. K consensus steps from the same start (each run is a prefix of the
+    next: fixed iterations per step) -> per run and agent: consensus slots, local poses, z, tilde."""
+    sw = synth.make_swarm(seed=5, n_agents=3, n_frames=4, n_landmarks=40, shared_per_pair=15)
+    runs = []
+    for k in range(ADMM_STEPS + 1):
+        ags = []
+        for p in sw:
+            o = orc.Oracle(max_num_iterations=ADMM_ITERS_PER_STEP * max(k, 1), consensus_max_steps=max(k, 1), **ADMM_KW); p.load(o); ags.append(o)
+        if k:
+            orc.admm_solve(ags, fixed_mode=True)
+        out = []
+        for p, o in zip(sw, ags):
+            refs, slots, _ = p["consensus"]
+            x = np.array([o.get_blocks(int(r["kind"]), [int(r["id"])])[0] for r in refs])
+            z, t = o.get_consensus(refs)
+            out.append((slots, x, z, t))
+        runs.append(out)
+    n_slots = sw[0]["consensus"][2]
+    present = np.zeros((len(sw), n_slots), np.uint8); traj = np.zeros((ADMM_STEPS + 1, len(sw), n_slots, 7)); traj[..., 6] = 1.0
+    for k, out in enumerate(runs):
+        for a, (slots, x, _, _) in enumerate(out):
+            present[a, slots] = 1; traj[k, a, slots] = x
+    return runs, present, traj
+
+
+def check_admm(runs, traj, z, tl, rs):
+    for k in range(1, ADMM_STEPS + 1):
+        for a, (slots, _, z_o, t_o) in enumerate(runs[k]):
+            z_r, t_r = z[k - 1, a, slots], tl[k - 1, a, slots]
+            sgn = np.sign(np.sum(z_r[:, 3:] * z_o[:, 3:], axis=1, keepdims=True))     # the averaged quaternion's sign is free
+            close(z_o[:, :3], z_r[:, :3], 1e-13); close(z_o[:, 3:], z_r[:, 3:] * sgn, 1e-13)
+            close(t_o, t_r, 1e-13)
+            # the ConsenusPoseFactor objects the reference loop created (argument order of rho / tilde segments included),
+            # evaluated at the step's local poses, vs the oracle's factor with the oracle's z / tilde
+            for i, s_ in enumerate(slots):
+                c = dict(z=z_o[i], x=traj[k - 1, a, s_], tt=t_o[i, :3].copy(), th=t_o[i, 3:].copy(), rho_T=ADMM_KW["rho_frame_T"], rho_theta=ADMM_KW["rho_frame_theta"])
+                close(orc_cons(c)[0], rs[k - 1, a, s_], 1e-12)
+
+
+@needs_ref
+def test_admm_bookkeeping_matches_the_reference_loop():
+    """The reference's own ConsensusSolver::solve loop (ConsensusSolver.cpp:39-235, compiled unmodified; syncData /
+    updateGlobal / updateTilde, 3 agents on 3 threads, relaxation 0.6) replays the oracle's trajectory of local poses: global
+    averages z, duals tilde and the created consensus factors must equal the oracle's at every step."""
+    runs, present, traj = admm_trajectory()
+    z, tl, rs = ref.admm_replay(present, traj, ADMM_KW["relaxation_alpha"], ADMM_KW["rho_frame_T"], ADMM_KW["rho_frame_theta"])
+    assert np.abs(tl[-1]).max() > 1e-3      # the duals are not trivially zero
+    check_admm(runs, traj, z, tl, rs)
+
+
 # ----------------------------------------------------------------------------------------------- loss corrector
 def loss_cases(seed=31):
     rng = np.random.default_rng(seed)
@@ -281,3 +337,5 @@ def test_oracle_matches_golden_reference_vectors():
     for i, c in enumerate(loss_cases()):
         r_o, J_o = orc_loss(c)
         close(r_o, g[f"loss{i}_r"], 1e-15); close(J_o, g[f"loss{i}_J"], 1e-15)
+    runs, _, traj = admm_trajectory()
+    check_admm(runs, traj, g["admm_z"], g["admm_tilde"], g["admm_res"])
