@@ -162,6 +162,10 @@ class MatrixBase {
   template <int BR, int BC> Block<const Derived, BR, BC> bottomLeftCorner() const { return block<BR, BC>(rows() - BR, 0); }
   Block<Derived, Dynamic, Dynamic> leftCols(int n) { return block(0, 0, rows(), n); }
   Block<const Derived, Dynamic, Dynamic> leftCols(int n) const { return block(0, 0, rows(), n); }
+  Block<Derived, Dynamic, Dynamic> middleCols(int j, int n) { return block(0, j, rows(), n); }
+  Block<const Derived, Dynamic, Dynamic> middleCols(int j, int n) const { return block(0, j, rows(), n); }
+  Block<Derived, Dynamic, Dynamic> middleRows(int i, int n) { return block(i, 0, n, cols()); }
+  Block<const Derived, Dynamic, Dynamic> middleRows(int i, int n) const { return block(i, 0, n, cols()); }
   Block<Derived, Dynamic, Dynamic> rightCols(int n) { return block(0, cols() - n, rows(), n); }
   Block<const Derived, Dynamic, Dynamic> rightCols(int n) const { return block(0, cols() - n, rows(), n); }
   Block<Derived, Dynamic, Dynamic> topRows(int n) { return block(0, 0, n, cols()); }
@@ -187,6 +191,23 @@ class MatrixBase {
   Block<const Derived, Dynamic, Dynamic> head(int n) const { return segment(0, n); }
   Block<Derived, Dynamic, Dynamic> tail(int n) { return segment(size() - n, n); }
   Block<const Derived, Dynamic, Dynamic> tail(int n) const { return segment(size() - n, n); }
+  // coefficient-wise helpers (eager); array() supports the `(a.array() > eps).select(a.array()[.inverse()], 0)` idiom
+  PlainObject cwiseSqrt() const { PlainObject r(*this); for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) { using std::sqrt; r.ref(i, j) = sqrt(coeff(i, j)); } return r; }
+  PlainObject cwiseInverse() const { PlainObject r(*this); for (int j = 0; j < cols(); j++) for (int i = 0; i < rows(); i++) r.ref(i, j) = Scalar(1) / coeff(i, j); return r; }
+  struct ArrayMask;
+  struct ArrayView {
+    PlainObject m;
+    ArrayView inverse() const { ArrayView r{m.cwiseInverse()}; return r; }
+    ArrayView sqrt() const { ArrayView r{m.cwiseSqrt()}; return r; }
+    ArrayMask operator>(const Scalar &t) const { ArrayMask k; k.rows = m.rows(); k.cols = m.cols(); k.b.resize((size_t)m.rows() * m.cols()); for (int j = 0; j < m.cols(); j++) for (int i = 0; i < m.rows(); i++) k.b[(size_t)j * m.rows() + i] = m.coeff(i, j) > t; return k; }
+    operator PlainObject() const { return m; }
+    PlainObject matrix() const { return m; }
+  };
+  struct ArrayMask {
+    std::vector<char> b; int rows = 0, cols = 0;
+    PlainObject select(const ArrayView &a, const Scalar &otherwise) const { PlainObject r(a.m); for (int j = 0; j < cols; j++) for (int i = 0; i < rows; i++) if (!b[(size_t)j * rows + i]) r.ref(i, j) = otherwise; return r; }
+  };
+  ArrayView array() const { ArrayView v{PlainObject(*this)}; return v; }
   // diagonal matrix from a vector (eager)
   Matrix<Scalar, Dynamic, Dynamic> asDiagonal() const { Matrix<Scalar, Dynamic, Dynamic> d(size(), size()); d.setZero(); for (int i = 0; i < size(); i++) d.ref(i, i) = vget(i); return d; }
   Matrix<Scalar, (RowsAtCompileTime == 1 || ColsAtCompileTime == 1) ? Dynamic : RowsAtCompileTime, 1> diagonal() const {
@@ -480,10 +501,12 @@ template <class M> class SelfAdjointEigenSolver {   // cyclic Jacobi; eigenvalue
   ComputationInfo info() const { return inf; }
 };
 
-template <class S, int Opt = 0, class I = int> class SparseMatrix {
+template <class S, int Opt = 0, class I = int> class SparseMatrix {   // interface only (dense storage)
+  Matrix<S, Dynamic, Dynamic> d_;
  public:
   SparseMatrix() {}
-  SparseMatrix(int, int) {}
+  SparseMatrix(int r, int c) : d_(r, c) { d_.setZero(); }
+  Matrix<S, Dynamic, Dynamic> toDense() const { return d_; }
 };
 template <class M, int UpLo = 1, class Ord = void> class SimplicialLLT;
 template <class M, int UpLo = 1, class Ord = void> class SimplicialLDLT;

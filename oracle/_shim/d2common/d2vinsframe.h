@@ -6,6 +6,8 @@
 #include <d2common/d2basetypes.h>
 #include <d2common/utils.hpp>
 #include <swarm_msgs/Pose.h>
+#include <swarm_msgs/Odometry.h>
+#include <d2common/d2imu.h>
 namespace D2Common {
 typedef std::lock_guard<std::recursive_mutex> Guard;   // d2common/d2imu.h:10
 struct D2BaseFrame {   // interface of d2common/d2baseframe.h:7-60 as far as d2state.hpp uses it
@@ -15,4 +17,6 @@ struct D2BaseFrame {   // interface of d2common/d2baseframe.h:7-60 as far as d2s
   virtual void moveByPose(int new_ref_frame_id, const Swarm::Pose &delta_pose) { reference_frame_id = new_ref_frame_id; odom.p = delta_pose * odom.p; }
   virtual ~D2BaseFrame() {}
 };
+struct VINSFrame : D2BaseFrame {};   // d2vinsframe.h:12-36 (fields not needed by the compiled sources)
+using VINSFramePtr = std::shared_ptr<VINSFrame>;
 }  // namespace D2Common

@@ -135,6 +135,25 @@ def admm_replay(present, traj, relaxation_alpha, rho_T, rho_theta):
     return z, tl, rs
 
 
+PRIOR_SIZE = (7, 7, 9, 1, 1); PRIOR_EFF = (6, 6, 9, 1, 1)   # POSE, EXTRINSIC, SPEED_BIAS, TD, LANDMARK
+
+
+def prior_eval(kinds, x0, x, A, b):
+    """PriorFactor(keep_params, A, b).Evaluate(x) (prior_factor.cpp:45-90, toJacRes :132-177): residual (m) and the m x m
+    tangent Jacobian assembled from the per-block Jacobians' leftCols(eff_size) (the remaining columns are asserted zero)."""
+    kinds = np.ascontiguousarray(kinds, dtype=np.int32); x0 = np.ascontiguousarray(x0, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64)
+    A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64); m = len(b)
+    r = np.zeros(m); J = np.zeros(sum(m * PRIOR_SIZE[k] for k in kinds))
+    n = lib().ref_prior_eval(C.c_int(len(kinds)), _p(kinds), _p(x0), _p(x), C.c_int(m), _p(A), _p(b), _p(r), _p(J))
+    assert n == m, n
+    Jt = np.zeros((m, m)); off = eo = 0
+    for k in kinds:
+        blk = J[off:off + m * PRIOR_SIZE[k]].reshape(m, PRIOR_SIZE[k])
+        assert np.all(blk[:, PRIOR_EFF[k]:] == 0.0)
+        Jt[:, eo:eo + PRIOR_EFF[k]] = blk[:, :PRIOR_EFF[k]]; off += m * PRIOR_SIZE[k]; eo += PRIOR_EFF[k]
+    return r, Jt
+
+
 def pose_plus(x, delta):
     x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
     lib().ref_pose_plus(_p(x), _p(d), _p(o))

@@ -23,6 +23,7 @@
 
 #include "d2vins_params.hpp"
 #include "factors/imu_factor.h"
+#include "factors/prior_factor.h"
 #include "factors/projectionOneFrameTwoCamFactor.h"
 #include "factors/projectionTwoFrameOneCamDepthFactor.h"
 #include "factors/projectionTwoFrameOneCamFactor.h"
@@ -319,4 +320,37 @@ extern "C" int ref_admm_replay(int n_agents, int n_blocks, int steps, double rel
   for (auto &t : th) t.join();
   pthread_barrier_destroy(&sh.bar);
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ marginalization prior
+// PriorFactor (d2vins/src/factors/prior_factor.cpp:45-90 Evaluate, :132-177 toJacRes, compiled unmodified): constructed from
+// the information form (A, b) and the kept blocks' linearisation points, evaluated at x.  kinds: 0 POSE, 1 EXTRINSIC,
+// 2 SPEED_BIAS, 3 TD, 4 LANDMARK.  x0 / x: the blocks' values concatenated (7, 7, 9, 1, 1 doubles); J_out: per block a
+// row-major m x size matrix, concatenated.
+extern "C" int ref_prior_eval(int nblk, const int *kinds, const double *x0, const double *x, int m, const double *A, const double *b, double *r_out, double *J_out) {
+  static D2VINSConfig cfg;                       // toJacRes reads params->debug_write_margin_matrix
+  if (!D2VINS::params) D2VINS::params = &cfg;
+  static const int kSize[5] = {7, 7, 9, 1, 1}, kEff[5] = {6, 6, 9, 1, 1};
+  static const D2Common::ParamsType kType[5] = {D2Common::POSE, D2Common::EXTRINSIC, D2Common::SPEED_BIAS, D2Common::TD, D2Common::LANDMARK};
+  std::vector<D2Common::ParamInfo> keep;
+  std::vector<const double *> px;
+  int off = 0, eff = 0;
+  for (int i = 0; i < nblk; i++) {
+    D2Common::ParamInfo p;
+    const int sz = kSize[kinds[i]];
+    p.pointer = std::shared_ptr<double>(new double[sz], std::default_delete<double[]>());
+    memcpy(p.pointer.get(), x0 + off, sizeof(double) * sz);
+    p.index = eff; p.size = sz; p.eff_size = kEff[kinds[i]]; p.type = kType[kinds[i]]; p.id = i;
+    p.data_copied = Map<VectorXd>(p.pointer.get(), sz);
+    keep.push_back(p); px.push_back(x + off);
+    off += sz; eff += p.eff_size;
+  }
+  if (eff != m) return -1;
+  MatrixXd Am(m, m); VectorXd bv(m);
+  for (int i = 0; i < m; i++) { bv(i) = b[i]; for (int j = 0; j < m; j++) Am(i, j) = A[i * m + j]; }
+  PriorFactor f(keep, Am, bv);
+  std::vector<double *> jac;
+  double *jp = J_out;
+  for (int i = 0; i < nblk; i++) { jac.push_back(jp); jp += (size_t)m * kSize[kinds[i]]; }
+  return f.Evaluate(px.data(), r_out, J_out ? jac.data() : nullptr) ? m : -2;
 }

@@ -189,6 +189,62 @@ def test_manifold_and_quaternion_helpers_match_reference():
     assert min(np.abs(a_r - a_o).max(), np.abs(a_r + a_o).max()) <= 1e-12      # eigenvector sign is free
 
 
+# ----------------------------------------------------------------------------------------------- marginalization prior
+def prior_cases(seed=41):
+    rng = np.random.default_rng(seed)
+    tof.RNG = np.random.default_rng(seed + 1)
+    out = []
+    for case in range(4):
+        kinds = [[0, 2], [0, 2, 1, 3, 4, 0], [0, 2, 0, 2, 4, 4, 4], [1, 0, 2]][case]
+        x0, x = [], []
+        for k in kinds:
+            if k in (0, 1):
+                p0 = tof.rand_pose(2.0); x0.append(p0)
+                p1 = tof.plus(p0, np.concatenate([rng.normal(size=3) * 0.1, rng.normal(size=3) * 0.05]))
+                if case == 3 and k == 0:
+                    p1[3:7] = -p1[3:7]            # other hemisphere: the `!(qerr.w() >= 0)` branch (prior_factor.cpp:64-66)
+                x.append(p1)
+            else:
+                v = rng.normal(size=ref.PRIOR_SIZE[k]); x0.append(v); x.append(v + 0.05 * rng.normal(size=ref.PRIOR_SIZE[k]))
+        m = sum(ref.PRIOR_EFF[k] for k in kinds)
+        M = rng.normal(size=(m - (3 if case % 2 else 0), m))                     # odd cases: rank deficient (eigenvalue clamp)
+        out.append(dict(kinds=np.array(kinds, np.int32), x0=np.concatenate(x0), x=np.concatenate(x), A=M.T @ M, b=rng.normal(size=m)))
+    return out
+
+
+def orc_prior(c):
+    m = len(c["b"]); J = np.zeros((m, m)); e0 = np.zeros(m)
+    L.orc_to_jac_res(C.c_int(m), abi.ptr(c["A"]), abi.ptr(c["b"]), abi.ptr(J), abi.ptr(e0))
+    dx = np.zeros(m); off = eo = 0
+    for k in c["kinds"]:
+        sz, ef = ref.PRIOR_SIZE[k], ref.PRIOR_EFF[k]
+        if k in (0, 1):
+            d = np.zeros(6); L.orc_prior_dx_pose(abi.ptr(c["x"][off:off + 7].copy()), abi.ptr(c["x0"][off:off + 7].copy()), abi.ptr(d)); dx[eo:eo + 6] = d
+        else:
+            dx[eo:eo + ef] = c["x"][off:off + sz] - c["x0"][off:off + sz]
+        off += sz; eo += ef
+    return e0 + J @ dx, J                                                        # orc_solver.c:495-512
+
+
+def check_prior(c, r_ref, J_ref):
+    r_o, J_o = orc_prior(c)
+    # the rows of (J, e0) are eigenvectors scaled by sqrt(eigenvalue): their sign is the eigen-solver's choice -- compare what
+    # enters the normal equations, and the rows themselves up to sign
+    close(J_o.T @ J_o, J_ref.T @ J_ref, 1e-12); close(J_o.T @ r_o, J_ref.T @ r_ref, 1e-12); close(r_o @ r_o, r_ref @ r_ref, 1e-12)
+    sg = np.sign(np.sum(J_o * J_ref, axis=1)); sg[sg == 0] = 1.0
+    close(J_o, J_ref * sg[:, None], 1e-11); close(r_o, r_ref * sg, 1e-11)
+
+
+@needs_ref
+def test_prior_factor_matches_reference():
+    """orc_to_jac_res + orc_prior_dx_pose + `r = e0 + J dx` (the oracle's prior) vs the reference's PriorFactor built from the
+    same information form (A, b): toJacRes (eigenvalue clamp at 1e-8, rank-deficient cases) and Evaluate (pose dx with the
+    hemisphere branch, Euclidean blocks), prior_factor.cpp:45-90, :132-177 compiled unmodified.  (The eigen-decomposition
+    under the reference code is the shim's cyclic-Jacobi stand-in of Eigen::SelfAdjointEigenSolver.)"""
+    for c in prior_cases():
+        check_prior(c, *ref.prior_eval(c["kinds"], c["x0"], c["x"], c["A"], c["b"]))
+
+
 # ----------------------------------------------------------------------------------------------- ADMM loop
 ADMM_KW = dict(rho_frame_T=30.0, rho_frame_theta=70.0, relaxation_alpha=0.6)
 ADMM_STEPS, ADMM_ITERS_PER_STEP = 4, 2
@@ -339,3 +395,5 @@ def test_oracle_matches_golden_reference_vectors():
         close(r_o, g[f"loss{i}_r"], 1e-15); close(J_o, g[f"loss{i}_J"], 1e-15)
     runs, _, traj = admm_trajectory()
     check_admm(runs, traj, g["admm_z"], g["admm_tilde"], g["admm_res"])
+    for i, c in enumerate(prior_cases()):
+        check_prior(c, g[f"prior{i}_r"], g[f"prior{i}_J"])
