@@ -110,8 +110,9 @@ struct HObs { int type, pi, pj, ea, eb, lm, fa; };   // index form of one residu
 
 // Per-window pinned staging of the observation constants in the compact upload format (d2ba_types.cuh: ObsJ /
 // ObsAnchor): the anchor half of a reprojection record (pts_i, vel_i, td_i) repeats for every observation of a
-// landmark, so it is stored once per run of identical anchors -- less than half the bytes of the caller's 160-byte
-// records cross PCIe.  The tiled layout and the tangent bases are built on the device by k_build_tiles.
+// landmark, so it is stored once per run of identical anchors, and feature velocities / stamps go to separate motion
+// arrays that stay on the host while td is a constant equal to every stamp -- a quarter of the caller's 160-byte records
+// crosses PCIe.  The tiled layout and the tangent bases are built on the device by k_build_tiles.
 // Capacity survives d2ba_reset.
 template <typename T, bool WC = true>
 struct PinArr {

@@ -18,3 +18,4 @@ class LandmarkManager {
   std::map<LandmarkIdType, LandmarkPerId> landmark_db;
 };
 }  // namespace D2FrontEnd
+using namespace D2Common;   // the real d2frontend headers open the namespace globally

@@ -395,3 +395,19 @@ def test_leaf_elimination_equals_dense_cholesky(monkeypatch):
     d = state_diff(out["leaf"], out["dense"])
     assert d["pos"] <= 1e-6 and d["rot"] <= 1e-6 and d["sb"] <= 1e-6 and d["lm_rel"] <= 1e-5, d
     assert abs(out["leaf_cost"] - out["dense_cost"]) <= 1e-7 * max(1.0, abs(out["dense_cost"]))
+
+
+def test_solver_time_budget_stops_the_iteration_loop():
+    """max_solver_time_in_seconds (d2vins_params.cpp:143; / max_steps for the consensus solver :156-160): the iteration loop stops
+    enqueueing once the budget is spent -- checked two iterations behind, so at least two run -- and is untouched by a generous one."""
+    pr = synth.make_window(seed=21)
+    from d2slam_b200.solver import Solver
+    tol = dict(function_tolerance=1e-30, gradient_tolerance=1e-30, parameter_tolerance=1e-30)   # (<= 0 selects the defaults)
+    runs = {}
+    for name, budget in (("tiny", 1e-7), ("ample", 30.0), ("none", 0.0)):
+        s = Solver(max_num_iterations=30, max_solver_time_in_seconds=budget, **tol); pr.load(s, 0); s.finalize()
+        runs[name] = s.solve()[0]
+    assert 1 <= runs["tiny"].total_iterations <= 3, runs["tiny"].total_iterations
+    assert runs["ample"].total_iterations == runs["none"].total_iterations > 3
+    assert abs(runs["ample"].final_cost - runs["none"].final_cost) <= 1e-9 * runs["none"].final_cost
+    assert runs["tiny"].final_cost <= runs["tiny"].initial_cost
