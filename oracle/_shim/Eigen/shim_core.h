@@ -501,17 +501,54 @@ template <class M> class SelfAdjointEigenSolver {   // cyclic Jacobi; eigenvalue
   ComputationInfo info() const { return inf; }
 };
 
-template <class S, int Opt = 0, class I = int> class SparseMatrix {   // interface only (dense storage)
-  Matrix<S, Dynamic, Dynamic> d_;
+// "Sparse" types with Eigen's interface on DENSE storage (the marginalization code of the reference assembles its Jacobian
+// from triplets and takes a sparse LLT; at oracle sizes a dense matrix computes the same numbers).
+template <class S> struct Triplet {
+  int r = 0, c = 0; S v = S(0);
+  Triplet() {}
+  Triplet(int r_, int c_, const S &v_) : r(r_), c(c_), v(v_) {}
+  int row() const { return r; } int col() const { return c; } const S &value() const { return v; }
+};
+template <class S, int Opt = 0, class I = int> class SparseMatrix : public Matrix<S, Dynamic, Dynamic> {
+  typedef Matrix<S, Dynamic, Dynamic> Dense;
  public:
   SparseMatrix() {}
-  SparseMatrix(int r, int c) : d_(r, c) { d_.setZero(); }
-  Matrix<S, Dynamic, Dynamic> toDense() const { return d_; }
+  SparseMatrix(int r, int c) : Dense(Dense::Zero(r, c)) {}
+  template <class O> SparseMatrix(const MatrixBase<O> &o) : Dense(o) {}
+  template <class O> SparseMatrix &operator=(const MatrixBase<O> &o) { Dense::operator=(o); return *this; }
+  template <class It> void setFromTriplets(It b, It e) { this->setZero(); for (It t = b; t != e; ++t) this->ref(t->row(), t->col()) += t->value(); }   // duplicates are summed
+  Dense toDense() const { return Dense(*this); }
+  int nonZeros() const { int n = 0; for (int j = 0; j < this->cols(); j++) for (int i = 0; i < this->rows(); i++) n += this->get(i, j) != S(0); return n; }
 };
-template <class M, int UpLo = 1, class Ord = void> class SimplicialLLT;
+template <class M, int UpLo = 1, class Ord = void> class SimplicialLLT {   // dense Cholesky behind the sparse-solver interface
+  typedef typename M::Scalar S;
+  Matrix<S, Dynamic, Dynamic> L; ComputationInfo inf = Success;
+ public:
+  SimplicialLLT() {}
+  template <class O> explicit SimplicialLLT(const MatrixBase<O> &a) { compute(a); }
+  template <class O> SimplicialLLT &compute(const MatrixBase<O> &a) {
+    const int n = a.rows(); L = Matrix<S, Dynamic, Dynamic>::Zero(n, n); inf = Success;
+    for (int j = 0; j < n; j++) {
+      S d = a.coeff(j, j);
+      for (int k = 0; k < j; k++) d -= L(j, k) * L(j, k);
+      if (!(d > S(0))) { inf = NumericalIssue; return *this; }
+      using std::sqrt; L(j, j) = sqrt(d);
+      for (int i = j + 1; i < n; i++) { S t = a.coeff(i, j); for (int k = 0; k < j; k++) t -= L(i, k) * L(j, k); L(i, j) = t / L(j, j); }
+    }
+    return *this;
+  }
+  ComputationInfo info() const { return inf; }
+  template <class O> Matrix<S, Dynamic, Dynamic> solve(const MatrixBase<O> &b) const {
+    const int n = L.rows(); Matrix<S, Dynamic, Dynamic> x(b);
+    for (int c = 0; c < x.cols(); c++) {
+      for (int i = 0; i < n; i++) { S t = x(i, c); for (int k = 0; k < i; k++) t -= L(i, k) * x(k, c); x(i, c) = t / L(i, i); }
+      for (int i = n - 1; i >= 0; i--) { S t = x(i, c); for (int k = i + 1; k < n; k++) t -= L(k, i) * x(k, c); x(i, c) = t / L(i, i); }
+    }
+    return x;
+  }
+};
 template <class M, int UpLo = 1, class Ord = void> class SimplicialLDLT;
 template <class T, int O = 0, class St = void> class Ref;
-template <class S> struct Triplet { Triplet() {} Triplet(int, int, const S &) {} };
 
 // ------------------------------------------------------------------------------------------------ quaternions
 template <class Derived> struct qtraits;

@@ -154,6 +154,35 @@ def prior_eval(kinds, x0, x, A, b):
     return r, Jt
 
 
+def marginalize(pr, remove_frame_ids, huber_delta=1.0, max_m=512):
+    """The reference's Marginalizer::marginalize over the reference factor objects of one synthetic window `pr` (a
+    d2slam_b200.synth.Problem): -> kept block refs, their linearisation points, and the new prior as (J, e0)."""
+    from d2slam_b200 import abi
+    obs = np.ascontiguousarray(pr["obs"]); imu = np.ascontiguousarray(pr["imu"])
+    lm_ids = np.ascontiguousarray(pr["lm_ids"], dtype=np.int64)
+    base = {}
+    for o in obs:
+        base.setdefault(int(o["landmark_id"]), int(o["frame_a"]))
+    lm_base = np.array([base[int(i)] for i in lm_ids], dtype=np.int64)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    if pr.get("prior") is not None:
+        A, b, refs, x0 = pr["prior"]; A = f64(A); b = f64(b); refs = np.ascontiguousarray(refs, dtype=abi.blockref_dtype); x0 = f64(x0); m = len(b)
+    else:
+        A = b = x0 = np.zeros(1); refs = np.zeros(1, dtype=abi.blockref_dtype); m = 0
+    rem = i64(remove_frame_ids)
+    nblk = C.c_int(); mo = C.c_int(); refs_out = np.zeros(256, dtype=abi.blockref_dtype); x0_out = np.zeros(256 * 9); J = np.zeros(max_m * max_m); e0 = np.zeros(max_m)
+    fid = i64(pr["frame_ids"]); cid = i64(pr["cam_ids"])
+    rc = lib().ref_marginalize(C.c_int(len(fid)), _p(fid), _p(f64(pr["poses"])), _p(f64(pr["sb"])), C.c_int(len(cid)), _p(cid), _p(f64(pr["ext"])), C.c_double(float(pr["td"])),
+                               C.c_int(len(lm_ids)), _p(lm_ids), _p(f64(pr["inv_dep"])), _p(lm_base), C.c_int(len(obs)), _p(obs), C.c_int(len(imu)), _p(imu),
+                               C.c_int(m), _p(A), _p(b), C.c_int(len(refs) if m else 0), _p(refs), _p(x0), C.c_int(len(rem)), _p(rem), C.c_double(huber_delta),
+                               C.byref(nblk), _p(refs_out), _p(x0_out), C.byref(mo), _p(J), _p(e0), C.c_int(max_m))
+    assert rc == 0, rc
+    mm = mo.value; refs_out = refs_out[: nblk.value].copy()
+    nx = int(sum(abi.KIND_SIZE[int(k)] for k in refs_out["kind"]))
+    return refs_out, x0_out[:nx].copy(), J[: mm * mm].reshape(mm, mm).copy(), e0[:mm].copy()
+
+
 def pose_plus(x, delta):
     x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
     lib().ref_pose_plus(_p(x), _p(d), _p(o))

@@ -24,6 +24,8 @@
 #include "d2vins_params.hpp"
 #include "factors/imu_factor.h"
 #include "factors/prior_factor.h"
+#include "estimator/marginalization/marginalization.hpp"
+#include "../include/d2ba.h"
 #include "factors/projectionOneFrameTwoCamFactor.h"
 #include "factors/projectionTwoFrameOneCamDepthFactor.h"
 #include "factors/projectionTwoFrameOneCamFactor.h"
@@ -353,4 +355,119 @@ extern "C" int ref_prior_eval(int nblk, const int *kinds, const double *x0, cons
   double *jp = J_out;
   for (int i = 0; i < nblk; i++) { jac.push_back(jp); jp += (size_t)m * kSize[kinds[i]]; }
   return f.Evaluate(px.data(), r_out, J_out ? jac.data() : nullptr) ? m : -2;
+}
+
+// ------------------------------------------------------------------------------------------------ marginalization
+// The reference's OWN Marginalizer::marginalize (d2vins/src/estimator/marginalization/marginalization.cpp:13-286), its
+// ResidualInfo classes (ParamResidualInfo.hpp / .cpp: relavant(), paramsList()), ResidualInfo::Evaluate with the Huber
+// corrector, Utility::schurComplement and the PriorFactor constructor -- all compiled unmodified -- over the reference's
+// factor objects of one window.  What is supplied here instead of d2vinsstate.cpp (the estimator's state class, which
+// needs the whole front end): the five D2EstimatorState lookups those sources call, answered from a table.
+namespace {
+struct MargTable {
+  std::map<FrameIdType, D2Common::StatePtr> pose, sb;
+  std::map<int, D2Common::StatePtr> ext;
+  std::map<LandmarkIdType, D2Common::StatePtr> lm;
+  std::map<LandmarkIdType, FrameIdType> lm_base;
+  D2Common::StatePtr td;
+};
+MargTable *g_marg = nullptr;
+D2Common::StatePtr make_state(const double *v, int n) {
+  D2Common::StatePtr p(new double[n], std::default_delete<double[]>());
+  memcpy(p.get(), v, sizeof(double) * n);
+  return p;
+}
+struct MargState : D2Common::D2State {      // D2State::getPoseState (d2state.hpp:87-95) reads _frame_pose_state
+  explicit MargState(const MargTable &t) : D2Common::D2State(0) { for (auto &kv : t.pose) _frame_pose_state[kv.first] = kv.second; }
+};
+}  // namespace
+namespace D2VINS {   // link-time stand-ins for d2vinsstate.cpp (`this` is never touched)
+StatePtr D2EstimatorState::getExtrinsicState(int i) const { return g_marg->ext.at(i); }
+StatePtr D2EstimatorState::getSpdBiasState(FrameIdType frame_id) const { return g_marg->sb.at(frame_id); }
+StatePtr D2EstimatorState::getLandmarkState(LandmarkIdType landmark_id) const { return g_marg->lm.at(landmark_id); }
+StatePtr D2EstimatorState::getTdState(int) { return g_marg->td; }
+FrameIdType D2EstimatorState::getLandmarkBaseFrame(LandmarkIdType landmark_id) const { return g_marg->lm_base.at(landmark_id); }
+}  // namespace D2VINS
+extern "C" int ref_marginalize(int n_pose, const int64_t *pose_ids, const double *poses, const double *sb, int n_ext, const int64_t *cam_ids, const double *ext,
+                               double td, int n_lm, const int64_t *lm_ids, const double *lm, const int64_t *lm_base, int n_obs, const d2ba_proj_obs *obs,
+                               int n_imu, const d2ba_imu *imu, int prior_m, const double *prior_A, const double *prior_b, int prior_nblk,
+                               const d2ba_blockref *prior_refs, const double *prior_x0, int n_remove, const int64_t *remove_ids, double huber_delta,
+                               int *nblk_out, d2ba_blockref *refs_out, double *x0_out, int *m_out, double *J_out, double *e0_out, int max_m) {
+  static D2VINSConfig cfg;
+  D2VINS::params = &cfg;
+  cfg.margin_enable_fej = false; cfg.margin_sparse_solver = true; cfg.remove_base_when_margin_remote = 2; cfg.verbose = false;
+  cfg.enable_perf_output = false; cfg.debug_write_margin_matrix = false; cfg.landmark_param = D2VINSConfig::LM_INV_DEP;
+  MargTable tab;
+  for (int i = 0; i < n_pose; i++) { tab.pose[pose_ids[i]] = make_state(poses + 7 * i, 7); tab.sb[pose_ids[i]] = make_state(sb + 9 * i, 9); }
+  for (int i = 0; i < n_ext; i++) tab.ext[(int)cam_ids[i]] = make_state(ext + 7 * i, 7);
+  for (int i = 0; i < n_lm; i++) { tab.lm[lm_ids[i]] = make_state(lm + i, 1); tab.lm_base[lm_ids[i]] = lm_base[i]; }
+  tab.td = make_state(&td, 1);
+  g_marg = &tab;
+  MargState state(tab);
+  auto *est = reinterpret_cast<D2VINS::D2EstimatorState *>(static_cast<D2Common::D2State *>(&state));   // only ever used as a D2State / by the stand-ins above
+  Marginalizer marg(est, nullptr);
+  std::shared_ptr<ceres::LossFunction> loss;
+  if (huber_delta > 0) loss = std::make_shared<ceres::HuberLoss>(huber_delta);
+  for (int i = 0; i < n_obs; i++) {
+    const d2ba_proj_obs &o = obs[i];
+    switch (o.type) {
+      case 0: marg.addResidualInfo(LandmarkTwoFrameOneCamResInfo::create(std::make_shared<ProjectionTwoFrameOneCamFactor>(v3(o.pts_i), v3(o.pts_j), v3(o.vel_i), v3(o.vel_j), o.td_i, o.td_j),
+                                                                          loss, o.frame_a, o.frame_b, o.landmark_id, o.cam_a, false)); break;
+      case 1: marg.addResidualInfo(LandmarkTwoFrameTwoCamResInfo::create(std::make_shared<ProjectionTwoFrameTwoCamFactor>(v3(o.pts_i), v3(o.pts_j), v3(o.vel_i), v3(o.vel_j), o.td_i, o.td_j),
+                                                                          loss, o.frame_a, o.frame_b, o.landmark_id, o.cam_a, o.cam_b)); break;
+      case 2: marg.addResidualInfo(LandmarkOneFrameTwoCamResInfo::create(std::make_shared<ProjectionOneFrameTwoCamFactor>(v3(o.pts_i), v3(o.pts_j), v3(o.vel_i), v3(o.vel_j), o.td_i, o.td_j),
+                                                                          loss, o.frame_a, o.landmark_id, o.cam_a, o.cam_b)); break;
+      case 3: marg.addResidualInfo(LandmarkTwoFrameOneCamResInfo::create(std::make_shared<ProjectionTwoFrameOneCamDepthFactor>(v3(o.pts_i), v3(o.pts_j), v3(o.vel_i), v3(o.vel_j), o.td_i, o.td_j, o.depth),
+                                                                          loss, o.frame_a, o.frame_b, o.landmark_id, o.cam_a, true)); break;
+      default: g_marg = nullptr; return -3;   // depth prior (autodiff) is not part of this replay
+    }
+  }
+  for (int i = 0; i < n_imu; i++) {
+    const d2ba_imu &m = imu[i];
+    IntegrationBasePtr pre = std::make_shared<IntegrationBase>(Vector3d(0, 0, 0), Vector3d(0, 0, 0), v3(m.linearized_ba), v3(m.linearized_bg));
+    pre->sum_dt = m.sum_dt; pre->delta_p = v3(m.delta_p); pre->delta_v = v3(m.delta_v);
+    pre->delta_q = Eigen::Quaterniond(m.delta_q[3], m.delta_q[0], m.delta_q[1], m.delta_q[2]);
+    for (int r = 0; r < 15; r++) for (int c = 0; c < 15; c++) { pre->jacobian(r, c) = m.jacobian[r * 15 + c]; pre->covariance(r, c) = m.covariance[r * 15 + c]; }
+    marg.addResidualInfo(ImuResInfo::create(std::make_shared<IMUFactor>(pre), m.frame_a, m.frame_b));
+  }
+  static const int kSize[5] = {7, 7, 9, 1, 1}, kEff[5] = {6, 6, 9, 1, 1};
+  static const D2Common::ParamsType kType[5] = {D2Common::POSE, D2Common::EXTRINSIC, D2Common::SPEED_BIAS, D2Common::TD, D2Common::LANDMARK};
+  if (prior_m > 0) {
+    std::vector<D2Common::ParamInfo> keep;
+    int off = 0, eff = 0;
+    for (int i = 0; i < prior_nblk; i++) {
+      const int k = prior_refs[i].kind; const int64_t id = prior_refs[i].id;
+      D2Common::ParamInfo p;
+      p.pointer = k == 0 ? tab.pose.at(id) : k == 1 ? tab.ext.at((int)id) : k == 2 ? tab.sb.at(id) : k == 3 ? tab.td : tab.lm.at(id);
+      p.index = eff; p.size = kSize[k]; p.eff_size = kEff[k]; p.type = kType[k]; p.id = id;
+      p.data_copied = Map<const VectorXd>(prior_x0 + off, kSize[k]);
+      keep.push_back(p); off += kSize[k]; eff += kEff[k];
+    }
+    if (eff != prior_m) { g_marg = nullptr; return -1; }
+    MatrixXd A(prior_m, prior_m); VectorXd b(prior_m);
+    for (int i = 0; i < prior_m; i++) { b(i) = prior_b[i]; for (int j = 0; j < prior_m; j++) A(i, j) = prior_A[i * prior_m + j]; }
+    marg.addResidualInfo(std::make_shared<PriorResInfo>(std::make_shared<PriorFactor>(keep, A, b)));
+  }
+  std::set<FrameIdType> rem(remove_ids, remove_ids + n_remove);
+  PriorFactorPtr prior = marg.marginalize(rem);
+  g_marg = nullptr;
+  if (!prior) return -2;
+  std::vector<D2Common::ParamInfo> kp = prior->getKeepParams();
+  const int m = prior->getEffParamsDim();
+  if (m > max_m) return -4;
+  *nblk_out = (int)kp.size(); *m_out = m;
+  std::vector<const double *> px; std::vector<std::vector<double>> Jb(kp.size()); std::vector<double *> jp;
+  int off = 0;
+  for (size_t i = 0; i < kp.size(); i++) {
+    int k = 0;
+    for (int q = 0; q < 5; q++) if (kType[q] == kp[i].type) k = q;
+    refs_out[i].kind = k; refs_out[i].pad = 0; refs_out[i].id = kp[i].id;
+    for (int q = 0; q < kp[i].size; q++) x0_out[off + q] = kp[i].data_copied(q);
+    px.push_back(x0_out + off); off += kp[i].size;
+    Jb[i].assign((size_t)m * kp[i].size, 0.0); jp.push_back(Jb[i].data());
+  }
+  if (!prior->Evaluate(px.data(), e0_out, jp.data())) return -5;   // at the linearisation point: residual = e0, Jacobian blocks = columns of J
+  for (size_t i = 0; i < kp.size(); i++)
+    for (int r = 0; r < m; r++) for (int c = 0; c < kp[i].eff_size; c++) J_out[(size_t)r * m + kp[i].index + c] = Jb[i][(size_t)r * kp[i].size + c];
+  return 0;
 }

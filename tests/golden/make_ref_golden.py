@@ -35,6 +35,10 @@ for i, c in enumerate(t.loss_cases()):
     out[f"loss{i}_r"] = r; out[f"loss{i}_J"] = J
 for i, c in enumerate(t.prior_cases()):
     out[f"prior{i}_r"], out[f"prior{i}_J"] = ref.prior_eval(c["kinds"], c["x0"], c["x"], c["A"], c["b"])
+ref.configure()
+for i, kw in enumerate(t.MARG_CASES):
+    pr = t.synth.make_window(**kw)
+    out[f"marg{i}_refs"], out[f"marg{i}_x0"], out[f"marg{i}_J"], out[f"marg{i}_e0"] = ref.marginalize(pr, [int(pr["frame_ids"][0])])
 _, present, traj = t.admm_trajectory()
 out["admm_z"], out["admm_tilde"], out["admm_res"] = ref.admm_replay(present, traj, t.ADMM_KW["relaxation_alpha"], t.ADMM_KW["rho_frame_T"], t.ADMM_KW["rho_frame_theta"])
 np.savez_compressed(os.path.join(HERE, "ref_factors.npz"), **out)

@@ -245,6 +245,52 @@ def test_prior_factor_matches_reference():
         check_prior(c, *ref.prior_eval(c["kinds"], c["x0"], c["x"], c["A"], c["b"]))
 
 
+# ----------------------------------------------------------------------------------------------- marginalization
+MARG_CASES = [dict(seed=9, n_landmarks=40, n_frames=5), dict(seed=10, n_landmarks=30, n_frames=4, cams="stereo"),
+              dict(seed=12, n_landmarks=30, n_frames=4, cams="stereo", estimate_extrinsic=True, estimate_td=True, td_offset=0.002)]
+_EFF = {0: 6, 1: 6, 2: 9, 3: 1, 4: 1}
+
+
+def _offsets(refs):
+    off, o_ = {}, 0
+    for r in refs:
+        off[(int(r["kind"]), int(r["id"]))] = (o_, _EFF[int(r["kind"])]); o_ += _EFF[int(r["kind"])]
+    return off
+
+
+def check_marginalization(kw, refs_r, x0_r, J_r, e0_r):
+    pr = synth.make_window(**kw)
+    o = orc.Oracle(); pr.load(o)
+    A, b, refs, x0 = o.marginalize([int(pr["frame_ids"][0])])
+    oo, ro = _offsets(refs), _offsets(refs_r)
+    assert set(oo) == set(ro)                                     # the same blocks are kept
+    perm = np.concatenate([np.arange(ro[k][0], ro[k][0] + ro[k][1]) for k in oo])
+    # the reference hands the new prior over as (J, e0) = toJacRes(A, b): J^T J = A and J^T e0 = b on the kept eigen-space
+    close(A, (J_r.T @ J_r)[np.ix_(perm, perm)], 1e-9); close(b, (J_r.T @ e0_r)[perm], 1e-9)
+    # linearisation points of the kept blocks = their current values, in the reference's block order
+    SIZE = {0: 7, 1: 7, 2: 9, 3: 1, 4: 1}
+    xo, xr, a, c = {}, {}, 0, 0
+    for r in refs:
+        k = (int(r["kind"]), int(r["id"])); xo[k] = x0[a:a + SIZE[k[0]]]; a += SIZE[k[0]]
+    for r in refs_r:
+        k = (int(r["kind"]), int(r["id"])); xr[k] = x0_r[c:c + SIZE[k[0]]]; c += SIZE[k[0]]
+    for k in xo:
+        close(xo[k], xr[k], 1e-15)
+
+
+@needs_ref
+def test_marginalization_matches_the_reference_marginalizer():
+    """orc_marginalize_x0 vs the reference's OWN Marginalizer::marginalize (marginalization.cpp, ParamResidualInfo.{hpp,cpp},
+    BaseParamResInfo.cpp, utils.hpp schurComplement, PriorFactor -- compiled unmodified) run over the reference's factor
+    objects of the same window with Huber(1): same kept blocks, A and b of the new prior, linearisation points.  Mono, stereo
+    (2F2C / 1F2C residual infos) and free-extrinsic / td windows; first frame removed, remove_base_when_margin_remote = 2,
+    FEJ off, sparse-LLT Schur complement (config/tum/tum_single.yaml:87-94)."""
+    ref.configure()
+    for kw in MARG_CASES:
+        pr = synth.make_window(**kw)
+        check_marginalization(kw, *ref.marginalize(pr, [int(pr["frame_ids"][0])]))
+
+
 # ----------------------------------------------------------------------------------------------- ADMM loop
 ADMM_KW = dict(rho_frame_T=30.0, rho_frame_theta=70.0, relaxation_alpha=0.6)
 ADMM_STEPS, ADMM_ITERS_PER_STEP = 4, 2
@@ -397,3 +443,5 @@ def test_oracle_matches_golden_reference_vectors():
     check_admm(runs, traj, g["admm_z"], g["admm_tilde"], g["admm_res"])
     for i, c in enumerate(prior_cases()):
         check_prior(c, g[f"prior{i}_r"], g[f"prior{i}_J"])
+    for i, kw in enumerate(MARG_CASES):
+        check_marginalization(kw, g[f"marg{i}_refs"], g[f"marg{i}_x0"], g[f"marg{i}_J"], g[f"marg{i}_e0"])
