@@ -57,7 +57,7 @@ struct D2GpuMarshalled {
 class D2GpuSolver : public D2Common::SolverWrapper {
  public:
   D2GpuSolver(D2Common::D2State *state, const D2GpuSolverConfig &cfg);
-  ~D2GpuSolver() override;
+  ~D2GpuSolver();   // (SolverWrapper has no virtual destructor, SolverWrapper.hpp:39-53)
   D2Common::SolverReport solve() override { return solve(nullptr); }
   D2Common::SolverReport solve(std::function<void()> func_set_properties) override;
   void reset() override;

@@ -111,7 +111,6 @@ class SolverWrapper {
 
  public:
   SolverWrapper(D2State *_state) : state(_state) { problem = new ceres::Problem(problem_options); }
-  virtual ~SolverWrapper() { delete problem; }
   virtual void addResidual(const std::shared_ptr<ResidualInfo> &residual_info) { residuals.push_back(residual_info); }
   virtual SolverReport solve() = 0;
   virtual SolverReport solve(std::function<void()> func_set_properties) = 0;

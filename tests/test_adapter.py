@@ -148,3 +148,12 @@ def test_adapter_solve_equals_direct_c_abi_solve(name, tmp_path):
     assert np.abs(sb - s.get_blocks(0, abi.SPEED_BIAS, pr["sb_ids"])).max() <= 1e-8
     assert np.abs(lm / s.get_blocks(0, abi.LANDMARK, pr["lm_ids"])[:, 0] - 1).max() <= 1e-8
     assert chg > 0 and abs(chg - rep.state_changes) <= 1e-9
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_adapter_source_compiles_against_the_reference_own_headers():
+    """adapter/d2gpu_solver.cpp, unchanged, against the reference's REAL SolverWrapper.hpp / BaseParamResInfo.hpp /
+    ParamResidualInfo.hpp / prior_factor.h (-DD2GPU_WITH_D2SLAM_HEADERS; third-party and front-end headers from oracle/_shim):
+    the re-declarations of adapter/d2slam_decls.hpp that the tested binary is built with cover exactly what the adapter uses."""
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "adapter"), "-B", "check_reference_headers"], capture_output=True, text=True)
+    assert out.returncode == 0 and "adapter compiles against the reference's own headers" in out.stdout, out.stderr[-2000:]
