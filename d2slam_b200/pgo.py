@@ -230,3 +230,26 @@ def read_g2o(path, max_agent_id=1000):
             si.append((V * np.sqrt(np.maximum(w, 0.0))) @ V.T)
     return dict(ids=np.array(ids, np.int64), poses=np.array(poses), id_a=np.array(ea, np.int64), id_b=np.array(eb, np.int64),
                 rel=np.array(rel), sqrt_info=np.array(si).reshape(-1, 36))
+
+
+def write_g2o_agents(directory, ids, poses, id_a, id_b, rel, sqrt_info):
+    """The reference's multi-agent layout (read_g2o_multi_agents, posegraph_g2o.cpp:177-195): one file `<agent>.g2o` per
+    agent with that agent's vertices and the edges that start at one of them (inter-agent edges name the other agent through the
+    agent byte of the vertex id)."""
+    import os
+    ids = np.asarray(ids); id_a = np.asarray(id_a)
+    agents = sorted(set(int(i) // 1_000_000 for i in ids))
+    for a in agents:
+        v = (ids // 1_000_000) == a; e = (id_a // 1_000_000) == a
+        write_g2o(os.path.join(directory, f"{a}.g2o"), ids[v], np.asarray(poses)[v], id_a[e], np.asarray(id_b)[e], np.asarray(rel)[e], np.asarray(sqrt_info).reshape(-1, 36)[e])
+    return agents
+
+
+def read_g2o_agents(directory, agents_num):
+    """Mirror of read_g2o_multi_agents: the numerically named *.g2o files in ascending order, the first `agents_num` of them,
+    vertices / edges of agents above agents_num - 1 dropped; concatenated into one graph."""
+    import os
+    files = sorted((int(f[:-4]), os.path.join(directory, f)) for f in os.listdir(directory) if f.endswith(".g2o") and f[:-4].isdigit())[:agents_num]
+    parts = [read_g2o(p, max_agent_id=agents_num - 1) for _, p in files]
+    cat = lambda k: np.concatenate([q[k] for q in parts]) if parts else np.zeros(0)
+    return dict(ids=cat("ids"), poses=cat("poses"), id_a=cat("id_a"), id_b=cat("id_b"), rel=cat("rel"), sqrt_info=cat("sqrt_info"))

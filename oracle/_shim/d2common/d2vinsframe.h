@@ -17,6 +17,7 @@ struct D2BaseFrame {   // interface of d2common/d2baseframe.h:7-60 as far as d2s
   virtual void moveByPose(int new_ref_frame_id, const Swarm::Pose &delta_pose) { reference_frame_id = new_ref_frame_id; odom.p = delta_pose * odom.p; }
   virtual ~D2BaseFrame() {}
 };
+using D2BaseFramePtr = std::shared_ptr<D2BaseFrame>;
 struct VINSFrame : D2BaseFrame {};   // d2vinsframe.h:12-36 (fields not needed by the compiled sources)
 using VINSFramePtr = std::shared_ptr<VINSFrame>;
 }  // namespace D2Common

@@ -4,6 +4,7 @@
 #pragma once
 #include <Eigen/Dense>
 #include <cmath>
+#include <istream>
 #include <memory>
 #include <cstdint>
 #include <vector>
@@ -53,8 +54,21 @@ class Pose {
 // Stand-in for Swarm::LoopEdge (swarm_msgs, un-vendored): the members RelPoseFactor.hpp's Create() helpers touch.  ASSUMED.
 struct LoopEdge {
   int64_t keyframe_id_a = -1, keyframe_id_b = -1; int id_a = -1, id_b = -1;
-  Pose relative_pose; Eigen::Matrix<double, 6, 6> sqrt_info;
+  Pose relative_pose; Eigen::Matrix<double, 6, 6> sqrt_info, info;
+  LoopEdge() {}
+  // (keyframe ids, relative pose, INFORMATION matrix) -- the constructor posegraph_g2o.cpp:160 uses; the square root kept beside
+  // it is the Cholesky factor transposed (any S with S^T S = info gives the same cost)
+  LoopEdge(int64_t a, int64_t b, const Pose &rel, const Eigen::Matrix<double, 6, 6> &information) : keyframe_id_a(a), keyframe_id_b(b), relative_pose(rel), info(information) {
+    Eigen::Matrix<double, 6, 6> L = Eigen::LLT<Eigen::Matrix<double, 6, 6>>(information).matrixL(); sqrt_info = L.transpose();
+  }
+  Eigen::Matrix<double, 6, 6> getInfoMat() const { return info; }
   Eigen::Matrix<double, 6, 6> getSqrtInfoMat() const { return sqrt_info; }
   Eigen::Matrix<double, 4, 4> getSqrtInfoMat4D() const { Eigen::Matrix<double, 4, 4> m; m.setZero(); for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = sqrt_info(i, j); m(3, 3) = sqrt_info(5, 5); return m; }
 };
 }  // namespace Swarm
+// ASSUMED (upstream swarm_msgs): a pose streams as x y z qx qy qz qw, the g2o column order
+inline std::istream &operator>>(std::istream &is, Swarm::Pose &p) {
+  double v[7]; for (int i = 0; i < 7; i++) is >> v[i];
+  p = Swarm::Pose(Eigen::Vector3d(v[0], v[1], v[2]), Eigen::Quaterniond(v[6], v[3], v[4], v[5]));
+  return is;
+}

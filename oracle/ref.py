@@ -183,6 +183,26 @@ def marginalize(pr, remove_frame_ids, huber_delta=1.0, max_m=512):
     return refs_out, x0_out[:nx].copy(), J[: mm * mm].reshape(mm, mm).copy(), e0[:mm].copy()
 
 
+def g2o_read(path, max_agent_id=100000, cap=200000):
+    """read_g2o_agent (d2pgo/test/posegraph_g2o.cpp:133-175) on one file -> vertices (agent, keyframe id, pose7), edges
+    (agent_a, id_a, agent_b, id_b, rel7, information 6x6)."""
+    nv = C.c_int(); ne = C.c_int()
+    va = np.zeros(cap, np.int32); vi = np.zeros(cap, np.int64); vp = np.zeros((cap, 7))
+    ea = np.zeros(cap, np.int32); eia = np.zeros(cap, np.int64); eb = np.zeros(cap, np.int32); eib = np.zeros(cap, np.int64); er = np.zeros((cap, 7)); ei = np.zeros((cap, 36))
+    rc = lib().ref_g2o_read(path.encode(), C.c_int(max_agent_id), C.c_int(cap), C.c_int(cap), C.byref(nv), _p(va), _p(vi), _p(vp), C.byref(ne), _p(ea), _p(eia), _p(eb), _p(eib), _p(er), _p(ei))
+    assert rc == 0, rc
+    n, m = nv.value, ne.value
+    return dict(v_agent=va[:n], v_id=vi[:n], v_pose=vp[:n], e_agent_a=ea[:m], e_id_a=eia[:m], e_agent_b=eb[:m], e_id_b=eib[:m], e_rel=er[:m], e_info=ei[:m].reshape(m, 6, 6))
+
+
+def g2o_write(path, v_id, v_pose, e_id_a, e_id_b, e_rel, e_info):
+    """write_result_to_g2o (posegraph_g2o.cpp:197-232)."""
+    a = [np.ascontiguousarray(v_id, np.int64), np.ascontiguousarray(v_pose, np.float64), np.ascontiguousarray(e_id_a, np.int64), np.ascontiguousarray(e_id_b, np.int64),
+         np.ascontiguousarray(e_rel, np.float64), np.ascontiguousarray(np.asarray(e_info).reshape(-1, 36), np.float64)]
+    rc = lib().ref_g2o_write(path.encode(), C.c_int(len(a[0])), _p(a[0]), _p(a[1]), C.c_int(len(a[2])), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]))
+    assert rc == 0, rc
+
+
 def pose_plus(x, delta):
     x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
     lib().ref_pose_plus(_p(x), _p(d), _p(o))

@@ -26,6 +26,8 @@
 #include "factors/prior_factor.h"
 #include "estimator/marginalization/marginalization.hpp"
 #include "../include/d2ba.h"
+#include "posegraph_g2o.hpp"
+#include <random>
 #include "factors/projectionOneFrameTwoCamFactor.h"
 #include "factors/projectionTwoFrameOneCamDepthFactor.h"
 #include "factors/projectionTwoFrameOneCamFactor.h"
@@ -469,5 +471,39 @@ extern "C" int ref_marginalize(int n_pose, const int64_t *pose_ids, const double
   if (!prior->Evaluate(px.data(), e0_out, jp.data())) return -5;   // at the linearisation point: residual = e0, Jacobian blocks = columns of J
   for (size_t i = 0; i < kp.size(); i++)
     for (int r = 0; r < m; r++) for (int c = 0; c < kp[i].eff_size; c++) J_out[(size_t)r * m + kp[i].index + c] = Jb[i][(size_t)r * kp[i].size + c];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ g2o files (d2pgo)
+// The reference's own reader / writer (d2pgo/test/posegraph_g2o.cpp:27-232, compiled unmodified): read_g2o_agent on one file,
+// write_result_to_g2o.  (The three random-number externs it declares belong to d2pgo_test.cpp.)
+namespace D2PGO { std::random_device rd; std::default_random_engine eng(0); std::normal_distribution<double> d(0, 1); }
+extern "C" int ref_g2o_read(const char *path, int max_agent_id, int max_v, int max_e, int *nv, int *v_agent, int64_t *v_id, double *v_pose7,
+                            int *ne, int *e_agent_a, int64_t *e_id_a, int *e_agent_b, int64_t *e_id_b, double *e_rel7, double *e_info36) {
+  std::map<FrameIdType, D2BaseFramePtr> frames; std::vector<Swarm::LoopEdge> edges;
+  D2PGO::read_g2o_agent(path, frames, edges, false, max_agent_id, -1, false);
+  if ((int)frames.size() > max_v || (int)edges.size() > max_e) return -1;
+  int i = 0;
+  for (auto &kv : frames) { v_agent[i] = kv.second->drone_id; v_id[i] = kv.second->frame_id; kv.second->odom.pose().to_vector(v_pose7 + 7 * i); i++; }
+  *nv = i; i = 0;
+  for (auto &e : edges) {
+    e_agent_a[i] = e.id_a; e_agent_b[i] = e.id_b; e_id_a[i] = e.keyframe_id_a; e_id_b[i] = e.keyframe_id_b; e.relative_pose.to_vector(e_rel7 + 7 * i);
+    const Eigen::Matrix6d I6 = e.getInfoMat();
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) e_info36[36 * i + r * 6 + c] = I6(r, c);
+    i++;
+  }
+  *ne = i;
+  return 0;
+}
+extern "C" int ref_g2o_write(const char *path, int nv, const int64_t *v_id, const double *v_pose7, int ne, const int64_t *e_id_a, const int64_t *e_id_b,
+                             const double *e_rel7, const double *e_info36) {
+  std::vector<D2BaseFramePtr> frames; std::vector<Swarm::LoopEdge> edges;
+  for (int i = 0; i < nv; i++) { auto f = std::make_shared<D2BaseFrame>(); f->frame_id = v_id[i]; f->odom.pose() = Swarm::Pose(v_pose7 + 7 * i); frames.push_back(f); }
+  for (int i = 0; i < ne; i++) {
+    Eigen::Matrix6d I6;
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) I6(r, c) = e_info36[36 * i + r * 6 + c];
+    edges.emplace_back(e_id_a[i], e_id_b[i], Swarm::Pose(e_rel7 + 7 * i), I6);
+  }
+  D2PGO::write_result_to_g2o(path, frames, edges, false);
   return 0;
 }

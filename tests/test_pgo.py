@@ -110,3 +110,55 @@ def test_pgo_edges_on_device_match_the_reference_functor():
         r, Ja, Jb = ref.relpose_ad_eval(g["init"][a], g["init"][b], g["rel"][e], S[e])
         want = np.concatenate([r, (Ja @ plus_jacobian(g["init"][a])).ravel(), (Jb @ plus_jacobian(g["init"][b])).ravel()])
         assert np.abs(dev[e] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), e
+
+
+def _ref_or_skip():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libd2ref.so not built and no reference tree")
+    return ref
+
+
+def test_g2o_written_here_is_read_by_the_reference_reader(tmp_path):
+    """pgo.write_g2o_agents (one `<agent>.g2o` per agent, chr('a' + agent) in the top byte of every vertex id) -> the reference's
+    OWN read_g2o_agent (d2pgo/test/posegraph_g2o.cpp, compiled unmodified into oracle/_ref) on every file: agents, keyframe ids,
+    poses, relative poses and information matrices come back exactly; the max_agent_id filter drops the same edges as ours."""
+    ref = _ref_or_skip()
+    g = small_graph(seed=2, n_agents=3, n=12, loops=20)
+    rng = np.random.default_rng(0)
+    S = g["sqrt_info"].reshape(-1, 6, 6) + 0.3 * rng.normal(size=(len(g["ea"]), 6, 6))        # full information matrices
+    info = np.einsum("eki,ekj->eij", S, S)
+    agents = pgo.write_g2o_agents(str(tmp_path), g["ids"], g["init"], g["id_a"], g["id_b"], g["rel"], S.reshape(-1, 36))
+    assert agents == [0, 1, 2]
+    for a in agents:
+        r = ref.g2o_read(str(tmp_path / f"{a}.g2o"), max_agent_id=len(agents) - 1)
+        v = (g["ids"] // 1_000_000) == a; e = (g["id_a"] // 1_000_000) == a
+        assert np.all(r["v_agent"] == a) and np.array_equal(np.sort(r["v_id"]), np.sort(g["ids"][v] % 1_000_000))
+        order = np.argsort(r["v_id"]); mine = np.argsort(g["ids"][v])
+        assert np.abs(r["v_pose"][order] - g["init"][v][mine]).max() <= 1e-15
+        assert np.array_equal(r["e_agent_a"].astype(np.int64) * 1_000_000 + r["e_id_a"], g["id_a"][e])
+        assert np.array_equal(r["e_agent_b"].astype(np.int64) * 1_000_000 + r["e_id_b"], g["id_b"][e])
+        assert np.abs(r["e_rel"] - g["rel"][e]).max() <= 1e-15
+        assert np.abs(r["e_info"] - info[e]).max() <= 1e-12 * np.abs(info).max()
+        # the agent filter (posegraph_g2o.cpp:72-74, 112-114): with max_agent_id = 0 only agent 0's own edges survive
+        r0 = ref.g2o_read(str(tmp_path / f"{a}.g2o"), max_agent_id=0); m0 = pgo.read_g2o(str(tmp_path / f"{a}.g2o"), max_agent_id=0)
+        assert len(r0["v_id"]) == len(m0["ids"]) and len(r0["e_id_a"]) == len(m0["id_a"])
+    h = pgo.read_g2o_agents(str(tmp_path), 3)
+    assert np.array_equal(np.sort(h["ids"]), np.sort(g["ids"])) and len(h["id_a"]) == len(g["id_a"])
+    h2 = pgo.read_g2o_agents(str(tmp_path), 2)
+    assert set(h2["ids"] // 1_000_000) == {0, 1} and np.all(h2["id_b"] // 1_000_000 <= 1)
+
+
+def test_g2o_written_by_the_reference_is_read_here(tmp_path):
+    """The reference's write_result_to_g2o (plain keyframe ids, default ostream precision: 6 significant digits) -> pgo.read_g2o."""
+    ref = _ref_or_skip()
+    g = small_graph(seed=3, n_agents=1, n=15, loops=10)
+    S = g["sqrt_info"].reshape(-1, 6, 6); info = np.einsum("eki,ekj->eij", S, S)
+    path = str(tmp_path / "out.g2o")
+    ref.g2o_write(path, g["ids"], g["init"], g["id_a"], g["id_b"], g["rel"], info)
+    h = pgo.read_g2o(path)
+    assert np.array_equal(h["ids"], g["ids"]) and np.array_equal(h["id_a"], g["id_a"]) and np.array_equal(h["id_b"], g["id_b"])
+    assert np.abs(h["poses"][:, :3] - g["init"][:, :3]).max() <= 1e-5 * max(1.0, np.abs(g["init"][:, :3]).max()) and np.abs(h["poses"][:, 3:] - g["init"][:, 3:]).max() <= 1e-5
+    assert np.abs(h["rel"] - g["rel"]).max() <= 1e-5 * max(1.0, np.abs(g["rel"]).max())
+    S1 = h["sqrt_info"].reshape(-1, 6, 6)
+    assert np.abs(np.einsum("eki,ekj->eij", S1, S1) - info).max() <= 1e-5 * np.abs(info).max()
