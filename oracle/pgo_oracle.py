@@ -48,6 +48,44 @@ def edge_eval(p0, p1, rel, S):
     return r, S @ A0, S @ A1
 
 
+def _vqmul(a, b):
+    ax, ay, az, aw = a[:, 0], a[:, 1], a[:, 2], a[:, 3]; bx, by, bz, bw = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], axis=1)
+
+
+def _vskew(v):
+    z = np.zeros(len(v))
+    return np.stack([np.stack([z, -v[:, 2], v[:, 1]], 1), np.stack([v[:, 2], z, -v[:, 0]], 1), np.stack([-v[:, 1], v[:, 0], z], 1)], 1)
+
+
+def _vrot(q):
+    """rotation matrices of unit quaternions (x y z w), batched"""
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    return np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], 1),
+                     np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], 1),
+                     np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)], 1)
+
+
+def edges_eval(poses, ea, eb, rel, S):
+    """edge_eval for all edges at once (same formulas, numpy-batched): r [E,6], J0 [E,6,6], J1 [E,6,6]."""
+    p0, p1 = poses[ea], poses[eb]
+    conj = np.array([-1.0, -1.0, -1.0, 1.0])
+    q0i, q1i, qm = p0[:, 3:7] * conj, p1[:, 3:7] * conj, rel[:, 3:7]
+    R0i = _vrot(q0i)
+    pab = np.einsum("eij,ej->ei", R0i, p1[:, :3] - p0[:, :3])
+    X = _vqmul(q1i, p0[:, 3:7]); dq = _vqmul(qm, X)
+    raw = np.concatenate([pab - rel[:, :3], 2.0 * dq[:, :3]], axis=1)
+    r = np.einsum("eij,ej->ei", S, raw)
+    E = len(ea); I3 = np.eye(3)[None]
+    A0 = np.zeros((E, 6, 6)); A1 = np.zeros((E, 6, 6))
+    A0[:, :3, :3] = -R0i; A0[:, :3, 3:] = _vskew(pab); A1[:, :3, :3] = R0i
+    A0[:, 3:, 3:] = dq[:, 3, None, None] * I3 + _vskew(dq[:, :3])
+    Lm = qm[:, 3, None, None] * I3 + _vskew(qm[:, :3]); Rx = X[:, 3, None, None] * I3 - _vskew(X[:, :3])
+    A1[:, 3:, 3:] = -(np.einsum("eij,ejk->eik", Lm, Rx) - np.einsum("ei,ej->eij", qm[:, :3], X[:, :3]))
+    return r, np.einsum("eij,ejk->eik", S, A0), np.einsum("eij,ejk->eik", S, A1)
+
+
 def cost(poses, ea, eb, rel, S):
     return 0.5 * sum(float(np.dot(*(2 * [edge_eval(poses[a], poses[b], rl, s)[0]]))) for a, b, rl, s in zip(ea, eb, rel, S))
 
@@ -57,16 +95,17 @@ def solve(poses, fixed, ea, eb, rel, sqrt_info, iters=30, ftol=1e-12):
     x = np.array(poses, float); N = len(x); S = np.asarray(sqrt_info).reshape(-1, 6, 6)
     free = np.nonzero(np.asarray(fixed) == 0)[0]; col = -np.ones(N, int); col[free] = np.arange(len(free)) * 6
     costs = []
+    ea = np.asarray(ea); eb = np.asarray(eb); rel = np.asarray(rel, float)
+    E = len(ea); rr, cc = np.meshgrid(np.arange(6), np.arange(6), indexing="ij")
     for it in range(iters):
-        rows, cols, vals = [], [], []; r_all = np.zeros(6 * len(ea))
-        for e, (a, b) in enumerate(zip(ea, eb)):
-            r, J0, J1 = edge_eval(x[a], x[b], rel[e], S[e])
-            r_all[6 * e:6 * e + 6] = r
-            for blk, J in ((a, J0), (b, J1)):
-                if col[blk] >= 0:
-                    rr, cc = np.meshgrid(np.arange(6), np.arange(6), indexing="ij")
-                    rows.append((6 * e + rr).ravel()); cols.append((col[blk] + cc).ravel()); vals.append(J.ravel())
-        J = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(6 * len(ea), 6 * len(free)))
+        r_e, J0, J1 = edges_eval(x, ea, eb, rel, S)                      # == edge_eval per edge (tests/test_pgo.py)
+        r_all = r_e.ravel()
+        rows, cols, vals = [], [], []
+        for blk, J in ((ea, J0), (eb, J1)):
+            keep = col[blk] >= 0
+            e_idx = np.nonzero(keep)[0]
+            rows.append((6 * e_idx[:, None, None] + rr[None]).ravel()); cols.append((col[blk[keep]][:, None, None] + cc[None]).ravel()); vals.append(J[keep].ravel())
+        J = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(6 * E, 6 * len(free)))
         c = 0.5 * float(r_all @ r_all); costs.append(c)
         if it and abs(costs[-2] - c) <= ftol * max(c, 1e-300):
             break

@@ -162,3 +162,13 @@ def test_g2o_written_by_the_reference_is_read_here(tmp_path):
     assert np.abs(h["rel"] - g["rel"]).max() <= 1e-5 * max(1.0, np.abs(g["rel"]).max())
     S1 = h["sqrt_info"].reshape(-1, 6, 6)
     assert np.abs(np.einsum("eki,ekj->eij", S1, S1) - info).max() <= 1e-5 * np.abs(info).max()
+
+
+def test_batched_linearisation_equals_the_per_edge_function():
+    g = small_graph(seed=7)
+    rng = np.random.default_rng(2)
+    S = g["sqrt_info"].reshape(-1, 6, 6) + 0.4 * rng.normal(size=(len(g["ea"]), 6, 6))
+    r, J0, J1 = po.edges_eval(g["init"], g["ea"], g["eb"], g["rel"], S)
+    for e in range(0, len(g["ea"]), 3):
+        r1, a, b = po.edge_eval(g["init"][g["ea"][e]], g["init"][g["eb"][e]], g["rel"][e], S[e])
+        assert np.abs(r[e] - r1).max() <= 1e-12 * max(1.0, np.abs(r1).max()) and np.abs(J0[e] - a).max() <= 1e-12 * np.abs(a).max() and np.abs(J1[e] - b).max() <= 1e-12 * np.abs(b).max()
