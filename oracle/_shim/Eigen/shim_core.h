@@ -549,6 +549,12 @@ template <class M, int UpLo = 1, class Ord = void> class SimplicialLLT {   // de
 };
 template <class M, int UpLo = 1, class Ord = void> class SimplicialLDLT;
 template <class T, int O = 0, class St = void> class Ref;
+// Ref<const Matrix<..>>: binds to any expression of that shape; here a copy (the callers only read through it)
+template <class S, int R, int C, int Opt, int MR, int MC, int O, class St>
+class Ref<const Matrix<S, R, C, Opt, MR, MC>, O, St> : public Matrix<S, R, C, Opt, MR, MC> {
+ public:
+  template <class D> Ref(const MatrixBase<D> &m) : Matrix<S, R, C, Opt, MR, MC>(m) {}
+};
 
 // ------------------------------------------------------------------------------------------------ quaternions
 template <class Derived> struct qtraits;

@@ -81,6 +81,7 @@ template <typename T, int N> Jet<T, N> acos(const Jet<T, N> &x) { return jet_cha
 template <typename T, int N> Jet<T, N> abs(const Jet<T, N> &x) { return x.a < T(0) ? -x : x; }
 template <typename T, int N> Jet<T, N> fabs(const Jet<T, N> &x) { return x.a < T(0) ? -x : x; }
 template <typename T, int N> bool isfinite(const Jet<T, N> &x) { return std::isfinite(x.a); }
+template <typename T, int N> Jet<T, N> floor(const Jet<T, N> &x) { return Jet<T, N>(std::floor(x.a)); }   // piecewise constant: zero derivative
 
 // Exact derivatives of a templated functor by dual numbers.  A free function on purpose: the class below does NOT
 // instantiate the functor (RelPoseFactor.hpp's Create() helpers name AutoDiffCostFunction for factors -- 4-DoF, perturbation,

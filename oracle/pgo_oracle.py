@@ -48,6 +48,25 @@ def edge_eval(p0, p1, rel, S):
     return r, S @ A0, S @ A1
 
 
+def normalize_angle(a):
+    """Utility::NormalizeAngle (utils.hpp:251-257)"""
+    return a - 2.0 * np.pi * np.floor((a + np.pi) / (2.0 * np.pi))
+
+
+def edge_eval_4d(pa, pb, rel_pos, rel_yaw, S):
+    """RelPoseFactor4D (RelPoseFactor.hpp:216-227 + Utility::poseError4D utils.hpp:266-280), the reference's default PGO factor
+    (pgo_pose_dof = PGO_POSE_4D): poses [x y z yaw]; r = S [p_meas - Rz(-yaw_a)(p_b - p_a) ; N(yaw_meas - N(yaw_b - yaw_a))] and its
+    Jacobians w.r.t. the two 4-vectors (the yaw manifold's tangent is the angle itself).  Oracle only: no device kernel yet."""
+    c, s_ = np.cos(-pa[3]), np.sin(-pa[3])
+    Rz = np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]]); dRz = np.array([[-s_, -c, 0.0], [c, -s_, 0.0], [0.0, 0.0, 0.0]])   # d Rz(t)/dt at t = -yaw_a
+    v = pb[:3] - pa[:3]
+    raw = np.concatenate([rel_pos - Rz @ v, [normalize_angle(rel_yaw - normalize_angle(pb[3] - pa[3]))]])
+    A0 = np.zeros((4, 4)); A1 = np.zeros((4, 4))
+    A0[:3, :3] = Rz; A0[:3, 3] = dRz @ v; A0[3, 3] = 1.0
+    A1[:3, :3] = -Rz; A1[3, 3] = -1.0
+    return S @ raw, S @ A0, S @ A1
+
+
 def _vqmul(a, b):
     ax, ay, az, aw = a[:, 0], a[:, 1], a[:, 2], a[:, 3]; bx, by, bz, bw = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
     return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,

@@ -203,6 +203,15 @@ def g2o_write(path, v_id, v_pose, e_id_a, e_id_b, e_rel, e_info):
     assert rc == 0, rc
 
 
+def relpose4d_eval(pose_a4, pose_b4, rel7, sqrt_info4):
+    """RelPoseFactor4D (RelPoseFactor.hpp:196-238): poses [x y z yaw]; residual (4) and the 4 x 4 Jacobians by dual numbers."""
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pose_a4, pose_b4, rel7, np.asarray(sqrt_info4).reshape(16))]
+    r = np.zeros(4); Ja = np.zeros((4, 4)); Jb = np.zeros((4, 4))
+    n = lib().ref_relpose4d_eval(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(r), _p(Ja), _p(Jb))
+    assert n == 4, n
+    return r, Ja, Jb
+
+
 def pose_plus(x, delta):
     x = np.ascontiguousarray(x, dtype=np.float64); d = np.ascontiguousarray(delta, dtype=np.float64); o = np.zeros(7)
     lib().ref_pose_plus(_p(x), _p(d), _p(o))

@@ -175,6 +175,17 @@ int ref_loss_correct(int n_res, int n_par, const double *r_in, const double *J_i
   return n_res;
 }
 
+// RelPoseFactor4D (RelPoseFactor.hpp:196-238), d2pgo's DEFAULT factor (pgo_pose_dof = PGO_POSE_4D, d2pgo_config.h): poses are
+// [x y z yaw]; same evaluation scheme as ref_relpose_ad_eval (doubles / dual numbers).  J: 4 x 4 row-major per pose.
+int ref_relpose4d_eval(const double *pose_a4, const double *pose_b4, const double *rel7, const double *sqrt_info16, double *r4, double *Ja4x4, double *Jb4x4) {
+  Eigen::Matrix4d S;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) S(i, j) = sqrt_info16[i * 4 + j];
+  D2Common::RelPoseFactor4D f(Swarm::Pose(rel7), S);
+  const double *params[2] = {pose_a4, pose_b4};
+  double *jac[2] = {Ja4x4, Jb4x4};
+  return ceres::AutoDiffEvaluate<4, 4, 4>(f, params, r4, Ja4x4 ? jac : nullptr) ? 4 : -2;
+}
+
 // PoseLocalParameterization (pose_local_parameterization.cpp:13-38); its members are private virtuals of
 // ceres::LocalParameterization, reached through the base interface exactly as ceres does
 void ref_pose_plus(const double *x7, const double *delta6, double *out7) {

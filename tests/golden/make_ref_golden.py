@@ -35,6 +35,8 @@ for i, c in enumerate(t.loss_cases()):
     out[f"loss{i}_r"] = r; out[f"loss{i}_J"] = J
 for i, c in enumerate(t.prior_cases()):
     out[f"prior{i}_r"], out[f"prior{i}_J"] = ref.prior_eval(c["kinds"], c["x0"], c["x"], c["A"], c["b"])
+for i, c in enumerate(t.relpose4d_cases()):
+    out[f"relpose4d{i}_r"], out[f"relpose4d{i}_Ja"], out[f"relpose4d{i}_Jb"] = ref.relpose4d_eval(c["pa"], c["pb"], c["rel"], c["S"])
 ref.configure()
 for i, kw in enumerate(t.MARG_CASES):
     pr = t.synth.make_window(**kw)

@@ -416,6 +416,35 @@ def test_rel_pose_factor_matches_reference():
         check_relpose(c, *ref.relpose_ad_eval(c["pa"], c["pb"], c["rel"], c["S"]))
 
 
+def relpose4d_cases(seed=29, n=8):
+    rng = np.random.default_rng(seed)
+    tof.RNG = np.random.default_rng(seed + 1)
+    out = []
+    for k in range(n):
+        pa = np.concatenate([rng.normal(size=3) * 3, [rng.uniform(-np.pi, np.pi)]]); pb = np.concatenate([rng.normal(size=3) * 3, [rng.uniform(-np.pi, np.pi)]])
+        if k == n - 1:
+            pa[3], pb[3] = 3.0, -3.0                      # yaw difference wraps through pi
+        S = np.diag([20.0, 20.0, 20.0, 57.0]) + (0.0 if k % 2 == 0 else 1.0) * rng.normal(size=(4, 4))
+        out.append(dict(pa=pa, pb=pb, rel=tof.rand_pose(2.0), S=S))
+    return out
+
+
+def check_relpose4d(c, r_ref, Ja, Jb):
+    from oracle import pgo_oracle as po
+    q = c["rel"][3:7]
+    yaw = np.arctan2(2 * (q[3] * q[2] + q[0] * q[1]), 1 - 2 * (q[1] * q[1] + q[2] * q[2]))      # Swarm::Pose::yaw (ASSUMED: the z Euler angle)
+    r_o, J0, J1 = po.edge_eval_4d(c["pa"], c["pb"], c["rel"][:3], yaw, c["S"])
+    close(r_o, r_ref, 1e-13); close(J0, Ja, 1e-13); close(J1, Jb, 1e-13)
+
+
+@needs_ref
+def test_rel_pose_factor_4d_matches_reference():
+    """oracle/pgo_oracle.py::edge_eval_4d vs the reference's RelPoseFactor4D functor (RelPoseFactor.hpp:196-238; d2pgo's default
+    4-DoF configuration) with doubles and dual numbers.  Oracle-level only: the device path carries the 6-DoF factor."""
+    for c in relpose4d_cases():
+        check_relpose4d(c, *ref.relpose4d_eval(c["pa"], c["pb"], c["rel"], c["S"]))
+
+
 # ----------------------------------------------------------------------------------------------- frozen reference outputs
 def test_oracle_matches_golden_reference_vectors():
     """Same comparisons against reference outputs frozen by tests/golden/make_ref_golden.py (runs everywhere)."""
@@ -445,3 +474,5 @@ def test_oracle_matches_golden_reference_vectors():
         check_prior(c, g[f"prior{i}_r"], g[f"prior{i}_J"])
     for i, kw in enumerate(MARG_CASES):
         check_marginalization(kw, g[f"marg{i}_refs"], g[f"marg{i}_x0"], g[f"marg{i}_J"], g[f"marg{i}_e0"])
+    for i, c in enumerate(relpose4d_cases()):
+        check_relpose4d(c, g[f"relpose4d{i}_r"], g[f"relpose4d{i}_Ja"], g[f"relpose4d{i}_Jb"])
